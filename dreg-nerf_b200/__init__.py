@@ -1,0 +1,10 @@
+"""dreg-nerf_b200: B200-native registration hot path of DReg-NeRF behind the reference's API.
+
+Only what the path needs: ``csrc/`` (hand-written sm_100a CUDA + the C ABI of
+``include/dregb200.h``), the ctypes binding, and the host-side mirrors of the reference
+interfaces (``NeRFRegTr``, ``NGPradianceField`` / ``SampleGrid`` extract).
+"""
+from ._lib import DrbError, load as load_library  # noqa: F401
+from .nerf_regtr import NeRFRegTr  # noqa: F401
+from .ngp import NGPradianceField, SampleGrid, extract_block  # noqa: F401
+from . import synthetic  # noqa: F401

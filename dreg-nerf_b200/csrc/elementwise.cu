@@ -1,0 +1,393 @@
+// HBM-bound helpers around the tensor-core GEMM: plane splitting, weight packing, im2col,
+// BatchNorm statistics / apply, max-pool, FPN nearest-upsample + add.  All channels-last.
+#include "common.cuh"
+
+#include <stdarg.h>
+
+namespace drb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* drb_last_error(void) { return g_err; }
+extern "C" int drb_abi_version(void) { return DRB_ABI_VERSION; }
+
+static inline int grid_for(long long n, int block, int cap = 148 * 16) {
+  long long g = (n + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void split_kernel(const float* __restrict__ x, bf16* __restrict__ hi,
+                             bf16* __restrict__ lo, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    bf16 h, l;
+    split_bf16(x[i], h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+extern "C" int drb_split_planes(const float* x, void* hi, void* lo, long long n,
+                                cudaStream_t stream) {
+  DRB_REQUIRE(x && hi && n >= 0, "drb_split_planes: bad arguments");
+  if (n == 0) return 0;
+  split_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, (bf16*)hi, (bf16*)lo, n);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// weights [cout][cin][taps] -> [taps][cout][cin_pad]
+__global__ void pack_w_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cin_pad,
+                              bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  const long long total = (long long)taps * cout * cin_pad;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % cin_pad);
+    const int o = (int)((i / cin_pad) % cout);
+    const int t = (int)(i / ((long long)cin_pad * cout));
+    const float v = (c < cin) ? w[((long long)o * cin + c) * taps + t] : 0.f;
+    bf16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+// weights [cout][cin][taps] -> [cout][kpad], k = tap*cin + c
+__global__ void pack_w_im2col_kernel(const float* __restrict__ w, int cout, int cin, int taps,
+                                     int kpad, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  const long long total = (long long)cout * kpad;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int k = (int)(i % kpad);
+    const int o = (int)(i / kpad);
+    float v = 0.f;
+    if (k < taps * cin) {
+      const int t = k / cin, c = k % cin;
+      v = w[((long long)o * cin + c) * taps + t];
+    }
+    bf16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+extern "C" int drb_pack_conv_weight(const float* w, int cout, int cin, int taps, int cin_pad,
+                                    void* hi, void* lo, cudaStream_t stream) {
+  DRB_REQUIRE(w && hi && cout > 0 && cin > 0 && taps > 0 && cin_pad >= cin,
+              "drb_pack_conv_weight: bad arguments");
+  pack_w_kernel<<<grid_for((long long)taps * cout * cin_pad, 256), 256, 0, stream>>>(
+      w, cout, cin, taps, cin_pad, (bf16*)hi, (bf16*)lo);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+extern "C" int drb_pack_conv_weight_im2col(const float* w, int cout, int cin, int taps, int kpad,
+                                           void* hi, void* lo, cudaStream_t stream) {
+  DRB_REQUIRE(w && hi && cout > 0 && cin > 0 && taps > 0 && kpad >= cin * taps,
+              "drb_pack_conv_weight_im2col: bad arguments");
+  pack_w_im2col_kernel<<<grid_for((long long)cout * kpad, 256), 256, 0, stream>>>(
+      w, cout, cin, taps, kpad, (bf16*)hi, (bf16*)lo);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// im2col: one thread per (output voxel, k) element; k fastest so that writes coalesce.
+__global__ void im2col_kernel(drb_im2col_desc d, int od, int oh, int ow, bf16* __restrict__ hi,
+                              bf16* __restrict__ lo) {
+  const long long rows = (long long)d.g * od * oh * ow;
+  const long long total = rows * d.kpad;
+  const int kk = d.k * d.k * d.k * d.c;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int k = (int)(i % d.kpad);
+    long long r = i / d.kpad;
+    float v = 0.f;
+    if (k < kk) {
+      const int ch = k % d.c;
+      int t = k / d.c;
+      const int kx = t % d.k; t /= d.k;
+      const int ky = t % d.k; t /= d.k;
+      const int kz = t;
+      const int x = (int)(r % ow); r /= ow;
+      const int y = (int)(r % oh); r /= oh;
+      const int z = (int)(r % od); r /= od;
+      const int g = (int)r;
+      const int iz = z * d.stride - d.pad + kz;
+      const int iy = y * d.stride - d.pad + ky;
+      const int ix = x * d.stride - d.pad + kx;
+      if (iz >= 0 && iz < d.d && iy >= 0 && iy < d.h && ix >= 0 && ix < d.w)
+        v = d.x[g * d.sg + ch * d.sc + iz * d.sd + iy * d.sh + ix * d.sw];
+    }
+    bf16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+extern "C" int drb_im2col(const drb_im2col_desc* d, void* hi, void* lo, cudaStream_t stream) {
+  DRB_REQUIRE(d && d->x && hi, "drb_im2col: null argument");
+  DRB_REQUIRE(d->k >= 1 && d->stride >= 1 && d->kpad >= d->k * d->k * d->k * d->c &&
+                  d->kpad % 64 == 0,
+              "drb_im2col: bad kernel/kpad");
+  const int od = (d->d + 2 * d->pad - d->k) / d->stride + 1;
+  const int oh = (d->h + 2 * d->pad - d->k) / d->stride + 1;
+  const int ow = (d->w + 2 * d->pad - d->k) / d->stride + 1;
+  const long long total = (long long)d->g * od * oh * ow * d->kpad;
+  im2col_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(*d, od, oh, ow, (bf16*)hi,
+                                                                    (bf16*)lo);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm statistics: x [g][m][c].  Block = 64 channels x 4 row lanes; double accumulation.
+__global__ void bn_stats_kernel(const float* __restrict__ x, long long m, int c, int rows_per_block,
+                                double* __restrict__ accum) {
+  const int g = blockIdx.z;
+  const int c0 = blockIdx.y * 64;
+  const int cl = threadIdx.x & 63;
+  const int rl = threadIdx.x >> 6;
+  const int ch = c0 + cl;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > m) r1 = m;
+  double s = 0.0, ss = 0.0;
+  if (ch < c) {
+    const float* base = x + ((long long)g * m) * c + ch;
+    for (long long r = r0 + rl; r < r1; r += 4) {
+      const float v = base[r * c];
+      s += (double)v;
+      ss += (double)v * (double)v;
+    }
+  }
+  __shared__ double sh[2][4][64];
+  sh[0][rl][cl] = s;
+  sh[1][rl][cl] = ss;
+  __syncthreads();
+  if (rl == 0 && ch < c) {
+    s = sh[0][0][cl] + sh[0][1][cl] + sh[0][2][cl] + sh[0][3][cl];
+    ss = sh[1][0][cl] + sh[1][1][cl] + sh[1][2][cl] + sh[1][3][cl];
+    atomicAdd(&accum[((long long)g * c + ch) * 2 + 0], s);
+    atomicAdd(&accum[((long long)g * c + ch) * 2 + 1], ss);
+  }
+}
+
+extern "C" int drb_bn_stats(const float* x, int g, long long m, int c, double* accum,
+                            cudaStream_t stream) {
+  DRB_REQUIRE(x && accum && g > 0 && m > 0 && c > 0, "drb_bn_stats: bad arguments");
+  DRB_CUDA_OK(cudaMemsetAsync(accum, 0, sizeof(double) * 2 * g * c, stream));
+  int rows_per_block = 256;
+  while ((m + rows_per_block - 1) / rows_per_block > 4096) rows_per_block *= 2;
+  dim3 grid((unsigned)((m + rows_per_block - 1) / rows_per_block), (unsigned)((c + 63) / 64),
+            (unsigned)g);
+  bn_stats_kernel<<<grid, 256, 0, stream>>>(x, m, c, rows_per_block, accum);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ accum, int g, long long m, int c,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_var, int training,
+                                   float momentum, float eps, float* __restrict__ scale,
+                                   float* __restrict__ shift) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const float ga = gamma ? gamma[ch] : 1.f;
+  const float be = beta ? beta[ch] : 0.f;
+  if (training) {
+    float rm = running_mean ? running_mean[ch] : 0.f;
+    float rv = running_var ? running_var[ch] : 1.f;
+    for (int gi = 0; gi < g; ++gi) {
+      const double s = accum[((long long)gi * c + ch) * 2 + 0];
+      const double ss = accum[((long long)gi * c + ch) * 2 + 1];
+      const double mean = s / (double)m;
+      double var = ss / (double)m - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float sc = ga * rstd;
+      scale[(long long)gi * c + ch] = sc;
+      shift[(long long)gi * c + ch] = be - (float)mean * sc;
+      const double unbiased = m > 1 ? var * ((double)m / (double)(m - 1)) : var;
+      rm = (1.f - momentum) * rm + momentum * (float)mean;
+      rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+    }
+    if (running_mean) running_mean[ch] = rm;
+    if (running_var) running_var[ch] = rv;
+  } else {
+    const float rstd = 1.f / sqrtf(running_var[ch] + eps);
+    const float sc = ga * rstd;
+    for (int gi = 0; gi < g; ++gi) {
+      scale[(long long)gi * c + ch] = sc;
+      shift[(long long)gi * c + ch] = be - running_mean[ch] * sc;
+    }
+  }
+}
+
+extern "C" int drb_bn_finalize(const double* accum, int g, long long m, int c, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var,
+                               int training, float momentum, float eps, float* scale, float* shift,
+                               cudaStream_t stream) {
+  DRB_REQUIRE(scale && shift && g > 0 && c > 0, "drb_bn_finalize: bad arguments");
+  DRB_REQUIRE(training ? accum != nullptr : (running_mean && running_var),
+              "drb_bn_finalize: missing statistics source");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(accum, g, m, c, gamma, beta, running_mean,
+                                                          running_var, training, momentum, eps,
+                                                          scale, shift);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+// y = relu?(x*scale + shift + residual); 4 channels per thread (c % 4 == 0).
+__global__ void scale_shift_act_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                       const float* __restrict__ shift,
+                                       const float* __restrict__ residual, int relu, long long m,
+                                       int c, long long total4, float* __restrict__ out,
+                                       bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int c4 = c >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const int cc = (int)(i % c4) * 4;
+    const long long row = i / c4;
+    const int g = (int)(row / m);
+    float4 v = *(const float4*)(x + i * 4);
+    if (scale) {
+      const float4 sc = *(const float4*)(scale + (long long)g * c + cc);
+      const float4 sf = *(const float4*)(shift + (long long)g * c + cc);
+      v.x = fmaf(v.x, sc.x, sf.x); v.y = fmaf(v.y, sc.y, sf.y);
+      v.z = fmaf(v.z, sc.z, sf.z); v.w = fmaf(v.w, sc.w, sf.w);
+    }
+    if (residual) {
+      const float4 r = *(const float4*)(residual + i * 4);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    if (out) *(float4*)(out + i * 4) = v;
+    if (out_hi) {
+      bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+      split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1);
+      split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+      *(uint2*)(out_hi + i * 4) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+      if (out_lo) *(uint2*)(out_lo + i * 4) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    }
+  }
+}
+
+extern "C" int drb_scale_shift_act(const float* x, const float* scale, const float* shift,
+                                   const float* residual, int relu, int g, long long m, int c,
+                                   float* out, void* out_hi, void* out_lo, cudaStream_t stream) {
+  DRB_REQUIRE(x && g > 0 && m > 0 && c > 0 && c % 4 == 0, "drb_scale_shift_act: bad arguments");
+  DRB_REQUIRE((scale == nullptr) == (shift == nullptr), "drb_scale_shift_act: scale/shift pair");
+  const long long total4 = (long long)g * m * c / 4;
+  scale_shift_act_kernel<<<grid_for(total4, 256, 148 * 32), 256, 0, stream>>>(
+      x, scale, shift, residual, relu, m, c, total4, out, (bf16*)out_hi, (bf16*)out_lo);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void maxpool_kernel(const float* __restrict__ x, int g, int d, int h, int w, int c,
+                               int od, int oh, int ow, float* __restrict__ out,
+                               bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+  const long long total = (long long)g * od * oh * ow * c;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int ch = (int)(i % c);
+    long long r = i / c;
+    const int ox = (int)(r % ow); r /= ow;
+    const int oy = (int)(r % oh); r /= oh;
+    const int oz = (int)(r % od); r /= od;
+    const int gi = (int)r;
+    float best = -INFINITY;
+    for (int kz = 0; kz < 3; ++kz) {
+      const int iz = oz * 2 - 1 + kz;
+      if (iz < 0 || iz >= d) continue;
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * 2 - 1 + ky;
+        if (iy < 0 || iy >= h) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ox * 2 - 1 + kx;
+          if (ix < 0 || ix >= w) continue;
+          best = fmaxf(best, x[((((long long)gi * d + iz) * h + iy) * w + ix) * c + ch]);
+        }
+      }
+    }
+    if (out) out[i] = best;
+    if (out_hi) {
+      bf16 hh, ll;
+      split_bf16(best, hh, ll);
+      out_hi[i] = hh;
+      if (out_lo) out_lo[i] = ll;
+    }
+  }
+}
+
+extern "C" int drb_maxpool3d(const float* x, int g, int d, int h, int w, int c, float* out,
+                             void* out_hi, void* out_lo, cudaStream_t stream) {
+  DRB_REQUIRE(x && (out || out_hi) && g > 0 && d > 0 && h > 0 && w > 0 && c > 0,
+              "drb_maxpool3d: bad arguments");
+  const int od = (d - 1) / 2 + 1, oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
+  const long long total = (long long)g * od * oh * ow * c;
+  maxpool_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(
+      x, g, d, h, w, c, od, oh, ow, out, (bf16*)out_hi, (bf16*)out_lo);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void upsample_add_kernel(const float* __restrict__ coarse, int dc, int hc, int wc,
+                                    const float* __restrict__ lateral, int g, int d, int h, int w,
+                                    int c, float* __restrict__ out, bf16* __restrict__ out_hi,
+                                    bf16* __restrict__ out_lo) {
+  const int c4 = c >> 2;
+  const long long total4 = (long long)g * d * h * w * c4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const int cc = (int)(i % c4) * 4;
+    long long r = i / c4;
+    const int x = (int)(r % w); r /= w;
+    const int y = (int)(r % h); r /= h;
+    const int z = (int)(r % d); r /= d;
+    const int gi = (int)r;
+    const float4 a = *(const float4*)(lateral + i * 4);
+    const float4 b = *(const float4*)(
+        coarse + ((((long long)gi * dc + (z >> 1)) * hc + (y >> 1)) * wc + (x >> 1)) * c + cc);
+    // torch.add(upsampled, lateral): upsampled is the first operand (feature_pyramid_net.py:74)
+    float4 v = make_float4(b.x + a.x, b.y + a.y, b.z + a.z, b.w + a.w);
+    if (out) *(float4*)(out + i * 4) = v;
+    if (out_hi) {
+      bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+      split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1);
+      split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+      *(uint2*)(out_hi + i * 4) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+      if (out_lo) *(uint2*)(out_lo + i * 4) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    }
+  }
+}
+
+extern "C" int drb_upsample2_add(const float* coarse, int dc, int hc, int wc, const float* lateral,
+                                 int g, int d, int h, int w, int c, float* out, void* out_hi,
+                                 void* out_lo, cudaStream_t stream) {
+  DRB_REQUIRE(coarse && lateral && (out || out_hi) && c % 4 == 0, "drb_upsample2_add: bad arguments");
+  DRB_REQUIRE(d <= 2 * dc && h <= 2 * hc && w <= 2 * wc, "drb_upsample2_add: lateral larger than 2x coarse");
+  const long long total4 = (long long)g * d * h * w * (c / 4);
+  upsample_add_kernel<<<grid_for(total4, 256, 148 * 32), 256, 0, stream>>>(
+      coarse, dc, hc, wc, lateral, g, d, h, w, c, out, (bf16*)out_hi, (bf16*)out_lo);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace drb

@@ -1,0 +1,455 @@
+// Implicit-GEMM 3-D convolution / linear layer on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces every nn.Conv3d (conerf/model/resnet3d.py:81-86,120; feature_pyramid_net.py:24,33) and
+// every nn.Linear / in_proj (conerf/register/transformer.py:128-138, nerf_regtr.py:268-270) on the
+// registration path.  One persistent kernel, warp specialised:
+//   warp 0   : TMA producer  - 5-D tiled loads of channels-last activation boxes (zero fill out of
+//              bounds == convolution padding) and 3-D loads of [tap][Cout][Cin] weight tiles
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 bf16 MMAs)
+//   warps 2-5: epilogue - tcgen05.ld the fp32 accumulator, fused bias / scale / residual / ReLU,
+//              store fp32 and/or split-bf16 planes for the next layer
+// Precision: operands are bf16 "planes".  planes == 1: plain bf16.  planes == 2: every fp32 value x
+// is carried as hi = bf16(x), lo = bf16(x - hi) and the product is accumulated as
+// Ah*Bh + Ah*Bl + Al*Bh in fp32 (error ~2^-17 per product, i.e. fp32-grade results from the bf16
+// tensor pipe at 3 MMAs per product instead of the 2x slower, 2^-11 accurate TF32 pipe).
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace drb {
+
+static constexpr int kBM = 128;       // accumulator rows = TMEM lanes
+static constexpr int kBK = 64;        // K chunk: 64 bf16 = one 128-byte swizzle row
+static constexpr int kMaxStages = 8;
+static constexpr int kThreads = 192;  // 6 warps
+
+struct IgemmArgs {
+  int G, D, H, W;        // output (== input) spatial extent, stride-1 "same" convolution
+  int Cin, Cout;
+  int kd, kh, kw;        // kernel extent
+  int pd, ph, pw;        // padding
+  int bg, bd, bh, bw;    // spatial box of one 128-row tile
+  int BN;                // N tile (<= 256, multiple of 16)
+  int planes;            // 1 or 2
+  int stages;
+  int relu;
+  float out_scale;
+  const float* bias;       // [Cout] or null
+  const float* residual;   // [M, ld] fp32 or null; out = relu((acc + bias) * scale + residual)
+  float* out;              // [M, ld] fp32 or null
+  bf16* out_hi;            // [M, ld] or null
+  bf16* out_lo;            // [M, ld] or null
+  long long ld;            // row pitch (elements) of out / residual / out_hi / out_lo
+  int* err;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+             const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+             const IgemmArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is only 16 B aligned by contract.
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t a_bytes = kBM * kBK * 2;                 // 16 KB per plane
+  const uint32_t b_bytes = (uint32_t)a.BN * kBK * 2;      // BN rows x 128 B per plane
+  const uint32_t stage_bytes = (uint32_t)a.planes * (a_bytes + b_bytes);
+
+  uint64_t* bars = (uint64_t*)(smem + (size_t)a.stages * stage_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 2 + s); };
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kMaxStages + 4);
+
+  const int tiles_w = (a.W + a.bw - 1) / a.bw;
+  const int tiles_h = (a.H + a.bh - 1) / a.bh;
+  const int tiles_d = (a.D + a.bd - 1) / a.bd;
+  const int tiles_g = (a.G + a.bg - 1) / a.bg;
+  const int tiles_n = (a.Cout + a.BN - 1) / a.BN;
+  const int total_tiles = tiles_w * tiles_h * tiles_d * tiles_g * tiles_n;
+  const int kchunks = a.Cin / kBK;
+  const int taps = a.kd * a.kh * a.kw;
+  const int kiters = taps * kchunks;
+  const uint32_t tmem_cols = (2 * a.BN <= 32) ? 32 : (2 * a.BN <= 64) ? 64 : (2 * a.BN <= 128) ? 128
+                             : (2 * a.BN <= 256) ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (a.planes == 2) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode_tile = [&](int t, int& n0, int& w0, int& h0, int& d0, int& g0) {
+    int n = t % tiles_n;
+    int m = t / tiles_n;
+    int tw = m % tiles_w; m /= tiles_w;
+    int th = m % tiles_h; m /= tiles_h;
+    int td = m % tiles_d; m /= tiles_d;
+    n0 = n * a.BN; w0 = tw * a.bw; h0 = th * a.bh; d0 = td * a.bd; g0 = m * a.bg;
+  };
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int n0, w0, h0, d0, g0;
+        decode_tile(t, n0, w0, h0, d0, g0);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int tw = tap % a.kw, th = (tap / a.kw) % a.kh, td = tap / (a.kw * a.kh);
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(empty_bar(s), ph ^ 1u, a.err, 1);
+            const uint32_t fb = full_bar(s);
+            mbar_expect_tx(fb, stage_bytes);
+            const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t sb = sa + (uint32_t)a.planes * a_bytes;
+            tma_load_5d(sa, &tmA0, fb, kc * kBK, w0 + tw - a.pw, h0 + th - a.ph, d0 + td - a.pd, g0);
+            tma_load_3d(sb, &tmB0, fb, kc * kBK, n0, tap);
+            if (a.planes == 2) {
+              tma_load_5d(sa + a_bytes, &tmA1, fb, kc * kBK, w0 + tw - a.pw, h0 + th - a.ph,
+                          d0 + td - a.pd, g0);
+              tma_load_3d(sb + b_bytes, &tmB1, fb, kc * kBK, n0, tap);
+            }
+            if (++s == a.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ----------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kBM, a.BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1u, a.err, 2);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * a.BN);
+        for (int ki = 0; ki < kiters; ++ki) {
+          mbar_wait(full_bar(s), ph, a.err, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + (uint32_t)a.planes * a_bytes;
+          const uint64_t da0 = umma_desc_sw128(sa);
+          const uint64_t db0 = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t koff = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units
+            umma_bf16(tmem_d, da0 + koff, db0 + koff, idesc, (ki | k) != 0);
+            if (a.planes == 2) {
+              const uint64_t da1 = umma_desc_sw128(sa + a_bytes);
+              const uint64_t db1 = umma_desc_sw128(sb + b_bytes);
+              umma_bf16(tmem_d, da0 + koff, db1 + koff, idesc, 1u);
+              umma_bf16(tmem_d, da1 + koff, db0 + koff, idesc, 1u);
+            }
+          }
+          umma_commit(empty_bar(s));               // frees the smem stage when the MMAs retire
+          if (ki == kiters - 1) umma_commit(tfull_bar(acc));
+          if (++s == a.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------- epilogue -------------------------------------------------
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;       // accumulator row == tile-local voxel
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      int n0, w0, h0, d0, g0;
+      decode_tile(t, n0, w0, h0, d0, g0);
+      int r = row;
+      const int ww = w0 + r % a.bw; r /= a.bw;
+      const int hh = h0 + r % a.bh; r /= a.bh;
+      const int dd = d0 + r % a.bd; r /= a.bd;
+      const int gg = g0 + r;
+      const bool row_ok = (ww < a.W) && (hh < a.H) && (dd < a.D) && (gg < a.G);
+      const long long m = (((long long)gg * a.D + dd) * a.H + hh) * a.W + ww;
+      mbar_wait(tfull_bar(acc), acc_ph, a.err, 4);
+      tc_fence_after();
+      for (int c0 = 0; c0 < a.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * a.BN + c0), v);
+        tmem_ld_wait();
+        const int n = n0 + c0;
+        if (row_ok && n < a.Cout) {
+          const long long off = m * a.ld + n;
+          const bool full = (n + 32 <= a.Cout);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (a.bias) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = __ldg((const float4*)(a.bias + n + j));
+                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+              }
+            } else {
+              for (int j = 0; j < 32 && n + j < a.Cout; ++j) f[j] += __ldg(a.bias + n + j);
+            }
+          }
+          if (a.out_scale != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= a.out_scale;
+          }
+          if (a.residual) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 r4 = *(const float4*)(a.residual + off + j);
+                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+              }
+            } else {
+              for (int j = 0; j < 32 && n + j < a.Cout; ++j) f[j] += a.residual[off + j];
+            }
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (a.out) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *(float4*)(a.out + off + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              for (int j = 0; j < 32 && n + j < a.Cout; ++j) a.out[off + j] = f[j];
+            }
+          }
+          if (a.out_hi) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  bf16 h0_, l0_, h1_, l1_;
+                  split_bf16(f[j + 2 * u], h0_, l0_);
+                  split_bf16(f[j + 2 * u + 1], h1_, l1_);
+                  hw[u] = pack_bf16x2(h0_, h1_);
+                  lw[u] = pack_bf16x2(l0_, l1_);
+                }
+                *(uint4*)(a.out_hi + off + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                if (a.out_lo) *(uint4*)(a.out_lo + off + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              }
+            } else {
+              for (int j = 0; j < 32 && n + j < a.Cout; ++j) {
+                bf16 h_, l_;
+                split_bf16(f[j], h_, l_);
+                a.out_hi[off + j] = h_;
+                if (a.out_lo) a.out_lo[off + j] = l_;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int ensure_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver (%d)", (int)e);
+    return DRB_ECUDA;
+  }
+  g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  return 0;
+}
+
+// bf16 tensor map, 128-byte swizzle, zero OOB fill.  dims/box are innermost-first.
+static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box) {
+  int rc = ensure_encode();
+  if (rc) return rc;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)base, gdim,
+                        gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu ...)",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)(rank > 2 ? dims[2] : 0));
+    return DRB_ECUDA;
+  }
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int* g_err_flag = nullptr;   // device int, lazily allocated
+
+int igemm_num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// Chooses the 128-row spatial box (bg, bd, bh, bw) for an output volume.
+static void choose_box(int G, int D, int H, int W, int& bg, int& bd, int& bh, int& bw) {
+  int rem = kBM;
+  auto take = [&](int extent) {
+    int b = 1;
+    while (b * 2 <= rem && b < extent) b *= 2;
+    rem /= b;
+    return b;
+  };
+  // prefer a compact box: cap w and h at 8 first so that 3-D halos overlap in L2
+  bw = 1; while (bw * 2 <= 8 && bw < W) bw *= 2;
+  if (H == 1 && D == 1) { bw = 1; while (bw * 2 <= kBM && bw < W) bw *= 2; }
+  rem /= bw;
+  bh = 1; while (bh * 2 <= (rem < 8 ? rem : 8) && bh < H) bh *= 2;
+  rem /= bh;
+  bd = take(D);
+  bg = take(G);
+  // whatever is left (tiny volumes) pads the innermost dimension; TMA zero-fills out of bounds rows
+  bw *= rem;
+}
+
+extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
+  DRB_REQUIRE(d != nullptr, "drb_conv3d_igemm: null descriptor");
+  DRB_REQUIRE(d->planes == 1 || d->planes == 2, "drb_conv3d_igemm: planes must be 1 or 2");
+  DRB_REQUIRE(d->cin > 0 && d->cin % kBK == 0, "drb_conv3d_igemm: Cin=%d must be a multiple of 64",
+              d->cin);
+  DRB_REQUIRE(d->cout > 0, "drb_conv3d_igemm: Cout must be positive");
+  DRB_REQUIRE(d->x_hi && d->w_hi, "drb_conv3d_igemm: null operand plane");
+  DRB_REQUIRE(d->planes == 1 || (d->x_lo && d->w_lo), "drb_conv3d_igemm: planes==2 needs lo planes");
+  DRB_REQUIRE(d->kd >= 1 && d->kh >= 1 && d->kw >= 1 && (d->kd & 1) && (d->kh & 1) && (d->kw & 1),
+              "drb_conv3d_igemm: kernel extents must be odd");
+  DRB_REQUIRE(d->out || d->out_hi, "drb_conv3d_igemm: no output requested");
+  const long long ld = d->ld_out > 0 ? d->ld_out : d->cout;
+
+  IgemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.G = d->g; a.D = d->d; a.H = d->h; a.W = d->w;
+  a.Cin = d->cin; a.Cout = d->cout;
+  a.kd = d->kd; a.kh = d->kh; a.kw = d->kw;
+  a.pd = d->kd / 2; a.ph = d->kh / 2; a.pw = d->kw / 2;
+  choose_box(a.G, a.D, a.H, a.W, a.bg, a.bd, a.bh, a.bw);
+  a.BN = d->cout >= 256 ? 256 : ((d->cout + 15) / 16) * 16;
+  a.planes = d->planes;
+  a.relu = d->relu;
+  a.out_scale = d->out_scale == 0.f ? 1.f : d->out_scale;
+  a.bias = d->bias; a.residual = d->residual; a.out = d->out; a.out_hi = (bf16*)d->out_hi; a.out_lo = (bf16*)d->out_lo;
+  a.ld = ld;
+  // vector stores in the epilogue need 16-byte aligned rows
+  DRB_REQUIRE(ld % 8 == 0, "drb_conv3d_igemm: row pitch %lld must be a multiple of 8 elements", ld);
+
+  const size_t stage_bytes = (size_t)a.planes * ((size_t)kBM * kBK * 2 + (size_t)a.BN * kBK * 2);
+  const size_t budget = 200 * 1024;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  DRB_REQUIRE(stages >= 2, "drb_conv3d_igemm: tile does not fit shared memory");
+  a.stages = stages;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * kMaxStages + 4) * 8 + 16;
+
+  if (!g_err_flag) {
+    DRB_CUDA_OK(cudaMalloc(&g_err_flag, sizeof(int)));
+    DRB_CUDA_OK(cudaMemset(g_err_flag, 0, sizeof(int)));
+  }
+  a.err = g_err_flag;
+
+  CUtensorMap mA[2], mB[2];
+  memset(mA, 0, sizeof(mA));
+  memset(mB, 0, sizeof(mB));
+  const uint64_t adims[5] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.D, (uint64_t)a.G};
+  const uint64_t astr[4] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2,
+                            (uint64_t)a.H * a.W * a.Cin * 2, (uint64_t)a.D * a.H * a.W * a.Cin * 2};
+  const uint32_t abox[5] = {(uint32_t)kBK, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bd, (uint32_t)a.bg};
+  const int taps = a.kd * a.kh * a.kw;
+  const uint64_t bdims[3] = {(uint64_t)a.Cin, (uint64_t)a.Cout, (uint64_t)taps};
+  const uint64_t bstr[2] = {(uint64_t)a.Cin * 2, (uint64_t)a.Cout * a.Cin * 2};
+  const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)a.BN, 1u};
+  int rc;
+  if ((rc = make_map(&mA[0], d->x_hi, 5, adims, astr, abox))) return rc;
+  if ((rc = make_map(&mB[0], d->w_hi, 3, bdims, bstr, bbox))) return rc;
+  if (a.planes == 2) {
+    if ((rc = make_map(&mA[1], d->x_lo, 5, adims, astr, abox))) return rc;
+    if ((rc = make_map(&mB[1], d->w_lo, 3, bdims, bstr, bbox))) return rc;
+  } else {
+    mA[1] = mA[0];
+    mB[1] = mB[0];
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    DRB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+    attr_set = true;
+  }
+  const int tiles = cdiv(a.W, a.bw) * cdiv(a.H, a.bh) * cdiv(a.D, a.bd) * cdiv(a.G, a.bg) *
+                    cdiv(a.Cout, a.BN);
+  int grid = tiles < igemm_num_sms() ? tiles : igemm_num_sms();
+  igemm_kernel<<<grid, kThreads, smem, stream>>>(mA[0], mA[1], mB[0], mB[1], a);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int drb_igemm_error_flag(int* host_value) {
+  if (!host_value) return DRB_EINVAL;
+  *host_value = 0;
+  if (!g_err_flag) return 0;
+  DRB_CUDA_OK(cudaMemcpy(host_value, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // namespace drb

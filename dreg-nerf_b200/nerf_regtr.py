@@ -1,0 +1,295 @@
+"""Drop-in ``NeRFRegTr`` backed by libdregb200 (hand-written sm_100a CUDA).
+
+Mirrors the reference's module surface (conerf/register/nerf_regtr.py:72-248): same constructor
+arguments, same ``forward(data) -> dict`` contract, same 772-entry ``state_dict`` (including the
+``fpn3d.feature_pyramid.resnet.*`` alias of ``fpn3d.backbone_net.*``,
+conerf/model/feature_pyramid_net.py:43,194-200), so checkpoints written by the reference's
+``CheckPointManager`` load unchanged.  The sub-modules below only *hold* parameters in the
+reference's layout; all arithmetic happens in the C-ABI engine.  There is no PyTorch fallback.
+"""
+import copy
+import ctypes as C
+import warnings
+
+import torch
+from torch import nn
+
+from . import _lib
+
+_PRECISION_PLANES = {"fp32": 2, "bf16x3": 2, "bf16": 1}
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter holders (construction order follows the reference so that torch.manual_seed(s) followed
+# by NeRFRegTr() yields the reference's initial weights)
+# ------------------------------------------------------------------------------------------------
+class _Bottleneck(nn.Module):
+    def __init__(self, inplanes, planes, stride, downsample):
+        super().__init__()
+        self.conv1 = nn.Conv3d(inplanes, planes, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm3d(planes)
+        self.conv2 = nn.Conv3d(planes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm3d(planes)
+        self.conv3 = nn.Conv3d(planes, planes * 4, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm3d(planes * 4)
+        self.downsample = downsample
+
+
+class _ResNet3D50(nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+        self.conv1 = nn.Conv3d(in_channels, 64, kernel_size=5, stride=2, padding=2, bias=False)
+        self.bn1 = nn.BatchNorm3d(64)
+        inplanes = 64
+        for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), (3, 4, 6, 3))):
+            stride = 1 if li == 0 else 2
+            down = nn.Sequential(nn.Conv3d(inplanes, planes * 4, kernel_size=1, stride=stride, bias=False),
+                                 nn.BatchNorm3d(planes * 4))
+            blocks = [_Bottleneck(inplanes, planes, stride, down)]
+            inplanes = planes * 4
+            blocks += [_Bottleneck(inplanes, planes, 1, None) for _ in range(1, nblk)]
+            setattr(self, "layer%d" % (li + 1), nn.Sequential(*blocks))
+        for m in self.modules():
+            if isinstance(m, nn.Conv3d):
+                nn.init.xavier_normal_(m.weight)
+            elif isinstance(m, nn.BatchNorm3d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+
+def _fpn_conv(cin, cout, k):
+    layer = nn.Conv3d(cin, cout, kernel_size=k, padding=k // 2)
+    nn.init.xavier_normal_(layer.weight)
+    nn.init.constant_(layer.bias.data, val=0)
+    return layer
+
+
+class _FeaturePyramid(nn.Module):
+    def __init__(self, resnet):
+        super().__init__()
+        self.resnet = resnet
+        self.pyramid_transformation_1 = _fpn_conv(64, 256, 3)
+        self.pyramid_transformation_2 = _fpn_conv(256, 256, 1)
+        self.pyramid_transformation_3 = _fpn_conv(512, 256, 1)
+        self.pyramid_transformation_4 = _fpn_conv(1024, 256, 1)
+        self.pyramid_transformation_5 = _fpn_conv(2048, 256, 1)
+        for i in range(1, 5):
+            setattr(self, "upsample_transform_%d" % i, _fpn_conv(256, 256, 3))
+
+
+class _FPN3D(nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+        self.backbone_net = _ResNet3D50(in_channels)
+        self.feature_pyramid = _FeaturePyramid(self.backbone_net)
+
+
+class _EncoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, dim_ff):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=0.0)
+        self.cross_attn = nn.MultiheadAttention(d_model, nhead, dropout=0.0)
+        self.linear1 = nn.Linear(d_model, dim_ff)
+        self.linear2 = nn.Linear(dim_ff, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+
+
+class _CrossEncoder(nn.Module):
+    def __init__(self, layer, num_layers, norm):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(layer) for _ in range(num_layers)])
+        self.norm = norm
+
+
+class _SinePosEmbed(nn.Module):
+    def __init__(self, scale):
+        super().__init__()
+        self.scale = scale
+
+
+class _Decoder(nn.Module):
+    def __init__(self, d_model, pos_embed):
+        super().__init__()
+        self.pos_embed = pos_embed
+        self.q_norm = nn.LayerNorm(d_model)     # declared but unused by the reference forward
+        self.q_proj = nn.Linear(d_model, d_model)
+        self.k_proj = nn.Linear(d_model, d_model)
+        self.conf_logits_decoder = nn.Linear(d_model, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+class NeRFRegTr(nn.Module):
+    """``NeRFRegTr(pos_emb_type='sine', pos_emb_dim=256, pos_emb_scaling=1.0, num_downsample=6)``.
+
+    Extra keyword (not in the reference): ``precision`` - ``'fp32'`` (default; split-bf16 tensor-core
+    products, fp32-grade results) or ``'bf16'`` (single bf16 product, the bf16 configs of
+    BASELINE.json).
+    """
+
+    def __init__(self, pos_emb_type: str = "sine", pos_emb_dim: int = 256, pos_emb_scaling: float = 1.0,
+                 num_downsample: int = 6, precision: str = "fp32") -> None:
+        super().__init__()
+        if pos_emb_type != "sine":
+            raise NotImplementedError("libdregb200 implements the 'sine' positional embedding only "
+                                      "(the reference's default, train_nerf_regtr.py:89-94)")
+        if pos_emb_dim != 256:
+            raise NotImplementedError("libdregb200 kernels are specialised for pos_emb_dim == 256")
+        if precision not in _PRECISION_PLANES:
+            raise ValueError("precision must be one of %s" % sorted(_PRECISION_PLANES))
+        self.num_downsample = num_downsample
+        self.pos_emb_scaling = float(pos_emb_scaling)
+        self.precision = precision
+        self.fpn3d = _FPN3D(in_channels=4)
+        self.pos_embed = _SinePosEmbed(pos_emb_scaling)
+        layer = _EncoderLayer(pos_emb_dim, 8, 1024)
+        self.transformer_encoder = _CrossEncoder(layer, 6, nn.LayerNorm(pos_emb_dim))
+        self.correspondence_decoder = _Decoder(pos_emb_dim, self.pos_embed)
+        self._engines = {}
+        self._warned_grad = False
+        self.last_token_counts = (0, 0)
+
+    # -------------------------------------------------------------------------------------------
+    def _named_tensors(self):
+        out = dict(self.named_parameters(remove_duplicate=False))
+        out.update(dict(self.named_buffers(remove_duplicate=False)))
+        return out
+
+    def _get_engine(self, res_xyz, device, max_mask):
+        key = (tuple(res_xyz), device.index, self.precision)
+        ent = self._engines.get(key)
+        if ent is not None and ent["max_mask"] >= max_mask:
+            return ent
+        lib = _lib.load()
+        if ent is not None:
+            lib.drb_engine_destroy(ent["handle"])
+        cap = max(int(max_mask * 1.25) + 1024, 4096)
+        cfg = _lib.EngineConfig(res_x=res_xyz[0], res_y=res_xyz[1], res_z=res_xyz[2],
+                                planes=_PRECISION_PLANES[self.precision],
+                                num_downsample=self.num_downsample,
+                                pos_emb_scaling=self.pos_emb_scaling, max_mask=cap,
+                                training_bn=1 if self.training else 0)
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.drb_engine_create(C.byref(cfg), C.byref(handle)), "drb_engine_create")
+        names = [lib.drb_engine_param_name(handle, i).decode() for i in range(lib.drb_engine_num_params(handle))]
+        ent = {"handle": handle, "names": names, "max_mask": cap, "sig": None, "device": device}
+        self._engines[key] = ent
+        return ent
+
+    def _sync_params(self, ent):
+        """(Re)binds and repacks the weights when any tensor was replaced or written to."""
+        lib = _lib.load()
+        tensors = self._named_tensors()
+        sig = tuple((tensors[n].data_ptr(), tensors[n]._version) for n in ent["names"])
+        if sig == ent["sig"]:
+            return
+        for i, n in enumerate(ent["names"]):
+            t = tensors[n]
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                raise _lib.DrbError("parameter %s must be a contiguous fp32 CUDA tensor" % n)
+            if t.numel() != lib.drb_engine_param_numel(ent["handle"], i):
+                raise _lib.DrbError("parameter %s has %d elements, engine expects %d"
+                                    % (n, t.numel(), lib.drb_engine_param_numel(ent["handle"], i)))
+            _lib.check(lib.drb_engine_bind_param(ent["handle"], i, _lib.ptr(t)), "drb_engine_bind_param")
+        _lib.check(lib.drb_engine_commit_params(ent["handle"], _lib.stream_ptr()), "drb_engine_commit_params")
+        ent["sig"] = sig
+
+    def launch_count(self):
+        lib = _lib.load()
+        return sum(int(lib.drb_engine_launch_count(e["handle"])) for e in self._engines.values())
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for ent in self._engines.values():
+                lib.drb_engine_destroy(ent["handle"])
+        except Exception:
+            pass
+
+    # -------------------------------------------------------------------------------------------
+    def forward(self, data):
+        """Same contract as conerf/register/nerf_regtr.py:112-248 (one pair per call)."""
+        if len(data["src_xyz_rgba"].shape) == 6:
+            data["src_xyz_rgba"] = data["src_xyz_rgba"].squeeze(0)
+            data["tgt_xyz_rgba"] = data["tgt_xyz_rgba"].squeeze(0)
+            data["src_mask"] = data["src_mask"].squeeze(0)
+            data["tgt_mask"] = data["tgt_mask"].squeeze(0)
+            if "src_nerf_path" in data:
+                data["src_nerf_path"] = data["src_nerf_path"][0]
+                data["tgt_nerf_path"] = data["tgt_nerf_path"][0]
+            if "pose" in data:
+                data["pose"] = data["pose"].squeeze(0)
+        src, tgt = data["src_xyz_rgba"], data["tgt_xyz_rgba"]
+        assert len(src.shape) == 5  # [batch_size, C, z_dim, x_dim, y_dim]
+        if src.shape[0] != 1 or tgt.shape[0] != 1:
+            raise _lib.DrbError("NeRFRegTr.forward processes one pair per call, as the reference does "
+                                "(nerf_regtr.py:144-147 index batch element 0 only)")
+        if not src.is_cuda:
+            raise _lib.DrbError("libdregb200 has no CPU path: move the inputs to a CUDA device")
+        if src.dtype != torch.float32 or tgt.dtype != torch.float32:
+            raise _lib.DrbError("grids must be float32")
+        if src.shape != tgt.shape or src.shape[1] != 7:
+            raise _lib.DrbError("expected two [1, 7, Z, X, Y] grids of equal resolution")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not self._warned_grad:
+            warnings.warn("libdregb200 round 1 implements the forward pass only; outputs carry no autograd graph")
+            self._warned_grad = True
+        device = src.device
+        src_mask = data["src_mask"].reshape(-1).to(device=device, dtype=torch.int64).contiguous()
+        tgt_mask = data["tgt_mask"].reshape(-1).to(device=device, dtype=torch.int64).contiguous()
+        _, _, Z, X, Y = src.shape
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            ent = self._get_engine((X, Y, Z), device, max(src_mask.numel(), tgt_mask.numel()))
+            self._sync_params(ent)
+            _lib.check(lib.drb_engine_set_training(ent["handle"], 1 if self.training else 0))
+            io = _lib.PairIO(
+                src_grid=src.data_ptr(), tgt_grid=tgt.data_ptr(),
+                s_ch=src.stride(1), s_z=src.stride(2), s_x=src.stride(3), s_y=src.stride(4),
+                t_ch=tgt.stride(1), t_z=tgt.stride(2), t_x=tgt.stride(3), t_y=tgt.stride(4),
+                src_mask=src_mask.data_ptr(), n_src_mask=src_mask.numel(),
+                tgt_mask=tgt_mask.data_ptr(), n_tgt_mask=tgt_mask.numel())
+            ns, nt = C.c_int(0), C.c_int(0)
+            stream = _lib.stream_ptr()
+            _lib.check(lib.drb_engine_encode(ent["handle"], C.byref(io), C.byref(ns), C.byref(nt), stream),
+                       "drb_engine_encode")
+            ns, nt = ns.value, nt.value
+            self.last_token_counts = (ns, nt)
+            f32 = dict(dtype=torch.float32, device=device)
+            src_feats = torch.empty((6, ns, 256), **f32)
+            tgt_feats = torch.empty((6, nt, 256), **f32)
+            src_kp, tgt_kp = torch.empty((ns, 3), **f32), torch.empty((nt, 3), **f32)
+            src_corr, tgt_corr = torch.empty((6, ns, 3), **f32), torch.empty((6, nt, 3), **f32)
+            src_ov, tgt_ov = torch.empty((6, ns, 1), **f32), torch.empty((6, nt, 1), **f32)
+            pose = torch.empty((6, 1, 3, 4), **f32)
+            out = _lib.PairOut(src_feats=src_feats.data_ptr(), tgt_feats=tgt_feats.data_ptr(),
+                               src_kp=src_kp.data_ptr(), tgt_kp=tgt_kp.data_ptr(),
+                               src_corr=src_corr.data_ptr(), tgt_corr=tgt_corr.data_ptr(),
+                               src_overlap=src_ov.data_ptr(), tgt_overlap=tgt_ov.data_ptr(),
+                               pose=pose.data_ptr())
+            _lib.check(lib.drb_engine_decode(ent["handle"], C.byref(out), stream), "drb_engine_decode")
+            if self.training:
+                # nn.BatchNorm3d bookkeeping: two training-mode calls (src, tgt) per forward
+                for name, buf in self.named_buffers():
+                    if name.endswith("num_batches_tracked") and name.startswith("fpn3d.backbone_net"):
+                        buf += 2
+        return {
+            "src_feats": [src_feats], "tgt_feats": [tgt_feats],
+            "src_kp": [src_kp], "src_kp_warped": [src_corr],
+            "tgt_kp": [tgt_kp], "tgt_kp_warped": [tgt_corr],
+            "src_overlap": [src_ov], "tgt_overlap": [tgt_ov],
+            "pose": pose,
+        }
+
+    def tap(self, name, which):
+        """Debug / parity tap of an engine intermediate (channels-last fp32), see drb_engine_tap."""
+        lib = _lib.load()
+        ent = next(iter(self._engines.values()))
+        cap = 1 << 28
+        buf = torch.empty(cap, dtype=torch.float32, device=ent["device"])
+        n = C.c_longlong(0)
+        _lib.check(lib.drb_engine_tap(ent["handle"], name.encode(), which, _lib.ptr(buf), cap, C.byref(n),
+                                      _lib.stream_ptr()), "drb_engine_tap")
+        torch.cuda.synchronize()
+        return buf[:n.value].clone()

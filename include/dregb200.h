@@ -1,0 +1,276 @@
+/*
+ * libdregb200 - C ABI of the B200-native DReg-NeRF registration hot path.
+ *
+ * Plain pointers and sizes only: every pointer is a CUDA device pointer unless the name says
+ * "host"; every call is asynchronous on `stream` unless documented otherwise; every function
+ * returns DRB_OK (0) or a negative DRB_E* code and records a message readable through
+ * drb_last_error().  No exceptions cross the boundary, no torch types, no hidden global state
+ * other than a lazily created device error flag and the cached driver entry point.
+ *
+ * bf16 "planes": an fp32 tensor x is carried as hi = bf16(x) and (optionally) lo = bf16(x - hi).
+ * Activations are channels-last: [g][d][h][w][c] with d = Z, h = X, w = Y of the reference's
+ * [1, C, Z, X, Y] tensors (conerf/register/nerf_regtr.py:112-134).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the DReg-NeRF
+ * repository root).
+ */
+#ifndef DREGB200_H_
+#define DREGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRB_OK 0
+#define DRB_EINVAL (-1)
+#define DRB_ECUDA (-2)
+#define DRB_ENOMEM (-3)
+#define DRB_ESTATE (-4)
+
+#define DRB_ABI_VERSION 1
+
+typedef struct CUstream_st* drb_stream_t; /* == cudaStream_t */
+
+int drb_abi_version(void);
+const char* drb_last_error(void);
+/* Value of the device-side pipeline watchdog flag (0 = healthy).  Synchronous. */
+int drb_igemm_error_flag(int* host_value);
+
+/* ------------------------------------------------------------------------------------------
+ * R2 / R6 / R7: nn.Conv3d (conerf/model/resnet3d.py:81-86,120, feature_pyramid_net.py:24,33)
+ * and nn.Linear / MultiheadAttention in/out projections (conerf/register/transformer.py:128-138,
+ * nerf_regtr.py:268-270) as one tcgen05 implicit GEMM.  Stride 1, padding k/2.
+ *   out = relu?((conv(x, w) + bias) * out_scale + residual)
+ * A linear layer over n tokens is the 1x1x1 case with g = d = h = 1, w = n.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct drb_conv3d_desc {
+  int g, d, h, w;          /* activation volume (output == input extent)                    */
+  int cin, cout;           /* cin multiple of 64                                            */
+  int kd, kh, kw;          /* odd kernel extents                                            */
+  int planes;              /* 1: bf16 operands, 2: split-bf16 (fp32-grade) operands         */
+  int relu;
+  float out_scale;         /* 0 is read as 1                                                */
+  const void* x_hi;        /* bf16 [g][d][h][w][cin]                                        */
+  const void* x_lo;        /* same shape, planes == 2 only                                  */
+  const void* w_hi;        /* bf16 [kd*kh*kw][cout][cin]  (see drb_pack_conv_weight)        */
+  const void* w_lo;
+  const float* bias;       /* [cout] or NULL                                                */
+  const float* residual;   /* fp32 [m][ld_out] or NULL                                      */
+  float* out;              /* fp32 [m][ld_out] or NULL,  m = g*d*h*w                        */
+  void* out_hi;            /* bf16 [m][ld_out] or NULL                                      */
+  void* out_lo;            /* bf16 [m][ld_out] or NULL                                      */
+  long long ld_out;        /* row pitch in elements, 0 -> cout; multiple of 8               */
+} drb_conv3d_desc;
+int drb_conv3d_igemm(const drb_conv3d_desc* desc, drb_stream_t stream);
+
+/* fp32 -> bf16 planes (lo may be NULL). */
+int drb_split_planes(const float* x, void* hi, void* lo, long long n, drb_stream_t stream);
+
+/* torch Conv3d weight [cout][cin][taps] fp32 -> planes [taps][cout][cin_pad], zero padded. */
+int drb_pack_conv_weight(const float* w, int cout, int cin, int taps, int cin_pad, void* hi,
+                         void* lo, drb_stream_t stream);
+/* same weight -> planes [cout][kpad] with k = tap*cin + c (pairs with drb_im2col). */
+int drb_pack_conv_weight_im2col(const float* w, int cout, int cin, int taps, int kpad, void* hi,
+                                void* lo, drb_stream_t stream);
+
+/* Generic strided / large-kernel convolutions (conv1 5^3 s2, resnet3d.py:120; 3^3 s2 and 1^3 s2
+ * in the first Bottleneck of layer2-4, resnet3d.py:83,140-146) are lowered to a 1x1x1 igemm over
+ * an explicit im2col buffer: planes [g][do][ho][wo][kpad], k = ((kz*K + ky)*K + kx)*c + ch. */
+typedef struct drb_im2col_desc {
+  const float* x;                 /* fp32, arbitrary element strides                        */
+  long long sg, sc, sd, sh, sw;
+  int g, c, d, h, w;              /* input extent                                           */
+  int k, stride, pad;             /* cubic kernel                                           */
+  int kpad;                       /* >= k^3*c, multiple of 64                               */
+} drb_im2col_desc;
+int drb_im2col(const drb_im2col_desc* desc, void* hi, void* lo, drb_stream_t stream);
+
+/* nn.BatchNorm3d (resnet3d.py:82-87,121).  x is fp32 [g][m][c]; statistics are per (g, c):
+ * the reference runs one grid per call with batch size 1 (nerf_regtr.py:135).  accum is
+ * [g][c][2] doubles of scratch. */
+int drb_bn_stats(const float* x, int g, long long m, int c, double* accum, drb_stream_t stream);
+/* training != 0: batch statistics, running buffers updated sequentially over g with momentum
+ * (unbiased variance), as g successive forward calls would.  training == 0: running statistics.
+ * Writes scale/shift [g][c] such that y = x*scale + shift. */
+int drb_bn_finalize(const double* accum, int g, long long m, int c, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var, int training,
+                    float momentum, float eps, float* scale, float* shift, drb_stream_t stream);
+/* y = relu?(x*scale[g][c] + shift[g][c] + residual); scale/shift may be NULL (identity). */
+int drb_scale_shift_act(const float* x, const float* scale, const float* shift,
+                        const float* residual, int relu, int g, long long m, int c, float* out,
+                        void* out_hi, void* out_lo, drb_stream_t stream);
+
+/* nn.MaxPool3d(3, 2, 1) (resnet3d.py:123) on fp32 [g][d][h][w][c]. */
+int drb_maxpool3d(const float* x, int g, int d, int h, int w, int c, float* out, void* out_hi,
+                  void* out_lo, drb_stream_t stream);
+/* FeaturePyramid_v1._upsample + torch.add (feature_pyramid_net.py:58-61,73-103):
+ * out[d][h][w] = coarse[d/2][h/2][w/2] + lateral[d][h][w]. */
+int drb_upsample2_add(const float* coarse, int dc, int hc, int wc, const float* lateral, int g,
+                      int d, int h, int w, int c, float* out, void* out_hi, void* out_lo,
+                      drb_stream_t stream);
+
+/* R3: F.interpolate(trilinear, align_corners=True) evaluated only at the masked voxels, plus the
+ * xyz gather (nerf_regtr.py:138-147).  p1 is one grid [dc][hc][wc][c]; mask holds flat indices
+ * x*(Y*Z) + y*Z + z; rows_out[i] = [x y z 0 | c features], pitch ld_rows (>= 4 + c). */
+int drb_trilinear_gather(const float* p1, int dc, int hc, int wc, int c, const float* grid,
+                         long long s_ch, long long s_z, long long s_x, long long s_y, int X, int Y,
+                         int Z, const long long* mask, int k, float* rows_out, int ld_rows,
+                         drb_stream_t stream);
+
+/* R4: hierarchical voxel-average down-sampling (conerf/register/grid_downsample.py:6-94).
+ * rows [n_src + n_tgt][ld] = [x y z 0 | 256 features]; cells of size dl0 * 2^round; rows of one
+ * cloud are emitted in ascending (cx, cy, cz) order; stops after the first round that leaves
+ * <= max_total rows.  Synchronous (reads the counts back).  workspace from
+ * drb_downsample_workspace_bytes(n). rows_out may alias neither input nor workspace. */
+size_t drb_downsample_workspace_bytes(int n_rows, int ld);
+int drb_hierarchical_downsample(const float* rows, int n_src, int n_tgt, int ld, int num_rounds,
+                                double dl0, int max_total, void* workspace, size_t workspace_bytes,
+                                float* rows_out, int* host_n_src_out, int* host_n_tgt_out,
+                                drb_stream_t stream);
+
+/* R5: PositionEmbeddingCoordsSine (conerf/register/position_embedding.py:30-53), d_model 256. */
+int drb_pos_embed_sine(const float* xyz, int ld_xyz, int n, float scale, float* out,
+                       drb_stream_t stream);
+/* nn.LayerNorm(256) (+ optional positional add) (transformer.py:237-238,262-264,285,291).
+ * out / out_hi / out_lo receive LN(x) + add; any of them may be NULL. */
+int drb_layernorm256(const float* x, int n, const float* gamma, const float* beta,
+                     const float* add, float* out, void* out_hi, void* out_lo,
+                     drb_stream_t stream);
+/* softmax(q k^T * scale) v per head (torch nn.MultiheadAttention core, transformer.py:240-281). */
+int drb_mha_core(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int nq,
+                 int nk, int heads, float scale, float* out, void* out_hi, void* out_lo, int ld_out,
+                 drb_stream_t stream);
+/* CorrespondenceDecoder.simple_attention tail (nerf_regtr.py:292-306): row softmax of s [nq][ld]
+ * over nk keys, weighted sum of xyz [nk][ld_xyz] -> out [nq][3]. */
+int drb_softmax_weighted_xyz(const float* s, int ld, int nq, int nk, const float* xyz, int ld_xyz,
+                             float* out, drb_stream_t stream);
+/* sigmoid(w . feat + b) (nerf_regtr.py:384-387); feat [n][256] -> out [n]. */
+int drb_overlap_sigmoid(const float* feat, int n, const float* w, const float* b, float* out,
+                        drb_stream_t stream);
+
+/* R8 + R9: weighted Procrustes (conerf/register/se3.py:89-140) over the stacked correspondences
+ * of nerf_regtr.py:208-230, for `layers` problems at once.  Segment 1 has n1 rows, segment 2 has
+ * n2 rows; *_ls are the per-layer strides in floats (0 broadcasts).  out [layers][3][4]. */
+int drb_procrustes(const float* a1, long long a1_ls, const float* b1, long long b1_ls,
+                   const float* w1, long long w1_ls, int n1, const float* a2, long long a2_ls,
+                   const float* b2, long long b2_ls, const float* w2, long long w2_ls, int n2,
+                   int ld_pts, int layers, float* out, drb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A1-A6: extract (conerf/radiance_fields/ngp.py:148-193, conerf/register/sample_grid.py:208-343,
+ * conerf/utils/nerfacc_utils.py:84-222, eval_ngp_nerf.py:337-412)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct drb_ngp_params {
+  const float* hash_table;   /* fp32 [total_entries][2], levels concatenated                 */
+  const float* w1;           /* density MLP 32 -> 64, row major [64][32]                      */
+  const float* w2;           /* 64 -> 16, [16][64]                                            */
+  const float* c1;           /* colour MLP [64][32] (input = 16 SH | 15 feat | 0)             */
+  const float* c2;           /* [64][64]                                                      */
+  const float* c3;           /* [3][64] (tcnn pads to 16 rows; only 3 are used)               */
+  float aabb[6];
+} drb_ngp_params;
+/* Number of [2]-float entries of the 16-level hash table (levels concatenated). Host only. */
+long long drb_ngp_table_entries(void);
+/* NGPradianceField.query_density (ngp.py:148-176): x world [n][3] -> density [n], feat [n][15]. */
+int drb_ngp_density(const drb_ngp_params* p, const float* x, int n, float* density, float* feat,
+                    drb_stream_t stream);
+/* mean over ndirs fixed view directions of NGPradianceField.query_rgb (ngp.py:178-193,
+ * sample_grid.py:332-340): feat [n][15], dirs host [ndirs][3] -> rgb [n][3]. */
+int drb_ngp_rgb_mean(const drb_ngp_params* p, const float* feat, int n, const float* host_dirs,
+                     int ndirs, float* rgb, drb_stream_t stream);
+/* Surface-field mask (sample_grid.py:245-318 + nerfacc 0.3.5 ray marching): for every point p and
+ * camera origin o march o->p through the binary occupancy grid with `step`; surface[p] = 1 when
+ * max over cameras/samples of alpha*T >= cut_off. */
+int drb_surface_mask(const drb_ngp_params* p, const uint8_t* occ_binary, int res,
+                     const float* roi_aabb_host, const float* scene_aabb_host, const float* points,
+                     int n, const float* cam_origins, int ncams, float step, float cut_off,
+                     uint8_t* surface, drb_stream_t stream);
+/* SampleGrid sampling + Evaluator.sample_points scatter (sample_grid.py:223-243,
+ * eval_ngp_nerf.py:383-412): fused extract of one NeRF block; see INTEGRATION.md. */
+typedef struct drb_extract_desc {
+  int res;                       /* grid resolution R                                          */
+  float roi_aabb[6];
+  float scene_aabb[6];
+  const long long* occupied;     /* flat indices of occupied cells (nonzero(binary))           */
+  int n_occupied;
+  const float* jitter;           /* U[0,1) [n_occupied][3] (torch.rand_like in the reference)   */
+  const uint8_t* occ_binary;     /* [R][R][R]                                                  */
+  const float* cam_origins;      /* [ncams][3]                                                 */
+  int ncams;
+  float render_step_size;
+  float density_thre;            /* 0.7 */
+  float cut_off;                 /* 0.5 */
+  const float* host_dirs;        /* [ndirs][3]                                                 */
+  int ndirs;
+} drb_extract_desc;
+/* Writes points [n][3], rgb [n][3], alpha [n], density_mask [n], surface_mask [n] and scatters
+ * rows of cells with both masks set into voxel_grid [R^3][7] (pre-zeroed by the call). */
+int drb_extract_block(const drb_ngp_params* p, const drb_extract_desc* e, float* points, float* rgb,
+                      float* alpha, uint8_t* density_mask, uint8_t* surface_mask, float* voxel_grid,
+                      drb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-path engine: NeRFRegTr.forward (conerf/register/nerf_regtr.py:112-248) without Python in
+ * the loop.  Parameters are addressed by the reference's state-dict key.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct drb_engine drb_engine;
+
+typedef struct drb_engine_config {
+  int res_x, res_y, res_z;     /* grid resolution X, Y, Z                                      */
+  int planes;                  /* 1 = bf16, 2 = split-bf16 (fp32-grade)                        */
+  int num_downsample;          /* NeRFRegTr(num_downsample=6)                                  */
+  float pos_emb_scaling;       /* NeRFRegTr(pos_emb_scaling=1.0)                               */
+  int max_mask;                /* capacity for masked voxels per cloud                         */
+  int training_bn;             /* 1: batch statistics + running-stat update (module.training)  */
+} drb_engine_config;
+
+int drb_engine_create(const drb_engine_config* cfg, drb_engine** out);
+void drb_engine_destroy(drb_engine* e);
+/* Parameter table (names are the reference's state_dict keys). */
+int drb_engine_num_params(const drb_engine* e);
+const char* drb_engine_param_name(const drb_engine* e, int i);
+long long drb_engine_param_numel(const drb_engine* e, int i);
+/* Binds fp32 device storage for parameter i (kept by reference: BN running buffers are updated in
+ * place in training mode).  Call drb_engine_commit_params after all are bound or changed. */
+int drb_engine_bind_param(drb_engine* e, int i, float* device_ptr);
+int drb_engine_commit_params(drb_engine* e, drb_stream_t stream);
+int drb_engine_set_training(drb_engine* e, int training_bn);
+
+typedef struct drb_pair_io {
+  const float* src_grid;   /* fp32 [1,7,Z,X,Y] view, element strides below                   */
+  const float* tgt_grid;
+  long long s_ch, s_z, s_x, s_y;          /* src strides                                     */
+  long long t_ch, t_z, t_x, t_y;          /* tgt strides                                     */
+  const long long* src_mask; int n_src_mask;
+  const long long* tgt_mask; int n_tgt_mask;
+} drb_pair_io;
+
+/* Stage 1: FPN + gather + down-sampling.  Synchronises once to return the token counts. */
+int drb_engine_encode(drb_engine* e, const drb_pair_io* io, int* host_n_src, int* host_n_tgt,
+                      drb_stream_t stream);
+/* Stage 2: transformer + decoder + Procrustes into caller buffers (sizes from stage 1):
+ *   src_feats [6][ns][256], tgt_feats [6][nt][256], src_kp [ns][3], tgt_kp [nt][3],
+ *   src_corr [6][ns][3], tgt_corr [6][nt][3], src_overlap [6][ns], tgt_overlap [6][nt],
+ *   pose [6][3][4]. */
+typedef struct drb_pair_out {
+  float* src_feats; float* tgt_feats;
+  float* src_kp; float* tgt_kp;
+  float* src_corr; float* tgt_corr;
+  float* src_overlap; float* tgt_overlap;
+  float* pose;
+} drb_pair_out;
+int drb_engine_decode(drb_engine* e, const drb_pair_out* out, drb_stream_t stream);
+/* Debug / parity taps: copies a named intermediate ("c1".."c5", "p1".."p5", "rows") of grid
+ * `which` (0 src, 1 tgt) as fp32 channels-last into dst; returns element count via *numel. */
+int drb_engine_tap(drb_engine* e, const char* name, int which, float* dst, long long capacity,
+                   long long* numel, drb_stream_t stream);
+/* Kernel launches issued by this engine since creation (for bench.py's gpu_launches). */
+long long drb_engine_launch_count(const drb_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DREGB200_H_ */

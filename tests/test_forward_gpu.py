@@ -1,0 +1,93 @@
+"""Full NeRFRegTr.forward on the GPU against the CPU oracle (oracle == reference bit-exact, see
+tests/test_oracle_golden.py) on identical seeded inputs and weights."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3   # BASELINE.json north_star: features / attention / SE(3) within 1e-3 rel fp32
+
+
+def _run(pkg, cuda, res, training, pair_id=0, gain=8.0, precision="fp32"):
+    from oracle import regtr
+    torch.manual_seed(0)
+    model = pkg.NeRFRegTr(precision=precision)
+    sd = pkg.synthetic.seeded_state_dict(model, seed=0, attn_gain=gain)
+    model.load_state_dict(sd)
+    model = model.to(cuda).train(training)
+    data = pkg.synthetic.make_pair(res=res, pair_id=pair_id)
+    with torch.no_grad():
+        out = model(pkg.synthetic.to_device(data, cuda))
+        torch.cuda.synchronize()
+        running = {}
+        ref = regtr.forward(sd, data, training=training, running=running)
+    return model, sd, data, out, ref, running
+
+
+def _relerr(a, b):
+    a, b = a.detach().double().cpu(), b.double()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def _check(out, ref, tol=TOL):
+    assert out["src_kp"][0].shape == ref["src_kp"][0].shape, "token counts differ"
+    assert out["tgt_kp"][0].shape == ref["tgt_kp"][0].shape
+    assert torch.equal(out["src_kp"][0].cpu(), ref["src_kp"][0]), "down-sampled key points must be bit exact"
+    assert torch.equal(out["tgt_kp"][0].cpu(), ref["tgt_kp"][0])
+    errs = {k: _relerr(out[k][0], ref[k][0]) for k in
+            ("src_feats", "tgt_feats", "src_kp_warped", "tgt_kp_warped", "src_overlap", "tgt_overlap")}
+    errs["pose"] = _relerr(out["pose"], ref["pose"])
+    print("relative errors:", {k: "%.2e" % v for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < tol, "%s relative error %.3e exceeds %.1e" % (k, v, tol)
+    return errs
+
+
+def test_forward_32_eval(pkg, cuda):
+    """BASELINE.json config 1 shape (32^3, running-statistics BatchNorm: at 32^3 the deepest
+    feature map is 1^3, where torch refuses batch statistics)."""
+    model, sd, data, out, ref, _ = _run(pkg, cuda, 32, training=False)
+    assert out["pose"].shape == (6, 1, 3, 4)
+    _check(out, ref)
+
+
+def test_forward_64_train_bn(pkg, cuda):
+    """Batch-statistics BatchNorm (the eval script never calls .eval()) plus the
+    running-statistics side effect."""
+    model, sd, data, out, ref, running = _run(pkg, cuda, 64, training=True)
+    _check(out, ref)
+    msd = model.state_dict()
+    for prefix, (rm, rv) in list(running.items())[:8] + list(running.items())[-4:]:
+        assert _relerr(msd[prefix + ".running_mean"], rm) < 1e-4
+        assert _relerr(msd[prefix + ".running_var"], rv) < 1e-4
+    assert int(msd["fpn3d.backbone_net.bn1.num_batches_tracked"]) == 2
+
+
+def test_stage_taps_64(pkg, cuda):
+    """Per-stage parity (backbone c1..c5, pyramid p1) to localise any drift."""
+    from oracle import regtr
+    torch.manual_seed(0)
+    model = pkg.NeRFRegTr()
+    sd = pkg.synthetic.seeded_state_dict(model, seed=0, attn_gain=8.0)
+    model.load_state_dict(sd)
+    model = model.to(cuda).train(True)
+    data = pkg.synthetic.make_pair(res=64, pair_id=1)
+    cap = {}
+    with torch.no_grad():
+        model(pkg.synthetic.to_device(data, cuda))
+        regtr.forward(sd, data, training=True, capture=cap)
+    for name in ("c1", "c2", "c3", "c4", "c5", "p5", "p4", "p3", "p2", "p1"):
+        for which, side in ((0, "src"), (1, "tgt")):
+            ref = cap["%s_%s" % (side, name)][0].permute(1, 2, 3, 0).reshape(-1)
+            got = model.tap(name, which).cpu()
+            err = _relerr(got, ref)
+            print(name, side, "%.2e" % err)
+            assert err < 2e-4, "%s/%s drifted: %.3e" % (name, side, err)
+
+
+def test_forward_bf16_mode_runs(pkg, cuda):
+    """precision='bf16' (single bf16 product): looser agreement, same shapes."""
+    model, sd, data, out, ref, _ = _run(pkg, cuda, 32, training=False, precision="bf16")
+    assert out["pose"].shape == (6, 1, 3, 4)
+    assert torch.isfinite(out["pose"]).all()
+    assert _relerr(out["src_feats"][0], ref["src_feats"][0]) < 0.15

@@ -1,0 +1,238 @@
+"""Per-kernel parity against torch CPU references (fp64 where cheap), through the C ABI."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import importlib
+    return importlib.import_module("dreg-nerf_b200.ops")
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def test_split_planes(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(100003, generator=g) * torch.logspace(-3, 3, 100003)
+    hi, lo = ops.split_planes(x.to(cuda))
+    rec = hi.float() + lo.float()
+    assert ((rec.cpu() - x).abs() <= x.abs() * 2.0 ** -16 + 1e-30).all()
+
+
+@pytest.mark.parametrize("planes,tol", [(2, 2e-5), (1, 2e-2)])
+@pytest.mark.parametrize("m,cin,cout", [(300, 256, 768), (128, 64, 64), (1000, 1024, 256), (77, 256, 200)])
+def test_igemm_linear(cuda, planes, tol, m, cin, cout):
+    """nn.Linear as the 1x1x1 case, ragged M and ragged N."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(m + cin + cout)
+    x = torch.randn(m, cin, generator=g)
+    w = torch.randn(cout, cin, generator=g) / math.sqrt(cin)
+    b = torch.randn(cout, generator=g)
+    ld = (cout + 7) // 8 * 8
+    xp = ops.split_planes(x.to(cuda).view(1, 1, 1, m, cin))
+    wp = ops.pack_conv_weight(w.to(cuda))
+    out, _ = ops.conv3d_igemm(xp, wp, 1, planes=planes, bias=b.to(cuda), ld_out=ld)
+    torch.cuda.synchronize()
+    assert ops.igemm_error_flag() == 0
+    ref = x.double() @ w.double().t() + b.double()
+    assert _rel(out[:, :cout], ref) < tol
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 8), (1, 6, 10, 12), (2, 4, 4, 4), (1, 2, 2, 2), (1, 16, 16, 16)])
+@pytest.mark.parametrize("cin,cout,k", [(64, 64, 3), (128, 256, 3), (64, 256, 1)])
+def test_igemm_conv3d(cuda, shape, cin, cout, k):
+    """nn.Conv3d stride 1 'same' through 5-D TMA boxes with zero-filled halos."""
+    ops = _ops()
+    g, d, h, w = shape
+    gen = torch.Generator().manual_seed(d * 100 + cin + k)
+    x = torch.randn(g, cin, d, h, w, generator=gen)
+    wt = torch.randn(cout, cin, k, k, k, generator=gen) / math.sqrt(cin * k ** 3)
+    bias = torch.randn(cout, generator=gen)
+    xp = ops.split_planes(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda))
+    wp = ops.pack_conv_weight(wt.to(cuda))
+    out, _ = ops.conv3d_igemm(xp, wp, k, planes=2, bias=bias.to(cuda))
+    torch.cuda.synchronize()
+    assert ops.igemm_error_flag() == 0
+    ref = F.conv3d(x.double(), wt.double(), bias.double(), padding=k // 2).permute(0, 2, 3, 4, 1).reshape(-1, cout)
+    assert _rel(out, ref) < 2e-5
+
+
+def test_igemm_epilogue(cuda):
+    """out = relu((acc + bias) * scale + residual), fp32 and plane outputs."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(5)
+    m, cin, cout = 500, 256, 256
+    x = torch.randn(m, cin, generator=gen)
+    w = torch.randn(cout, cin, generator=gen) / 16
+    b = torch.randn(cout, generator=gen)
+    res = torch.randn(m, cout, generator=gen)
+    xp = ops.split_planes(x.to(cuda).view(1, 1, 1, m, cin))
+    wp = ops.pack_conv_weight(w.to(cuda))
+    out, (ohi, olo) = ops.conv3d_igemm(xp, wp, 1, bias=b.to(cuda), residual=res.to(cuda), relu=True,
+                                       out_scale=0.25, want_planes=True)
+    torch.cuda.synchronize()
+    ref = torch.relu((x.double() @ w.double().t() + b.double()) * 0.25 + res.double())
+    assert _rel(out, ref) < 2e-5
+    assert _rel(ohi.float() + olo.float(), ref) < 5e-5
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,size", [(4, 64, 5, 2, 16), (128, 128, 3, 2, 8), (256, 512, 1, 2, 8)])
+def test_im2col_conv(cuda, cin, cout, k, stride, size):
+    """conv1 (5^3 s2, Cin 4) and the stride-2 convs via im2col + 1x1x1 igemm; strided input view."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(cin + k)
+    base = torch.randn(2, size, size, size, cin + 3, generator=gen)       # [g, X, Y, Z, C] storage
+    x = base.permute(0, 4, 3, 1, 2)[:, 3:]                                 # [g, C, Z, X, Y] strided view
+    wt = torch.randn(cout, cin, k, k, k, generator=gen) / math.sqrt(cin * k ** 3)
+    kpad = (cin * k ** 3 + 63) // 64 * 64
+    xd = base.to(cuda).permute(0, 4, 3, 1, 2)[:, 3:]
+    cols = ops.im2col(xd, k, stride, k // 2, kpad)
+    wp = ops.pack_conv_weight_im2col(wt.to(cuda), kpad)
+    out, _ = ops.conv3d_igemm(cols, wp, 1)
+    torch.cuda.synchronize()
+    ref = F.conv3d(x.double(), wt.double(), stride=stride, padding=k // 2).permute(0, 2, 3, 4, 1).reshape(-1, cout)
+    assert _rel(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm(cuda, training):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(3)
+    g, m, c = 2, 1000, 128
+    x = torch.randn(g, m, c, generator=gen) * 3 + 1.5
+    gamma, beta = torch.rand(c, generator=gen) + 0.5, torch.randn(c, generator=gen)
+    rm, rv = torch.randn(c, generator=gen) * 0.1, torch.rand(c, generator=gen) + 0.5
+    res = torch.randn(g, m, c, generator=gen)
+    rm_d, rv_d = rm.clone().to(cuda), rv.clone().to(cuda)
+    out, (hi, lo) = ops.batchnorm(x.to(cuda), gamma.to(cuda), beta.to(cuda), rm_d, rv_d, training,
+                                  residual=res.to(cuda), relu=True, want_planes=True)
+    torch.cuda.synchronize()
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    refs = []
+    for gi in range(g):   # the reference runs the grids as successive B = 1 calls
+        xi = x[gi].t().reshape(1, c, m, 1, 1)
+        yi = F.batch_norm(xi, rm_ref, rv_ref, gamma, beta, training, 0.1, 1e-5)
+        refs.append(torch.relu(yi.reshape(c, m).t() + res[gi]))
+    ref = torch.stack(refs)
+    assert _rel(out, ref) < 1e-5
+    assert _rel(hi.float() + lo.float(), ref) < 5e-5
+    assert _rel(rm_d, rm_ref) < 1e-5 and _rel(rv_d, rv_ref) < 1e-5
+
+
+def test_maxpool_upsample(cuda):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 64, 9, 8, 7, generator=gen)
+    out = ops.maxpool3d(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda))
+    ref = F.max_pool3d(x, 3, 2, 1).permute(0, 2, 3, 4, 1)
+    assert torch.equal(out.cpu(), ref)
+    coarse = torch.randn(2, 256, 4, 4, 4, generator=gen)
+    lat = torch.randn(2, 256, 7, 8, 8, generator=gen)
+    got = ops.upsample2_add(coarse.permute(0, 2, 3, 4, 1).contiguous().to(cuda),
+                            lat.permute(0, 2, 3, 4, 1).contiguous().to(cuda))
+    ref = (F.interpolate(coarse, scale_factor=2)[:, :, :7, :8, :8] + lat).permute(0, 2, 3, 4, 1)
+    assert torch.equal(got.cpu(), ref)
+
+
+def test_trilinear_gather(cuda):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(11)
+    X, Y, Z, c = 12, 10, 14, 256
+    p1 = torch.randn(1, c, Z // 2, X // 2, Y // 2, generator=gen)
+    store = torch.randn(X, Y, Z, 7, generator=gen)
+    grid = store.permute(3, 2, 0, 1).unsqueeze(0)
+    mask = torch.randperm(X * Y * Z, generator=gen)[:500].sort().values
+    rows = ops.trilinear_gather(p1[0].permute(1, 2, 3, 0).contiguous().to(cuda),
+                                store.to(cuda).permute(3, 2, 0, 1).unsqueeze(0), mask.to(cuda))
+    up = F.interpolate(p1, size=(Z, X, Y), mode="trilinear", align_corners=True)
+    ref_f = up.permute(0, 3, 4, 2, 1).reshape(1, -1, c)[0, mask]
+    ref_xyz = grid[:, :3].permute(0, 3, 4, 2, 1).reshape(1, -1, 3)[0, mask]
+    assert torch.equal(rows[:, :3].cpu(), ref_xyz)
+    assert (rows[:, 4:].cpu() - ref_f).abs().max() < 1e-5
+
+
+def test_downsample_bitexact(cuda):
+    """R4 against the oracle's defined order / arithmetic: bit exact."""
+    ops = _ops()
+    from oracle.downsample import hierarchical_grid_subsample
+    gen = torch.Generator().manual_seed(13)
+    n_src, n_tgt = 5000, 4200
+    pts = torch.rand(n_src + n_tgt, 3, generator=gen) * 2.4 - 1.2
+    feats = torch.randn(n_src + n_tgt, 256, generator=gen)
+    rows = torch.cat([pts, torch.zeros(n_src + n_tgt, 1), feats], dim=1)
+    out, a, b = ops.hierarchical_downsample(rows.to(cuda), n_src, n_tgt, num_rounds=6)
+    p_ref, f_ref, l_ref = hierarchical_grid_subsample(pts, feats, torch.tensor([n_src, n_tgt]), 6)
+    assert [a, b] == l_ref.tolist()
+    assert torch.equal(out[:, :3].cpu(), p_ref)
+    assert torch.equal(out[:, 4:].cpu(), f_ref)
+
+
+def test_pos_embed_and_layernorm(cuda):
+    ops = _ops()
+    from oracle.regtr import pos_embed_sine
+    gen = torch.Generator().manual_seed(17)
+    xyz = torch.rand(777, 3, generator=gen) * 3 - 1.5
+    pe = ops.pos_embed_sine(xyz.to(cuda), 1.0)
+    assert (pe.cpu() - pos_embed_sine(xyz)).abs().max() < 2e-5
+    x = torch.randn(777, 256, generator=gen) * 2 + 0.3
+    gamma, beta = torch.rand(256, generator=gen) + 0.5, torch.randn(256, generator=gen)
+    out, (hi, lo) = ops.layernorm256(x.to(cuda), gamma.to(cuda), beta.to(cuda), add=pe, want_planes=True)
+    ref = F.layer_norm(x, (256,), gamma, beta, 1e-5) + pos_embed_sine(xyz)
+    assert (out.cpu() - ref).abs().max() < 2e-5
+    assert _rel(hi.float() + lo.float(), ref) < 5e-5
+
+
+@pytest.mark.parametrize("nq,nk", [(100, 100), (333, 517), (1500, 1400), (31, 5)])
+def test_mha_core(cuda, nq, nk):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(nq + nk)
+    qkv_q = torch.randn(nq, 768, generator=gen)
+    qkv_k = torch.randn(nk, 768, generator=gen)
+    qd, kd = qkv_q.to(cuda), qkv_k.to(cuda)
+    out = ops.mha_core(qd[:, :256], kd[:, 256:512], kd[:, 512:])
+    q = qkv_q[:, :256].double().view(nq, 8, 32).transpose(0, 1)
+    k = qkv_k[:, 256:512].double().view(nk, 8, 32).transpose(0, 1)
+    v = qkv_k[:, 512:].double().view(nk, 8, 32).transpose(0, 1)
+    att = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(32), dim=-1)
+    ref = (att @ v).transpose(0, 1).reshape(nq, 256)
+    assert _rel(out, ref) < 1e-5
+
+
+def test_decoder_tail_and_overlap(cuda):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(23)
+    nq, nk = 400, 517
+    s = torch.randn(nq, 520, generator=gen) * 4
+    xyz = torch.randn(nk, 3, generator=gen)
+    out = ops.softmax_weighted_xyz(s.to(cuda), nk, xyz.to(cuda))
+    ref = torch.softmax(s[:, :nk].double(), dim=-1) @ xyz.double()
+    assert _rel(out, ref) < 1e-5
+    feat = torch.randn(nq, 256, generator=gen)
+    w, b = torch.randn(256, generator=gen) / 16, torch.randn(1, generator=gen)
+    ov = ops.overlap_sigmoid(feat.to(cuda), w.to(cuda), b.to(cuda))
+    assert _rel(ov, torch.sigmoid(feat.double() @ w.double() + b.double())) < 1e-5
+
+
+def test_procrustes(cuda):
+    ops = _ops()
+    from oracle.regtr import compute_rigid_transform
+    gen = torch.Generator().manual_seed(29)
+    L, n = 6, 900
+    a = torch.randn(L, n, 3, generator=gen)
+    ang = 0.7
+    R = torch.tensor([[math.cos(ang), -math.sin(ang), 0], [math.sin(ang), math.cos(ang), 0], [0, 0, 1.0]])
+    t = torch.tensor([0.3, -0.2, 0.5])
+    b = a @ R.t() + t + 0.01 * torch.randn(L, n, 3, generator=gen)
+    w = torch.rand(L, n, generator=gen)
+    out = ops.procrustes(a.to(cuda), b.to(cuda), w.to(cuda))
+    ref = compute_rigid_transform(a, b, w)
+    assert (out.cpu() - ref).abs().max() < 1e-5
+    assert (out.cpu()[0, :, :3] - R).abs().max() < 5e-3
