@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the DReg-NeRF registration hot path on B200 (see DESIGN.md "Measurement").
+
+Metric (BASELINE.json): NeRF pairs/sec at a 128^3 grid.  Workload = configs[1]: single pair per
+step, 128^3, fp32-grade arithmetic, synthetic random-weight network and synthetic pairs.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W     # reference CPU arm (oracle port)
+
+One JSON line on stdout (rank 0).  `value` = whole-job pairs/s with the inputs already resident in
+HBM; `e2e` = the same metric through the public API from pinned HOST buffers (H2D of both grids and
+masks and the D2H of the pose inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+RES = 128
+N_RESIDENT_PAIRS = 3        # distinct synthetic pairs cycled through the timed steps
+FPN_FLOPS_PER_GRID_128 = 1384.0e9   # BASELINE.md section 2 (measured, 2*MAC)
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.samples.append([f.strip() for f in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = sorted(int(s[0]) for s in self.samples if len(s) == 6 and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) == 6 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) == 6 and s[2 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def _state(pkg, model):
+    return pkg.synthetic.seeded_state_dict(model, seed=0, attn_gain=4.0)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path (oracle/regtr.py, which is
+    bit-identical to the reference modules - tests/golden) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    import dreg_nerf_b200 as pkg   # synthetic inputs only; the CUDA path is not touched by this arm
+    from oracle import regtr
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = pkg.NeRFRegTr()
+    sd = _state(pkg, model)
+    del model
+    data = pkg.synthetic.make_pair(res=RES, pair_id=0)
+    sample = "1 pair, 128^3, full NeRFRegTr.forward (oracle port of the reference, fp32, torch CPU ops)"
+    reduced = False
+
+    def full_step():
+        with torch.no_grad():
+            regtr.forward(sd, data, training=True)
+
+    def tail_and_fpn_once():
+        # FPN of one grid (half the pair's conv work) + everything after the FPN, timed separately
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            p1 = regtr.fpn3d(data["src_xyz_rgba"][:, 3:], sd, training=True)
+            t_fpn = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            xyz, feats = regtr.gather_masked(data["src_xyz_rgba"], p1, data["src_mask"])
+            t_gather = time.perf_counter() - t0
+        return t_fpn, t_gather
+
+    t0 = time.perf_counter()
+    full_step()
+    first = time.perf_counter() - t0
+    budget = 240.0
+    if first * (args.steps + max(args.warmup - 1, 0)) > budget:
+        reduced = True
+    times = []
+    if not reduced:
+        for _ in range(max(args.warmup - 1, 0)):
+            full_step()
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            full_step()
+            times.append(time.perf_counter() - t0)
+    else:
+        # bounded sample: per step one grid's FPN; pair time = first full step's tail + 2 x FPN
+        t_fpn0, _ = tail_and_fpn_once()
+        tail = max(first - 2.0 * t_fpn0, 0.0)
+        sample = ("per step: FPN of ONE 128^3 grid (half a pair's conv work); pair time = 2 x that + the "
+                  "non-FPN tail (%.2f s) measured on one full pair" % tail)
+        for _ in range(args.steps):
+            t_fpn, _ = tail_and_fpn_once()
+            times.append(2.0 * t_fpn + tail)
+    total = sum(times)
+    value = len(times) / total
+    line = {
+        "impl": "reference", "metric": "nerf_pairs_per_sec_128cube", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "single pair, 128^3 grid, register forward (NeRFRegTr.forward), fp32",
+                   "resolution": RES, "pairs_per_step": 1, "bn_mode": "batch statistics"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import dreg_nerf_b200 as pkg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU: there is no CPU fallback for our arm"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    model = pkg.NeRFRegTr(precision=args.precision)
+    model.load_state_dict(_state(pkg, model))
+    model = model.to(dev).train(True)       # batch-statistics BatchNorm, as eval_nerf_regtr.py runs it
+    # rank r owns pairs r, r + world, ... (independent units, no data-path collective)
+    host_pairs = [pkg.synthetic.make_pair(res=RES, pair_id=rank + world * i) for i in range(N_RESIDENT_PAIRS)]
+    dev_pairs = [pkg.synthetic.to_device(p, dev) for p in host_pairs]
+    pinned = []
+    for p in host_pairs:
+        q = {}
+        for k, v in p.items():
+            if torch.is_tensor(v):
+                # keep the [X,Y,Z,7] storage order of voxel_grid.pt: pin the underlying contiguous storage
+                if v.dim() == 5:
+                    store = v.permute(0, 3, 4, 2, 1).contiguous().pin_memory()
+                    q[k] = store.permute(0, 4, 3, 1, 2)
+                else:
+                    q[k] = v.contiguous().pin_memory()
+            else:
+                q[k] = v
+        pinned.append(q)
+    h2d_bytes = sum(v.numel() * v.element_size() for k, v in pinned[0].items()
+                    if torch.is_tensor(v) and k != "pose")
+    gathered = [torch.empty((1, 3, 4), device=dev) for _ in range(world)] if world > 1 else None
+
+    def step_resident(i):
+        with torch.no_grad():
+            out = model(dict(dev_pairs[i % N_RESIDENT_PAIRS]))
+        pose = out["pose"][-1]
+        if world > 1:
+            dist.all_gather(gathered, pose.contiguous())      # per-pair SE(3), 48 B per rank
+        return out
+
+    def step_e2e(i):
+        src = pinned[i % N_RESIDENT_PAIRS]
+        with torch.no_grad():
+            data = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in src.items()}
+            out = model(data)
+            pose = out["pose"][-1]
+            if world > 1:
+                dist.all_gather(gathered, pose.contiguous())
+            return pose.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        model.set_profile(profile)
+        if profile:
+            model.read_profile()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = model.launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        prof = model.read_profile() if profile else None
+        model.set_profile(False)
+        return float(t.item()), model.launch_count() - l0, prof
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, prof = timed(step_resident, args.steps, profile=True)
+    clocks = sampler.summary() if sampler else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        peaks = _peaks()
+        value = world * args.steps / (ms / 1e3)
+        e2e = world * args.steps / (ms_e2e / 1e3)
+        ig_ms, ig_flops, ig_n = prof
+        achieved = ig_flops / (ig_ms / 1e3) / 1e12 if ig_ms > 0 else 0.0
+        mma_factor = 3 if args.precision == "fp32" else 1
+        peak = peaks["bf16_tflops_sustained"]
+        ns, nt = model.last_token_counts
+        line = {
+            "metric": "nerf_pairs_per_sec_128cube", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (split-bf16 x3 tensor-core products, fp32 accumulate)" if args.precision == "fp32" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": "single pair, 128^3 grid, register forward (NeRFRegTr.forward) on 1xB200, fp32"
+                                   if args.precision == "fp32" else "single pair, 128^3, register forward, bf16",
+                       "resolution": RES, "pairs_per_step_per_gpu": 1, "masked_voxels": [int(dev_pairs[0]["src_mask"].numel()),
+                                                                                          int(dev_pairs[0]["tgt_mask"].numel())],
+                       "tokens": [ns, nt], "bn_mode": "batch statistics",
+                       "l2": "working set per step (2 x 58.7 MB grids, 0.6 GB weight planes, >3 GB activations) exceeds the 126 MB L2",
+                       "parallelism": "pairs sharded over %d GPU(s), one NCCL all-gather of the per-pair SE(3)" % world},
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": 48, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv3d/linear), all launches of the timed steps",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": peaks["source"] + ", bf16 sustained",
+                         "traffic": None, "launches": int(ig_n), "kernel_ms_per_step": ig_ms / args.steps,
+                         "kernel_share_of_step": ig_ms / ms,
+                         "mma_flops_factor": mma_factor, "tensor_pipe_frac_est": mma_factor * achieved / peak},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(pkg, model)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(pkg, model):
+    """The oracle (port of the reference, bit-identical to it) timed on the host cores: one pair."""
+    import torch
+    from oracle import regtr
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    data = pkg.synthetic.make_pair(res=RES, pair_id=0)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        regtr.forward(sd, data, training=True)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": "1 pair, 128^3, full NeRFRegTr.forward, fp32 torch CPU ops, %d threads, single cold run (%.1f s)"
+                      % (cores, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

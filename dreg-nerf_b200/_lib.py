@@ -17,7 +17,7 @@ class Conv3dDesc(C.Structure):
     _fields_ = [("g", c_int), ("d", c_int), ("h", c_int), ("w", c_int),
                 ("cin", c_int), ("cout", c_int),
                 ("kd", c_int), ("kh", c_int), ("kw", c_int),
-                ("planes", c_int), ("relu", c_int), ("out_scale", c_float),
+                ("planes", c_int), ("relu", c_int), ("acc_scale", c_float), ("out_scale", c_float),
                 ("x_hi", c_void_p), ("x_lo", c_void_p), ("w_hi", c_void_p), ("w_lo", c_void_p),
                 ("bias", c_void_p), ("residual", c_void_p),
                 ("out", c_void_p), ("out_hi", c_void_p), ("out_lo", c_void_p),
@@ -70,8 +70,10 @@ SIGNATURES = {
     "drb_igemm_error_flag": (c_int, [C.POINTER(c_int)]),
     "drb_conv3d_igemm": (c_int, [C.POINTER(Conv3dDesc), c_void_p]),
     "drb_split_planes": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
-    "drb_pack_conv_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "drb_pack_conv_weight_im2col": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "drb_weight_scale": (c_int, [c_void_p, c_ll, C.POINTER(c_float), c_void_p]),
+    "drb_pack_conv_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "drb_pack_conv_weight_im2col": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                            c_void_p]),
     "drb_im2col": (c_int, [C.POINTER(Im2colDesc), c_void_p, c_void_p, c_void_p]),
     "drb_bn_stats": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p]),
     "drb_bn_finalize": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
@@ -116,6 +118,8 @@ SIGNATURES = {
     "drb_engine_decode": (c_int, [c_void_p, C.POINTER(PairOut), c_void_p]),
     "drb_engine_tap": (c_int, [c_void_p, C.c_char_p, c_int, c_void_p, c_ll, C.POINTER(c_ll), c_void_p]),
     "drb_engine_launch_count": (c_ll, [c_void_p]),
+    "drb_engine_set_profile": (c_int, [c_void_p, c_int]),
+    "drb_engine_profile_read": (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll)]),
 }
 
 _lib = None

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -38,16 +39,27 @@ void set_error(const char* fmt, ...);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-typedef __nv_bfloat16 bf16;
+// 16-bit operand "planes" of the tensor-core GEMM (raw storage).
+//   pair mode   (lo plane present): x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significand
+//               bits survive as long as |x| stays inside fp16's normal range (weights are pre-scaled by a
+//               power of two for that, see drb_pack_conv_weight); |x| > 65504 saturates.
+//   single mode (no lo plane): hi = bf16(x) (the bf16 configurations).
+typedef uint16_t plane_t;
 
-// x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits survive.
-__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+__device__ __forceinline__ void split16(float x, bool pair, plane_t& hi, plane_t& lo) {
+  if (pair) {
+    x = fminf(fmaxf(x, -65504.f), 65504.f);
+    const __half h = __float2half_rn(x);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(__float2half_rn(x - __half2float(h)));
+  } else {
+    hi = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+    lo = 0;
+  }
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+__device__ __forceinline__ uint32_t pack16x2(plane_t a, plane_t b) {
+  return (uint32_t)a | ((uint32_t)b << 16);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -147,8 +159,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
                : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate, one CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc], 16-bit float inputs, fp32 accumulate, one CTA.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -190,9 +202,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major, M x N tile.
-__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
+// kind::f16 instruction descriptor: (fp16 | bf16) x same -> f32, both operands K-major, M x N tile.
+__host__ __device__ __forceinline__ uint32_t umma_idesc_16(int M, int N, bool is_bf16) {
+  const uint32_t fmt = is_bf16 ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
 

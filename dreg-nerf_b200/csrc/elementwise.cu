@@ -2,6 +2,7 @@
 // BatchNorm statistics / apply, max-pool, FPN nearest-upsample + add.  All channels-last.
 #include "common.cuh"
 
+#include <math.h>
 #include <stdarg.h>
 
 namespace drb {
@@ -25,12 +26,12 @@ static inline int grid_for(long long n, int block, int cap = 148 * 16) {
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void split_kernel(const float* __restrict__ x, bf16* __restrict__ hi,
-                             bf16* __restrict__ lo, long long n) {
+__global__ void split_kernel(const float* __restrict__ x, plane_t* __restrict__ hi,
+                             plane_t* __restrict__ lo, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    bf16 h, l;
-    split_bf16(x[i], h, l);
+    plane_t h, l;
+    split16(x[i], lo != nullptr, h, l);
     hi[i] = h;
     if (lo) lo[i] = l;
   }
@@ -40,7 +41,7 @@ extern "C" int drb_split_planes(const float* x, void* hi, void* lo, long long n,
                                 cudaStream_t stream) {
   DRB_REQUIRE(x && hi && n >= 0, "drb_split_planes: bad arguments");
   if (n == 0) return 0;
-  split_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, (bf16*)hi, (bf16*)lo, n);
+  split_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, (plane_t*)hi, (plane_t*)lo, n);
   DRB_LAUNCH_OK();
   return 0;
 }
@@ -48,23 +49,24 @@ extern "C" int drb_split_planes(const float* x, void* hi, void* lo, long long n,
 // ------------------------------------------------------------------------------------------
 // weights [cout][cin][taps] -> [taps][cout][cin_pad]
 __global__ void pack_w_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cin_pad,
-                              bf16* __restrict__ hi, bf16* __restrict__ lo) {
+                              float scale, plane_t* __restrict__ hi, plane_t* __restrict__ lo) {
   const long long total = (long long)taps * cout * cin_pad;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int c = (int)(i % cin_pad);
     const int o = (int)((i / cin_pad) % cout);
     const int t = (int)(i / ((long long)cin_pad * cout));
-    const float v = (c < cin) ? w[((long long)o * cin + c) * taps + t] : 0.f;
-    bf16 h, l;
-    split_bf16(v, h, l);
+    const float v = (c < cin) ? w[((long long)o * cin + c) * taps + t] * scale : 0.f;
+    plane_t h, l;
+    split16(v, lo != nullptr, h, l);
     hi[i] = h;
     if (lo) lo[i] = l;
   }
 }
 // weights [cout][cin][taps] -> [cout][kpad], k = tap*cin + c
 __global__ void pack_w_im2col_kernel(const float* __restrict__ w, int cout, int cin, int taps,
-                                     int kpad, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+                                     int kpad, float scale, plane_t* __restrict__ hi,
+                                     plane_t* __restrict__ lo) {
   const long long total = (long long)cout * kpad;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -73,38 +75,72 @@ __global__ void pack_w_im2col_kernel(const float* __restrict__ w, int cout, int 
     float v = 0.f;
     if (k < taps * cin) {
       const int t = k / cin, c = k % cin;
-      v = w[((long long)o * cin + c) * taps + t];
+      v = w[((long long)o * cin + c) * taps + t] * scale;
     }
-    bf16 h, l;
-    split_bf16(v, h, l);
+    plane_t h, l;
+    split16(v, lo != nullptr, h, l);
     hi[i] = h;
     if (lo) lo[i] = l;
   }
 }
 
 extern "C" int drb_pack_conv_weight(const float* w, int cout, int cin, int taps, int cin_pad,
-                                    void* hi, void* lo, cudaStream_t stream) {
+                                    float scale, void* hi, void* lo, cudaStream_t stream) {
   DRB_REQUIRE(w && hi && cout > 0 && cin > 0 && taps > 0 && cin_pad >= cin,
               "drb_pack_conv_weight: bad arguments");
   pack_w_kernel<<<grid_for((long long)taps * cout * cin_pad, 256), 256, 0, stream>>>(
-      w, cout, cin, taps, cin_pad, (bf16*)hi, (bf16*)lo);
+      w, cout, cin, taps, cin_pad, scale == 0.f ? 1.f : scale, (plane_t*)hi, (plane_t*)lo);
   DRB_LAUNCH_OK();
   return 0;
 }
 extern "C" int drb_pack_conv_weight_im2col(const float* w, int cout, int cin, int taps, int kpad,
-                                           void* hi, void* lo, cudaStream_t stream) {
+                                           float scale, void* hi, void* lo, cudaStream_t stream) {
   DRB_REQUIRE(w && hi && cout > 0 && cin > 0 && taps > 0 && kpad >= cin * taps,
               "drb_pack_conv_weight_im2col: bad arguments");
   pack_w_im2col_kernel<<<grid_for((long long)cout * kpad, 256), 256, 0, stream>>>(
-      w, cout, cin, taps, kpad, (bf16*)hi, (bf16*)lo);
+      w, cout, cin, taps, kpad, scale == 0.f ? 1.f : scale, (plane_t*)hi, (plane_t*)lo);
   DRB_LAUNCH_OK();
+  return 0;
+}
+
+// max |w| of a tensor (weight pre-scale selection); result accumulates into *out (caller zeroes it).
+__global__ void absmax_kernel(const float* __restrict__ w, long long n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    m = fmaxf(m, fabsf(w[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order as uints
+}
+
+// Power-of-two scale that maps max|w| into [256, 512): keeps hi and lo = fp16(x - hi) in fp16's
+// normal range with head-room against overflow.  Synchronous (one 4-byte read back).
+extern "C" int drb_weight_scale(const float* w, long long n, float* host_scale, cudaStream_t stream) {
+  DRB_REQUIRE(w && host_scale && n > 0, "drb_weight_scale: bad arguments");
+  unsigned int* d = nullptr;
+  DRB_CUDA_OK(cudaMallocAsync(&d, sizeof(unsigned int), stream));
+  DRB_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(unsigned int), stream));
+  absmax_kernel<<<grid_for(n, 256, 296), 256, 0, stream>>>(w, n, d);
+  unsigned int bits = 0;
+  DRB_CUDA_OK(cudaMemcpyAsync(&bits, d, sizeof(bits), cudaMemcpyDeviceToHost, stream));
+  DRB_CUDA_OK(cudaStreamSynchronize(stream));
+  DRB_CUDA_OK(cudaFreeAsync(d, stream));
+  float mx;
+  memcpy(&mx, &bits, sizeof(mx));
+  float scale = 1.f;
+  if (mx > 0.f && isfinite(mx)) {
+    int e = 0;
+    frexpf(mx, &e);                 // mx = f * 2^e, f in [0.5, 1)
+    scale = ldexpf(1.f, 9 - e);     // mx * scale in [256, 512)
+  }
+  *host_scale = scale;
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------
 // im2col: one thread per (output voxel, k) element; k fastest so that writes coalesce.
-__global__ void im2col_kernel(drb_im2col_desc d, int od, int oh, int ow, bf16* __restrict__ hi,
-                              bf16* __restrict__ lo) {
+__global__ void im2col_kernel(drb_im2col_desc d, int od, int oh, int ow, plane_t* __restrict__ hi,
+                              plane_t* __restrict__ lo) {
   const long long rows = (long long)d.g * od * oh * ow;
   const long long total = rows * d.kpad;
   const int kk = d.k * d.k * d.k * d.c;
@@ -129,8 +165,8 @@ __global__ void im2col_kernel(drb_im2col_desc d, int od, int oh, int ow, bf16* _
       if (iz >= 0 && iz < d.d && iy >= 0 && iy < d.h && ix >= 0 && ix < d.w)
         v = d.x[g * d.sg + ch * d.sc + iz * d.sd + iy * d.sh + ix * d.sw];
     }
-    bf16 h, l;
-    split_bf16(v, h, l);
+    plane_t h, l;
+    split16(v, lo != nullptr, h, l);
     hi[i] = h;
     if (lo) lo[i] = l;
   }
@@ -145,8 +181,8 @@ extern "C" int drb_im2col(const drb_im2col_desc* d, void* hi, void* lo, cudaStre
   const int oh = (d->h + 2 * d->pad - d->k) / d->stride + 1;
   const int ow = (d->w + 2 * d->pad - d->k) / d->stride + 1;
   const long long total = (long long)d->g * od * oh * ow * d->kpad;
-  im2col_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(*d, od, oh, ow, (bf16*)hi,
-                                                                    (bf16*)lo);
+  im2col_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(*d, od, oh, ow, (plane_t*)hi,
+                                                                    (plane_t*)lo);
   DRB_LAUNCH_OK();
   return 0;
 }
@@ -254,7 +290,7 @@ __global__ void scale_shift_act_kernel(const float* __restrict__ x, const float*
                                        const float* __restrict__ shift,
                                        const float* __restrict__ residual, int relu, long long m,
                                        int c, long long total4, float* __restrict__ out,
-                                       bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+                                       plane_t* __restrict__ out_hi, plane_t* __restrict__ out_lo) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int c4 = c >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
@@ -277,11 +313,12 @@ __global__ void scale_shift_act_kernel(const float* __restrict__ x, const float*
     }
     if (out) *(float4*)(out + i * 4) = v;
     if (out_hi) {
-      bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-      split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1);
-      split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
-      *(uint2*)(out_hi + i * 4) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-      if (out_lo) *(uint2*)(out_lo + i * 4) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+      const bool pair = out_lo != nullptr;
+      plane_t h0, l0, h1, l1, h2, l2, h3, l3;
+      split16(v.x, pair, h0, l0); split16(v.y, pair, h1, l1);
+      split16(v.z, pair, h2, l2); split16(v.w, pair, h3, l3);
+      *(uint2*)(out_hi + i * 4) = make_uint2(pack16x2(h0, h1), pack16x2(h2, h3));
+      if (pair) *(uint2*)(out_lo + i * 4) = make_uint2(pack16x2(l0, l1), pack16x2(l2, l3));
     }
   }
 }
@@ -293,7 +330,7 @@ extern "C" int drb_scale_shift_act(const float* x, const float* scale, const flo
   DRB_REQUIRE((scale == nullptr) == (shift == nullptr), "drb_scale_shift_act: scale/shift pair");
   const long long total4 = (long long)g * m * c / 4;
   scale_shift_act_kernel<<<grid_for(total4, 256, 148 * 32), 256, 0, stream>>>(
-      x, scale, shift, residual, relu, m, c, total4, out, (bf16*)out_hi, (bf16*)out_lo);
+      x, scale, shift, residual, relu, m, c, total4, out, (plane_t*)out_hi, (plane_t*)out_lo);
   DRB_LAUNCH_OK();
   return 0;
 }
@@ -301,7 +338,7 @@ extern "C" int drb_scale_shift_act(const float* x, const float* scale, const flo
 // ------------------------------------------------------------------------------------------
 __global__ void maxpool_kernel(const float* __restrict__ x, int g, int d, int h, int w, int c,
                                int od, int oh, int ow, float* __restrict__ out,
-                               bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+                               plane_t* __restrict__ out_hi, plane_t* __restrict__ out_lo) {
   const long long total = (long long)g * od * oh * ow * c;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -327,8 +364,8 @@ __global__ void maxpool_kernel(const float* __restrict__ x, int g, int d, int h,
     }
     if (out) out[i] = best;
     if (out_hi) {
-      bf16 hh, ll;
-      split_bf16(best, hh, ll);
+      plane_t hh, ll;
+      split16(best, out_lo != nullptr, hh, ll);
       out_hi[i] = hh;
       if (out_lo) out_lo[i] = ll;
     }
@@ -342,7 +379,7 @@ extern "C" int drb_maxpool3d(const float* x, int g, int d, int h, int w, int c, 
   const int od = (d - 1) / 2 + 1, oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
   const long long total = (long long)g * od * oh * ow * c;
   maxpool_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(
-      x, g, d, h, w, c, od, oh, ow, out, (bf16*)out_hi, (bf16*)out_lo);
+      x, g, d, h, w, c, od, oh, ow, out, (plane_t*)out_hi, (plane_t*)out_lo);
   DRB_LAUNCH_OK();
   return 0;
 }
@@ -350,8 +387,8 @@ extern "C" int drb_maxpool3d(const float* x, int g, int d, int h, int w, int c, 
 // ------------------------------------------------------------------------------------------
 __global__ void upsample_add_kernel(const float* __restrict__ coarse, int dc, int hc, int wc,
                                     const float* __restrict__ lateral, int g, int d, int h, int w,
-                                    int c, float* __restrict__ out, bf16* __restrict__ out_hi,
-                                    bf16* __restrict__ out_lo) {
+                                    int c, float* __restrict__ out, plane_t* __restrict__ out_hi,
+                                    plane_t* __restrict__ out_lo) {
   const int c4 = c >> 2;
   const long long total4 = (long long)g * d * h * w * c4;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -369,11 +406,12 @@ __global__ void upsample_add_kernel(const float* __restrict__ coarse, int dc, in
     float4 v = make_float4(b.x + a.x, b.y + a.y, b.z + a.z, b.w + a.w);
     if (out) *(float4*)(out + i * 4) = v;
     if (out_hi) {
-      bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-      split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1);
-      split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
-      *(uint2*)(out_hi + i * 4) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-      if (out_lo) *(uint2*)(out_lo + i * 4) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+      const bool pair = out_lo != nullptr;
+      plane_t h0, l0, h1, l1, h2, l2, h3, l3;
+      split16(v.x, pair, h0, l0); split16(v.y, pair, h1, l1);
+      split16(v.z, pair, h2, l2); split16(v.w, pair, h3, l3);
+      *(uint2*)(out_hi + i * 4) = make_uint2(pack16x2(h0, h1), pack16x2(h2, h3));
+      if (pair) *(uint2*)(out_lo + i * 4) = make_uint2(pack16x2(l0, l1), pack16x2(l2, l3));
     }
   }
 }
@@ -385,7 +423,7 @@ extern "C" int drb_upsample2_add(const float* coarse, int dc, int hc, int wc, co
   DRB_REQUIRE(d <= 2 * dc && h <= 2 * hc && w <= 2 * wc, "drb_upsample2_add: lateral larger than 2x coarse");
   const long long total4 = (long long)g * d * h * w * (c / 4);
   upsample_add_kernel<<<grid_for(total4, 256, 148 * 32), 256, 0, stream>>>(
-      coarse, dc, hc, wc, lateral, g, d, h, w, c, out, (bf16*)out_hi, (bf16*)out_lo);
+      coarse, dc, hc, wc, lateral, g, d, h, w, c, out, (plane_t*)out_hi, (plane_t*)out_lo);
   DRB_LAUNCH_OK();
   return 0;
 }

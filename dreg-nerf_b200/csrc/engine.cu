@@ -19,8 +19,8 @@ static constexpr int kD = 256;
 
 struct Act {                 // channels-last activation [g][d][h][w][c]
   float* f = nullptr;
-  bf16* hi = nullptr;
-  bf16* lo = nullptr;
+  plane_t* hi = nullptr;
+  plane_t* lo = nullptr;
   int d = 0, h = 0, w = 0, c = 0;
   long long m() const { return (long long)d * h * w; }          // voxels per grid
   long long numel() const { return (long long)kG * m() * c; }
@@ -37,10 +37,11 @@ struct Param {
 struct ConvW {               // packed weight planes
   int p_w = -1, p_b = -1;    // param indices (bias optional)
   int cout = 0, cin = 0, k = 1, stride = 1;
+  float scale = 1.f;         // power-of-two pre-scale applied when packing (pair mode)
   bool im2col = false;       // lowered through an explicit im2col buffer
   int kpad = 0;              // im2col K (multiple of 64)
-  bf16* hi = nullptr;
-  bf16* lo = nullptr;
+  plane_t* hi = nullptr;
+  plane_t* lo = nullptr;
 };
 
 struct BnP {
@@ -74,6 +75,9 @@ struct drb_engine {
   std::vector<void*> allocs;
   long long launches = 0;
   bool committed = false;
+  bool profile = false;
+  struct ProfRec { cudaEvent_t a, b; double flops; };
+  std::vector<ProfRec> prof;
   std::string fail;
 
   // topology
@@ -87,7 +91,7 @@ struct drb_engine {
 
   // FPN buffers
   int D, H, W;                      // conv volume axes: D = Z, H = X, W = Y
-  bf16 *col_hi = nullptr, *col_lo = nullptr;   // shared im2col scratch
+  plane_t *col_hi = nullptr, *col_lo = nullptr;   // shared im2col scratch
   long long col_elems = 0;
   float* raw = nullptr;             // shared raw conv output scratch (largest BN'd conv)
   long long raw_elems = 0;
@@ -104,9 +108,9 @@ struct drb_engine {
   // transformer buffers (capacity tok_cap rows)
   int tok_cap = 0;
   float *x = nullptr, *pos = nullptr, *qkv = nullptr, *kp_xyz = nullptr, *sbuf = nullptr;
-  bf16 *xn_hi = nullptr, *xn_lo = nullptr, *att_hi = nullptr, *att_lo = nullptr;
-  bf16 *ffn_hi = nullptr, *ffn_lo = nullptr, *dec_hi = nullptr, *dec_lo = nullptr;
-  bf16 *qp_hi = nullptr, *qp_lo = nullptr, *kp_hi = nullptr, *kp_lo = nullptr;
+  plane_t *xn_hi = nullptr, *xn_lo = nullptr, *att_hi = nullptr, *att_lo = nullptr;
+  plane_t *ffn_hi = nullptr, *ffn_lo = nullptr, *dec_hi = nullptr, *dec_lo = nullptr;
+  plane_t *qp_hi = nullptr, *qp_lo = nullptr, *kp_hi = nullptr, *kp_lo = nullptr;
   std::vector<void*> tok_allocs;
 
   template <typename T> T* alloc(long long n) {
@@ -138,11 +142,11 @@ static ConvW make_conv(drb_engine* e, const std::string& name, int cout, int cin
   w.im2col = (stride != 1) || (cin % 64 != 0);
   if (w.im2col) {
     w.kpad = ((taps * cin + 63) / 64) * 64;
-    w.hi = e->alloc<bf16>((long long)cout * w.kpad);
-    w.lo = e->alloc<bf16>((long long)cout * w.kpad);
+    w.hi = e->alloc<plane_t>((long long)cout * w.kpad);
+    if (e->cfg.planes == 2) w.lo = e->alloc<plane_t>((long long)cout * w.kpad);
   } else {
-    w.hi = e->alloc<bf16>((long long)taps * cout * cin);
-    w.lo = e->alloc<bf16>((long long)taps * cout * cin);
+    w.hi = e->alloc<plane_t>((long long)taps * cout * cin);
+    if (e->cfg.planes == 2) w.lo = e->alloc<plane_t>((long long)taps * cout * cin);
   }
   return w;
 }
@@ -164,8 +168,8 @@ static Act make_act(drb_engine* e, int d, int h, int w, int c, bool f32, bool pl
   a.d = d; a.h = h; a.w = w; a.c = c;
   if (f32) a.f = e->alloc<float>(a.numel());
   if (planes) {
-    a.hi = e->alloc<bf16>(a.numel());
-    a.lo = e->alloc<bf16>(a.numel());
+    a.hi = e->alloc<plane_t>(a.numel());
+    if (e->cfg.planes == 2) a.lo = e->alloc<plane_t>(a.numel());
   }
   return a;
 }
@@ -217,8 +221,8 @@ static int build(drb_engine* e) {
       a.in_proj.cout = 768; a.in_proj.cin = 256;
       a.in_proj.p_w = e->add_param(pn + "." + an + ".in_proj_weight", 768 * 256);
       a.in_proj.p_b = e->add_param(pn + "." + an + ".in_proj_bias", 768);
-      a.in_proj.hi = e->alloc<bf16>(768 * 256);
-      a.in_proj.lo = e->alloc<bf16>(768 * 256);
+      a.in_proj.hi = e->alloc<plane_t>(768 * 256);
+      if (e->cfg.planes == 2) a.in_proj.lo = e->alloc<plane_t>(768 * 256);
       a.out_proj = make_conv(e, pn + "." + an + ".out_proj", 256, 256, 1, 1, true);
       return a;
     };
@@ -271,8 +275,8 @@ static int build(drb_engine* e) {
     e->c[li] = e->tmp.back();
   }
   e->col_elems = col_max;
-  e->col_hi = e->alloc<bf16>(col_max);
-  e->col_lo = e->alloc<bf16>(col_max);
+  e->col_hi = e->alloc<plane_t>(col_max);
+  if (cfg.planes == 2) e->col_lo = e->alloc<plane_t>(col_max);
   e->raw_elems = raw_max;
   e->raw = e->alloc<float>(raw_max);
   e->raw2 = e->alloc<float>(raw_max);
@@ -301,10 +305,10 @@ static int build(drb_engine* e) {
     if (_rc != 0) return _rc;    \
   } while (0)
 
-static int run_igemm(drb_engine* e, const ConvW& w, const bf16* x_hi, const bf16* x_lo, int g, int d,
+static int run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const plane_t* x_lo, int g, int d,
                      int h, int wd, int cin, int k, const float* bias, const float* residual,
-                     int relu, float scale, float* out, bf16* out_hi, bf16* out_lo, long long ld,
-                     cudaStream_t s, const bf16* w_hi = nullptr, const bf16* w_lo = nullptr,
+                     int relu, float scale, float* out, plane_t* out_hi, plane_t* out_lo, long long ld,
+                     cudaStream_t s, const plane_t* w_hi = nullptr, const plane_t* w_lo = nullptr,
                      int cout_override = 0) {
   drb_conv3d_desc cd;
   memset(&cd, 0, sizeof(cd));
@@ -313,16 +317,27 @@ static int run_igemm(drb_engine* e, const ConvW& w, const bf16* x_hi, const bf16
   cd.kd = cd.kh = cd.kw = k;
   cd.planes = e->cfg.planes;
   cd.relu = relu; cd.out_scale = scale;
+  cd.acc_scale = w_hi ? 1.f : 1.f / w.scale;
   cd.x_hi = x_hi; cd.x_lo = x_lo;
   cd.w_hi = w_hi ? w_hi : w.hi; cd.w_lo = w_lo ? w_lo : w.lo;
   cd.bias = bias; cd.residual = residual;
   cd.out = out; cd.out_hi = out_hi; cd.out_lo = out_lo;
   cd.ld_out = ld;
   e->launches += 1;
-  return drb_conv3d_igemm(&cd, s);
+  if (!e->profile) return drb_conv3d_igemm(&cd, s);
+  drb_engine::ProfRec r;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  r.flops = 2.0 * (double)g * d * h * wd * (double)cd.cout * (double)cin * k * k * k;
+  cudaEventRecord(r.a, s);
+  const int rc = drb_conv3d_igemm(&cd, s);
+  cudaEventRecord(r.b, s);
+  e->prof.push_back(r);
+  return rc;
 }
 
 static inline float* P(drb_engine* e, int idx) { return idx >= 0 ? e->params[idx].ptr : nullptr; }
+static inline plane_t* off(plane_t* p, long long n) { return p ? p + n : nullptr; }
 
 // conv (stride 1 via TMA implicit GEMM, otherwise im2col + 1x1x1 GEMM) into raw fp32 [g][m][cout]
 static int conv_any(drb_engine* e, const ConvW& w, const Act& in, int od, int oh, int ow, float* out,
@@ -346,7 +361,7 @@ static int conv_any(drb_engine* e, const ConvW& w, const Act& in, int od, int oh
 
 // BatchNorm (+ residual, ReLU) of raw [g][m][c] into out (fp32 and/or planes)
 static int bn_apply(drb_engine* e, const BnP& b, const float* rawp, long long m, const float* residual,
-                    int relu, float* out, bf16* out_hi, bf16* out_lo, cudaStream_t s) {
+                    int relu, float* out, plane_t* out_hi, plane_t* out_lo, cudaStream_t s) {
   const int training = e->cfg.training_bn;
   if (training) {
     e->launches += 2;
@@ -377,7 +392,7 @@ static int run_fpn(drb_engine* e, const drb_pair_io* io, cudaStream_t s) {
       d.g = 1; d.c = 4; d.d = e->D; d.h = e->H; d.w = e->W;
       d.k = 5; d.stride = 2; d.pad = 2; d.kpad = w.kpad;
       e->launches += 1;
-      DRB_TRY(drb_im2col(&d, e->col_hi + g * per_grid, e->col_lo + g * per_grid, s));
+      DRB_TRY(drb_im2col(&d, e->col_hi + g * per_grid, off(e->col_lo, g * per_grid), s));
     }
     DRB_TRY(run_igemm(e, w, e->col_hi, e->col_lo, kG, e->c1.d, e->c1.h, e->c1.w, w.kpad, 1, nullptr,
                       nullptr, 0, 1.f, e->raw, nullptr, nullptr, 0, s));
@@ -454,15 +469,17 @@ static int ensure_tokens(drb_engine* e, int m) {
   e->x = (float*)A(cap * kD * 4); e->pos = (float*)A(cap * kD * 4);
   e->qkv = (float*)A(cap * 768 * 4); e->kp_xyz = (float*)A(cap * 3 * 4 + 64);
   e->sbuf = (float*)A(cap * cap_ld * 4);
-  e->xn_hi = (bf16*)A(cap * kD * 2); e->xn_lo = (bf16*)A(cap * kD * 2);
-  e->att_hi = (bf16*)A(cap * kD * 2); e->att_lo = (bf16*)A(cap * kD * 2);
-  e->ffn_hi = (bf16*)A(cap * 1024 * 2); e->ffn_lo = (bf16*)A(cap * 1024 * 2);
-  e->dec_hi = (bf16*)A(kLayers * cap * kD * 2); e->dec_lo = (bf16*)A(kLayers * cap * kD * 2);
-  e->qp_hi = (bf16*)A(kLayers * cap * kD * 2); e->qp_lo = (bf16*)A(kLayers * cap * kD * 2);
-  e->kp_hi = (bf16*)A(kLayers * cap * kD * 2); e->kp_lo = (bf16*)A(kLayers * cap * kD * 2);
-  if (!e->x || !e->pos || !e->qkv || !e->kp_xyz || !e->sbuf || !e->xn_hi || !e->xn_lo || !e->att_hi ||
-      !e->att_lo || !e->ffn_hi || !e->ffn_lo || !e->dec_hi || !e->dec_lo || !e->qp_hi || !e->qp_lo ||
-      !e->kp_hi || !e->kp_lo) {
+  const bool pair = e->cfg.planes == 2;
+  auto AL = [&](long long bytes) -> plane_t* { return pair ? (plane_t*)A(bytes) : nullptr; };
+  e->xn_hi = (plane_t*)A(cap * kD * 2); e->xn_lo = AL(cap * kD * 2);
+  e->att_hi = (plane_t*)A(cap * kD * 2); e->att_lo = AL(cap * kD * 2);
+  e->ffn_hi = (plane_t*)A(cap * 1024 * 2); e->ffn_lo = AL(cap * 1024 * 2);
+  e->dec_hi = (plane_t*)A(kLayers * cap * kD * 2); e->dec_lo = AL(kLayers * cap * kD * 2);
+  e->qp_hi = (plane_t*)A(kLayers * cap * kD * 2); e->qp_lo = AL(kLayers * cap * kD * 2);
+  e->kp_hi = (plane_t*)A(kLayers * cap * kD * 2); e->kp_lo = AL(kLayers * cap * kD * 2);
+  const bool lo_ok = !pair || (e->xn_lo && e->att_lo && e->ffn_lo && e->dec_lo && e->qp_lo && e->kp_lo);
+  if (!e->x || !e->pos || !e->qkv || !e->kp_xyz || !e->sbuf || !e->xn_hi || !e->att_hi || !e->ffn_hi ||
+      !e->dec_hi || !e->qp_hi || !e->kp_hi || !lo_ok) {
     set_error("drb_engine: out of device memory for %d tokens", m);
     e->tok_cap = 0;
     return DRB_ENOMEM;
@@ -518,14 +535,42 @@ extern "C" int drb_engine_set_training(drb_engine* e, int training_bn) {
 }
 extern "C" long long drb_engine_launch_count(const drb_engine* e) { return e ? e->launches : 0; }
 
+extern "C" int drb_engine_set_profile(drb_engine* e, int on) {
+  DRB_REQUIRE(e, "drb_engine_set_profile: null engine");
+  e->profile = on != 0;
+  return 0;
+}
+
+extern "C" int drb_engine_profile_read(drb_engine* e, double* igemm_ms, double* igemm_flops, long long* n) {
+  DRB_REQUIRE(e && igemm_ms && igemm_flops && n, "drb_engine_profile_read: null argument");
+  double ms = 0.0, fl = 0.0;
+  for (auto& r : e->prof) {
+    DRB_CUDA_OK(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    DRB_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+    fl += r.flops;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  *igemm_ms = ms; *igemm_flops = fl; *n = (long long)e->prof.size();
+  e->prof.clear();
+  return 0;
+}
+
 extern "C" int drb_engine_commit_params(drb_engine* e, cudaStream_t s) {
   DRB_REQUIRE(e, "drb_engine_commit_params: null engine");
   for (const Param& p : e->params)
     DRB_REQUIRE(p.ptr != nullptr, "drb_engine_commit_params: parameter %s is not bound", p.name.c_str());
-  auto pack = [&](const ConvW& w) -> int {
+  const bool pair = e->cfg.planes == 2;
+  auto pack = [&](ConvW& w) -> int {
     const int taps = w.k * w.k * w.k;
-    if (w.im2col) return drb_pack_conv_weight_im2col(P(e, w.p_w), w.cout, w.cin, taps, w.kpad, w.hi, w.lo, s);
-    return drb_pack_conv_weight(P(e, w.p_w), w.cout, w.cin, taps, w.cin, w.hi, w.lo, s);
+    w.scale = 1.f;
+    if (pair) DRB_TRY(drb_weight_scale(P(e, w.p_w), (long long)w.cout * w.cin * taps, &w.scale, s));
+    plane_t* lo = pair ? w.lo : nullptr;
+    if (w.im2col)
+      return drb_pack_conv_weight_im2col(P(e, w.p_w), w.cout, w.cin, taps, w.kpad, w.scale, w.hi, lo, s);
+    return drb_pack_conv_weight(P(e, w.p_w), w.cout, w.cin, taps, w.cin, w.scale, w.hi, lo, s);
   };
   DRB_TRY(pack(e->conv1));
   for (int li = 0; li < 4; ++li)
@@ -586,8 +631,8 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
   DRB_LAUNCH_OK();
   DRB_TRY(drb_pos_embed_sine(e->kp_xyz, 3, m, e->cfg.pos_emb_scaling, e->pos, s));
   const float att_scale = 1.f / sqrtf(32.f);
-  auto linear = [&](const ConvW& w, const bf16* in_hi, const bf16* in_lo, int rows, int cin, const float* res,
-                    int relu, float scale, float* out, bf16* ohi, bf16* olo) {
+  auto linear = [&](const ConvW& w, const plane_t* in_hi, const plane_t* in_lo, int rows, int cin, const float* res,
+                    int relu, float scale, float* out, plane_t* ohi, plane_t* olo) {
     return run_igemm(e, w, in_hi, in_lo, 1, 1, 1, rows, cin, 1, P(e, w.p_b), res, relu, scale, out, ohi, olo, 0, s);
   };
   for (int l = 0; l < kLayers; ++l) {
@@ -601,7 +646,7 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
                          e->att_hi, e->att_lo, 256, s));
     DRB_TRY(drb_mha_core(e->qkv + (long long)ns * 768, 768, e->qkv + (long long)ns * 768 + 256, 768,
                          e->qkv + (long long)ns * 768 + 512, 768, nt, nt, 8, att_scale, nullptr,
-                         e->att_hi + (long long)ns * 256, e->att_lo + (long long)ns * 256, 256, s));
+                         e->att_hi + (long long)ns * 256, off(e->att_lo, (long long)ns * 256), 256, s));
     DRB_TRY(linear(t.self_attn.out_proj, e->att_hi, e->att_lo, m, 256, e->x, 0, 1.f, e->x, nullptr, nullptr));
     // cross attention, both directions from the same pre-update normalised features
     e->launches += 1;
@@ -612,7 +657,7 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
                          e->qkv + (long long)ns * 768 + 512, 768, ns, nt, 8, att_scale, nullptr, e->att_hi,
                          e->att_lo, 256, s));
     DRB_TRY(drb_mha_core(e->qkv + (long long)ns * 768, 768, e->qkv + 256, 768, e->qkv + 512, 768, nt, ns, 8,
-                         att_scale, nullptr, e->att_hi + (long long)ns * 256, e->att_lo + (long long)ns * 256,
+                         att_scale, nullptr, e->att_hi + (long long)ns * 256, off(e->att_lo, (long long)ns * 256),
                          256, s));
     DRB_TRY(linear(t.cross_attn.out_proj, e->att_hi, e->att_lo, m, 256, e->x, 0, 1.f, e->x, nullptr, nullptr));
     // feed forward
@@ -628,7 +673,7 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
     DRB_TRY(drb_layernorm256(e->x + (long long)ns * kD, nt, P(e, e->fin_w), P(e, e->fin_b), nullptr, tf, nullptr,
                              nullptr, s));
     DRB_TRY(drb_layernorm256(e->x, m, P(e, e->fin_w), P(e, e->fin_b), e->pos, nullptr,
-                             e->dec_hi + (long long)l * m * kD, e->dec_lo + (long long)l * m * kD, s));
+                             e->dec_hi + (long long)l * m * kD, off(e->dec_lo, (long long)l * m * kD), s));
     DRB_TRY(drb_overlap_sigmoid(sf, ns, P(e, e->conf_w), P(e, e->conf_b), o->src_overlap + (long long)l * ns, s));
     DRB_TRY(drb_overlap_sigmoid(tf, nt, P(e, e->conf_w), P(e, e->conf_b), o->tgt_overlap + (long long)l * nt, s));
   }
@@ -645,16 +690,16 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
   for (int l = 0; l < kLayers; ++l) {
     const long long base = (long long)l * m * kD;
     // src queries against tgt keys
-    DRB_TRY(run_igemm(e, e->q_proj, e->qp_hi + base, e->qp_lo + base, 1, 1, 1, ns, 256, 1, nullptr, nullptr, 0,
+    DRB_TRY(run_igemm(e, e->q_proj, e->qp_hi + base, off(e->qp_lo, base), 1, 1, 1, ns, 256, 1, nullptr, nullptr, 0,
                       1.f, e->sbuf, nullptr, nullptr, ld_t, s, e->kp_hi + base + (long long)ns * kD,
-                      e->kp_lo + base + (long long)ns * kD, nt));
+                      off(e->kp_lo, base + (long long)ns * kD), nt));
     e->launches += 1;
     DRB_TRY(drb_softmax_weighted_xyz(e->sbuf, (int)ld_t, ns, nt, o->tgt_kp, 3,
                                      o->src_corr + (long long)l * ns * 3, s));
     // tgt queries against src keys
-    DRB_TRY(run_igemm(e, e->q_proj, e->qp_hi + base + (long long)ns * kD, e->qp_lo + base + (long long)ns * kD, 1,
+    DRB_TRY(run_igemm(e, e->q_proj, e->qp_hi + base + (long long)ns * kD, off(e->qp_lo, base + (long long)ns * kD), 1,
                       1, 1, nt, 256, 1, nullptr, nullptr, 0, 1.f, e->sbuf, nullptr, nullptr, ld_s, s,
-                      e->kp_hi + base, e->kp_lo + base, ns));
+                      e->kp_hi + base, off(e->kp_lo, base), ns));
     e->launches += 1;
     DRB_TRY(drb_softmax_weighted_xyz(e->sbuf, (int)ld_s, nt, ns, o->src_kp, 3,
                                      o->tgt_corr + (long long)l * nt * 3, s));

@@ -5,13 +5,15 @@
 // registration path.  One persistent kernel, warp specialised:
 //   warp 0   : TMA producer  - 5-D tiled loads of channels-last activation boxes (zero fill out of
 //              bounds == convolution padding) and 3-D loads of [tap][Cout][Cin] weight tiles
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 bf16 MMAs)
-//   warps 2-5: epilogue - tcgen05.ld the fp32 accumulator, fused bias / scale / residual / ReLU,
-//              store fp32 and/or split-bf16 planes for the next layer
-// Precision: operands are bf16 "planes".  planes == 1: plain bf16.  planes == 2: every fp32 value x
-// is carried as hi = bf16(x), lo = bf16(x - hi) and the product is accumulated as
-// Ah*Bh + Ah*Bl + Al*Bh in fp32 (error ~2^-17 per product, i.e. fp32-grade results from the bf16
-// tensor pipe at 3 MMAs per product instead of the 2x slower, 2^-11 accurate TF32 pipe).
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 MMAs)
+//   warps 2-9: accumulate + epilogue - drain each finished K chunk from TMEM (tcgen05.ld) into fp32
+//              registers, then fused bias / scale / residual / ReLU and stores of fp32 and/or
+//              16-bit planes for the next layer
+// Precision: operands are 16-bit "planes".  planes == 1: plain bf16.  planes == 2: every fp32 value x
+// is carried as hi = fp16(x), lo = fp16(x - hi) (22 significand bits) and the product is accumulated
+// as Ah*Bh + Ah*Bl + Al*Bh in fp32 (error ~2^-22 per product, i.e. fp32-grade results from the
+// 16-bit tensor pipe at 3 MMAs per product instead of the 2x slower, 2^-11 accurate TF32 pipe).
+// Weights are pre-scaled by a power of two into fp16's normal range; acc_scale undoes it.
 #include "common.cuh"
 
 #include <cudaTypedefs.h>
@@ -19,9 +21,10 @@
 namespace drb {
 
 static constexpr int kBM = 128;       // accumulator rows = TMEM lanes
-static constexpr int kBK = 64;        // K chunk: 64 bf16 = one 128-byte swizzle row
+static constexpr int kBK = 64;        // K chunk: 64 x 16-bit = one 128-byte swizzle row
 static constexpr int kMaxStages = 8;
-static constexpr int kThreads = 192;  // 6 warps
+static constexpr int kAccWarps = 8;   // accumulate / epilogue warps
+static constexpr int kThreads = 64 + kAccWarps * 32;   // warp 0 TMA, warp 1 MMA, warps 2-9 accumulate
 
 struct IgemmArgs {
   int G, D, H, W;        // output (== input) spatial extent, stride-1 "same" convolution
@@ -29,20 +32,109 @@ struct IgemmArgs {
   int kd, kh, kw;        // kernel extent
   int pd, ph, pw;        // padding
   int bg, bd, bh, bw;    // spatial box of one 128-row tile
-  int BN;                // N tile (<= 256, multiple of 16)
+  int BN;                // N tile: 64, 128, 192 or 256
   int planes;            // 1 or 2
   int stages;
+  int chunk;             // k-iterations accumulated in TMEM before the fp32 register add
   int relu;
+  float acc_scale;         // multiplies the raw accumulator (undoes the weight pre-scale)
   float out_scale;
   const float* bias;       // [Cout] or null
-  const float* residual;   // [M, ld] fp32 or null; out = relu((acc + bias) * scale + residual)
+  const float* residual;   // [M, ld] fp32 or null; out = relu((acc*acc_scale + bias)*out_scale + residual)
   float* out;              // [M, ld] fp32 or null
-  bf16* out_hi;            // [M, ld] or null
-  bf16* out_lo;            // [M, ld] or null
+  plane_t* out_hi;         // [M, ld] or null
+  plane_t* out_lo;         // [M, ld] or null (present => fp16 pair mode)
   long long ld;            // row pitch (elements) of out / residual / out_hi / out_lo
   int* err;
 };
 
+// Fused epilogue of 32 consecutive output channels of one row.
+__device__ __forceinline__ void epilogue_store32(const IgemmArgs& a, float (&f)[32], long long m, int n) {
+  const long long off = m * a.ld + n;
+  const bool full = (n + 32 <= a.Cout);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] *= a.acc_scale;
+  if (a.bias) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg((const float4*)(a.bias + n + j));
+        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < a.Cout) f[j] += __ldg(a.bias + n + j);
+    }
+  }
+  if (a.out_scale != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= a.out_scale;
+  }
+  if (a.residual) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 r4 = *(const float4*)(a.residual + off + j);
+        f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < a.Cout) f[j] += a.residual[off + j];
+    }
+  }
+  if (a.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (a.out) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *(float4*)(a.out + off + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < a.Cout) a.out[off + j] = f[j];
+    }
+  }
+  if (a.out_hi) {
+    const bool pair = a.out_lo != nullptr;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          plane_t h0_, l0_, h1_, l1_;
+          split16(f[j + 2 * u], pair, h0_, l0_);
+          split16(f[j + 2 * u + 1], pair, h1_, l1_);
+          hw[u] = pack16x2(h0_, h1_);
+          lw[u] = pack16x2(l0_, l1_);
+        }
+        *(uint4*)(a.out_hi + off + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        if (pair) *(uint4*)(a.out_lo + off + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (n + j < a.Cout) {
+          plane_t h_, l_;
+          split16(f[j], pair, h_, l_);
+          a.out_hi[off + j] = h_;
+          if (pair) a.out_lo[off + j] = l_;
+        }
+      }
+    }
+  }
+}
+
+// The tensor core adds every MMA into the fp32 TMEM accumulator with truncation, so a long K chain
+// (K = 6912 -> 1296 MMAs in pair mode) drifts by ~1e-5.  The chain is therefore cut into chunks of
+// `chunk` k-iterations that ping-pong between two TMEM regions; the 8 accumulate warps drain each
+// finished chunk with tcgen05.ld and add it into fp32 registers (round-to-nearest), which also lets
+// the MMA warp start the next tile while the previous tile's epilogue is still storing.
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
              const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -75,8 +167,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   const int kchunks = a.Cin / kBK;
   const int taps = a.kd * a.kh * a.kw;
   const int kiters = taps * kchunks;
-  const uint32_t tmem_cols = (2 * a.BN <= 32) ? 32 : (2 * a.BN <= 64) ? 64 : (2 * a.BN <= 128) ? 128
-                             : (2 * a.BN <= 256) ? 256 : 512;
+  const uint32_t tmem_cols = (2 * a.BN <= 128) ? 128 : (2 * a.BN <= 256) ? 256 : 512;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) {
@@ -85,7 +176,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), kAccWarps * 32);
     }
     mbar_fence_init();
   }
@@ -143,138 +234,91 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ----------------------------------------------
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kBM, a.BN);
+      const uint32_t idesc = umma_idesc_16(kBM, a.BN, a.planes == 1);
       int s = 0;
       uint32_t ph = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), acc_ph ^ 1u, a.err, 2);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * a.BN);
-        for (int ki = 0; ki < kiters; ++ki) {
-          mbar_wait(full_bar(s), ph, a.err, 3);
+      uint32_t cc = 0;                       // running chunk counter -> TMEM region + phase
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int k0 = 0; k0 < kiters; k0 += a.chunk, ++cc) {
+          const uint32_t r = cc & 1u, rph = (cc >> 1) & 1u;
+          mbar_wait(tempty_bar(r), rph ^ 1u, a.err, 2);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + (uint32_t)a.planes * a_bytes;
-          const uint64_t da0 = umma_desc_sw128(sa);
-          const uint64_t db0 = umma_desc_sw128(sb);
+          const uint32_t tmem_d = tmem_base + r * (uint32_t)a.BN;
+          const int kend = min(k0 + a.chunk, kiters);
+          for (int ki = k0; ki < kend; ++ki) {
+            mbar_wait(full_bar(s), ph, a.err, 3);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t sb = sa + (uint32_t)a.planes * a_bytes;
+            const uint64_t da0 = umma_desc_sw128(sa);
+            const uint64_t db0 = umma_desc_sw128(sb);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t koff = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units
-            umma_bf16(tmem_d, da0 + koff, db0 + koff, idesc, (ki | k) != 0);
-            if (a.planes == 2) {
-              const uint64_t da1 = umma_desc_sw128(sa + a_bytes);
-              const uint64_t db1 = umma_desc_sw128(sb + b_bytes);
-              umma_bf16(tmem_d, da0 + koff, db1 + koff, idesc, 1u);
-              umma_bf16(tmem_d, da1 + koff, db0 + koff, idesc, 1u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t koff = (uint64_t)(k * 2);  // 16 elements = 32 B = 2 x 16 B units
+              umma_f16(tmem_d, da0 + koff, db0 + koff, idesc, (ki != k0 || k != 0) ? 1u : 0u);
+              if (a.planes == 2) {
+                const uint64_t da1 = umma_desc_sw128(sa + a_bytes);
+                const uint64_t db1 = umma_desc_sw128(sb + b_bytes);
+                umma_f16(tmem_d, da0 + koff, db1 + koff, idesc, 1u);
+                umma_f16(tmem_d, da1 + koff, db0 + koff, idesc, 1u);
+              }
             }
+            umma_commit(empty_bar(s));               // frees the smem stage when the MMAs retire
+            if (++s == a.stages) { s = 0; ph ^= 1u; }
           }
-          umma_commit(empty_bar(s));               // frees the smem stage when the MMAs retire
-          if (ki == kiters - 1) umma_commit(tfull_bar(acc));
-          if (++s == a.stages) { s = 0; ph ^= 1u; }
+          umma_commit(tfull_bar(r));                  // chunk complete -> accumulate warps
         }
       }
     }
   } else {
-    // ------------------------------- epilogue -------------------------------------------------
-    const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;       // accumulator row == tile-local voxel
-    int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+    // ------------------------------- accumulate + epilogue ------------------------------------
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int colhalf = (warp - 2) >> 2;     // warps 2-5: first half of the columns, 6-9: second
+    const int half = a.BN >> 1;              // columns per warp (multiple of 32)
+    const int row = q * 32 + lane;           // accumulator row == tile-local voxel
+    float acc[128];
+    uint32_t cc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int n0, w0, h0, d0, g0;
       decode_tile(t, n0, w0, h0, d0, g0);
-      int r = row;
-      const int ww = w0 + r % a.bw; r /= a.bw;
-      const int hh = h0 + r % a.bh; r /= a.bh;
-      const int dd = d0 + r % a.bd; r /= a.bd;
-      const int gg = g0 + r;
+      int rr = row;
+      const int ww = w0 + rr % a.bw; rr /= a.bw;
+      const int hh = h0 + rr % a.bh; rr /= a.bh;
+      const int dd = d0 + rr % a.bd; rr /= a.bd;
+      const int gg = g0 + rr;
       const bool row_ok = (ww < a.W) && (hh < a.H) && (dd < a.D) && (gg < a.G);
       const long long m = (((long long)gg * a.D + dd) * a.H + hh) * a.W + ww;
-      mbar_wait(tfull_bar(acc), acc_ph, a.err, 4);
-      tc_fence_after();
-      for (int c0 = 0; c0 < a.BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * a.BN + c0), v);
-        tmem_ld_wait();
-        const int n = n0 + c0;
-        if (row_ok && n < a.Cout) {
-          const long long off = m * a.ld + n;
-          const bool full = (n + 32 <= a.Cout);
-          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (a.bias) {
-            if (full) {
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      for (int k0 = 0; k0 < kiters; k0 += a.chunk, ++cc) {
+        const uint32_t r = cc & 1u, rph = (cc >> 1) & 1u;
+        mbar_wait(tfull_bar(r), rph, a.err, 4);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + r * (uint32_t)a.BN +
+                               (uint32_t)(colhalf * half);
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = __ldg((const float4*)(a.bias + n + j));
-                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-              }
-            } else {
-              for (int j = 0; j < 32 && n + j < a.Cout; ++j) f[j] += __ldg(a.bias + n + j);
-            }
-          }
-          if (a.out_scale != 1.f) {
+        for (int b = 0; b < 4; ++b) {
+          if (b * 32 < half) {               // warp-uniform
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + (uint32_t)(b * 32), v);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= a.out_scale;
-          }
-          if (a.residual) {
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r4 = *(const float4*)(a.residual + off + j);
-                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-              }
-            } else {
-              for (int j = 0; j < 32 && n + j < a.Cout; ++j) f[j] += a.residual[off + j];
-            }
-          }
-          if (a.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (a.out) {
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *(float4*)(a.out + off + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              for (int j = 0; j < 32 && n + j < a.Cout; ++j) a.out[off + j] = f[j];
-            }
-          }
-          if (a.out_hi) {
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint32_t hw[4], lw[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  bf16 h0_, l0_, h1_, l1_;
-                  split_bf16(f[j + 2 * u], h0_, l0_);
-                  split_bf16(f[j + 2 * u + 1], h1_, l1_);
-                  hw[u] = pack_bf16x2(h0_, h1_);
-                  lw[u] = pack_bf16x2(l0_, l1_);
-                }
-                *(uint4*)(a.out_hi + off + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                if (a.out_lo) *(uint4*)(a.out_lo + off + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-              }
-            } else {
-              for (int j = 0; j < 32 && n + j < a.Cout; ++j) {
-                bf16 h_, l_;
-                split_bf16(f[j], h_, l_);
-                a.out_hi[off + j] = h_;
-                if (a.out_lo) a.out_lo[off + j] = l_;
-              }
-            }
+            for (int j = 0; j < 32; ++j) acc[b * 32 + j] += __uint_as_float(v[j]);
           }
         }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(r));
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int n = n0 + colhalf * half + b * 32;
+        if (b * 32 < half && row_ok && n < a.Cout) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = acc[b * 32 + j];
+          epilogue_store32(a, f, m, n);
+        }
+      }
     }
   }
 
@@ -304,9 +348,9 @@ static int ensure_encode() {
   return 0;
 }
 
-// bf16 tensor map, 128-byte swizzle, zero OOB fill.  dims/box are innermost-first.
+// 16-bit float tensor map, 128-byte swizzle, zero OOB fill.  dims/box are innermost-first.
 static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box) {
+                    const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, bool is_bf16) {
   int rc = ensure_encode();
   if (rc) return rc;
   cuuint64_t gdim[5];
@@ -319,7 +363,7 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t
     es[i] = 1;
     if (i) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)base, gdim,
+  CUresult r = g_encode(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, (void*)base, gdim,
                         gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -376,6 +420,7 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   DRB_REQUIRE(d->kd >= 1 && d->kh >= 1 && d->kw >= 1 && (d->kd & 1) && (d->kh & 1) && (d->kw & 1),
               "drb_conv3d_igemm: kernel extents must be odd");
   DRB_REQUIRE(d->out || d->out_hi, "drb_conv3d_igemm: no output requested");
+  DRB_REQUIRE(!(d->out_lo && !d->out_hi), "drb_conv3d_igemm: out_lo without out_hi");
   const long long ld = d->ld_out > 0 ? d->ld_out : d->cout;
 
   IgemmArgs a;
@@ -385,11 +430,13 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   a.kd = d->kd; a.kh = d->kh; a.kw = d->kw;
   a.pd = d->kd / 2; a.ph = d->kh / 2; a.pw = d->kw / 2;
   choose_box(a.G, a.D, a.H, a.W, a.bg, a.bd, a.bh, a.bw);
-  a.BN = d->cout >= 256 ? 256 : ((d->cout + 15) / 16) * 16;
+  a.BN = d->cout >= 256 ? 256 : ((d->cout + 63) / 64) * 64;
+  a.chunk = d->planes == 2 ? 2 : 4;
   a.planes = d->planes;
   a.relu = d->relu;
   a.out_scale = d->out_scale == 0.f ? 1.f : d->out_scale;
-  a.bias = d->bias; a.residual = d->residual; a.out = d->out; a.out_hi = (bf16*)d->out_hi; a.out_lo = (bf16*)d->out_lo;
+  a.acc_scale = d->acc_scale == 0.f ? 1.f : d->acc_scale;
+  a.bias = d->bias; a.residual = d->residual; a.out = d->out; a.out_hi = (plane_t*)d->out_hi; a.out_lo = (plane_t*)d->out_lo;
   a.ld = ld;
   // vector stores in the epilogue need 16-byte aligned rows
   DRB_REQUIRE(ld % 8 == 0, "drb_conv3d_igemm: row pitch %lld must be a multiple of 8 elements", ld);
@@ -420,11 +467,11 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   const uint64_t bstr[2] = {(uint64_t)a.Cin * 2, (uint64_t)a.Cout * a.Cin * 2};
   const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)a.BN, 1u};
   int rc;
-  if ((rc = make_map(&mA[0], d->x_hi, 5, adims, astr, abox))) return rc;
-  if ((rc = make_map(&mB[0], d->w_hi, 3, bdims, bstr, bbox))) return rc;
+  if ((rc = make_map(&mA[0], d->x_hi, 5, adims, astr, abox, a.planes == 1))) return rc;
+  if ((rc = make_map(&mB[0], d->w_hi, 3, bdims, bstr, bbox, a.planes == 1))) return rc;
   if (a.planes == 2) {
-    if ((rc = make_map(&mA[1], d->x_lo, 5, adims, astr, abox))) return rc;
-    if ((rc = make_map(&mB[1], d->w_lo, 3, bdims, bstr, bbox))) return rc;
+    if ((rc = make_map(&mA[1], d->x_lo, 5, adims, astr, abox, false))) return rc;
+    if ((rc = make_map(&mB[1], d->w_lo, 3, bdims, bstr, bbox, false))) return rc;
   } else {
     mA[1] = mA[0];
     mB[1] = mB[0];

@@ -27,7 +27,7 @@ __device__ double block_sum(double v, double* sh) {
 }
 
 // A (3x3, row major) = U diag(S) V^T, S descending.
-__device__ void svd3(const double A_in[9], double U[9], double S[3], double V[9]) {
+__host__ __device__ __noinline__ void svd3(const double A_in[9], double U[9], double S[3], double V[9]) {
   double A[9];
   for (int i = 0; i < 9; ++i) { A[i] = A_in[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
   for (int sweep = 0; sweep < 30; ++sweep) {
@@ -131,8 +131,16 @@ __global__ void __launch_bounds__(256) procrustes_kernel(ProcArgs p) {
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) cov[r * 3 + c] += ((double)a[r] - ca[r]) * (((double)b[c] - cb[c]) * wn);
   }
-  for (int i = 0; i < 9; ++i) cov[i] = block_sum(cov[i], sh);
+  __shared__ double scov[9];
+  for (int i = 0; i < 9; ++i) {
+    const double tot = block_sum(cov[i], sh);
+    if (threadIdx.x == 0) scov[i] = tot;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    // the reduced covariance goes through shared memory and svd3 stays out of line: the fully
+    // inlined register-only variant was observed to miscompile (wrong rotation angle) with nvcc 12.9
+    for (int i = 0; i < 9; ++i) cov[i] = scov[i];
     double U[9], S[3], V[9];
     svd3(cov, U, S, V);
     double R[9];

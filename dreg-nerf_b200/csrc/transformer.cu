@@ -12,7 +12,7 @@ namespace drb {
 __global__ void layernorm256_kernel(const float* __restrict__ x, int n,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ add, float* __restrict__ out,
-                                    bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+                                    plane_t* __restrict__ out_hi, plane_t* __restrict__ out_lo) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -47,14 +47,15 @@ __global__ void layernorm256_kernel(const float* __restrict__ x, int n,
     *(float4*)(out + (long long)row * 256 + c1) = make_float4(v[4], v[5], v[6], v[7]);
   }
   if (out_hi) {
-    bf16 h[8], l[8];
+    const bool pair = out_lo != nullptr;
+    plane_t h[8], l[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
-    *(uint2*)(out_hi + (long long)row * 256 + c0) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-    *(uint2*)(out_hi + (long long)row * 256 + c1) = make_uint2(pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+    for (int i = 0; i < 8; ++i) split16(v[i], pair, h[i], l[i]);
+    *(uint2*)(out_hi + (long long)row * 256 + c0) = make_uint2(pack16x2(h[0], h[1]), pack16x2(h[2], h[3]));
+    *(uint2*)(out_hi + (long long)row * 256 + c1) = make_uint2(pack16x2(h[4], h[5]), pack16x2(h[6], h[7]));
     if (out_lo) {
-      *(uint2*)(out_lo + (long long)row * 256 + c0) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
-      *(uint2*)(out_lo + (long long)row * 256 + c1) = make_uint2(pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+      *(uint2*)(out_lo + (long long)row * 256 + c0) = make_uint2(pack16x2(l[0], l[1]), pack16x2(l[2], l[3]));
+      *(uint2*)(out_lo + (long long)row * 256 + c1) = make_uint2(pack16x2(l[4], l[5]), pack16x2(l[6], l[7]));
     }
   }
 }
@@ -64,8 +65,8 @@ extern "C" int drb_layernorm256(const float* x, int n, const float* gamma, const
                                 cudaStream_t stream) {
   DRB_REQUIRE(x && gamma && beta && (out || out_hi), "drb_layernorm256: bad arguments");
   if (n == 0) return 0;
-  layernorm256_kernel<<<cdiv(n, 8), 256, 0, stream>>>(x, n, gamma, beta, add, out, (bf16*)out_hi,
-                                                      (bf16*)out_lo);
+  layernorm256_kernel<<<cdiv(n, 8), 256, 0, stream>>>(x, n, gamma, beta, add, out, (plane_t*)out_hi,
+                                                      (plane_t*)out_lo);
   DRB_LAUNCH_OK();
   return 0;
 }
@@ -82,7 +83,7 @@ static constexpr int kKeyTile = 64;
 __global__ void __launch_bounds__(128)
 mha_core_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
                 const float* __restrict__ v, int ldv, int nq, int nk, float scale_log2,
-                float* __restrict__ out, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
+                float* __restrict__ out, plane_t* __restrict__ out_hi, plane_t* __restrict__ out_lo,
                 int ld_out) {
   __shared__ __align__(16) float sk[kKeyTile][kHd];
   __shared__ __align__(16) float sv[kKeyTile][kHd];
@@ -188,14 +189,15 @@ mha_core_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ 
       *(float4*)(out + off + 4) = make_float4(r[4], r[5], r[6], r[7]);
     }
     if (out_hi) {
-      bf16 h[8], lo8[8];
+      const bool pair = out_lo != nullptr;
+      plane_t h[8], lo8[8];
 #pragma unroll
-      for (int d = 0; d < 8; ++d) split_bf16(r[d], h[d], lo8[d]);
-      *(uint4*)(out_hi + off) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]),
-                                           pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+      for (int d = 0; d < 8; ++d) split16(r[d], pair, h[d], lo8[d]);
+      *(uint4*)(out_hi + off) = make_uint4(pack16x2(h[0], h[1]), pack16x2(h[2], h[3]),
+                                           pack16x2(h[4], h[5]), pack16x2(h[6], h[7]));
       if (out_lo)
-        *(uint4*)(out_lo + off) = make_uint4(pack_bf16x2(lo8[0], lo8[1]), pack_bf16x2(lo8[2], lo8[3]),
-                                             pack_bf16x2(lo8[4], lo8[5]), pack_bf16x2(lo8[6], lo8[7]));
+        *(uint4*)(out_lo + off) = make_uint4(pack16x2(lo8[0], lo8[1]), pack16x2(lo8[2], lo8[3]),
+                                             pack16x2(lo8[4], lo8[5]), pack16x2(lo8[6], lo8[7]));
     }
   }
 }
@@ -211,7 +213,7 @@ extern "C" int drb_mha_core(const float* q, int ldq, const float* k, int ldk, co
   const float scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((unsigned)cdiv(nq, 32), (unsigned)heads);
   mha_core_kernel<<<grid, 128, 0, stream>>>(q, ldq, k, ldk, v, ldv, nq, nk, scale_log2, out,
-                                            (bf16*)out_hi, (bf16*)out_lo, ld_out);
+                                            (plane_t*)out_hi, (plane_t*)out_lo, ld_out);
   DRB_LAUNCH_OK();
   return 0;
 }

@@ -175,6 +175,8 @@ class NeRFRegTr(nn.Module):
             _lib.check(lib.drb_engine_create(C.byref(cfg), C.byref(handle)), "drb_engine_create")
         names = [lib.drb_engine_param_name(handle, i).decode() for i in range(lib.drb_engine_num_params(handle))]
         ent = {"handle": handle, "names": names, "max_mask": cap, "sig": None, "device": device}
+        if getattr(self, "_profile", False):
+            _lib.check(lib.drb_engine_set_profile(handle, 1))
         self._engines[key] = ent
         return ent
 
@@ -199,6 +201,24 @@ class NeRFRegTr(nn.Module):
     def launch_count(self):
         lib = _lib.load()
         return sum(int(lib.drb_engine_launch_count(e["handle"])) for e in self._engines.values())
+
+    def set_profile(self, on):
+        """Event-brackets every tensor-core GEMM launch (roofline instrumentation for bench.py)."""
+        lib = _lib.load()
+        self._profile = bool(on)
+        for ent in self._engines.values():
+            _lib.check(lib.drb_engine_set_profile(ent["handle"], int(on)))
+
+    def read_profile(self):
+        """-> (igemm device ms, algorithmic FLOPs, launches) since the last read."""
+        lib = _lib.load()
+        ms = fl = 0.0
+        cnt = 0
+        for ent in self._engines.values():
+            a, b, c = C.c_double(0), C.c_double(0), C.c_longlong(0)
+            _lib.check(lib.drb_engine_profile_read(ent["handle"], C.byref(a), C.byref(b), C.byref(c)))
+            ms, fl, cnt = ms + a.value, fl + b.value, cnt + c.value
+        return ms, fl, cnt
 
     def __del__(self):
         try:
@@ -271,9 +291,9 @@ class NeRFRegTr(nn.Module):
             _lib.check(lib.drb_engine_decode(ent["handle"], C.byref(out), stream), "drb_engine_decode")
             if self.training:
                 # nn.BatchNorm3d bookkeeping: two training-mode calls (src, tgt) per forward
-                for name, buf in self.named_buffers():
-                    if name.endswith("num_batches_tracked") and name.startswith("fpn3d.backbone_net"):
-                        buf += 2
+                if getattr(self, "_nbt", None) is None or self._nbt[0].device != device:
+                    self._nbt = [b for n, b in self.named_buffers() if n.endswith("num_batches_tracked")]
+                torch._foreach_add_(self._nbt, 2)
         return {
             "src_feats": [src_feats], "tgt_feats": [tgt_feats],
             "src_kp": [src_kp], "src_kp_warped": [src_corr],

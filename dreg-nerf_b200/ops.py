@@ -17,56 +17,72 @@ def _dev(t):
     return torch.cuda.device(t.device)
 
 
+def _plane_dtype(pair):
+    return torch.float16 if pair else torch.bfloat16
+
+
 def split_planes(x, want_lo=True):
+    """fp32 -> (hi, lo): an fp16 pair when want_lo, else one bf16 plane (lo None)."""
     x = x.contiguous().float()
-    hi = torch.empty_like(x, dtype=torch.bfloat16)
-    lo = torch.empty_like(x, dtype=torch.bfloat16) if want_lo else None
+    hi = torch.empty_like(x, dtype=_plane_dtype(want_lo))
+    lo = torch.empty_like(x, dtype=torch.float16) if want_lo else None
     with _dev(x):
         check(_lib.load().drb_split_planes(ptr(x), ptr(hi), ptr(lo), x.numel(), stream_ptr()), "drb_split_planes")
     return hi, lo
 
 
-def pack_conv_weight(w, cin_pad=None):
-    """torch Conv3d / Linear weight [cout, cin, *k] -> planes [taps, cout, cin_pad]."""
+def weight_scale(w):
+    """Power-of-two pre-scale for the fp16 pair mode (max|w| -> [256, 512))."""
+    s = C.c_float(1.0)
+    with _dev(w):
+        check(_lib.load().drb_weight_scale(ptr(w), w.numel(), C.byref(s), stream_ptr()), "drb_weight_scale")
+    return s.value
+
+
+def pack_conv_weight(w, cin_pad=None, pair=True):
+    """torch Conv3d / Linear weight [cout, cin, *k] -> (hi, lo, scale), planes [taps, cout, cin_pad]."""
     w = w.contiguous().float()
     cout, cin = w.shape[0], w.shape[1]
     taps = w.numel() // (cout * cin)
     cin_pad = cin_pad or cin
-    hi = torch.empty((taps, cout, cin_pad), dtype=torch.bfloat16, device=w.device)
-    lo = torch.empty_like(hi)
+    scale = weight_scale(w) if pair else 1.0
+    hi = torch.empty((taps, cout, cin_pad), dtype=_plane_dtype(pair), device=w.device)
+    lo = torch.empty_like(hi) if pair else None
     with _dev(w):
-        check(_lib.load().drb_pack_conv_weight(ptr(w), cout, cin, taps, cin_pad, ptr(hi), ptr(lo), stream_ptr()),
-              "drb_pack_conv_weight")
-    return hi, lo
+        check(_lib.load().drb_pack_conv_weight(ptr(w), cout, cin, taps, cin_pad, scale, ptr(hi), ptr(lo),
+                                               stream_ptr()), "drb_pack_conv_weight")
+    return hi, lo, scale
 
 
-def pack_conv_weight_im2col(w, kpad):
+def pack_conv_weight_im2col(w, kpad, pair=True):
     w = w.contiguous().float()
     cout, cin = w.shape[0], w.shape[1]
     taps = w.numel() // (cout * cin)
-    hi = torch.empty((1, cout, kpad), dtype=torch.bfloat16, device=w.device)
-    lo = torch.empty_like(hi)
+    scale = weight_scale(w) if pair else 1.0
+    hi = torch.empty((1, cout, kpad), dtype=_plane_dtype(pair), device=w.device)
+    lo = torch.empty_like(hi) if pair else None
     with _dev(w):
-        check(_lib.load().drb_pack_conv_weight_im2col(ptr(w), cout, cin, taps, kpad, ptr(hi), ptr(lo),
+        check(_lib.load().drb_pack_conv_weight_im2col(ptr(w), cout, cin, taps, kpad, scale, ptr(hi), ptr(lo),
                                                       stream_ptr()), "drb_pack_conv_weight_im2col")
-    return hi, lo
+    return hi, lo, scale
 
 
 def conv3d_igemm(x_planes, w_planes, k, planes=2, bias=None, residual=None, relu=False, out_scale=1.0,
                  want_f32=True, want_planes=False, cout=None, ld_out=0):
-    """x_planes: (hi, lo) of [g, d, h, w, cin]; w_planes: (hi, lo) of [taps, cout, cin]."""
+    """x_planes: (hi, lo) of [g, d, h, w, cin]; w_planes: (hi, lo, scale) of [taps, cout, cin]."""
     x_hi, x_lo = x_planes
-    w_hi, w_lo = w_planes
+    w_hi, w_lo, w_scale = w_planes
+    pair = planes == 2
     g, d, h, w, cin = x_hi.shape
     cout = cout or w_hi.shape[1]
     ld = ld_out or cout
     m = g * d * h * w
     dev = x_hi.device
     out = torch.empty((m, ld), dtype=torch.float32, device=dev) if want_f32 else None
-    o_hi = torch.empty((m, ld), dtype=torch.bfloat16, device=dev) if want_planes else None
-    o_lo = torch.empty((m, ld), dtype=torch.bfloat16, device=dev) if want_planes else None
+    o_hi = torch.empty((m, ld), dtype=_plane_dtype(pair), device=dev) if want_planes else None
+    o_lo = torch.empty((m, ld), dtype=torch.float16, device=dev) if (want_planes and pair) else None
     desc = _lib.Conv3dDesc(g=g, d=d, h=h, w=w, cin=cin, cout=cout, kd=k, kh=k, kw=k, planes=planes,
-                           relu=int(relu), out_scale=out_scale,
+                           relu=int(relu), acc_scale=1.0 / w_scale, out_scale=out_scale,
                            x_hi=x_hi.data_ptr(), x_lo=x_lo.data_ptr() if x_lo is not None else None,
                            w_hi=w_hi.data_ptr(), w_lo=w_lo.data_ptr() if w_lo is not None else None,
                            bias=bias.data_ptr() if bias is not None else None,
@@ -90,7 +106,7 @@ def im2col(x, k, stride, pad, kpad, channel_slice=None):
     [g, do, ho, wo, kpad]."""
     g, c, d, h, w = x.shape
     od, oh, ow = [(n + 2 * pad - k) // stride + 1 for n in (d, h, w)]
-    hi = torch.empty((g, od, oh, ow, kpad), dtype=torch.bfloat16, device=x.device)
+    hi = torch.empty((g, od, oh, ow, kpad), dtype=torch.float16, device=x.device)
     lo = torch.empty_like(hi)
     desc = _lib.Im2colDesc(x=x.data_ptr(), sg=x.stride(0), sc=x.stride(1), sd=x.stride(2), sh=x.stride(3),
                            sw=x.stride(4), g=g, c=c, d=d, h=h, w=w, k=k, stride=stride, pad=pad, kpad=kpad)
@@ -108,8 +124,8 @@ def batchnorm(x, gamma, beta, running_mean, running_var, training, residual=None
     scale = torch.empty((g, c), dtype=torch.float32, device=x.device)
     shift = torch.empty_like(scale)
     out = torch.empty_like(x)
-    o_hi = torch.empty_like(x, dtype=torch.bfloat16) if want_planes else None
-    o_lo = torch.empty_like(x, dtype=torch.bfloat16) if want_planes else None
+    o_hi = torch.empty_like(x, dtype=torch.float16) if want_planes else None
+    o_lo = torch.empty_like(x, dtype=torch.float16) if want_planes else None
     with _dev(x):
         if training:
             check(lib.drb_bn_stats(ptr(x), g, m, c, ptr(accum), stream_ptr()), "drb_bn_stats")
@@ -184,8 +200,8 @@ def pos_embed_sine(xyz, scale=1.0):
 def layernorm256(x, gamma, beta, add=None, want_planes=False):
     n = x.shape[0]
     out = torch.empty_like(x)
-    o_hi = torch.empty_like(x, dtype=torch.bfloat16) if want_planes else None
-    o_lo = torch.empty_like(x, dtype=torch.bfloat16) if want_planes else None
+    o_hi = torch.empty_like(x, dtype=torch.float16) if want_planes else None
+    o_lo = torch.empty_like(x, dtype=torch.float16) if want_planes else None
     with _dev(x):
         check(_lib.load().drb_layernorm256(ptr(x), n, ptr(gamma), ptr(beta), ptr(add), ptr(out), ptr(o_hi),
                                            ptr(o_lo), stream_ptr()), "drb_layernorm256")

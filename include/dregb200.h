@@ -7,7 +7,11 @@
  * drb_last_error().  No exceptions cross the boundary, no torch types, no hidden global state
  * other than a lazily created device error flag and the cached driver entry point.
  *
- * bf16 "planes": an fp32 tensor x is carried as hi = bf16(x) and (optionally) lo = bf16(x - hi).
+ * 16-bit "planes": an fp32 tensor x is carried either as ONE bf16 plane (hi only; the bf16
+ * configurations) or as a PAIR of fp16 planes hi = fp16(x), lo = fp16(x - hi) (22 significand bits;
+ * fp32-grade GEMM results at three tensor-core products).  Everywhere below a NULL lo pointer selects
+ * the single bf16 plane and a non-NULL lo pointer selects the fp16 pair.  |x| > 65504 saturates in
+ * pair mode; weights are pre-scaled by a power of two (drb_weight_scale) to sit in fp16's normal range.
  * Activations are channels-last: [g][d][h][w][c] with d = Z, h = X, w = Y of the reference's
  * [1, C, Z, X, Y] tensors (conerf/register/nerf_regtr.py:112-134).
  *
@@ -43,38 +47,43 @@ int drb_igemm_error_flag(int* host_value);
  * R2 / R6 / R7: nn.Conv3d (conerf/model/resnet3d.py:81-86,120, feature_pyramid_net.py:24,33)
  * and nn.Linear / MultiheadAttention in/out projections (conerf/register/transformer.py:128-138,
  * nerf_regtr.py:268-270) as one tcgen05 implicit GEMM.  Stride 1, padding k/2.
- *   out = relu?((conv(x, w) + bias) * out_scale + residual)
+ *   out = relu?((conv(x, w) * acc_scale + bias) * out_scale + residual)
  * A linear layer over n tokens is the 1x1x1 case with g = d = h = 1, w = n.
  * ---------------------------------------------------------------------------------------- */
 typedef struct drb_conv3d_desc {
   int g, d, h, w;          /* activation volume (output == input extent)                    */
   int cin, cout;           /* cin multiple of 64                                            */
   int kd, kh, kw;          /* odd kernel extents                                            */
-  int planes;              /* 1: bf16 operands, 2: split-bf16 (fp32-grade) operands         */
+  int planes;              /* 1: one bf16 plane, 2: fp16 hi/lo pair (fp32-grade)            */
   int relu;
+  float acc_scale;         /* 1 / (weight pre-scale); 0 is read as 1                        */
   float out_scale;         /* 0 is read as 1                                                */
-  const void* x_hi;        /* bf16 [g][d][h][w][cin]                                        */
+  const void* x_hi;        /* 16-bit [g][d][h][w][cin]                                      */
   const void* x_lo;        /* same shape, planes == 2 only                                  */
-  const void* w_hi;        /* bf16 [kd*kh*kw][cout][cin]  (see drb_pack_conv_weight)        */
+  const void* w_hi;        /* 16-bit [kd*kh*kw][cout][cin]  (see drb_pack_conv_weight)      */
   const void* w_lo;
   const float* bias;       /* [cout] or NULL                                                */
   const float* residual;   /* fp32 [m][ld_out] or NULL                                      */
   float* out;              /* fp32 [m][ld_out] or NULL,  m = g*d*h*w                        */
-  void* out_hi;            /* bf16 [m][ld_out] or NULL                                      */
-  void* out_lo;            /* bf16 [m][ld_out] or NULL                                      */
+  void* out_hi;            /* 16-bit [m][ld_out] or NULL                                    */
+  void* out_lo;            /* fp16 [m][ld_out] or NULL (non-NULL => hi is fp16 too)         */
   long long ld_out;        /* row pitch in elements, 0 -> cout; multiple of 8               */
 } drb_conv3d_desc;
 int drb_conv3d_igemm(const drb_conv3d_desc* desc, drb_stream_t stream);
 
-/* fp32 -> bf16 planes (lo may be NULL). */
+/* fp32 -> planes (lo == NULL: one bf16 plane; else fp16 hi/lo pair). */
 int drb_split_planes(const float* x, void* hi, void* lo, long long n, drb_stream_t stream);
 
-/* torch Conv3d weight [cout][cin][taps] fp32 -> planes [taps][cout][cin_pad], zero padded. */
-int drb_pack_conv_weight(const float* w, int cout, int cin, int taps, int cin_pad, void* hi,
-                         void* lo, drb_stream_t stream);
+/* Power-of-two pre-scale that maps max|w| into [256, 512) (fp16 normal range for hi AND lo).
+ * Synchronous: reads 4 bytes back.  Pass 1 / scale as drb_conv3d_desc.acc_scale. */
+int drb_weight_scale(const float* w, long long n, float* host_scale, drb_stream_t stream);
+/* torch Conv3d weight [cout][cin][taps] fp32, times `scale` -> planes [taps][cout][cin_pad], zero
+ * padded. */
+int drb_pack_conv_weight(const float* w, int cout, int cin, int taps, int cin_pad, float scale,
+                         void* hi, void* lo, drb_stream_t stream);
 /* same weight -> planes [cout][kpad] with k = tap*cin + c (pairs with drb_im2col). */
-int drb_pack_conv_weight_im2col(const float* w, int cout, int cin, int taps, int kpad, void* hi,
-                                void* lo, drb_stream_t stream);
+int drb_pack_conv_weight_im2col(const float* w, int cout, int cin, int taps, int kpad, float scale,
+                                void* hi, void* lo, drb_stream_t stream);
 
 /* Generic strided / large-kernel convolutions (conv1 5^3 s2, resnet3d.py:120; 3^3 s2 and 1^3 s2
  * in the first Bottleneck of layer2-4, resnet3d.py:83,140-146) are lowered to a 1x1x1 igemm over
@@ -269,6 +278,11 @@ int drb_engine_tap(drb_engine* e, const char* name, int which, float* dst, long 
                    long long* numel, drb_stream_t stream);
 /* Kernel launches issued by this engine since creation (for bench.py's gpu_launches). */
 long long drb_engine_launch_count(const drb_engine* e);
+/* Roofline instrumentation: when on, every tcgen05 GEMM launch is bracketed by CUDA events on the
+ * launching stream.  drb_engine_profile_read synchronises, returns the summed device time (ms), the
+ * summed algorithmic FLOPs (2*M*N*K, dense) and the number of launches, and clears the records. */
+int drb_engine_set_profile(drb_engine* e, int on);
+int drb_engine_profile_read(drb_engine* e, double* igemm_ms, double* igemm_flops, long long* n);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ def subsample_dl_schedule(num_hierarchical, init_subsample_dl=0.025, subsample_r
 def batched_grid_subsample(points, features, batched_lengths, sample_dl=0.1):
     """grid_downsample.py:6-44 with the order/arith defined in the module docstring."""
     lengths = [int(v) for v in batched_lengths]
-    rows = torch.cat([points, features], dim=-1).float()
+    rows = torch.cat([points, features], dim=-1)      # fp32 in the reference; dtype-generic for fp64 studies
     dl32 = torch.tensor(sample_dl, dtype=torch.float32)
     out_rows, out_len = [], []
     start = 0
@@ -39,12 +39,12 @@ def batched_grid_subsample(points, features, batched_lengths, sample_dl=0.1):
             out_rows.append(r)
             out_len.append(0)
             continue
-        cell = torch.floor(r[:, :3] / dl32).to(torch.int64)          # int32 range in ME
+        cell = torch.floor(r[:, :3].float() / dl32).to(torch.int64)  # int32 range in ME
         uniq, inverse = torch.unique(cell, dim=0, sorted=True, return_inverse=True)
-        acc = torch.zeros((uniq.shape[0], r.shape[1]), dtype=torch.float32)
+        acc = torch.zeros((uniq.shape[0], r.shape[1]), dtype=rows.dtype)
         acc.index_add_(0, inverse, r)                                # ascending row order
-        cnt = torch.zeros(uniq.shape[0], dtype=torch.float32)
-        cnt.index_add_(0, inverse, torch.ones(n, dtype=torch.float32))
+        cnt = torch.zeros(uniq.shape[0], dtype=rows.dtype)
+        cnt.index_add_(0, inverse, torch.ones(n, dtype=rows.dtype))
         out_rows.append(acc / cnt[:, None])
         out_len.append(uniq.shape[0])
     return torch.cat(out_rows, dim=0), torch.tensor(out_len, dtype=torch.int64)

@@ -1,0 +1,94 @@
+"""Generates tests/golden/*.pt from the REFERENCE's own modules (TEST INFRASTRUCTURE).
+
+Run in the build container only (needs /root/reference):  python -m oracle.make_goldens
+It (1) imports the reference through oracle/ref_shim.py, (2) loads the seeded synthetic state dict
+into the reference's NeRFRegTr, (3) runs the reference forward on the seeded synthetic pairs,
+(4) asserts that the functional oracle (oracle/regtr.py) reproduces it BIT-EXACTLY, and (5) writes
+the reference's outputs as small fixtures that the CPU test-suite re-checks the oracle against on
+any machine (the GPU box has no /root/reference).
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import regtr  # noqa: E402
+from oracle.ref_shim import import_reference  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CASES = [  # (name, resolution, batch-stat BN, pair id, decoder q/k gain)
+    ("fwd_32_eval", 32, False, 0, 4.0),
+    ("fwd_64_train", 64, True, 0, 4.0),
+]
+
+
+def _digest(t):
+    t = t.double()
+    return torch.stack([t.sum(), t.abs().sum(), (t * t).sum()])
+
+
+def main():
+    import dreg_nerf_b200 as pkg
+    ref = import_reference()
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.manual_seed(0)
+    model = ref.NeRFRegTr()
+    # --- known-answer vectors of the importable reference pieces -----------------------------
+    from conerf.register.position_embedding import PositionEmbeddingCoordsSine
+    from conerf.register.se3 import compute_rigid_transform
+    pe_in = torch.tensor([[0.1, 0.2, 0.3], [-1.2, 0.7, 1.45]])
+    pe_out = PositionEmbeddingCoordsSine(3, 256, scale=1.0)(pe_in)
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(6, 50, 3, generator=g)
+    b = torch.randn(6, 50, 3, generator=g)
+    w = torch.rand(6, 50, generator=g)
+    kat = {"pe_in": pe_in, "pe_out": pe_out, "proc_a": a, "proc_b": b, "proc_w": w,
+           "proc_out": compute_rigid_transform(a, b, w),
+           # conerf/utils/nerfacc_utils.py:56-63 (the only golden vector in the reference repo)
+           "alphas": torch.tensor([0.4, 0.8, 0.1, 0.8, 0.1, 0.0, 0.9]),
+           "ray_indices": torch.tensor([0, 0, 0, 1, 1, 2, 2]),
+           "transmittance": torch.tensor([1.0, 0.6, 0.12, 1.0, 0.2, 1.0, 1.0])}
+    assert torch.equal(regtr.pos_embed_sine(pe_in), pe_out)
+    assert torch.allclose(regtr.compute_rigid_transform(a, b, w), kat["proc_out"], atol=1e-6)
+    torch.save(kat, os.path.join(GOLDEN, "kat.pt"))
+    keys = list(model.state_dict().keys())
+    with open(os.path.join(GOLDEN, "state_dict_keys.txt"), "w") as fh:
+        for k in keys:
+            fh.write("%s %s\n" % (k, "x".join(str(s) for s in model.state_dict()[k].shape)))
+    for name, res, train, pair_id, gain in CASES:
+        sd = pkg.synthetic.seeded_state_dict(model, seed=0, attn_gain=gain)
+        model.load_state_dict(sd)
+        model.train(train)
+        data = pkg.synthetic.make_pair(res=res, pair_id=pair_id)
+        with torch.no_grad():
+            out_ref = model({k: (v.clone() if torch.is_tensor(v) else v) for k, v in data.items()})
+            out_or = regtr.forward(sd, data, training=train)
+        for k in ("src_feats", "tgt_feats", "src_kp", "tgt_kp", "src_kp_warped", "tgt_kp_warped",
+                  "src_overlap", "tgt_overlap"):
+            assert torch.equal(out_ref[k][0], out_or[k][0]), (name, k)
+        assert torch.equal(out_ref["pose"], out_or["pose"]), name
+        fix = {"case": name, "res": res, "train": train, "pair_id": pair_id, "gain": gain, "seed": 0,
+               "pose": out_ref["pose"],
+               "src_kp": out_ref["src_kp"][0], "tgt_kp": out_ref["tgt_kp"][0],
+               "src_kp_warped": out_ref["src_kp_warped"][0], "tgt_kp_warped": out_ref["tgt_kp_warped"][0],
+               "src_overlap": out_ref["src_overlap"][0], "tgt_overlap": out_ref["tgt_overlap"][0],
+               "src_feats_digest": _digest(out_ref["src_feats"][0]),
+               "tgt_feats_digest": _digest(out_ref["tgt_feats"][0]),
+               "src_feats_sample": out_ref["src_feats"][0][:, ::37, ::5].clone(),
+               "tgt_feats_sample": out_ref["tgt_feats"][0][:, ::37, ::5].clone(),
+               "mask_digest": torch.tensor([int(data["src_mask"].sum()), int(data["tgt_mask"].sum()),
+                                            data["src_mask"].numel(), data["tgt_mask"].numel()]),
+               "weights_digest": _digest(torch.cat([v.reshape(-1)[:1000] for v in sd.values()
+                                                    if v.is_floating_point()]))}
+        fix = {k: (v.clone().contiguous() if torch.is_tensor(v) else v) for k, v in fix.items()}
+        torch.save(fix, os.path.join(GOLDEN, name + ".pt"))
+        print("wrote", name, "tokens", fix["src_kp"].shape[0], fix["tgt_kp"].shape[0],
+              "oracle == reference bit-exact")
+
+
+if __name__ == "__main__":
+    main()

@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3   # BASELINE.json north_star: features / attention / SE(3) within 1e-3 rel fp32
 
 
-def _run(pkg, cuda, res, training, pair_id=0, gain=8.0, precision="fp32"):
+def _run(pkg, cuda, res, training, pair_id=0, gain=4.0, precision="fp32"):
     from oracle import regtr
     torch.manual_seed(0)
     model = pkg.NeRFRegTr(precision=precision)
@@ -68,7 +68,7 @@ def test_stage_taps_64(pkg, cuda):
     from oracle import regtr
     torch.manual_seed(0)
     model = pkg.NeRFRegTr()
-    sd = pkg.synthetic.seeded_state_dict(model, seed=0, attn_gain=8.0)
+    sd = pkg.synthetic.seeded_state_dict(model, seed=0, attn_gain=4.0)
     model.load_state_dict(sd)
     model = model.to(cuda).train(True)
     data = pkg.synthetic.make_pair(res=64, pair_id=1)
