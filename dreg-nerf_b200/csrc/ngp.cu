@@ -34,7 +34,8 @@ static LevelTable host_levels() {
   uint32_t off = 0;
   const double b = 1.4472692012786865;
   for (int l = 0; l < kLevels; ++l) {
-    const float scale = exp2f((float)l * log2f((float)b)) * 16.f - 1.f;
+    // evaluated in double, rounded once to fp32 so that host libraries cannot disagree by an ulp
+    const float scale = (float)(exp2((double)l * log2(b)) * 16.0 - 1.0);
     const uint32_t res = (uint32_t)ceilf(scale) + 1u;
     uint64_t n = (uint64_t)res * res * res;
     n = (n + 7) / 8 * 8;

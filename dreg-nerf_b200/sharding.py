@@ -1,0 +1,38 @@
+"""Pair sharding across the GPUs of one box.
+
+The path shards into independent units: every (src, tgt) pair is registered with no cross-pair
+interaction (the reference's forward is literally B = 1, conerf/register/nerf_regtr.py:144-147) and
+the weights are replicated.  Rank r owns pairs r, r + world, r + 2*world, ...; there is NO data-path
+collective.  The only exchange is one all-gather of the per-pair SE(3) ([3, 4] fp32, 48 B per pair)
+so that every rank ends up with all poses.  Works with the ``nccl`` backend on CUDA tensors and with
+``gloo`` on CPU tensors (the CPU test-suite runs it at world_size 2).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_pairs(n_pairs: int, rank: int, world: int):
+    """Indices of the pairs rank ``rank`` registers (round robin: load balances ragged pairs)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world of %d" % (rank, world))
+    return list(range(rank, n_pairs, world))
+
+
+def gather_poses(local_poses: torch.Tensor, n_pairs: int, rank: int = None, world: int = None):
+    """local_poses [n_local, 3, 4] (order of shard_pairs) -> [n_pairs, 3, 4] on every rank."""
+    if not dist.is_available() or not dist.is_initialized():
+        if local_poses.shape[0] != n_pairs:
+            raise ValueError("single process must hold all %d poses" % n_pairs)
+        return local_poses
+    world = dist.get_world_size() if world is None else world
+    rank = dist.get_rank() if rank is None else rank
+    per_rank = (n_pairs + world - 1) // world            # pad to equal size for all_gather
+    buf = torch.zeros((per_rank, 3, 4), dtype=local_poses.dtype, device=local_poses.device)
+    buf[:local_poses.shape[0]] = local_poses
+    gathered = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(gathered, buf)
+    out = torch.empty((n_pairs, 3, 4), dtype=local_poses.dtype, device=local_poses.device)
+    for r in range(world):
+        idx = shard_pairs(n_pairs, r, world)
+        out[idx] = gathered[r][:len(idx)]
+    return out

@@ -90,5 +90,60 @@ def main():
               "oracle == reference bit-exact")
 
 
+def extract_case():
+    """Extract fixture: a 32^3 block of a seeded random-weight field, evaluated by the (slow, pure
+    Python) oracle here so that the GPU box only has to load the result."""
+    import math
+    import dreg_nerf_b200 as pkg
+    from oracle import extract
+    res, n_pts, n_cam, table_std, step = 32, 120, 3, 3.0, 0.15
+    field = make_field(pkg, seed=3, table_std=table_std)[1]
+    occ, cams = extract_scene(res, n_cam)
+    gen = torch.Generator().manual_seed(5)
+    idx = torch.nonzero(occ.flatten())[:, 0]
+    sub = idx[torch.randperm(idx.numel(), generator=gen)[:n_pts]].sort().values
+    jitter = torch.rand(sub.numel(), 3, generator=gen)
+    roi = [-1.5, -1.5, -1.5, 1.5, 1.5, 1.5]
+    o = extract.extract_block(field, sub, jitter, occ, res, roi, roi, cams, step)
+    fix = {"res": res, "seed": 3, "table_std": table_std, "step": step, "n_cam": n_cam, "sub": sub, "jitter": jitter,
+           "points": o["points"], "rgb": o["rgb"], "alpha": o["alpha"], "density": o["density"],
+           "density_mask": o["density_mask"], "surface_mask": o["surface_mask"], "mask": o["mask"],
+           "rows": o["grid"].reshape(-1, 7)[sub]}
+    fix = {k: (v.clone().contiguous() if torch.is_tensor(v) else v) for k, v in fix.items()}
+    torch.save(fix, os.path.join(GOLDEN, "extract_32.pt"))
+    print("wrote extract_32: density>0.7 %d / %d, surface %d, both %d" % (
+        int(o["density_mask"].sum()), sub.numel(), int(o["surface_mask"].sum()), o["mask"].numel()))
+
+
+def make_field(pkg, seed, table_std):
+    """(module, oracle parameter dict) of a seeded random-weight NGP field."""
+    from importlib import import_module
+    m = import_module("dreg-nerf_b200.ngp")
+    torch.manual_seed(seed)
+    f = pkg.NGPradianceField(aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5])
+    f.reset_parameters(table_std=table_std)
+    p, c = f.mlp_base.params.detach().clone(), f.color_mlp.params.detach().clone()
+    ref = {"aabb": f.aabb.clone(),
+           "w1": p[:m.N_W1].reshape(64, 32), "w2": p[m.N_W1:m.N_W1 + m.N_W2].reshape(16, 64),
+           "table": p[m.N_W1 + m.N_W2:].reshape(-1, 2),
+           "c1": c[:m.N_C1].reshape(64, 32), "c2": c[m.N_C1:m.N_C1 + m.N_C2].reshape(64, 64),
+           "c3": c[m.N_C1 + m.N_C2:].reshape(16, 64)}
+    return f, ref
+
+
+def extract_scene(res, n_cam):
+    """Ellipsoid-shell occupancy and a ring of cameras at radius 4."""
+    import math
+    ax = (torch.arange(res, dtype=torch.float32) + 0.5) / res * 3.0 - 1.5
+    X, Y, Z = torch.meshgrid(ax, ax, ax, indexing="ij")
+    r = torch.sqrt(X ** 2 + (Y * 1.2) ** 2 + (Z * 0.9) ** 2)
+    occ = (r < 0.9) & (r > 0.55)
+    ang = torch.arange(n_cam, dtype=torch.float32) * (2 * math.pi / n_cam)
+    cams = torch.stack([4 * torch.cos(ang), 4 * torch.sin(ang), 1.0 + 0 * ang], dim=1)
+    return occ, cams
+
+
 if __name__ == "__main__":
-    main()
+    if "--extract-only" not in sys.argv:
+        main()
+    extract_case()
