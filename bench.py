@@ -73,9 +73,41 @@ def _state(pkg, model):
 
 
 # ------------------------------------------------------------------------------------------------
+def cpu_extract_seconds(pkg, cams, ray_sample=20000):
+    """CPU time of ONE block's extract (oracle port: the reference's own extract is CUDA-only, tcnn +
+    nerfacc, so no reference CPU implementation exists).  Density / colour over all candidate cells is
+    timed in full; the surface-field ray march is timed on a bounded sample of rays and scaled by the
+    ray count (every (camera, point) ray is marched, as sample_grid.py:245-318 does)."""
+    import torch
+    from oracle import extract, ngp
+    from oracle.make_goldens import make_field
+    occ, poses = pkg.synthetic.extract_scene(RES, cams)
+    meta = pkg.synthetic.extract_meta(poses)
+    _, ref = make_field(pkg, 500, 8.0)
+    idx = torch.nonzero(occ.flatten())[:, 0]
+    gen = torch.Generator().manual_seed(0)
+    jitter = torch.rand(idx.numel(), 3, generator=gen)
+    roi = list(pkg.synthetic.AABB)
+    t0 = time.perf_counter()
+    pts = extract.sample_points(idx, jitter, RES, roi)
+    dens, feat = ngp.query_density(pts, ref["aabb"], ref["table"], ref["w1"], ref["w2"])
+    ngp.query_rgb_mean(ngp.fixed_viewing_directions(), feat, ref["c1"], ref["c2"], ref["c3"])
+    t_field = time.perf_counter() - t0
+    total_rays = idx.numel() * cams
+    sample = torch.randperm(total_rays, generator=gen)[:min(ray_sample, total_rays)]
+    dens_fn = lambda x: ngp.query_density(x, ref["aabb"], ref["table"], ref["w1"], ref["w2"])[0]
+    t0 = time.perf_counter()
+    extract.surface_mask_vectorized(pts, poses[:, :3, 3].contiguous(), occ, RES, roi, roi, meta["render_step_size"],
+                                    0.5, dens_fn, ray_subset=sample)
+    t_rays = (time.perf_counter() - t0) * (total_rays / sample.numel())
+    return t_field + t_rays, {"field_s": t_field, "rays_s_extrapolated": t_rays, "rays_total": int(total_rays),
+                              "rays_sampled": int(sample.numel())}
+
+
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path (oracle/regtr.py, which is
-    bit-identical to the reference modules - tests/golden) on all host threads."""
+    """Reference arm: the reference's own CPU implementation of the path on all host threads.  Register
+    half = oracle/regtr.py, bit-identical to the reference's modules (tests/golden).  Extract half = the
+    oracle port (the reference has no CPU extract), bounded sample, see cpu_extract_seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -89,55 +121,55 @@ def run_reference(args):
     sd = _state(pkg, model)
     del model
     data = pkg.synthetic.make_pair(res=RES, pair_id=0)
+    full = args.stage == "full"
     sample = "1 pair, 128^3, full NeRFRegTr.forward (oracle port of the reference, fp32, torch CPU ops)"
-    reduced = False
 
     def full_step():
         with torch.no_grad():
             regtr.forward(sd, data, training=True)
 
-    def tail_and_fpn_once():
-        # FPN of one grid (half the pair's conv work) + everything after the FPN, timed separately
+    def fpn_once():
         with torch.no_grad():
             t0 = time.perf_counter()
-            p1 = regtr.fpn3d(data["src_xyz_rgba"][:, 3:], sd, training=True)
-            t_fpn = time.perf_counter() - t0
-            t0 = time.perf_counter()
-            xyz, feats = regtr.gather_masked(data["src_xyz_rgba"], p1, data["src_mask"])
-            t_gather = time.perf_counter() - t0
-        return t_fpn, t_gather
+            regtr.fpn3d(data["src_xyz_rgba"][:, 3:], sd, training=True)
+            return time.perf_counter() - t0
 
+    extract_s, extract_info = (0.0, None)
+    if full:
+        one_block, extract_info = cpu_extract_seconds(pkg, args.cams)
+        extract_s = 2.0 * one_block
     t0 = time.perf_counter()
     full_step()
     first = time.perf_counter() - t0
-    budget = 240.0
-    if first * (args.steps + max(args.warmup - 1, 0)) > budget:
-        reduced = True
+    budget = 200.0
     times = []
-    if not reduced:
+    if first * (args.steps + max(args.warmup - 1, 0)) <= budget:
         for _ in range(max(args.warmup - 1, 0)):
             full_step()
         for _ in range(args.steps):
             t0 = time.perf_counter()
             full_step()
-            times.append(time.perf_counter() - t0)
+            times.append(time.perf_counter() - t0 + extract_s)
     else:
-        # bounded sample: per step one grid's FPN; pair time = first full step's tail + 2 x FPN
-        t_fpn0, _ = tail_and_fpn_once()
-        tail = max(first - 2.0 * t_fpn0, 0.0)
+        # bounded sample: per step one grid's FPN; pair time = 2 x FPN + the non-FPN tail of one full pair
+        tail = max(first - 2.0 * fpn_once(), 0.0)
         sample = ("per step: FPN of ONE 128^3 grid (half a pair's conv work); pair time = 2 x that + the "
                   "non-FPN tail (%.2f s) measured on one full pair" % tail)
         for _ in range(args.steps):
-            t_fpn, _ = tail_and_fpn_once()
-            times.append(2.0 * t_fpn + tail)
+            times.append(2.0 * fpn_once() + tail + extract_s)
+    if full:
+        sample += ("; + extract of 2 blocks by the oracle port (%.1f s, ray march extrapolated from %d of %d rays)"
+                   % (extract_s, extract_info["rays_sampled"], extract_info["rays_total"]))
     total = sum(times)
     value = len(times) / total
     line = {
         "impl": "reference", "metric": "nerf_pairs_per_sec_128cube", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "single pair, 128^3 grid, register forward (NeRFRegTr.forward), fp32",
-                   "resolution": RES, "pairs_per_step": 1, "bn_mode": "batch statistics"},
+        "config": {"workload": ("single pair, 128^3 grid, full extract->register forward, fp32" if full else
+                                "single pair, 128^3 grid, register forward (NeRFRegTr.forward), fp32"),
+                   "stage": args.stage, "resolution": RES, "pairs_per_step": 1, "bn_mode": "batch statistics",
+                   "extract": extract_info, "register_s": (total / len(times)) - extract_s},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -166,43 +198,106 @@ def run_ours(args):
     model.load_state_dict(_state(pkg, model))
     model = model.to(dev).train(True)       # batch-statistics BatchNorm, as eval_nerf_regtr.py runs it
     # rank r owns pairs r, r + world, ... (independent units, no data-path collective)
-    host_pairs = [pkg.synthetic.make_pair(res=RES, pair_id=rank + world * i) for i in range(N_RESIDENT_PAIRS)]
-    dev_pairs = [pkg.synthetic.to_device(p, dev) for p in host_pairs]
-    pinned = []
-    for p in host_pairs:
+    full = args.stage == "full"
+    gathered = [torch.empty((1, 3, 4), device=dev) for _ in range(world)] if world > 1 else None
+    stage_ms = {"extract": 0.0, "register": 0.0, "n": 0}
+
+    def pin_grid_dict(p):
         q = {}
         for k, v in p.items():
             if torch.is_tensor(v):
-                # keep the [X,Y,Z,7] storage order of voxel_grid.pt: pin the underlying contiguous storage
-                if v.dim() == 5:
+                if v.dim() == 5:     # keep the [X,Y,Z,7] storage order of voxel_grid.pt
                     store = v.permute(0, 3, 4, 2, 1).contiguous().pin_memory()
                     q[k] = store.permute(0, 4, 3, 1, 2)
                 else:
                     q[k] = v.contiguous().pin_memory()
             else:
                 q[k] = v
-        pinned.append(q)
-    h2d_bytes = sum(v.numel() * v.element_size() for k, v in pinned[0].items()
-                    if torch.is_tensor(v) and k != "pose")
-    gathered = [torch.empty((1, 3, 4), device=dev) for _ in range(world)] if world > 1 else None
+        return q
 
-    def step_resident(i):
-        with torch.no_grad():
-            out = model(dict(dev_pairs[i % N_RESIDENT_PAIRS]))
-        pose = out["pose"][-1]
-        if world > 1:
-            dist.all_gather(gathered, pose.contiguous())      # per-pair SE(3), 48 B per rank
-        return out
+    if not full:
+        host_pairs = [pkg.synthetic.make_pair(res=RES, pair_id=rank + world * i) for i in range(N_RESIDENT_PAIRS)]
+        dev_pairs = [pkg.synthetic.to_device(p, dev) for p in host_pairs]
+        pinned = [pin_grid_dict(p) for p in host_pairs]
+        h2d_bytes = sum(v.numel() * v.element_size() for k, v in pinned[0].items()
+                        if torch.is_tensor(v) and k != "pose")
+        masked = [int(dev_pairs[0]["src_mask"].numel()), int(dev_pairs[0]["tgt_mask"].numel())]
 
-    def step_e2e(i):
-        src = pinned[i % N_RESIDENT_PAIRS]
-        with torch.no_grad():
-            data = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in src.items()}
+        def step_resident(i):
+            with torch.no_grad():
+                out = model(dict(dev_pairs[i % N_RESIDENT_PAIRS]))
+            pose = out["pose"][-1]
+            if world > 1:
+                dist.all_gather(gathered, pose.contiguous())      # per-pair SE(3), 48 B per rank
+            return out
+
+        def step_e2e(i):
+            src = pinned[i % N_RESIDENT_PAIRS]
+            with torch.no_grad():
+                data = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in src.items()}
+                out = model(data)
+                pose = out["pose"][-1]
+                if world > 1:
+                    dist.all_gather(gathered, pose.contiguous())
+                return pose.cpu()
+    else:
+        # extract inputs: two random-weight NeRF blocks per pair, a shell occupancy, a ring of cameras
+        occ, poses = pkg.synthetic.extract_scene(RES, args.cams)
+        meta_host = pkg.synthetic.extract_meta(poses)
+        meta = dict(meta_host, camera_poses=poses.to(dev))
+        occ_dev = occ.to(dev)
+        sgrid = pkg.SampleGrid(list(pkg.synthetic.AABB), RES)
+        host_fields, dev_fields = [], []
+        for i in range(N_RESIDENT_PAIRS):
+            pid = rank + world * i
+            pair = [pkg.synthetic.make_ngp_field(seed=500 + 2 * pid + side) for side in (0, 1)]
+            host_fields.append([(f.mlp_base.params.detach().clone().pin_memory(),
+                                 f.color_mlp.params.detach().clone().pin_memory()) for f in pair])
+            dev_fields.append([f.to(dev) for f in pair])
+        occ_pinned, poses_pinned = occ.to(torch.uint8).pin_memory(), poses.pin_memory()
+        h2d_bytes = (sum(a.numel() * 4 + b.numel() * 4 for a, b in host_fields[0]) + occ_pinned.numel()
+                     + poses_pinned.numel() * 4)
+        masked = [0, 0]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+        def extract_and_register(fields, occ_d, meta_d, timed_stages):
+            grids = []
+            if timed_stages:
+                ev[0].record()
+            for f in fields:
+                grids.append(pkg.extract_block(f, sgrid, occ_d, meta_d, dev))
+            if timed_stages:
+                ev[1].record()
+            data = {"src_xyz_rgba": grids[0][0].permute(3, 2, 0, 1).unsqueeze(0), "src_mask": grids[0][1],
+                    "tgt_xyz_rgba": grids[1][0].permute(3, 2, 0, 1).unsqueeze(0), "tgt_mask": grids[1][1]}
+            masked[0], masked[1] = int(grids[0][1].numel()), int(grids[1][1].numel())
             out = model(data)
+            if timed_stages:
+                ev[2].record()
             pose = out["pose"][-1]
             if world > 1:
                 dist.all_gather(gathered, pose.contiguous())
-            return pose.cpu()
+            return pose
+
+        def step_resident(i, timed_stages=False):
+            with torch.no_grad():
+                pose = extract_and_register(dev_fields[i % N_RESIDENT_PAIRS], occ_dev, meta, timed_stages)
+            if timed_stages:
+                torch.cuda.synchronize()
+                stage_ms["extract"] += ev[0].elapsed_time(ev[1])
+                stage_ms["register"] += ev[1].elapsed_time(ev[2])
+                stage_ms["n"] += 1
+            return pose
+
+        def step_e2e(i):
+            j = i % N_RESIDENT_PAIRS
+            with torch.no_grad():
+                for f, (hp, hc) in zip(dev_fields[j], host_fields[j]):
+                    f.mlp_base.params.data.copy_(hp, non_blocking=True)
+                    f.color_mlp.params.data.copy_(hc, non_blocking=True)
+                occ_d = occ_pinned.to(dev, non_blocking=True).bool()
+                meta_d = dict(meta_host, camera_poses=poses_pinned.to(dev, non_blocking=True))
+                return extract_and_register(dev_fields[j], occ_d, meta_d, False).cpu()
 
     def barrier():
         if world > 1:
@@ -239,6 +334,9 @@ def run_ours(args):
     for i in range(2):
         step_e2e(i)
     ms_e2e, _, _ = timed(step_e2e, args.steps)
+    if full:
+        for i in range(min(args.steps, 3)):          # untimed extra steps: per-stage split
+            step_resident(i, timed_stages=True)
 
     if rank == 0:
         peaks = _peaks()
@@ -255,10 +353,15 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (split-bf16 x3 tensor-core products, fp32 accumulate)" if args.precision == "fp32" else "bf16",
             "data": "synthetic",
-            "config": {"workload": "single pair, 128^3 grid, register forward (NeRFRegTr.forward) on 1xB200, fp32"
-                                   if args.precision == "fp32" else "single pair, 128^3, register forward, bf16",
-                       "resolution": RES, "pairs_per_step_per_gpu": 1, "masked_voxels": [int(dev_pairs[0]["src_mask"].numel()),
-                                                                                          int(dev_pairs[0]["tgt_mask"].numel())],
+            "config": {"workload": ("single pair, 128^3 grid, full extract->register forward on 1xB200, %s" if full else
+                                    "single pair, 128^3 grid, register forward (NeRFRegTr.forward) on 1xB200, %s")
+                                   % ("fp32" if args.precision == "fp32" else "bf16"),
+                       "stage": args.stage,
+                       "extract": ({"candidate_cells_per_block": int(occ.sum()), "cameras": args.cams,
+                                    "render_step_size": meta_host["render_step_size"],
+                                    "stage_ms": {k: (v / max(stage_ms["n"], 1)) for k, v in stage_ms.items() if k != "n"}}
+                                   if full else None),
+                       "resolution": RES, "pairs_per_step_per_gpu": 1, "masked_voxels": masked,
                        "tokens": [ns, nt], "bn_mode": "batch statistics",
                        "l2": "working set per step (2 x 58.7 MB grids, 0.6 GB weight planes, >3 GB activations) exceeds the 126 MB L2",
                        "parallelism": "pairs sharded over %d GPU(s), one NCCL all-gather of the per-pair SE(3)" % world},
@@ -274,14 +377,15 @@ def run_ours(args):
                          "mma_flops_factor": mma_factor, "tensor_pipe_frac_est": mma_factor * achieved / peak},
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(pkg, model)
+            line["cpu_baseline"] = cpu_baseline(pkg, model, args.stage, args.cams)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(pkg, model):
-    """The oracle (port of the reference, bit-identical to it) timed on the host cores: one pair."""
+def cpu_baseline(pkg, model, stage, cams):
+    """The oracle (port of the reference, bit-identical to it for the register half) timed on the host
+    cores: one pair (+ the bounded extract sample for the full path)."""
     import torch
     from oracle import regtr
     cores = os.cpu_count() or 1
@@ -292,9 +396,13 @@ def cpu_baseline(pkg, model):
     with torch.no_grad():
         regtr.forward(sd, data, training=True)
     dt = time.perf_counter() - t0
-    return {"value": 1.0 / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-            "sample": "1 pair, 128^3, full NeRFRegTr.forward, fp32 torch CPU ops, %d threads, single cold run (%.1f s)"
-                      % (cores, dt)}
+    sample = "1 pair, 128^3, NeRFRegTr.forward, fp32 torch CPU ops, %d threads, single cold run (%.1f s)" % (cores, dt)
+    if stage == "full":
+        one_block, info = cpu_extract_seconds(pkg, cams, ray_sample=10000)
+        dt += 2.0 * one_block
+        sample += ("; + extract of 2 blocks by the oracle port (%.1f s; ray march extrapolated from %d of %d rays)"
+                   % (2.0 * one_block, info["rays_sampled"], info["rays_total"]))
+    return {"value": 1.0 / dt, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
 
 
 def main():
@@ -305,6 +413,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage", default="full", choices=["full", "register"],
+                    help="full = extract (2 NeRF blocks -> voxel grids) + register; register = NeRFRegTr.forward only")
+    ap.add_argument("--cams", type=int, default=50)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -40,7 +40,7 @@ class ExtractDesc(C.Structure):
                 ("occupied", c_void_p), ("n_occupied", c_int), ("jitter", c_void_p),
                 ("occ_binary", c_void_p), ("cam_origins", c_void_p), ("ncams", c_int),
                 ("render_step_size", c_float), ("density_thre", c_float), ("cut_off", c_float),
-                ("host_dirs", C.POINTER(c_float)), ("ndirs", c_int)]
+                ("host_dirs", C.POINTER(c_float)), ("ndirs", c_int), ("surface_only_where_dense", c_int)]
 
 
 class EngineConfig(C.Structure):

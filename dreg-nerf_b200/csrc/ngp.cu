@@ -14,8 +14,11 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace drb {
+
+int igemm_num_sms();
 
 static constexpr int kLevels = 16;
 static constexpr int kHashSize = 1 << 19;
@@ -369,10 +372,11 @@ __device__ __forceinline__ float dist_to_next_voxel(const MarchArgs& a, const fl
   return fmaxf(t, 0.f);
 }
 
-__global__ void __launch_bounds__(256, 1)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict__ occ,
                     const float* __restrict__ points, int n, const float* __restrict__ cams, int ncams,
-                    uint8_t* __restrict__ surface) {
+                    const uint8_t* __restrict__ active, uint8_t* __restrict__ surface) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   const FieldSmem sm = stage_field(p, smem, &bar);
@@ -381,6 +385,7 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict
        r += (long long)gridDim.x * blockDim.x) {
     const int pi = (int)(r % n), ci = (int)(r / n);
     if (surface[pi]) continue;                 // another camera already saw this point
+    if (active && !active[pi]) continue;       // caller only consumes surface & density
     float o[3], dir[3], inv_dir[3];
     float len = 0.f;
 #pragma unroll
@@ -422,6 +427,8 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict
         best = fmaxf(best, alpha * T);
         if (best >= a.cut_off) break;
         T *= 1.f - alpha;
+        // exact early out: every later sample contributes alpha * T' <= T' <= T < cut_off
+        if (T < a.cut_off) break;
         t0 = t1; t1 = t0 + a.step; tm = 0.5f * (t0 + t1);
       } else {
         const float tt = tm + dist_to_next_voxel(a, x, dir, inv_dir);
@@ -433,10 +440,10 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict
   }
 }
 
-extern "C" int drb_surface_mask(const drb_ngp_params* pp, const uint8_t* occ_binary, int res,
-                                const float* roi_aabb_host, const float* scene_aabb_host, const float* points,
-                                int n, const float* cam_origins, int ncams, float step, float cut_off,
-                                uint8_t* surface, cudaStream_t stream) {
+static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary, int res,
+                             const float* roi_aabb_host, const float* scene_aabb_host, const float* points,
+                             int n, const float* cam_origins, int ncams, float step, float cut_off,
+                             const uint8_t* active, uint8_t* surface, cudaStream_t stream) {
   DRB_REQUIRE(pp && occ_binary && roi_aabb_host && scene_aabb_host && points && cam_origins && surface,
               "drb_surface_mask: null argument");
   DRB_REQUIRE(res > 0 && step > 0.f, "drb_surface_mask: bad grid / step");
@@ -450,15 +457,32 @@ extern "C" int drb_surface_mask(const drb_ngp_params* pp, const uint8_t* occ_bin
   }
   a.res = res; a.step = step; a.cut_off = cut_off;
   const size_t smem = field_smem_bytes(p.lv);
-  static bool attr = false;
-  if (!attr) {
-    DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    attr = true;
+  static int threads = 0;
+  if (!threads) {
+    const char* env = getenv("DRB_SURFACE_THREADS");
+    threads = env ? atoi(env) : 512;
+    if (threads != 256 && threads != 512 && threads != 1024) threads = 512;
+    DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  surface_mask_kernel<<<148, 256, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, surface);
+  const int grid = igemm_num_sms();
+  if (threads == 256)
+    surface_mask_kernel<256><<<grid, 256, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, active, surface);
+  else if (threads == 512)
+    surface_mask_kernel<512><<<grid, 512, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, active, surface);
+  else
+    surface_mask_kernel<1024><<<grid, 1024, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, active, surface);
   DRB_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int drb_surface_mask(const drb_ngp_params* pp, const uint8_t* occ_binary, int res,
+                                const float* roi_aabb_host, const float* scene_aabb_host, const float* points,
+                                int n, const float* cam_origins, int ncams, float step, float cut_off,
+                                uint8_t* surface, cudaStream_t stream) {
+  return surface_mask_impl(pp, occ_binary, res, roi_aabb_host, scene_aabb_host, points, n, cam_origins, ncams,
+                           step, cut_off, nullptr, surface, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -482,19 +506,24 @@ __global__ void sample_points_kernel(const long long* __restrict__ occupied, con
   (void)roi;
 }
 
-__global__ void finish_extract_kernel(const long long* __restrict__ occupied, int n, const float* __restrict__ points,
-                                      const float* __restrict__ rgb, const float* __restrict__ density,
-                                      float thre, const uint8_t* __restrict__ surface, float* __restrict__ alpha,
-                                      uint8_t* __restrict__ dmask, float* __restrict__ grid) {
+__global__ void density_mask_kernel(const float* __restrict__ density, int n, float thre,
+                                    float* __restrict__ alpha, uint8_t* __restrict__ dmask) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float d = density[i];
   // alpha = clip(1 - exp(-delta * density), 0, 1), delta = 1e-2 (sample_grid.py:112,341)
-  const float al = fminf(fmaxf(1.f - expf(-1e-2f * d), 0.f), 1.f);
-  alpha[i] = al;
-  const uint8_t dm = d > thre ? 1 : 0;
-  dmask[i] = dm;
-  if (dm && surface[i] && grid) {
+  alpha[i] = fminf(fmaxf(1.f - expf(-1e-2f * d), 0.f), 1.f);
+  dmask[i] = d > thre ? 1 : 0;
+}
+
+__global__ void finish_extract_kernel(const long long* __restrict__ occupied, int n, const float* __restrict__ points,
+                                      const float* __restrict__ rgb, const uint8_t* __restrict__ surface,
+                                      const float* __restrict__ alpha, const uint8_t* __restrict__ dmask,
+                                      float* __restrict__ grid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float al = alpha[i];
+  if (dmask[i] && surface[i] && grid) {
     float* g = grid + occupied[i] * 7;
     g[0] = points[i * 3]; g[1] = points[i * 3 + 1]; g[2] = points[i * 3 + 2];
     g[3] = rgb[i * 3]; g[4] = rgb[i * 3 + 1]; g[5] = rgb[i * 3 + 2];
@@ -522,13 +551,18 @@ extern "C" int drb_extract_block(const drb_ngp_params* pp, const drb_extract_des
   DRB_CUDA_OK(cudaMallocAsync(&feat, sizeof(float) * 15 * (size_t)n, stream));
   DRB_CUDA_OK(cudaMallocAsync(&density, sizeof(float) * (size_t)n, stream));
   int rc = drb_ngp_density(pp, points, n, density, feat, stream);
+  if (!rc) {
+    density_mask_kernel<<<cdiv(n, 256), 256, 0, stream>>>(density, n, e->density_thre, alpha, density_mask);
+    if (cudaGetLastError() != cudaSuccess) rc = DRB_ECUDA;
+  }
   if (!rc) rc = drb_ngp_rgb_mean(pp, feat, n, e->host_dirs, e->ndirs, rgb, stream);
   if (!rc)
-    rc = drb_surface_mask(pp, e->occ_binary, e->res, e->roi_aabb, e->scene_aabb, points, n, e->cam_origins,
-                          e->ncams, e->render_step_size, e->cut_off, surface_mask, stream);
+    rc = surface_mask_impl(pp, e->occ_binary, e->res, e->roi_aabb, e->scene_aabb, points, n, e->cam_origins,
+                           e->ncams, e->render_step_size, e->cut_off,
+                           e->surface_only_where_dense ? density_mask : nullptr, surface_mask, stream);
   if (!rc) {
-    finish_extract_kernel<<<cdiv(n, 256), 256, 0, stream>>>(e->occupied, n, points, rgb, density, e->density_thre,
-                                                           surface_mask, alpha, density_mask, voxel_grid);
+    finish_extract_kernel<<<cdiv(n, 256), 256, 0, stream>>>(e->occupied, n, points, rgb, surface_mask, alpha,
+                                                           density_mask, voxel_grid);
     if (cudaGetLastError() != cudaSuccess) rc = DRB_ECUDA;
   }
   cudaFreeAsync(feat, stream);

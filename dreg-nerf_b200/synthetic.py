@@ -127,3 +127,37 @@ def seeded_state_dict(module, seed=0, attn_gain=1.0):
             v = 0.05 * torch.randn(shape, generator=gen)
         out[name] = v.float()
     return out
+
+
+def make_ngp_field(seed=0, table_std=8.0):
+    """Seeded random-weight Instant-NGP field on the world AABB.  tiny-cuda-nn's default init gives
+    density ~ e^-1 < 0.7 everywhere (empty mask), so the hash table is drawn from N(0, table_std):
+    table_std ~ 8 yields a few percent of samples dense enough to pass both the 0.7 density
+    threshold and the surface-field test at the reference's step size."""
+    from .ngp import NGPradianceField
+    torch.manual_seed(seed)
+    f = NGPradianceField(aabb=list(AABB))
+    f.reset_parameters(table_std=table_std)
+    return f
+
+
+def extract_scene(res, n_cam):
+    """Binary occupancy (an ellipsoid shell, ~8 % of the cells) and camera-to-world poses on a ring of
+    radius 4 looking at the origin (only the camera centres matter for the surface-field mask)."""
+    ax = (torch.arange(res, dtype=torch.float32) + 0.5) / res * 3.0 - 1.5
+    X, Y, Z = torch.meshgrid(ax, ax, ax, indexing="ij")
+    r = torch.sqrt(X ** 2 + (Y * 1.2) ** 2 + (Z * 0.9) ** 2)
+    occ = (r < 0.9) & (r > 0.55)
+    ang = torch.arange(n_cam, dtype=torch.float32) * (2 * math.pi / n_cam)
+    poses = torch.eye(4).repeat(n_cam, 1, 1)
+    poses[:, 0, 3] = 4 * torch.cos(ang)
+    poses[:, 1, 3] = 4 * torch.sin(ang)
+    poses[:, 2, 3] = 1.0
+    return occ, poses
+
+
+def extract_meta(poses, render_n_samples=1024):
+    """meta_data dict of eval_ngp_nerf.py (aabb, render_step_size as train_ngp_nerf.py:88-92)."""
+    ext = max(AABB[3] - AABB[0], AABB[4] - AABB[1], AABB[5] - AABB[2])
+    return {"aabb": list(AABB), "render_step_size": ext * math.sqrt(3) / render_n_samples,
+            "cone_angle": 0.0, "alpha_thre": 0.0, "camera_poses": poses}

@@ -214,6 +214,9 @@ typedef struct drb_extract_desc {
   float cut_off;                 /* 0.5 */
   const float* host_dirs;        /* [ndirs][3]                                                 */
   int ndirs;
+  int surface_only_where_dense;  /* 1: march rays only for cells with density > density_thre; their
+                                  * surface_mask entries stay 0.  Exact for voxel_grid / voxel_mask
+                                  * (eval_ngp_nerf.py:383 keeps surface & density only).             */
 } drb_extract_desc;
 /* Writes points [n][3], rgb [n][3], alpha [n], density_mask [n], surface_mask [n] and scatters
  * rows of cells with both masks set into voxel_grid [R^3][7] (pre-zeroed by the call). */

@@ -119,9 +119,7 @@ def make_field(pkg, seed, table_std):
     """(module, oracle parameter dict) of a seeded random-weight NGP field."""
     from importlib import import_module
     m = import_module("dreg-nerf_b200.ngp")
-    torch.manual_seed(seed)
-    f = pkg.NGPradianceField(aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5])
-    f.reset_parameters(table_std=table_std)
+    f = pkg.synthetic.make_ngp_field(seed, table_std)
     p, c = f.mlp_base.params.detach().clone(), f.color_mlp.params.detach().clone()
     ref = {"aabb": f.aabb.clone(),
            "w1": p[:m.N_W1].reshape(64, 32), "w2": p[m.N_W1:m.N_W1 + m.N_W2].reshape(16, 64),
@@ -132,15 +130,10 @@ def make_field(pkg, seed, table_std):
 
 
 def extract_scene(res, n_cam):
-    """Ellipsoid-shell occupancy and a ring of cameras at radius 4."""
-    import math
-    ax = (torch.arange(res, dtype=torch.float32) + 0.5) / res * 3.0 - 1.5
-    X, Y, Z = torch.meshgrid(ax, ax, ax, indexing="ij")
-    r = torch.sqrt(X ** 2 + (Y * 1.2) ** 2 + (Z * 0.9) ** 2)
-    occ = (r < 0.9) & (r > 0.55)
-    ang = torch.arange(n_cam, dtype=torch.float32) * (2 * math.pi / n_cam)
-    cams = torch.stack([4 * torch.cos(ang), 4 * torch.sin(ang), 1.0 + 0 * ang], dim=1)
-    return occ, cams
+    """(occupancy, camera centres) of the synthetic extract scene."""
+    import dreg_nerf_b200 as pkg
+    occ, poses = pkg.synthetic.extract_scene(res, n_cam)
+    return occ, poses[:, :3, 3].contiguous()
 
 
 if __name__ == "__main__":

@@ -83,6 +83,12 @@ def test_extract_block_small(pkg, cuda):
     untouched = torch.ones(res ** 3, dtype=torch.bool)
     untouched[sub] = False
     assert (rows[untouched] == 0).all()
+    # fused variant used by extract_block (rays only where density passes): same files
+    sg.set_binary_fields(occ_sub.reshape(res, res, res))
+    out2 = sg.query_radiance_and_density_from_camera(f, occ, meta, cuda, jitter=jitter, return_grid=True,
+                                                     surface_only_where_dense=True)
+    assert torch.equal(out2[6].cpu(), grid.cpu())
+    assert torch.equal((out2[4] & out2[5]).cpu(), keep)
 
 
 def test_extract_then_register_128(pkg, cuda):

@@ -114,3 +114,21 @@ def test_hash_grid_level_table():
     assert [r for _, r, _, _ in levels[:5]] == [16, 24, 34, 49, 71]
     assert [n for _, _, n, _ in levels[:5]] == [4096, 13824, 39304, 117656, 357912]
     assert all(n == 1 << 19 for _, _, n, _ in levels[5:])
+
+
+def test_vectorized_surface_mask_equals_scalar_oracle(pkg):
+    """The lock-step (timed-baseline) marcher and the scalar restatement agree on the extract fixture."""
+    from oracle import extract, ngp
+    from oracle.make_goldens import make_field, extract_scene
+    fix = torch.load(os.path.join(GOLDEN, "extract_32.pt"))
+    _, ref = make_field(pkg, fix["seed"], fix["table_std"])
+    occ, cams = extract_scene(fix["res"], fix["n_cam"])
+    roi = [-1.5] * 3 + [1.5] * 3
+    pts = extract.sample_points(fix["sub"], fix["jitter"], fix["res"], roi)
+    assert torch.equal(pts, fix["points"])
+    dens_fn = lambda x: ngp.query_density(x, ref["aabb"], ref["table"], ref["w1"], ref["w2"])[0]
+    m = extract.surface_mask_vectorized(pts, cams, occ, fix["res"], roi, roi, fix["step"], 0.5, dens_fn)
+    assert torch.equal(m, fix["surface_mask"])
+    d, feat = ngp.query_density(pts, ref["aabb"], ref["table"], ref["w1"], ref["w2"])
+    assert torch.allclose(d, fix["density"], rtol=1e-5, atol=1e-6)
+    assert torch.equal(d > 0.7, fix["density_mask"])
