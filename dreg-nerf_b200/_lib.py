@@ -75,6 +75,8 @@ SIGNATURES = {
     "drb_pack_conv_weight_im2col": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                             c_void_p]),
     "drb_im2col": (c_int, [C.POINTER(Im2colDesc), c_void_p, c_void_p, c_void_p]),
+    "drb_im2col_stem": (c_int, [c_void_p, c_ll, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
     "drb_bn_stats": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p]),
     "drb_bn_finalize": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_float, c_float, c_void_p, c_void_p, c_void_p]),

@@ -188,6 +188,80 @@ extern "C" int drb_im2col(const drb_im2col_desc* d, void* hi, void* lo, cudaStre
 }
 
 // ------------------------------------------------------------------------------------------
+// Stem fast path (conv1 5^3 s2 over the 4 rgba channels of the caller's strided [1,7,Z,X,Y] view):
+// (1) pack channels 3..6 into a compact channels-last fp32 volume [d][h][w][4], (2) im2col from it
+// with one warp per output voxel: lane j owns taps 4j..4j+3 (16 consecutive k), float4 reads,
+// 32-byte plane writes (1 KB contiguous per warp and plane).
+__global__ void pack_rgba_kernel(const float* __restrict__ x, long long sc, long long sd, long long sh,
+                                 long long sw, int d, int h, int w, float4* __restrict__ out) {
+  const long long total = (long long)d * h * w;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int xw = (int)(i % w);
+    const int yh = (int)((i / w) % h);
+    const int zd = (int)(i / ((long long)w * h));
+    const float* p = x + zd * sd + yh * sh + xw * sw;
+    out[i] = make_float4(p[0], p[sc], p[2 * sc], p[3 * sc]);
+  }
+}
+
+__global__ void im2col_stem_kernel(const float4* __restrict__ x, int g, int d, int h, int w, int od,
+                                   int oh, int ow, plane_t* __restrict__ hi, plane_t* __restrict__ lo) {
+  const long long rows = (long long)g * od * oh * ow;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  long long r = warp;
+  const int ox = (int)(r % ow); r /= ow;
+  const int oy = (int)(r % oh); r /= oh;
+  const int oz = (int)(r % od); r /= od;
+  const int gi = (int)r;
+  const bool pair = lo != nullptr;
+  uint32_t hw[8], lw[8];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int tap = lane * 4 + t;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tap < 125) {
+      const int kx = tap % 5, ky = (tap / 5) % 5, kz = tap / 25;
+      const int iz = oz * 2 - 2 + kz, iy = oy * 2 - 2 + ky, ix = ox * 2 - 2 + kx;
+      if (iz >= 0 && iz < d && iy >= 0 && iy < h && ix >= 0 && ix < w)
+        v = x[(((long long)gi * d + iz) * h + iy) * w + ix];
+    }
+    plane_t h0, l0, h1, l1, h2, l2, h3, l3;
+    split16(v.x, pair, h0, l0); split16(v.y, pair, h1, l1);
+    split16(v.z, pair, h2, l2); split16(v.w, pair, h3, l3);
+    hw[2 * t] = pack16x2(h0, h1); hw[2 * t + 1] = pack16x2(h2, h3);
+    lw[2 * t] = pack16x2(l0, l1); lw[2 * t + 1] = pack16x2(l2, l3);
+  }
+  const long long off = warp * 512 + lane * 16;
+  *(uint4*)(hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  *(uint4*)(hi + off + 8) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+  if (pair) {
+    *(uint4*)(lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    *(uint4*)(lo + off + 8) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+  }
+}
+
+// x: fp32 view of ONE grid with element strides (sc, sd, sh, sw) already offset to the first of the 4
+// channels; scratch: d*h*w float4; planes [do][ho][wo][512].
+extern "C" int drb_im2col_stem(const float* x, long long sc, long long sd, long long sh, long long sw,
+                               int d, int h, int w, void* scratch, void* hi, void* lo,
+                               cudaStream_t stream) {
+  DRB_REQUIRE(x && scratch && hi, "drb_im2col_stem: null argument");
+  const long long vox = (long long)d * h * w;
+  pack_rgba_kernel<<<grid_for(vox, 256, 148 * 32), 256, 0, stream>>>(x, sc, sd, sh, sw, d, h, w,
+                                                                    (float4*)scratch);
+  DRB_LAUNCH_OK();
+  const int od = (d + 4 - 5) / 2 + 1, oh = (h + 4 - 5) / 2 + 1, ow = (w + 4 - 5) / 2 + 1;
+  const long long rows = (long long)od * oh * ow;
+  im2col_stem_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>((const float4*)scratch, 1, d, h, w, od, oh,
+                                                              ow, (plane_t*)hi, (plane_t*)lo);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // BatchNorm statistics: x [g][m][c].  Block = 64 channels x 4 row lanes; double accumulation.
 __global__ void bn_stats_kernel(const float* __restrict__ x, long long m, int c, int rows_per_block,
                                 double* __restrict__ accum) {

@@ -277,6 +277,7 @@ static int build(drb_engine* e) {
   e->col_elems = col_max;
   e->col_hi = e->alloc<plane_t>(col_max);
   if (cfg.planes == 2) e->col_lo = e->alloc<plane_t>(col_max);
+  if ((long long)e->D * e->H * e->W * 4 > raw_max) raw_max = (long long)e->D * e->H * e->W * 4;   // rgba pack scratch
   e->raw_elems = raw_max;
   e->raw = e->alloc<float>(raw_max);
   e->raw2 = e->alloc<float>(raw_max);
@@ -379,20 +380,12 @@ static int run_fpn(drb_engine* e, const drb_pair_io* io, cudaStream_t s) {
     const ConvW& w = e->conv1;
     const long long per_grid = e->c1.m() * w.kpad;
     for (int g = 0; g < kG; ++g) {
-      drb_im2col_desc d;
-      memset(&d, 0, sizeof(d));
       const float* base = g == 0 ? io->src_grid : io->tgt_grid;
       const long long sc = g == 0 ? io->s_ch : io->t_ch;
-      d.x = base + 3 * sc;
-      d.sc = sc;
-      d.sd = g == 0 ? io->s_z : io->t_z;
-      d.sh = g == 0 ? io->s_x : io->t_x;
-      d.sw = g == 0 ? io->s_y : io->t_y;
-      d.sg = 0;
-      d.g = 1; d.c = 4; d.d = e->D; d.h = e->H; d.w = e->W;
-      d.k = 5; d.stride = 2; d.pad = 2; d.kpad = w.kpad;
-      e->launches += 1;
-      DRB_TRY(drb_im2col(&d, e->col_hi + g * per_grid, off(e->col_lo, g * per_grid), s));
+      e->launches += 2;
+      DRB_TRY(drb_im2col_stem(base + 3 * sc, sc, g == 0 ? io->s_z : io->t_z, g == 0 ? io->s_x : io->t_x,
+                              g == 0 ? io->s_y : io->t_y, e->D, e->H, e->W, e->raw2,
+                              e->col_hi + g * per_grid, off(e->col_lo, g * per_grid), s));
     }
     DRB_TRY(run_igemm(e, w, e->col_hi, e->col_lo, kG, e->c1.d, e->c1.h, e->c1.w, w.kpad, 1, nullptr,
                       nullptr, 0, 1.f, e->raw, nullptr, nullptr, 0, s));

@@ -17,6 +17,7 @@
 #include "common.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace drb {
 
@@ -36,6 +37,7 @@ struct IgemmArgs {
   int planes;            // 1 or 2
   int stages;
   int chunk;             // k-iterations accumulated in TMEM before the fp32 register add
+  int cs;                // cluster size along M (1, 2 or 4): the weight tile is TMA-multicast
   int relu;
   float acc_scale;         // multiplies the raw accumulator (undoes the weight pre-scale)
   float out_scale;
@@ -163,7 +165,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   const int tiles_d = (a.D + a.bd - 1) / a.bd;
   const int tiles_g = (a.G + a.bg - 1) / a.bg;
   const int tiles_n = (a.Cout + a.BN - 1) / a.BN;
-  const int total_tiles = tiles_w * tiles_h * tiles_d * tiles_g * tiles_n;
+  // Clusters of `cs` CTAs take `cs` consecutive M tiles of the same N tile; each CTA loads 1/cs of the
+  // weight rows and multicasts them, so the L2 -> SM traffic of B drops by cs.
+  const int cs = a.cs;
+  const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+  const int tiles_m = tiles_w * tiles_h * tiles_d * tiles_g;
+  const int groups_m = (tiles_m + cs - 1) / cs;
+  const int total_tiles = groups_m * tiles_n;      // per cluster: one "super tile" = cs M tiles
+  const int cluster_id = blockIdx.x / cs;
+  const int num_clusters = gridDim.x / cs;
   const int kchunks = a.Cin / kBK;
   const int taps = a.kd * a.kh * a.kw;
   const int kiters = taps * kchunks;
@@ -172,7 +183,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), (uint32_t)cs);      // one tcgen05.commit from every CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -191,16 +202,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();    // peers' barriers must exist before any multicast / remote commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   auto decode_tile = [&](int t, int& n0, int& w0, int& h0, int& d0, int& g0) {
     int n = t % tiles_n;
-    int m = t / tiles_n;
+    int m = (t / tiles_n) * cs + (int)crank;
+    n0 = n * a.BN;
+    if (m >= tiles_m) {              // padding tile of the last group: all rows out of bounds
+      w0 = 0; h0 = 0; d0 = 0; g0 = a.G;
+      return;
+    }
     int tw = m % tiles_w; m /= tiles_w;
     int th = m % tiles_h; m /= tiles_h;
     int td = m % tiles_d; m /= tiles_d;
-    n0 = n * a.BN; w0 = tw * a.bw; h0 = th * a.bh; d0 = td * a.bd; g0 = m * a.bg;
+    w0 = tw * a.bw; h0 = th * a.bh; d0 = td * a.bd; g0 = m * a.bg;
   };
 
   if (warp == 0) {
@@ -208,7 +225,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         int n0, w0, h0, d0, g0;
         decode_tile(t, n0, w0, h0, d0, g0);
         for (int tap = 0; tap < taps; ++tap) {
@@ -220,11 +237,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
             const uint32_t sb = sa + (uint32_t)a.planes * a_bytes;
             tma_load_5d(sa, &tmA0, fb, kc * kBK, w0 + tw - a.pw, h0 + th - a.ph, d0 + td - a.pd, g0);
-            tma_load_3d(sb, &tmB0, fb, kc * kBK, n0, tap);
-            if (a.planes == 2) {
+            if (a.planes == 2)
               tma_load_5d(sa + a_bytes, &tmA1, fb, kc * kBK, w0 + tw - a.pw, h0 + th - a.ph,
                           d0 + td - a.pd, g0);
-              tma_load_3d(sb + b_bytes, &tmB1, fb, kc * kBK, n0, tap);
+            if (cs == 1) {
+              tma_load_3d(sb, &tmB0, fb, kc * kBK, n0, tap);
+              if (a.planes == 2) tma_load_3d(sb + b_bytes, &tmB1, fb, kc * kBK, n0, tap);
+            } else {
+              // this CTA's slice of the weight rows, delivered to every CTA of the cluster
+              const int rows = a.BN / cs;
+              const uint32_t soff = crank * (uint32_t)rows * (kBK * 2);
+              tma_load_3d_mc(sb + soff, &tmB0, fb, kc * kBK, n0 + (int)crank * rows, tap, cmask);
+              if (a.planes == 2)
+                tma_load_3d_mc(sb + b_bytes + soff, &tmB1, fb, kc * kBK, n0 + (int)crank * rows, tap, cmask);
             }
             if (++s == a.stages) { s = 0; ph ^= 1u; }
           }
@@ -238,7 +263,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       int s = 0;
       uint32_t ph = 0;
       uint32_t cc = 0;                       // running chunk counter -> TMEM region + phase
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         for (int k0 = 0; k0 < kiters; k0 += a.chunk, ++cc) {
           const uint32_t r = cc & 1u, rph = (cc >> 1) & 1u;
           mbar_wait(tempty_bar(r), rph ^ 1u, a.err, 2);
@@ -263,7 +288,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                 umma_f16(tmem_d, da1 + koff, db0 + koff, idesc, 1u);
               }
             }
-            umma_commit(empty_bar(s));               // frees the smem stage when the MMAs retire
+            // frees the smem stage (in every CTA that multicasts into it) when the MMAs retire
+            if (cs == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), cmask);
             if (++s == a.stages) { s = 0; ph ^= 1u; }
           }
           umma_commit(tfull_bar(r));                  // chunk complete -> accumulate warps
@@ -278,7 +304,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     const int row = q * 32 + lane;           // accumulator row == tile-local voxel
     float acc[128];
     uint32_t cc = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
       int n0, w0, h0, d0, g0;
       decode_tile(t, n0, w0, h0, d0, g0);
       int rr = row;
@@ -324,6 +350,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();    // no CTA may exit while a peer can still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -375,6 +402,7 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t
   return 0;
 }
 
+int igemm_num_sms();
 static int g_num_sms = 0;
 static int* g_err_flag = nullptr;   // device int, lazily allocated
 
@@ -432,6 +460,23 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   choose_box(a.G, a.D, a.H, a.W, a.bg, a.bd, a.bh, a.bw);
   a.BN = d->cout >= 256 ? 256 : ((d->cout + 63) / 64) * 64;
   a.chunk = d->planes == 2 ? 2 : 4;
+  {
+    // cluster size along M: multicast pays off when there are enough tiles to keep every CTA busy
+    static int forced = -1;
+    if (forced < 0) {
+      const char* env = getenv("DRB_IGEMM_CLUSTER");
+      forced = env ? atoi(env) : 0;
+    }
+    const long long tm = (long long)cdiv(a.W, a.bw) * cdiv(a.H, a.bh) * cdiv(a.D, a.bd) * cdiv(a.G, a.bg);
+    const long long tn = cdiv(a.Cout, a.BN);
+    // Measured on B200 (round 1): the large FPN convolutions already run at ~90 % of the bf16 MMA rate
+    // with cs = 1 and multicast brings nothing (cs = 2: +-0 %, cs = 4: -30 % from stranded SMs), so the
+    // cluster path stays opt-in (DRB_IGEMM_CLUSTER=2|4); it is covered by the parity tests.
+    (void)tn;
+    a.cs = 1;
+    if (forced == 1 || forced == 2 || forced == 4) a.cs = forced;
+    if (tm < a.cs) a.cs = 1;
+  }
   a.planes = d->planes;
   a.relu = d->relu;
   a.out_scale = d->out_scale == 0.f ? 1.f : d->out_scale;
@@ -465,7 +510,7 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   const int taps = a.kd * a.kh * a.kw;
   const uint64_t bdims[3] = {(uint64_t)a.Cin, (uint64_t)a.Cout, (uint64_t)taps};
   const uint64_t bstr[2] = {(uint64_t)a.Cin * 2, (uint64_t)a.Cout * a.Cin * 2};
-  const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)a.BN, 1u};
+  const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)(a.BN / a.cs), 1u};
   int rc;
   if ((rc = make_map(&mA[0], d->x_hi, 5, adims, astr, abox, a.planes == 1))) return rc;
   if ((rc = make_map(&mB[0], d->w_hi, 3, bdims, bstr, bbox, a.planes == 1))) return rc;
@@ -483,11 +528,24 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
                                      227 * 1024));
     attr_set = true;
   }
-  const int tiles = cdiv(a.W, a.bw) * cdiv(a.H, a.bh) * cdiv(a.D, a.bd) * cdiv(a.G, a.bg) *
-                    cdiv(a.Cout, a.BN);
-  int grid = tiles < igemm_num_sms() ? tiles : igemm_num_sms();
-  igemm_kernel<<<grid, kThreads, smem, stream>>>(mA[0], mA[1], mB[0], mB[1], a);
-  DRB_LAUNCH_OK();
+  const int tiles_m = cdiv(a.W, a.bw) * cdiv(a.H, a.bh) * cdiv(a.D, a.bd) * cdiv(a.G, a.bg);
+  const int tiles = cdiv(tiles_m, a.cs) * cdiv(a.Cout, a.BN);     // super tiles (one per cluster)
+  const int max_clusters = igemm_num_sms() / a.cs;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(clusters * a.cs));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)a.cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DRB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel, mA[0], mA[1], mB[0], mB[1], a));
   return 0;
 }
 

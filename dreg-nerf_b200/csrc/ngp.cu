@@ -13,6 +13,7 @@
 // shared memory and are read as warp-uniform broadcasts.
 #include "common.cuh"
 
+#include <cub/cub.cuh>
 #include <math.h>
 #include <stdlib.h>
 
@@ -372,72 +373,125 @@ __device__ __forceinline__ float dist_to_next_voxel(const MarchArgs& a, const fl
   return fmaxf(t, 0.f);
 }
 
+// Persistent ray queue.  The naive one-thread-per-ray loop ran with 2.9 of 32 lanes active (rays of
+// a warp end at very different times, and the expensive density sample alternates with cheap empty-
+// space skips).  Here every lane owns a ray slot and refills it from a global counter (chunks of 8
+// consecutive rays = neighbouring points of one camera); per iteration each lane first advances its
+// ray through empty space on its own until a sample position inside an occupied cell is pending
+// (phase A, cheap, divergent), then ALL lanes evaluate the hash grid + MLP for their pending sample
+// together (phase B, expensive, convergent).  The per-ray arithmetic (t0/t1/tm updates, skip rule,
+// termination tests) is unchanged, so masks are identical to the scalar oracle.
+struct RayState {
+  float o[3], dir[3], inv[3];
+  float len, t0, t1, tm, T, best;
+  int pi;
+};
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict__ occ,
                     const float* __restrict__ points, int n, const float* __restrict__ cams, int ncams,
-                    const uint8_t* __restrict__ active, uint8_t* __restrict__ surface) {
+                    const int* __restrict__ active_idx, const int* __restrict__ active_count,
+                    unsigned long long* __restrict__ counter, uint8_t* __restrict__ surface) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   const FieldSmem sm = stage_field(p, smem, &bar);
-  const long long total = (long long)n * ncams;
-  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total;
-       r += (long long)gridDim.x * blockDim.x) {
-    const int pi = (int)(r % n), ci = (int)(r / n);
-    if (surface[pi]) continue;                 // another camera already saw this point
-    if (active && !active[pi]) continue;       // caller only consumes surface & density
-    float o[3], dir[3], inv_dir[3];
-    float len = 0.f;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      o[d] = cams[ci * 3 + d];
-      dir[d] = points[pi * 3 + d] - o[d];
-      len += dir[d] * dir[d];
-    }
-    len = sqrtf(len);
-    if (!(len > 0.f)) continue;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) { dir[d] = dir[d] / len; inv_dir[d] = 1.f / dir[d]; }
-    // ray / scene AABB intersection -> t_min (nerfacc ray_aabb_intersect); t_max = |p - o|
-    float tn = -1e30f, tf = 1e30f;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      float t0 = (a.scene_min[d] - o[d]) * inv_dir[d], t1 = (a.scene_max[d] - o[d]) * inv_dir[d];
-      if (t0 > t1) { const float tmp = t0; t0 = t1; t1 = tmp; }
-      tn = fmaxf(tn, t0); tf = fminf(tf, t1);
-    }
-    if (tn > tf) continue;                    // misses the box: nerfacc returns t_min = 1e10
-    const float near = fmaxf(tn, 0.f), far = len;
-    float t0 = near, t1 = t0 + a.step, tm = 0.5f * (t0 + t1);
-    float T = 1.f, best = 0.f;
-    while (tm < far) {
-      const float x[3] = {o[0] + tm * dir[0], o[1] + tm * dir[1], o[2] + tm * dir[2]};
-      if (occupied_at(a, occ, x)) {
-        float xn[3];
-        const bool inside = normalise(p, x, xn);
-        float sigma = 0.f;
-        if (inside) {
-          float f[32], out[1];
-          hash_encode(p, sm, xn, f);
-          density_mlp<1>(sm, f, out);
-          sigma = expf(out[0] - 1.f);
+  const int n_act = active_count ? *active_count : n;
+  const unsigned long long total = (unsigned long long)n_act * (unsigned long long)ncams;
+  constexpr unsigned long long kChunk = 8;
+  unsigned long long r_cur = 0, r_end = 0;
+  bool have = false, exhausted = false;
+  RayState ray;
+  while (true) {
+    // ---------------- phase A: advance until a sample is pending (or no rays are left) -----------
+    bool pending = false;
+    float x[3];
+    while (!pending && !exhausted) {
+      if (!have) {
+        if (r_cur >= r_end) {
+          r_cur = atomicAdd(counter, kChunk);
+          r_end = r_cur + kChunk < total ? r_cur + kChunk : total;
+          if (r_cur >= total) { exhausted = true; break; }
         }
-        const float alpha = 1.f - expf(-sigma * (t1 - t0));
-        if (T < 1e-4f) break;                  // samples past early_stop_eps are dropped (:209)
-        best = fmaxf(best, alpha * T);
-        if (best >= a.cut_off) break;
-        T *= 1.f - alpha;
-        // exact early out: every later sample contributes alpha * T' <= T' <= T < cut_off
-        if (T < a.cut_off) break;
-        t0 = t1; t1 = t0 + a.step; tm = 0.5f * (t0 + t1);
+        const unsigned long long r = r_cur++;
+        const int j = (int)(r % (unsigned long long)n_act), ci = (int)(r / (unsigned long long)n_act);
+        const int pi = active_idx ? active_idx[j] : j;
+        if (surface[pi]) continue;               // another camera already saw this point
+        float len = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          ray.o[d] = cams[ci * 3 + d];
+          ray.dir[d] = points[pi * 3 + d] - ray.o[d];
+          len += ray.dir[d] * ray.dir[d];
+        }
+        len = sqrtf(len);
+        if (!(len > 0.f)) continue;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { ray.dir[d] = ray.dir[d] / len; ray.inv[d] = 1.f / ray.dir[d]; }
+        // ray / scene AABB intersection -> t_min (nerfacc ray_aabb_intersect); t_max = |p - o|
+        float tn = -1e30f, tf = 1e30f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          float ta = (a.scene_min[d] - ray.o[d]) * ray.inv[d], tb = (a.scene_max[d] - ray.o[d]) * ray.inv[d];
+          if (ta > tb) { const float tmp = ta; ta = tb; tb = tmp; }
+          tn = fmaxf(tn, ta); tf = fminf(tf, tb);
+        }
+        if (tn > tf) continue;                    // misses the box
+        ray.len = len; ray.pi = pi;
+        ray.t0 = fmaxf(tn, 0.f); ray.t1 = ray.t0 + a.step; ray.tm = 0.5f * (ray.t0 + ray.t1);
+        ray.T = 1.f; ray.best = 0.f;
+        have = true;
+      }
+      if (!(ray.tm < ray.len)) { have = false; continue; }     // reached the point without a hit
+#pragma unroll
+      for (int d = 0; d < 3; ++d) x[d] = ray.o[d] + ray.tm * ray.dir[d];
+      if (occupied_at(a, occ, x)) {
+        pending = true;
       } else {
-        const float tt = tm + dist_to_next_voxel(a, x, dir, inv_dir);
-        do { tm += a.step; } while (tm < tt);
-        t0 = tm - 0.5f * a.step; t1 = tm + 0.5f * a.step;
+        const float tt = ray.tm + dist_to_next_voxel(a, x, ray.dir, ray.inv);
+        do { ray.tm += a.step; } while (ray.tm < tt);
+        ray.t0 = ray.tm - 0.5f * a.step; ray.t1 = ray.tm + 0.5f * a.step;
       }
     }
-    if (best >= a.cut_off) surface[pi] = 1;
+    if (!__any_sync(0xffffffffu, pending)) break;               // every lane of the warp is out of rays
+    // ---------------- phase B: one density sample per lane, in lock-step -------------------------
+    if (pending) {
+      float xn[3];
+      const bool inside = normalise(p, x, xn);
+      float sigma = 0.f;
+      if (inside) {
+        float f[32], out[1];
+        hash_encode(p, sm, xn, f);
+        density_mlp<1>(sm, f, out);
+        sigma = expf(out[0] - 1.f);
+      }
+      const float alpha = 1.f - expf(-sigma * (ray.t1 - ray.t0));
+      bool done = false;
+      if (ray.T < 1e-4f) {                       // samples past early_stop_eps are dropped (:209)
+        done = true;
+      } else {
+        ray.best = fmaxf(ray.best, alpha * ray.T);
+        if (ray.best >= a.cut_off) {
+          surface[ray.pi] = 1;
+          done = true;
+        } else {
+          ray.T *= 1.f - alpha;
+          // exact early out: every later sample contributes alpha * T' <= T' <= T < cut_off
+          if (ray.T < a.cut_off || surface[ray.pi]) done = true;
+        }
+      }
+      if (done) {
+        have = false;
+      } else {
+        ray.t0 = ray.t1; ray.t1 = ray.t0 + a.step; ray.tm = 0.5f * (ray.t0 + ray.t1);
+      }
+    }
   }
+}
+
+__global__ void iota_kernel(int* __restrict__ v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
 }
 
 static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary, int res,
@@ -466,14 +520,35 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
     DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
+  // scratch: ray counter, active count, compacted (order preserving) list of active points
+  uint8_t* scratch = nullptr;
+  size_t cub_bytes = 0;
+  cub::DeviceSelect::Flagged(nullptr, cub_bytes, (const int*)nullptr, (const uint8_t*)nullptr, (int*)nullptr,
+                             (int*)nullptr, n, stream);
+  const size_t off_idx = 256, off_iota = off_idx + (((size_t)n * 4 + 255) & ~(size_t)255);
+  const size_t off_cub = off_iota + (((size_t)n * 4 + 255) & ~(size_t)255);
+  DRB_CUDA_OK(cudaMallocAsync(&scratch, off_cub + cub_bytes + 256, stream));
+  DRB_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, stream));
+  unsigned long long* counter = (unsigned long long*)scratch;
+  int* count = (int*)(scratch + 64);
+  int* idx = nullptr;
+  if (active) {
+    idx = (int*)(scratch + off_idx);
+    int* iota = (int*)(scratch + off_iota);
+    iota_kernel<<<cdiv(n, 256), 256, 0, stream>>>(iota, n);
+    DRB_LAUNCH_OK();
+    DRB_CUDA_OK(cub::DeviceSelect::Flagged(scratch + off_cub, cub_bytes, iota, active, idx, count, n, stream));
+  }
   const int grid = igemm_num_sms();
+  const int* cnt = active ? count : nullptr;
   if (threads == 256)
-    surface_mask_kernel<256><<<grid, 256, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, active, surface);
+    surface_mask_kernel<256><<<grid, 256, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, idx, cnt, counter, surface);
   else if (threads == 512)
-    surface_mask_kernel<512><<<grid, 512, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, active, surface);
+    surface_mask_kernel<512><<<grid, 512, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, idx, cnt, counter, surface);
   else
-    surface_mask_kernel<1024><<<grid, 1024, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, active, surface);
+    surface_mask_kernel<1024><<<grid, 1024, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, idx, cnt, counter, surface);
   DRB_LAUNCH_OK();
+  DRB_CUDA_OK(cudaFreeAsync(scratch, stream));
   return 0;
 }
 

@@ -115,6 +115,20 @@ def im2col(x, k, stride, pad, kpad, channel_slice=None):
     return hi, lo
 
 
+def im2col_stem(x):
+    """x: fp32 [1, 4, d, h, w] strided view -> planes [1, do, ho, wo, 512] (conv1 fast path)."""
+    _, c, d, h, w = x.shape
+    assert c == 4
+    od, oh, ow = [(n + 4 - 5) // 2 + 1 for n in (d, h, w)]
+    hi = torch.empty((1, od, oh, ow, 512), dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    scratch = torch.empty(d * h * w * 4, dtype=torch.float32, device=x.device)
+    with _dev(x):
+        check(_lib.load().drb_im2col_stem(ptr(x), x.stride(1), x.stride(2), x.stride(3), x.stride(4), d, h, w,
+                                          ptr(scratch), ptr(hi), ptr(lo), stream_ptr()), "drb_im2col_stem")
+    return hi, lo
+
+
 def batchnorm(x, gamma, beta, running_mean, running_var, training, residual=None, relu=False,
               momentum=0.1, eps=1e-5, want_planes=False):
     """x fp32 [g, m, c] -> y (and planes).  Updates running buffers in place when training."""

@@ -96,6 +96,11 @@ typedef struct drb_im2col_desc {
   int kpad;                       /* >= k^3*c, multiple of 64                               */
 } drb_im2col_desc;
 int drb_im2col(const drb_im2col_desc* desc, void* hi, void* lo, drb_stream_t stream);
+/* Stem fast path (conv1: 5^3, stride 2, pad 2 over 4 channels, resnet3d.py:120): x points at the first
+ * of 4 channels of ONE grid with element strides (sc, sd, sh, sw); scratch holds d*h*w*4 floats;
+ * planes [do][ho][wo][512] with the k order of drb_im2col.  Same result as drb_im2col. */
+int drb_im2col_stem(const float* x, long long sc, long long sd, long long sh, long long sw, int d, int h,
+                    int w, void* scratch, void* hi, void* lo, drb_stream_t stream);
 
 /* nn.BatchNorm3d (resnet3d.py:82-87,121).  x is fp32 [g][m][c]; statistics are per (g, c):
  * the reference runs one grid per call with batch size 1 (nerf_regtr.py:135).  accum is

@@ -108,6 +108,17 @@ def test_im2col_conv(cuda, cin, cout, k, stride, size):
     assert _rel(out, ref) < 2e-6
 
 
+def test_im2col_stem_matches_generic(cuda):
+    """The stem fast path (pack + warp-per-voxel im2col) writes exactly what the generic kernel does."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(41)
+    base = torch.randn(1, 20, 18, 22, 7, generator=gen)                    # [g, X, Y, Z, C] storage
+    xd = base.to(cuda).permute(0, 4, 3, 1, 2)[:, 3:]                        # [1, 4, Z, X, Y] strided view
+    a_hi, a_lo = ops.im2col(xd, 5, 2, 2, 512)
+    b_hi, b_lo = ops.im2col_stem(xd)
+    assert torch.equal(a_hi, b_hi) and torch.equal(a_lo, b_lo)
+
+
 @pytest.mark.parametrize("training", [True, False])
 def test_batchnorm(cuda, training):
     ops = _ops()
