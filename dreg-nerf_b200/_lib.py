@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdregb200.so")
+LIB_PATH = os.environ.get("DRB_LIB_PATH") or os.path.join(HERE, "libdregb200.so")
 
 c_void_p, c_int, c_ll, c_float, c_size_t = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 

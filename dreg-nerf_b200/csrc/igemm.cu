@@ -38,6 +38,8 @@ struct IgemmArgs {
   int stages;
   int chunk;             // k-iterations accumulated in TMEM before the fp32 register add
   int cs;                // cluster size along M (1, 2 or 4): the weight tile is TMA-multicast
+  int splits;            // split-K factor (> 1: partial sums are red.add'ed into a pre-zeroed `out`)
+  int kper;              // k-iterations per split (multiple of chunk)
   int relu;
   float acc_scale;         // multiplies the raw accumulator (undoes the weight pre-scale)
   float out_scale;
@@ -51,11 +53,24 @@ struct IgemmArgs {
 };
 
 // Fused epilogue of 32 consecutive output channels of one row.
-__device__ __forceinline__ void epilogue_store32(const IgemmArgs& a, float (&f)[32], long long m, int n) {
+__device__ __forceinline__ void epilogue_store32(const IgemmArgs& a, float (&f)[32], long long m, int n,
+                                                 int split) {
   const long long off = m * a.ld + n;
   const bool full = (n + 32 <= a.Cout);
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] *= a.acc_scale;
+  if (a.splits > 1) {
+    // split-K: partial sums of the K slices meet in a pre-zeroed fp32 output (bias joins slice 0)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (n + j < a.Cout) {
+        float v = f[j];
+        if (a.bias && split == 0) v += __ldg(a.bias + n + j);
+        atomicAdd(a.out + off + j, v);
+      }
+    }
+    return;
+  }
   if (a.bias) {
     if (full) {
 #pragma unroll
@@ -173,6 +188,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   const int tiles_m = tiles_w * tiles_h * tiles_d * tiles_g;
   const int groups_m = (tiles_m + cs - 1) / cs;
   const int total_tiles = groups_m * tiles_n;      // per cluster: one "super tile" = cs M tiles
+  const int total_items = total_tiles * a.splits;   // (super tile, K slice) work items
   const int cluster_id = blockIdx.x / cs;
   const int num_clusters = gridDim.x / cs;
   const int kchunks = a.Cin / kBK;
@@ -225,12 +241,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      for (int it = cluster_id; it < total_items; it += num_clusters) {
+        const int t = it / a.splits, sp = it % a.splits;
+        const int ki0 = sp * a.kper, ki1 = min(kiters, ki0 + a.kper);
         int n0, w0, h0, d0, g0;
         decode_tile(t, n0, w0, h0, d0, g0);
-        for (int tap = 0; tap < taps; ++tap) {
-          const int tw = tap % a.kw, th = (tap / a.kw) % a.kh, td = tap / (a.kw * a.kh);
-          for (int kc = 0; kc < kchunks; ++kc) {
+        {
+          for (int ki = ki0; ki < ki1; ++ki) {
+            const int tap = ki / kchunks, kc = ki - tap * kchunks;
+            const int tw = tap % a.kw, th = (tap / a.kw) % a.kh, td = tap / (a.kw * a.kh);
             mbar_wait(empty_bar(s), ph ^ 1u, a.err, 1);
             const uint32_t fb = full_bar(s);
             mbar_expect_tx(fb, stage_bytes);
@@ -263,13 +282,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       int s = 0;
       uint32_t ph = 0;
       uint32_t cc = 0;                       // running chunk counter -> TMEM region + phase
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-        for (int k0 = 0; k0 < kiters; k0 += a.chunk, ++cc) {
+      for (int it = cluster_id; it < total_items; it += num_clusters) {
+        const int sp = it % a.splits;
+        const int ki0 = sp * a.kper, ki1 = min(kiters, ki0 + a.kper);
+        for (int k0 = ki0; k0 < ki1; k0 += a.chunk, ++cc) {
           const uint32_t r = cc & 1u, rph = (cc >> 1) & 1u;
           mbar_wait(tempty_bar(r), rph ^ 1u, a.err, 2);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + r * (uint32_t)a.BN;
-          const int kend = min(k0 + a.chunk, kiters);
+          const int kend = min(k0 + a.chunk, ki1);
           for (int ki = k0; ki < kend; ++ki) {
             mbar_wait(full_bar(s), ph, a.err, 3);
             tc_fence_after();
@@ -304,7 +325,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     const int row = q * 32 + lane;           // accumulator row == tile-local voxel
     float acc[128];
     uint32_t cc = 0;
-    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+    for (int it = cluster_id; it < total_items; it += num_clusters) {
+      const int t = it / a.splits, sp = it % a.splits;
+      const int ki0 = sp * a.kper, ki1 = min(kiters, ki0 + a.kper);
       int n0, w0, h0, d0, g0;
       decode_tile(t, n0, w0, h0, d0, g0);
       int rr = row;
@@ -316,7 +339,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       const long long m = (((long long)gg * a.D + dd) * a.H + hh) * a.W + ww;
 #pragma unroll
       for (int j = 0; j < 128; ++j) acc[j] = 0.f;
-      for (int k0 = 0; k0 < kiters; k0 += a.chunk, ++cc) {
+      for (int k0 = ki0; k0 < ki1; k0 += a.chunk, ++cc) {
         const uint32_t r = cc & 1u, rph = (cc >> 1) & 1u;
         mbar_wait(tfull_bar(r), rph, a.err, 4);
         tc_fence_after();
@@ -342,7 +365,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = acc[b * 32 + j];
-          epilogue_store32(a, f, m, n);
+          epilogue_store32(a, f, m, n, sp);
         }
       }
     }
@@ -458,8 +481,40 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   a.kd = d->kd; a.kh = d->kh; a.kw = d->kw;
   a.pd = d->kd / 2; a.ph = d->kh / 2; a.pw = d->kw / 2;
   choose_box(a.G, a.D, a.H, a.W, a.bg, a.bd, a.bh, a.bw);
-  a.BN = d->cout >= 256 ? 256 : ((d->cout + 63) / 64) * 64;
   a.chunk = d->planes == 2 ? 2 : 4;
+  const int nsm = igemm_num_sms();
+  const long long tiles_m_h = (long long)cdiv(a.W, a.bw) * cdiv(a.H, a.bh) * cdiv(a.D, a.bd) * cdiv(a.G, a.bg);
+  // N tile: the widest of 256 / 128 / 64 that still yields at least one tile per SM (small problems are
+  // latency bound: more, narrower tiles beat fewer wide ones); never wider than Cout rounded to 64.
+  a.BN = 64;
+  for (int bn = 256; bn >= 64; bn >>= 1) {
+    if (bn > ((d->cout + 63) / 64) * 64 && bn != 64) continue;
+    if (tiles_m_h * cdiv(d->cout, bn) >= nsm || bn == 64) { a.BN = bn; break; }
+  }
+  if (a.BN > ((d->cout + 63) / 64) * 64) a.BN = ((d->cout + 63) / 64) * 64;
+  // split-K: few tiles but a long reduction (deep backbone layers: 1-8 tiles, K up to 13824).  Only for
+  // the plain "fp32 out (+ bias)" epilogue; partial sums are added atomically into a zeroed output.
+  const int kiters_h = d->kd * d->kh * d->kw * (d->cin / kBK);
+  const long long tiles_h = tiles_m_h * cdiv(d->cout, a.BN);
+  a.splits = 1;
+  a.kper = kiters_h;
+  const bool plain = d->out && !d->out_hi && !d->residual && !d->relu && (d->out_scale == 0.f || d->out_scale == 1.f);
+  if (plain && tiles_h * 2 <= nsm && kiters_h >= 4 * a.chunk) {
+    int want = (int)(nsm / tiles_h);
+    int maxs = kiters_h / (2 * a.chunk);
+    int sp = want < maxs ? want : maxs;
+    if (sp > 1) {
+      int kper = (kiters_h + sp - 1) / sp;
+      kper = ((kper + a.chunk - 1) / a.chunk) * a.chunk;
+      a.kper = kper;
+      a.splits = (kiters_h + kper - 1) / kper;
+    }
+  }
+  {
+    static int no_split = -1;
+    if (no_split < 0) { const char* env = getenv("DRB_IGEMM_NO_SPLITK"); no_split = env ? atoi(env) : 0; }
+    if (no_split) { a.splits = 1; a.kper = kiters_h; }
+  }
   {
     // cluster size along M: multicast pays off when there are enough tiles to keep every CTA busy
     static int forced = -1;
@@ -529,7 +584,9 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
     attr_set = true;
   }
   const int tiles_m = cdiv(a.W, a.bw) * cdiv(a.H, a.bh) * cdiv(a.D, a.bd) * cdiv(a.G, a.bg);
-  const int tiles = cdiv(tiles_m, a.cs) * cdiv(a.Cout, a.BN);     // super tiles (one per cluster)
+  const int tiles = cdiv(tiles_m, a.cs) * cdiv(a.Cout, a.BN) * a.splits;     // work items (one per cluster)
+  if (a.splits > 1)
+    DRB_CUDA_OK(cudaMemsetAsync(a.out, 0, sizeof(float) * (size_t)a.G * a.D * a.H * a.W * (size_t)a.ld, stream));
   const int max_clusters = igemm_num_sms() / a.cs;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   cudaLaunchConfig_t cfg;

@@ -89,6 +89,8 @@ __device__ __forceinline__ uint32_t grid_index(const uint32_t g[3], uint32_t res
     }
   }
   if (size < stride) index = (g[0] * 1u) ^ (g[1] * 2654435761u) ^ (g[2] * 805459861u);
+  // NB: replacing this modulo by a mask for the 2^19-entry levels (and a compare for the dense ones) was
+  // measured 30 % SLOWER on B200 (same box A/B, round 1), so the plain form stays.
   return index % size;
 }
 
@@ -381,6 +383,13 @@ __device__ __forceinline__ float dist_to_next_voxel(const MarchArgs& a, const fl
 // (phase A, cheap, divergent), then ALL lanes evaluate the hash grid + MLP for their pending sample
 // together (phase B, expensive, convergent).  The per-ray arithmetic (t0/t1/tm updates, skip rule,
 // termination tests) is unchanged, so masks are identical to the scalar oracle.
+__device__ unsigned long long g_march_stats[4];   // rays, skip events, samples, outer iterations (debug)
+extern "C" int drb_debug_march_stats(unsigned long long* host4, int reset) {
+  cudaMemcpyFromSymbol(host4, g_march_stats, sizeof(unsigned long long) * 4);
+  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_march_stats, z, sizeof(z)); }
+  return 0;
+}
+
 struct RayState {
   float o[3], dir[3], inv[3];
   float len, t0, t1, tm, T, best;
@@ -399,14 +408,27 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict
   const int n_act = active_count ? *active_count : n;
   const unsigned long long total = (unsigned long long)n_act * (unsigned long long)ncams;
   constexpr unsigned long long kChunk = 8;
+  constexpr int kMaxSkips = 8;
+  const bool pow2_res = (a.res & (a.res - 1)) == 0;
+  const float inv_res = 1.f / (float)a.res;
   unsigned long long r_cur = 0, r_end = 0;
   bool have = false, exhausted = false;
   RayState ray;
+#ifdef DRB_MARCH_STATS
+  unsigned long long st_rays = 0, st_skips = 0, st_samples = 0, st_iters = 0;
+#endif
   while (true) {
+#ifdef DRB_MARCH_STATS
+    ++st_iters;
+#endif
     // ---------------- phase A: advance until a sample is pending (or no rays are left) -----------
+    // At most kMaxSkips empty-space events per outer iteration: a lane that has just started a ray
+    // (~60 empty voxels before the first occupied one) must not hold back the lanes whose next sample
+    // is already pending; it simply sits out a few of the (expensive, lock-step) phase B rounds.
     bool pending = false;
     float x[3];
-    while (!pending && !exhausted) {
+    int budget = kMaxSkips;
+    while (!pending && !exhausted && budget > 0) {
       if (!have) {
         if (r_cur >= r_end) {
           r_cur = atomicAdd(counter, kChunk);
@@ -441,19 +463,59 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict
         ray.t0 = fmaxf(tn, 0.f); ray.t1 = ray.t0 + a.step; ray.tm = 0.5f * (ray.t0 + ray.t1);
         ray.T = 1.f; ray.best = 0.f;
         have = true;
+#ifdef DRB_MARCH_STATS
+        ++st_rays;
+#endif
       }
       if (!(ray.tm < ray.len)) { have = false; continue; }     // reached the point without a hit
 #pragma unroll
       for (int d = 0; d < 3; ++d) x[d] = ray.o[d] + ray.tm * ray.dir[d];
-      if (occupied_at(a, occ, x)) {
+      // occupancy test and distance to the next voxel share u = (x - roi_min) / extent (IEEE division,
+      // as nerfacc's roi_to_unit); res is a power of two in practice, where "/ res" is an exact scaling
+      float u[3];
+      bool in_roi = true;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        u[d] = __fdiv_rn(x[d] - a.roi_min[d], a.roi_max[d] - a.roi_min[d]);
+        in_roi = in_roi && (u[d] >= 0.f) && (u[d] < 1.f);
+      }
+      bool is_occ = false;
+      if (in_roi) {
+        int idx[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int i = (int)(u[d] * (float)a.res);
+          idx[d] = i < 0 ? 0 : (i > a.res - 1 ? a.res - 1 : i);
+        }
+        is_occ = occ[((long long)idx[0] * a.res + idx[1]) * a.res + idx[2]] != 0;
+      }
+      if (is_occ) {
         pending = true;
       } else {
-        const float tt = ray.tm + dist_to_next_voxel(a, x, ray.dir, ray.inv);
+        --budget;
+        float dist = 1e30f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float ur = u[d] * (float)a.res;
+          const float sgn = ray.dir[d] > 0.f ? 1.f : (ray.dir[d] < 0.f ? -1.f : 0.f);
+          float td = (floorf(ur + 0.5f + 0.5f * sgn) - ur) * ray.inv[d];
+          td = pow2_res ? td * inv_res : __fdiv_rn(td, (float)a.res);
+          dist = fminf(dist, td * (a.roi_max[d] - a.roi_min[d]));
+        }
+        const float tt = ray.tm + fmaxf(dist, 0.f);
         do { ray.tm += a.step; } while (ray.tm < tt);
         ray.t0 = ray.tm - 0.5f * a.step; ray.t1 = ray.tm + 0.5f * a.step;
+#ifdef DRB_MARCH_STATS
+        ++st_skips;
+#endif
       }
     }
-    if (!__any_sync(0xffffffffu, pending)) break;               // every lane of the warp is out of rays
+#ifdef DRB_MARCH_STATS
+    if (pending) ++st_samples;
+#endif
+    // leave only when every lane of the warp is out of rays (a lane without a pending sample may just
+    // have used up its skip budget)
+    if (!__any_sync(0xffffffffu, pending || have || !exhausted)) break;
     // ---------------- phase B: one density sample per lane, in lock-step -------------------------
     if (pending) {
       float xn[3];
@@ -487,6 +549,11 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict
       }
     }
   }
+#ifdef DRB_MARCH_STATS
+  atomicAdd(&g_march_stats[0], st_rays); atomicAdd(&g_march_stats[1], st_skips);
+  atomicAdd(&g_march_stats[2], st_samples);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&g_march_stats[3], st_iters);
+#endif
 }
 
 __global__ void iota_kernel(int* __restrict__ v, int n) {

@@ -71,6 +71,25 @@ def test_igemm_conv3d(cuda, shape, cin, cout, k):
     assert _rel(out, ref) < 2e-6
 
 
+@pytest.mark.parametrize("shape,cin,cout,k", [((2, 4, 4, 4), 512, 512, 3), ((2, 8, 8, 8), 256, 256, 3),
+                                              ((1, 1, 1, 90), 2048, 256, 1)])
+def test_igemm_split_k(cuda, shape, cin, cout, k):
+    """Deep backbone layers: 1-8 output tiles, K up to 13824 -> split-K work items + atomic reduction."""
+    ops = _ops()
+    g, d, h, w = shape
+    gen = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(g, cin, d, h, w, generator=gen)
+    wt = torch.randn(cout, cin, k, k, k, generator=gen) / math.sqrt(cin * k ** 3)
+    bias = torch.randn(cout, generator=gen)
+    xp = ops.split_planes(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda))
+    wp = ops.pack_conv_weight(wt.to(cuda))
+    out, _ = ops.conv3d_igemm(xp, wp, k, planes=2, bias=bias.to(cuda))
+    torch.cuda.synchronize()
+    assert ops.igemm_error_flag() == 0
+    ref = F.conv3d(x.double(), wt.double(), bias.double(), padding=k // 2).permute(0, 2, 3, 4, 1).reshape(-1, cout)
+    assert _rel(out, ref) < 2e-6
+
+
 def test_igemm_epilogue(cuda):
     """out = relu((acc + bias) * scale + residual), fp32 and plane outputs."""
     ops = _ops()
