@@ -21,7 +21,7 @@ class Conv3dDesc(C.Structure):
                 ("x_hi", c_void_p), ("x_lo", c_void_p), ("w_hi", c_void_p), ("w_lo", c_void_p),
                 ("bias", c_void_p), ("residual", c_void_p),
                 ("out", c_void_p), ("out_hi", c_void_p), ("out_lo", c_void_p),
-                ("ld_out", c_ll)]
+                ("ld_out", c_ll), ("tile_list", c_void_p), ("tile_count", c_void_p)]
 
 
 class Im2colDesc(C.Structure):
@@ -69,6 +69,7 @@ SIGNATURES = {
     "drb_last_error": (C.c_char_p, []),
     "drb_igemm_error_flag": (c_int, [C.POINTER(c_int)]),
     "drb_conv3d_igemm": (c_int, [C.POINTER(Conv3dDesc), c_void_p]),
+    "drb_conv3d_tile_shape": (c_int, [c_int, c_int, c_int, c_int, C.POINTER(c_int * 4), C.POINTER(c_int * 4)]),
     "drb_split_planes": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "drb_weight_scale": (c_int, [c_void_p, c_ll, C.POINTER(c_float), c_void_p]),
     "drb_pack_conv_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
@@ -87,6 +88,8 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "drb_trilinear_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_ll, c_ll, c_ll,
                                      c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "drb_fpn_need_tiles": (c_int, [C.POINTER(c_void_p), C.POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "drb_downsample_workspace_bytes": (c_size_t, [c_int, c_int]),
     "drb_hierarchical_downsample": (c_int, [c_void_p, c_int, c_int, c_int, c_int, C.c_double, c_int, c_void_p,
                                             c_size_t, c_void_p, C.POINTER(c_int), C.POINTER(c_int), c_void_p]),
@@ -108,6 +111,7 @@ SIGNATURES = {
                                  c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_void_p, c_void_p]),
     "drb_extract_block": (c_int, [C.POINTER(NgpParams), C.POINTER(ExtractDesc), c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "drb_extract_last_surface_ms": (c_int, [C.POINTER(c_float)]),
     "drb_engine_create": (c_int, [C.POINTER(EngineConfig), C.POINTER(c_void_p)]),
     "drb_engine_destroy": (None, [c_void_p]),
     "drb_engine_num_params": (c_int, [c_void_p]),
@@ -116,6 +120,7 @@ SIGNATURES = {
     "drb_engine_bind_param": (c_int, [c_void_p, c_int, c_void_p]),
     "drb_engine_commit_params": (c_int, [c_void_p, c_void_p]),
     "drb_engine_set_training": (c_int, [c_void_p, c_int]),
+    "drb_engine_set_sparse_fpn": (c_int, [c_void_p, c_int]),
     "drb_engine_encode": (c_int, [c_void_p, C.POINTER(PairIO), C.POINTER(c_int), C.POINTER(c_int), c_void_p]),
     "drb_engine_decode": (c_int, [c_void_p, C.POINTER(PairOut), c_void_p]),
     "drb_engine_tap": (c_int, [c_void_p, C.c_char_p, c_int, c_void_p, c_ll, C.POINTER(c_ll), c_void_p]),

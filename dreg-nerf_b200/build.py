@@ -15,6 +15,8 @@ NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]   # IEEE ma
 for _flag in ("DRB_MARCH_STATS",):      # experiment switches (never set in production)
     if os.environ.get(_flag):
         NVCC_FLAGS.append("-D" + _flag)
+if os.environ.get("DRB_SMEM_LEVELS"):
+    NVCC_FLAGS.append("-DDRB_SMEM_LEVELS=" + os.environ["DRB_SMEM_LEVELS"])
 
 
 def _nvcc():

@@ -76,7 +76,7 @@ struct drb_engine {
   long long launches = 0;
   bool committed = false;
   bool profile = false;
-  struct ProfRec { cudaEvent_t a, b; double flops; };
+  struct ProfRec { cudaEvent_t a, b; double flops; int list_id; double flops_per_tile; };
   std::vector<ProfRec> prof;
   std::string fail;
 
@@ -100,6 +100,11 @@ struct drb_engine {
   Act c1, x0, c[4];                 // c[0..3] = c2..c5
   std::vector<Act> tmp;             // per-block temporaries
   Act lat[5], sum[4], p[5];         // p[0] = p1 ... p[4] = p5
+  // output-sparse evaluation of the two level-1 FPN convolutions
+  bool sparse_fpn = true;
+  uint8_t* need = nullptr;
+  int *tiles_out = nullptr, *tiles_in = nullptr, *tile_counts = nullptr;
+  unsigned long long* tile_totals = nullptr;   // running sums of the list lengths (profiling)
   // point stage
   float* rows = nullptr;            // [2*max_mask][260]
   float* rows_ds = nullptr;
@@ -292,6 +297,22 @@ static int build(drb_engine* e) {
       e->sum[i] = make_act(e, f.d, f.h, f.w, 256, false, true);
     }
   }
+  {
+    int box[4], tiles[4];
+    drb_conv3d_tile_shape(kG, e->c1.d, e->c1.h, e->c1.w, box, tiles);
+    const long long nt = (long long)tiles[0] * tiles[1] * tiles[2] * tiles[3];
+    e->need = e->alloc<uint8_t>((long long)kG * e->c1.m());
+    e->tiles_out = e->alloc<int>(nt);
+    e->tiles_in = e->alloc<int>(nt);
+    e->tile_counts = e->alloc<int>(2);
+    e->tile_totals = e->alloc<unsigned long long>(2);
+    cudaMemset(e->tile_totals, 0, 2 * sizeof(unsigned long long));
+    // rows of tiles that are skipped keep whatever they held: start from zeros, not from garbage
+    if (e->lat[0].f) cudaMemset(e->lat[0].f, 0, sizeof(float) * e->lat[0].numel());
+    if (e->p[0].f) cudaMemset(e->p[0].f, 0, sizeof(float) * e->p[0].numel());
+    if (e->sum[0].hi) cudaMemset(e->sum[0].hi, 0, sizeof(plane_t) * e->sum[0].numel());
+    if (e->sum[0].lo) cudaMemset(e->sum[0].lo, 0, sizeof(plane_t) * e->sum[0].numel());
+  }
   e->rows = e->alloc<float>((long long)2 * cfg.max_mask * kRowLd);
   e->rows_ds = e->alloc<float>((long long)2 * cfg.max_mask * kRowLd);
   e->ds_ws_bytes = drb_downsample_workspace_bytes(2 * cfg.max_mask, kRowLd);
@@ -310,7 +331,7 @@ static int run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
                      int h, int wd, int cin, int k, const float* bias, const float* residual,
                      int relu, float scale, float* out, plane_t* out_hi, plane_t* out_lo, long long ld,
                      cudaStream_t s, const plane_t* w_hi = nullptr, const plane_t* w_lo = nullptr,
-                     int cout_override = 0) {
+                     int cout_override = 0, const int* tile_list = nullptr, const int* tile_count = nullptr) {
   drb_conv3d_desc cd;
   memset(&cd, 0, sizeof(cd));
   cd.g = g; cd.d = d; cd.h = h; cd.w = wd;
@@ -324,12 +345,15 @@ static int run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
   cd.bias = bias; cd.residual = residual;
   cd.out = out; cd.out_hi = out_hi; cd.out_lo = out_lo;
   cd.ld_out = ld;
+  cd.tile_list = tile_list; cd.tile_count = tile_count;
   e->launches += 1;
   if (!e->profile) return drb_conv3d_igemm(&cd, s);
   drb_engine::ProfRec r;
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   r.flops = 2.0 * (double)g * d * h * wd * (double)cd.cout * (double)cin * k * k * k;
+  r.list_id = tile_list == nullptr ? -1 : (tile_list == e->tiles_out ? 0 : 1);
+  r.flops_per_tile = 2.0 * 128.0 * (double)cd.cout * (double)cin * k * k * k;   // executed work of one listed tile
   cudaEventRecord(r.a, s);
   const int rc = drb_conv3d_igemm(&cd, s);
   cudaEventRecord(r.b, s);
@@ -425,14 +449,17 @@ static int run_fpn(drb_engine* e, const drb_pair_io* io, cudaStream_t s) {
   }
   for (int i = 3; i >= 0; --i) {
     const Act& f = *feats[i];
+    const bool sparse = (i == 0) && e->sparse_fpn;
     DRB_TRY(run_igemm(e, e->pyr[i], f.hi, f.lo, kG, f.d, f.h, f.w, f.c, e->pyr[i].k, P(e, e->pyr[i].p_b),
-                      nullptr, 0, 1.f, e->lat[i].f, nullptr, nullptr, 0, s));
+                      nullptr, 0, 1.f, e->lat[i].f, nullptr, nullptr, 0, s, nullptr, nullptr, 0,
+                      sparse ? e->tiles_in : nullptr, sparse ? e->tile_counts + 1 : nullptr));
     const Act& top = e->p[i + 1];
     e->launches += 1;
     DRB_TRY(drb_upsample2_add(top.f, top.d, top.h, top.w, e->lat[i].f, kG, f.d, f.h, f.w, 256, nullptr,
                               e->sum[i].hi, e->sum[i].lo, s));
     DRB_TRY(run_igemm(e, e->ups[i], e->sum[i].hi, e->sum[i].lo, kG, f.d, f.h, f.w, 256, 3,
-                      P(e, e->ups[i].p_b), nullptr, 0, 1.f, e->p[i].f, nullptr, nullptr, 0, s));
+                      P(e, e->ups[i].p_b), nullptr, 0, 1.f, e->p[i].f, nullptr, nullptr, 0, s, nullptr, nullptr, 0,
+                      sparse ? e->tiles_out : nullptr, sparse ? e->tile_counts : nullptr));
   }
   return 0;
 }
@@ -528,6 +555,12 @@ extern "C" int drb_engine_set_training(drb_engine* e, int training_bn) {
 }
 extern "C" long long drb_engine_launch_count(const drb_engine* e) { return e ? e->launches : 0; }
 
+extern "C" int drb_engine_set_sparse_fpn(drb_engine* e, int on) {
+  DRB_REQUIRE(e, "drb_engine_set_sparse_fpn: null engine");
+  e->sparse_fpn = on != 0;
+  return 0;
+}
+
 extern "C" int drb_engine_set_profile(drb_engine* e, int on) {
   DRB_REQUIRE(e, "drb_engine_set_profile: null engine");
   e->profile = on != 0;
@@ -537,15 +570,24 @@ extern "C" int drb_engine_set_profile(drb_engine* e, int on) {
 extern "C" int drb_engine_profile_read(drb_engine* e, double* igemm_ms, double* igemm_flops, long long* n) {
   DRB_REQUIRE(e && igemm_ms && igemm_flops && n, "drb_engine_profile_read: null argument");
   double ms = 0.0, fl = 0.0;
+  // output-sparse launches: executed FLOPs = (sum of their tile-list lengths) x FLOPs of one tile
+  unsigned long long totals[2] = {0, 0};
+  double per_tile[2] = {0.0, 0.0};
+  DRB_CUDA_OK(cudaDeviceSynchronize());
+  if (e->tile_totals) {
+    DRB_CUDA_OK(cudaMemcpy(totals, e->tile_totals, sizeof(totals), cudaMemcpyDeviceToHost));
+    DRB_CUDA_OK(cudaMemset(e->tile_totals, 0, sizeof(totals)));
+  }
   for (auto& r : e->prof) {
     DRB_CUDA_OK(cudaEventSynchronize(r.b));
     float t = 0.f;
     DRB_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
     ms += t;
-    fl += r.flops;
+    if (r.list_id >= 0) per_tile[r.list_id] = r.flops_per_tile; else fl += r.flops;
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
+  fl += (double)totals[0] * per_tile[0] + (double)totals[1] * per_tile[1];
   *igemm_ms = ms; *igemm_flops = fl; *n = (long long)e->prof.size();
   e->prof.clear();
   return 0;
@@ -592,9 +634,16 @@ extern "C" int drb_engine_encode(drb_engine* e, const drb_pair_io* io, int* host
   DRB_REQUIRE(io->n_src_mask > 0 && io->n_tgt_mask > 0, "drb_engine_encode: empty mask");
   DRB_REQUIRE(io->n_src_mask <= e->cfg.max_mask && io->n_tgt_mask <= e->cfg.max_mask,
               "drb_engine_encode: mask larger than max_mask=%d", e->cfg.max_mask);
-  DRB_TRY(run_fpn(e, io, s));
   const Act& p1 = e->p[0];
   const int X = e->cfg.res_x, Y = e->cfg.res_y, Z = e->cfg.res_z;
+  if (e->sparse_fpn) {
+    const long long* masks[2] = {io->src_mask, io->tgt_mask};
+    const int ks[2] = {io->n_src_mask, io->n_tgt_mask};
+    e->launches += 4;
+    DRB_TRY(drb_fpn_need_tiles(masks, ks, kG, X, Y, Z, p1.d, p1.h, p1.w, e->need, e->tiles_out, e->tiles_in,
+                               e->tile_counts, e->profile ? e->tile_totals : nullptr, s));
+  }
+  DRB_TRY(run_fpn(e, io, s));
   e->launches += 2;
   DRB_TRY(drb_trilinear_gather(p1.f, p1.d, p1.h, p1.w, 256, io->src_grid, io->s_ch, io->s_z, io->s_x,
                                io->s_y, X, Y, Z, io->src_mask, io->n_src_mask, e->rows, kRowLd, s));

@@ -40,6 +40,8 @@ struct IgemmArgs {
   int cs;                // cluster size along M (1, 2 or 4): the weight tile is TMA-multicast
   int splits;            // split-K factor (> 1: partial sums are red.add'ed into a pre-zeroed `out`)
   int kper;              // k-iterations per split (multiple of chunk)
+  const int* tile_list;  // optional: compacted list of M-tile indices to compute (output-sparse conv)
+  const int* tile_count; // device scalar: number of entries in tile_list
   int relu;
   float acc_scale;         // multiplies the raw accumulator (undoes the weight pre-scale)
   float out_scale;
@@ -187,7 +189,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
   const int tiles_m = tiles_w * tiles_h * tiles_d * tiles_g;
   const int groups_m = (tiles_m + cs - 1) / cs;
-  const int total_tiles = groups_m * tiles_n;      // per cluster: one "super tile" = cs M tiles
+  // output-sparse mode: only the listed M tiles are computed (cs == 1, splits == 1 enforced by the host)
+  const int listed = a.tile_list ? *a.tile_count : 0;
+  const int total_tiles = (a.tile_list ? listed : groups_m) * tiles_n;   // per cluster: cs M tiles
   const int total_items = total_tiles * a.splits;   // (super tile, K slice) work items
   const int cluster_id = blockIdx.x / cs;
   const int num_clusters = gridDim.x / cs;
@@ -224,7 +228,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 
   auto decode_tile = [&](int t, int& n0, int& w0, int& h0, int& d0, int& g0) {
     int n = t % tiles_n;
-    int m = (t / tiles_n) * cs + (int)crank;
+    int m = a.tile_list ? a.tile_list[t / tiles_n] : (t / tiles_n) * cs + (int)crank;
     n0 = n * a.BN;
     if (m >= tiles_m) {              // padding tile of the last group: all rows out of bounds
       w0 = 0; h0 = 0; d0 = 0; g0 = a.G;
@@ -510,6 +514,10 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
       a.splits = (kiters_h + kper - 1) / kper;
     }
   }
+  a.tile_list = d->tile_list;
+  a.tile_count = d->tile_count;
+  DRB_REQUIRE((d->tile_list == nullptr) == (d->tile_count == nullptr), "drb_conv3d_igemm: tile_list / tile_count pair");
+  if (a.tile_list) { a.splits = 1; a.kper = kiters_h; }
   {
     static int no_split = -1;
     if (no_split < 0) { const char* env = getenv("DRB_IGEMM_NO_SPLITK"); no_split = env ? atoi(env) : 0; }
@@ -530,7 +538,7 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
     (void)tn;
     a.cs = 1;
     if (forced == 1 || forced == 2 || forced == 4) a.cs = forced;
-    if (tm < a.cs) a.cs = 1;
+    if (tm < a.cs || d->tile_list) a.cs = 1;
   }
   a.planes = d->planes;
   a.relu = d->relu;
@@ -603,6 +611,15 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   DRB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel, mA[0], mA[1], mB[0], mB[1], a));
+  return 0;
+}
+
+extern "C" int drb_conv3d_tile_shape(int g, int d, int h, int w, int box[4], int tiles[4]) {
+  DRB_REQUIRE(box && tiles && g > 0 && d > 0 && h > 0 && w > 0, "drb_conv3d_tile_shape: bad arguments");
+  int bg, bd, bh, bw;
+  choose_box(g, d, h, w, bg, bd, bh, bw);
+  box[0] = bg; box[1] = bd; box[2] = bh; box[3] = bw;
+  tiles[0] = cdiv(g, bg); tiles[1] = cdiv(d, bd); tiles[2] = cdiv(h, bh); tiles[3] = cdiv(w, bw);
   return 0;
 }
 

@@ -23,7 +23,10 @@ int igemm_num_sms();
 
 static constexpr int kLevels = 16;
 static constexpr int kHashSize = 1 << 19;
-static constexpr int kSmemLevels = 2;
+#ifndef DRB_SMEM_LEVELS
+#define DRB_SMEM_LEVELS 2
+#endif
+static constexpr int kSmemLevels = DRB_SMEM_LEVELS;
 
 struct LevelTable {
   float scale[kLevels];
@@ -347,6 +350,7 @@ struct MarchArgs {
   float roi_min[3], roi_max[3], scene_min[3], scene_max[3];
   int res;
   float step, cut_off;
+  int max_skips;      // empty-space events a lane may take per outer iteration
 };
 
 __device__ __forceinline__ bool occupied_at(const MarchArgs& a, const uint8_t* occ, const float x[3]) {
@@ -408,7 +412,7 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict
   const int n_act = active_count ? *active_count : n;
   const unsigned long long total = (unsigned long long)n_act * (unsigned long long)ncams;
   constexpr unsigned long long kChunk = 8;
-  constexpr int kMaxSkips = 8;
+  const int kMaxSkips = a.max_skips;
   const bool pow2_res = (a.res & (a.res - 1)) == 0;
   const float inv_res = 1.f / (float)a.res;
   unsigned long long r_cur = 0, r_end = 0;
@@ -556,6 +560,21 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict
 #endif
 }
 
+// The stream-ordered allocator gives memory back to the OS at every synchronisation unless a release
+// threshold is set; re-acquiring it costs milliseconds with a long tail.  Keep the pool.
+static void keep_async_pool() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done = true;
+}
+
 __global__ void iota_kernel(int* __restrict__ v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = i;
@@ -577,17 +596,24 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
     a.scene_min[d] = scene_aabb_host[d]; a.scene_max[d] = scene_aabb_host[3 + d];
   }
   a.res = res; a.step = step; a.cut_off = cut_off;
+  {
+    static int skips = 0;
+    if (!skips) { const char* env = getenv("DRB_MARCH_SKIPS"); skips = env ? atoi(env) : 16; if (skips < 1) skips = 16; }
+    a.max_skips = skips;
+  }
   const size_t smem = field_smem_bytes(p.lv);
   static int threads = 0;
   if (!threads) {
     const char* env = getenv("DRB_SURFACE_THREADS");
     threads = env ? atoi(env) : 512;
-    if (threads != 256 && threads != 512 && threads != 1024) threads = 512;
+    if (threads != 256 && threads != 512 && threads != 768 && threads != 1024) threads = 512;
+    DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   // scratch: ray counter, active count, compacted (order preserving) list of active points
+  keep_async_pool();
   uint8_t* scratch = nullptr;
   size_t cub_bytes = 0;
   cub::DeviceSelect::Flagged(nullptr, cub_bytes, (const int*)nullptr, (const uint8_t*)nullptr, (int*)nullptr,
@@ -612,6 +638,8 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
     surface_mask_kernel<256><<<grid, 256, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, idx, cnt, counter, surface);
   else if (threads == 512)
     surface_mask_kernel<512><<<grid, 512, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, idx, cnt, counter, surface);
+  else if (threads == 768)
+    surface_mask_kernel<768><<<grid, 768, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, idx, cnt, counter, surface);
   else
     surface_mask_kernel<1024><<<grid, 1024, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, idx, cnt, counter, surface);
   DRB_LAUNCH_OK();
@@ -673,6 +701,19 @@ __global__ void finish_extract_kernel(const long long* __restrict__ occupied, in
   }
 }
 
+// Roofline instrumentation: device time of the surface-field kernel of the most recent
+// drb_extract_block on this thread (CUDA events on the launching stream).  Synchronises on the event.
+static thread_local cudaEvent_t g_surf_ev[2] = {nullptr, nullptr};
+static thread_local bool g_surf_valid = false;
+extern "C" int drb_extract_last_surface_ms(float* host_ms) {
+  DRB_REQUIRE(host_ms, "drb_extract_last_surface_ms: null argument");
+  *host_ms = 0.f;
+  if (!g_surf_valid) return 0;
+  DRB_CUDA_OK(cudaEventSynchronize(g_surf_ev[1]));
+  DRB_CUDA_OK(cudaEventElapsedTime(host_ms, g_surf_ev[0], g_surf_ev[1]));
+  return 0;
+}
+
 extern "C" int drb_extract_block(const drb_ngp_params* pp, const drb_extract_desc* e, float* points, float* rgb,
                                  float* alpha, uint8_t* density_mask, uint8_t* surface_mask, float* voxel_grid,
                                  cudaStream_t stream) {
@@ -690,6 +731,7 @@ extern "C" int drb_extract_block(const drb_ngp_params* pp, const drb_extract_des
   // density / features go through scratch carved from the outputs: feat needs its own buffer
   float* feat = nullptr;
   float* density = nullptr;
+  keep_async_pool();
   DRB_CUDA_OK(cudaMallocAsync(&feat, sizeof(float) * 15 * (size_t)n, stream));
   DRB_CUDA_OK(cudaMallocAsync(&density, sizeof(float) * (size_t)n, stream));
   int rc = drb_ngp_density(pp, points, n, density, feat, stream);
@@ -698,10 +740,15 @@ extern "C" int drb_extract_block(const drb_ngp_params* pp, const drb_extract_des
     if (cudaGetLastError() != cudaSuccess) rc = DRB_ECUDA;
   }
   if (!rc) rc = drb_ngp_rgb_mean(pp, feat, n, e->host_dirs, e->ndirs, rgb, stream);
-  if (!rc)
+  if (!rc) {
+    if (!g_surf_ev[0]) { cudaEventCreate(&g_surf_ev[0]); cudaEventCreate(&g_surf_ev[1]); }
+    cudaEventRecord(g_surf_ev[0], stream);
     rc = surface_mask_impl(pp, e->occ_binary, e->res, e->roi_aabb, e->scene_aabb, points, n, e->cam_origins,
                            e->ncams, e->render_step_size, e->cut_off,
                            e->surface_only_where_dense ? density_mask : nullptr, surface_mask, stream);
+    cudaEventRecord(g_surf_ev[1], stream);
+    g_surf_valid = true;
+  }
   if (!rc) {
     finish_extract_kernel<<<cdiv(n, 256), 256, 0, stream>>>(e->occupied, n, points, rgb, surface_mask, alpha,
                                                            density_mask, voxel_grid);

@@ -76,6 +76,93 @@ extern "C" int drb_trilinear_gather(const float* p1, int dc, int hc, int wc, int
 }
 
 // ------------------------------------------------------------------------------------------
+// Output-sparse FPN support.  p1 is only ever read by the gather above, so the two convolutions that
+// hold 84 % of the FLOPs (pyramid_transformation_1, upsample_transform_1) need only the 128-voxel output
+// tiles that contain a voxel the gather touches (plus a one-voxel halo for the layer before).
+// mark: need[d][h][w] = 1 for the 8 trilinear corners of every masked voxel (same index arithmetic as
+// trilinear_gather_kernel).  list: tiles whose (optionally 1-dilated) box contains a needed voxel.
+// ------------------------------------------------------------------------------------------
+__global__ void mark_need_kernel(const long long* __restrict__ mask, int k, int X, int Y, int Z, int dc,
+                                 int hc, int wc, uint8_t* __restrict__ need) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  const long long idx = mask[i];
+  const int z = (int)(idx % Z);
+  const int y = (int)((idx / Z) % Y);
+  const int x = (int)(idx / ((long long)Z * Y));
+  const float sd = Z > 1 ? (float)(dc - 1) / (float)(Z - 1) : 0.f;
+  const float sh = X > 1 ? (float)(hc - 1) / (float)(X - 1) : 0.f;
+  const float sw = Y > 1 ? (float)(wc - 1) / (float)(Y - 1) : 0.f;
+  const int d0 = (int)(sd * (float)z), h0 = (int)(sh * (float)x), w0 = (int)(sw * (float)y);
+  const int d1 = d0 + (d0 < dc - 1 ? 1 : 0), h1 = h0 + (h0 < hc - 1 ? 1 : 0), w1 = w0 + (w0 < wc - 1 ? 1 : 0);
+  const int ds[2] = {d0, d1}, hs[2] = {h0, h1}, ws[2] = {w0, w1};
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) need[((long long)ds[a] * hc + hs[b]) * wc + ws[c]] = 1;
+}
+
+__global__ void tile_list_kernel(const uint8_t* __restrict__ need, int g, int d, int h, int w, int bg, int bd,
+                                 int bh, int bw, int tg, int td, int th, int tw, int dilate,
+                                 int* __restrict__ list, int* __restrict__ count,
+                                 unsigned long long* __restrict__ total) {
+  const int t = blockIdx.x;                     // one block per tile
+  if (t >= tg * td * th * tw) return;
+  int r = t;
+  const int iw = r % tw; r /= tw;
+  const int ih = r % th; r /= th;
+  const int id = r % td; r /= td;
+  const int ig = r;
+  const int ew = bw + 2 * dilate, eh = bh + 2 * dilate, ed = bd + 2 * dilate;
+  const int vox = bg * ed * eh * ew;
+  int any = 0;
+  for (int v = threadIdx.x; v < vox && !any; v += blockDim.x) {
+    int q = v;
+    const int xw = iw * bw - dilate + q % ew; q /= ew;
+    const int yh = ih * bh - dilate + q % eh; q /= eh;
+    const int zd = id * bd - dilate + q % ed; q /= ed;
+    const int gg = ig * bg + q;
+    if (xw >= 0 && xw < w && yh >= 0 && yh < h && zd >= 0 && zd < d && gg < g)
+      any |= need[(((long long)gg * d + zd) * h + yh) * w + xw];
+  }
+  if (__syncthreads_or(any) && threadIdx.x == 0) {
+    list[atomicAdd(count, 1)] = t;
+    if (total) atomicAdd(total, 1ull);          // running total for the roofline bookkeeping
+  }
+}
+
+// need: uint8 [g][dc][hc][wc] (zeroed by the call), masks of the g grids, tile lists for the conv
+// output (dilate 0) and for its input side (dilate 1).  counts: int[2] device.
+extern "C" int drb_fpn_need_tiles(const long long* const* masks_host, const int* ks_host, int g, int X, int Y,
+                                  int Z, int dc, int hc, int wc, uint8_t* need, int* list_out, int* list_in,
+                                  int* counts, unsigned long long* totals, cudaStream_t stream) {
+  DRB_REQUIRE(masks_host && ks_host && need && list_out && list_in && counts && g > 0,
+              "drb_fpn_need_tiles: null argument");
+  const long long vol = (long long)dc * hc * wc;
+  DRB_CUDA_OK(cudaMemsetAsync(need, 0, (size_t)g * vol, stream));
+  DRB_CUDA_OK(cudaMemsetAsync(counts, 0, 2 * sizeof(int), stream));
+  for (int i = 0; i < g; ++i) {
+    if (ks_host[i] == 0) continue;
+    mark_need_kernel<<<cdiv(ks_host[i], 256), 256, 0, stream>>>(masks_host[i], ks_host[i], X, Y, Z, dc, hc, wc,
+                                                              need + i * vol);
+    DRB_LAUNCH_OK();
+  }
+  int box[4], tiles[4];
+  int rc = drb_conv3d_tile_shape(g, dc, hc, wc, box, tiles);
+  if (rc) return rc;
+  const int nt = tiles[0] * tiles[1] * tiles[2] * tiles[3];
+  tile_list_kernel<<<nt, 128, 0, stream>>>(need, g, dc, hc, wc, box[0], box[1], box[2], box[3], tiles[0],
+                                           tiles[1], tiles[2], tiles[3], 0, list_out, counts, totals);
+  DRB_LAUNCH_OK();
+  tile_list_kernel<<<nt, 128, 0, stream>>>(need, g, dc, hc, wc, box[0], box[1], box[2], box[3], tiles[0],
+                                           tiles[1], tiles[2], tiles[3], 1, list_in, counts + 1, totals ? totals + 1 : nullptr);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // R4.  One round: key = (cloud, cx, cy, cz) packed into 64 bits (21-bit biased cell coordinates),
 // stable radix sort of (key, row), segment heads by key change, one warp per output cell averaging
 // its member rows in ascending input-row order (the oracle's defined order).

@@ -147,6 +147,8 @@ class NeRFRegTr(nn.Module):
         self.transformer_encoder = _CrossEncoder(layer, 6, nn.LayerNorm(pos_emb_dim))
         self.correspondence_decoder = _Decoder(pos_emb_dim, self.pos_embed)
         self._engines = {}
+        # evaluate the two level-1 FPN convolutions only where the masked gather reads p1 (exact)
+        self.sparse_fpn = True
         self._warned_grad = False
         self.last_token_counts = (0, 0)
 
@@ -264,6 +266,7 @@ class NeRFRegTr(nn.Module):
             ent = self._get_engine((X, Y, Z), device, max(src_mask.numel(), tgt_mask.numel()))
             self._sync_params(ent)
             _lib.check(lib.drb_engine_set_training(ent["handle"], 1 if self.training else 0))
+            _lib.check(lib.drb_engine_set_sparse_fpn(ent["handle"], 1 if self.sparse_fpn else 0))
             io = _lib.PairIO(
                 src_grid=src.data_ptr(), tgt_grid=tgt.data_ptr(),
                 s_ch=src.stride(1), s_z=src.stride(2), s_x=src.stride(3), s_y=src.stride(4),

@@ -16,9 +16,13 @@ for seed in (500, 501, 502, 503):
     st = (ctypes.c_ulonglong * 4)()
     lib.drb_debug_march_stats(st, 1)
     g, m = pkg.extract_block(f, sg, occ_d, meta, dev)
-    torch.cuda.synchronize(); t = time.time()
-    g, m = pkg.extract_block(f, sg, occ_d, meta, dev)
-    torch.cuda.synchronize(); dt = (time.time() - t) * 1e3
+    ts = []
+    for rep in range(6):
+        torch.cuda.synchronize(); t = time.time()
+        g, m = pkg.extract_block(f, sg, occ_d, meta, dev)
+        torch.cuda.synchronize(); ts.append((time.time() - t) * 1e3)
+    ts.sort(); dt = ts[len(ts)//2]
+    print('   times', [round(v,1) for v in ts])
     lib.drb_debug_march_stats(st, 1)
     rays, skips, samples, iters = [int(v) / 2 for v in st]
     print('seed', seed, 'kept', m.numel(), 'ms', round(dt, 1), 'rays %.2fM skips/ray %.1f samples/ray %.2f warp-iters %.2fM samples/warp-iter %.1f' % (rays/1e6, skips/max(rays,1), samples/max(rays,1), iters/1e6, samples/max(iters,1)))

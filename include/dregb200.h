@@ -68,7 +68,15 @@ typedef struct drb_conv3d_desc {
   void* out_hi;            /* 16-bit [m][ld_out] or NULL                                    */
   void* out_lo;            /* fp16 [m][ld_out] or NULL (non-NULL => hi is fp16 too)         */
   long long ld_out;        /* row pitch in elements, 0 -> cout; multiple of 8               */
+  /* Output-sparse mode (optional, both or neither): only the 128-row output tiles listed in
+   * tile_list[0 .. *tile_count) are computed; rows of other tiles are left untouched.  Tile
+   * numbering: see drb_conv3d_tile_shape.  Device pointers.                                         */
+  const int* tile_list;
+  const int* tile_count;
 } drb_conv3d_desc;
+/* Geometry of the 128-row output tiles drb_conv3d_igemm uses for a [g][d][h][w] volume: box extents
+ * (bg, bd, bh, bw) and tile counts (tg, td, th, tw); tile index = ((ig*td + id)*th + ih)*tw + iw. */
+int drb_conv3d_tile_shape(int g, int d, int h, int w, int box[4], int tiles[4]);
 int drb_conv3d_igemm(const drb_conv3d_desc* desc, drb_stream_t stream);
 
 /* fp32 -> planes (lo == NULL: one bf16 plane; else fp16 hi/lo pair). */
@@ -133,6 +141,15 @@ int drb_trilinear_gather(const float* p1, int dc, int hc, int wc, int c, const f
                          long long s_ch, long long s_z, long long s_x, long long s_y, int X, int Y,
                          int Z, const long long* mask, int k, float* rows_out, int ld_rows,
                          drb_stream_t stream);
+
+/* Output-sparse FPN: p1 is only read by drb_trilinear_gather, so pyramid_transformation_1 and
+ * upsample_transform_1 (84 % of the FLOPs) are evaluated on the tiles the gather needs.  need: uint8
+ * [g][dc][hc][wc] scratch; masks_host / ks_host: host arrays of g device mask pointers and lengths;
+ * list_out: tiles holding a needed p1 voxel; list_in: tiles holding a voxel within one voxel of one
+ * (inputs of the 3^3 convolution); counts: device int[2].  Tile numbering: drb_conv3d_tile_shape. */
+int drb_fpn_need_tiles(const long long* const* masks_host, const int* ks_host, int g, int X, int Y, int Z,
+                       int dc, int hc, int wc, uint8_t* need, int* list_out, int* list_in, int* counts,
+                       unsigned long long* totals /* optional running totals [2] */, drb_stream_t stream);
 
 /* R4: hierarchical voxel-average down-sampling (conerf/register/grid_downsample.py:6-94).
  * rows [n_src + n_tgt][ld] = [x y z 0 | 256 features]; cells of size dl0 * 2^round; rows of one
@@ -229,6 +246,10 @@ int drb_extract_block(const drb_ngp_params* p, const drb_extract_desc* e, float*
                       float* alpha, uint8_t* density_mask, uint8_t* surface_mask, float* voxel_grid,
                       drb_stream_t stream);
 
+/* Device time (ms) of the surface-field kernel inside the calling thread's most recent
+ * drb_extract_block (roofline instrumentation; waits for that kernel). */
+int drb_extract_last_surface_ms(float* host_ms);
+
 /* ------------------------------------------------------------------------------------------
  * Whole-path engine: NeRFRegTr.forward (conerf/register/nerf_regtr.py:112-248) without Python in
  * the loop.  Parameters are addressed by the reference's state-dict key.
@@ -255,6 +276,9 @@ long long drb_engine_param_numel(const drb_engine* e, int i);
 int drb_engine_bind_param(drb_engine* e, int i, float* device_ptr);
 int drb_engine_commit_params(drb_engine* e, drb_stream_t stream);
 int drb_engine_set_training(drb_engine* e, int training_bn);
+/* on (default): evaluate the level-1 FPN convolutions only on the output tiles the masked gather reads
+ * (identical results at every voxel that is read); off: dense evaluation (debug taps of p1). */
+int drb_engine_set_sparse_fpn(drb_engine* e, int on);
 
 typedef struct drb_pair_io {
   const float* src_grid;   /* fp32 [1,7,Z,X,Y] view, element strides below                   */

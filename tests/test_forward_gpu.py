@@ -71,6 +71,7 @@ def test_stage_taps_64(pkg, cuda):
     sd = pkg.synthetic.seeded_state_dict(model, seed=0, attn_gain=4.0)
     model.load_state_dict(sd)
     model = model.to(cuda).train(True)
+    model.sparse_fpn = False            # the taps compare whole feature maps
     data = pkg.synthetic.make_pair(res=64, pair_id=1)
     cap = {}
     with torch.no_grad():
@@ -83,6 +84,24 @@ def test_stage_taps_64(pkg, cuda):
             err = _relerr(got, ref)
             print(name, side, "%.2e" % err)
             assert err < 2e-4, "%s/%s drifted: %.3e" % (name, side, err)
+
+
+def test_sparse_fpn_equals_dense(pkg, cuda):
+    """Output-sparse level-1 FPN convolutions: every output the path reads is unchanged (the backbone's
+    split-K layers add atomically, so agreement is to rounding, not bit for bit)."""
+    torch.manual_seed(0)
+    model = pkg.NeRFRegTr()
+    model.load_state_dict(pkg.synthetic.seeded_state_dict(model, seed=0, attn_gain=4.0))
+    model = model.to(cuda).train(True)
+    data = pkg.synthetic.to_device(pkg.synthetic.make_pair(res=64, pair_id=2), cuda)
+    outs = []
+    for sparse in (True, False):
+        model.sparse_fpn = sparse
+        with torch.no_grad():
+            outs.append(model(dict(data)))
+    for k in ("src_feats", "tgt_feats", "src_kp_warped", "tgt_kp_warped"):
+        assert _relerr(outs[0][k][0], outs[1][k][0].cpu()) < 1e-4, k
+    assert torch.equal(outs[0]["src_kp"][0], outs[1]["src_kp"][0])
 
 
 def test_forward_bf16_mode_runs(pkg, cuda):
