@@ -216,7 +216,7 @@ def run_ours(args):
         return q
 
     if not full:
-        host_pairs = [pkg.synthetic.make_pair(res=RES, pair_id=rank + world * i) for i in range(N_RESIDENT_PAIRS)]
+        host_pairs = [pkg.synthetic.make_pair(res=RES, pair_id=i) for i in range(N_RESIDENT_PAIRS)]
         dev_pairs = [pkg.synthetic.to_device(p, dev) for p in host_pairs]
         pinned = [pin_grid_dict(p) for p in host_pairs]
         h2d_bytes = sum(v.numel() * v.element_size() for k, v in pinned[0].items()
@@ -231,14 +231,47 @@ def run_ours(args):
                 dist.all_gather(gathered, pose.contiguous())      # per-pair SE(3), 48 B per rank
             return out
 
-        def step_e2e(i):
+        # e2e: double-buffered H2D on a side stream (the copy of step i+1 overlaps the compute of step i);
+        # every timed step still pays one full H2D of its inputs and one D2H of its pose.
+        side = torch.cuda.Stream()
+        slots = [{k: (torch.empty_strided(v.shape, v.stride(), dtype=v.dtype, device=dev) if torch.is_tensor(v) else v)
+                  for k, v in pinned[0].items()} for _ in range(2)]
+        for sl in slots:        # masks differ in length between pairs: allocate the longest
+            for k in ("src_mask", "tgt_mask"):
+                sl[k] = torch.empty(max(p[k].numel() for p in pinned), dtype=torch.int64, device=dev)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        state = {"primed": False}
+
+        def prefetch(i):
+            sl, src = slots[i % 2], pinned[i % N_RESIDENT_PAIRS]
+            side.wait_event(consumed[i % 2])
+            with torch.cuda.stream(side):
+                for k, v in src.items():
+                    if torch.is_tensor(v):
+                        (sl[k][:v.numel()] if k.endswith("_mask") else sl[k]).copy_(v, non_blocking=True)
+                ready[i % 2].record(side)
+
+        def step_e2e(_):
+            i = state["n"] = state.get("n", -1) + 1          # running step index (warm-up and timed steps)
+            if not state["primed"]:
+                for e_ in consumed:
+                    e_.record()
+                prefetch(i)
+                state["primed"] = True
             src = pinned[i % N_RESIDENT_PAIRS]
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            prefetch(i + 1)
+            sl = slots[i % 2]
+            data = dict(sl)
+            data["src_mask"] = sl["src_mask"][:src["src_mask"].numel()]
+            data["tgt_mask"] = sl["tgt_mask"][:src["tgt_mask"].numel()]
             with torch.no_grad():
-                data = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in src.items()}
                 out = model(data)
                 pose = out["pose"][-1]
                 if world > 1:
                     dist.all_gather(gathered, pose.contiguous())
+                consumed[i % 2].record()
                 return pose.cpu()
     else:
         # extract inputs: two random-weight NeRF blocks per pair, a shell occupancy, a ring of cameras
@@ -249,7 +282,7 @@ def run_ours(args):
         sgrid = pkg.SampleGrid(list(pkg.synthetic.AABB), RES)
         host_fields, dev_fields = [], []
         for i in range(N_RESIDENT_PAIRS):
-            pid = rank + world * i
+            pid = i          # every rank runs the same synthetic pairs: per-GPU work is fixed (weak scaling)
             pair = [pkg.synthetic.make_ngp_field(seed=500 + 2 * pid + side) for side in (0, 1)]
             host_fields.append([(f.mlp_base.params.detach().clone().pin_memory(),
                                  f.color_mlp.params.detach().clone().pin_memory()) for f in pair])
@@ -302,15 +335,42 @@ def run_ours(args):
                     tot += ms_.value
             return tot
 
-        def step_e2e(i):
-            j = i % N_RESIDENT_PAIRS
-            with torch.no_grad():
-                for f, (hp, hc) in zip(dev_fields[j], host_fields[j]):
+        # e2e: the NeRF parameters of step i+1 are copied on a side stream while step i computes
+        side = torch.cuda.Stream()
+        slot_fields = [[pkg.synthetic.make_ngp_field(seed=900 + s_ * 2 + side_).to(dev) for side_ in (0, 1)]
+                       for s_ in range(2)]
+        slot_occ = [torch.empty_like(occ_pinned, device=dev) for _ in range(2)]
+        slot_poses = [torch.empty_like(poses_pinned, device=dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        state = {"primed": False}
+
+        def prefetch(i):
+            j, sl = i % N_RESIDENT_PAIRS, i % 2
+            side.wait_event(consumed[sl])
+            with torch.cuda.stream(side), torch.no_grad():
+                for f, (hp, hc) in zip(slot_fields[sl], host_fields[j]):
                     f.mlp_base.params.data.copy_(hp, non_blocking=True)
                     f.color_mlp.params.data.copy_(hc, non_blocking=True)
-                occ_d = occ_pinned.to(dev, non_blocking=True).bool()
-                meta_d = dict(meta_host, camera_poses=poses_pinned.to(dev, non_blocking=True))
-                return extract_and_register(dev_fields[j], occ_d, meta_d, False).cpu()
+                slot_occ[sl].copy_(occ_pinned, non_blocking=True)
+                slot_poses[sl].copy_(poses_pinned, non_blocking=True)
+                ready[sl].record(side)
+
+        def step_e2e(_):
+            i = state["n"] = state.get("n", -1) + 1          # running step index (warm-up and timed steps)
+            if not state["primed"]:
+                for e_ in consumed:
+                    e_.record()
+                prefetch(i)
+                state["primed"] = True
+            sl = i % 2
+            torch.cuda.current_stream().wait_event(ready[sl])
+            prefetch(i + 1)
+            with torch.no_grad():
+                meta_d = dict(meta_host, camera_poses=slot_poses[sl])
+                pose = extract_and_register(slot_fields[sl], slot_occ[sl].bool(), meta_d, False)
+                consumed[sl].record()
+                return pose.cpu()
 
     def barrier():
         if world > 1:
@@ -366,12 +426,15 @@ def run_ours(args):
             "metric": "nerf_pairs_per_sec_128cube", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (split-bf16 x3 tensor-core products, fp32 accumulate)" if args.precision == "fp32" else "bf16",
+            "dtype": "f32" if args.precision == "fp32" else "bf16",
             "data": "synthetic",
-            "config": {"workload": ("single pair, 128^3 grid, full extract->register forward on 1xB200, %s" if full else
-                                    "single pair, 128^3 grid, register forward (NeRFRegTr.forward) on 1xB200, %s")
-                                   % ("fp32" if args.precision == "fp32" else "bf16"),
+            "config": {"workload": ("single pair per GPU, 128^3 grid, full extract->register forward on %dxB200, %s" if full else
+                                    "single pair per GPU, 128^3 grid, register forward (NeRFRegTr.forward) on %dxB200, %s")
+                                   % (world, "fp32" if args.precision == "fp32" else "bf16"),
                        "stage": args.stage,
+                       "arithmetic": ("fp32 storage / accumulation; GEMM products as fp16 hi+lo operand pairs (22-bit "
+                                      "significands, 3 tensor-core MMAs per product)") if args.precision == "fp32"
+                                     else "bf16 GEMM operands, fp32 accumulation",
                        "extract": ({"candidate_cells_per_block": int(occ.sum()), "cameras": args.cams,
                                     "render_step_size": meta_host["render_step_size"],
                                     "stage_ms": {k: (v / max(stage_ms["n"], 1)) for k, v in stage_ms.items() if k != "n"}}
@@ -379,7 +442,8 @@ def run_ours(args):
                        "resolution": RES, "pairs_per_step_per_gpu": 1, "masked_voxels": masked,
                        "tokens": [ns, nt], "bn_mode": "batch statistics",
                        "l2": "working set per step (2 x 58.7 MB grids, 0.6 GB weight planes, >3 GB activations) exceeds the 126 MB L2",
-                       "parallelism": "pairs sharded over %d GPU(s), one NCCL all-gather of the per-pair SE(3)" % world},
+                       "parallelism": "pairs sharded over %d GPU(s) (every rank times the same %d synthetic pairs: fixed "
+                                      "per-GPU work), one NCCL all-gather of the per-pair SE(3) per step" % (world, N_RESIDENT_PAIRS)},
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": 48, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),

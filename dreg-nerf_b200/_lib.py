@@ -21,7 +21,7 @@ class Conv3dDesc(C.Structure):
                 ("x_hi", c_void_p), ("x_lo", c_void_p), ("w_hi", c_void_p), ("w_lo", c_void_p),
                 ("bias", c_void_p), ("residual", c_void_p),
                 ("out", c_void_p), ("out_hi", c_void_p), ("out_lo", c_void_p),
-                ("ld_out", c_ll), ("tile_list", c_void_p), ("tile_count", c_void_p)]
+                ("ld_out", c_ll), ("bn_accum", c_void_p), ("tile_list", c_void_p), ("tile_count", c_void_p)]
 
 
 class Im2colDesc(C.Structure):
@@ -83,6 +83,8 @@ SIGNATURES = {
                                 c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "drb_scale_shift_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "drb_bn_apply": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                             c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "drb_maxpool3d": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "drb_upsample2_add": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -409,6 +409,100 @@ extern "C" int drb_scale_shift_act(const float* x, const float* scale, const flo
   return 0;
 }
 
+// Fused finalize + apply: every block derives scale / shift of all (g, c) from the fp64 sums (or the
+// running statistics) into shared memory, block 0 also performs the running-statistics update; then
+// y = relu?(x * scale + shift + residual).  One launch instead of bn_finalize + scale_shift_act.
+__global__ void bn_apply_kernel(const float* __restrict__ x, const double* __restrict__ accum, int g, long long m,
+                                int c, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                float* running_mean, float* running_var, int training, float momentum, float eps,
+                                const float* __restrict__ residual, int relu, long long total4,
+                                float* __restrict__ out, plane_t* __restrict__ out_hi,
+                                plane_t* __restrict__ out_lo) {
+  extern __shared__ float s_ss[];          // [g*c] scale, [g*c] shift
+  float* s_scale = s_ss;
+  float* s_shift = s_ss + (long long)g * c;
+  for (int i = threadIdx.x; i < g * c; i += blockDim.x) {
+    const int ch = i % c;
+    const float ga = gamma ? gamma[ch] : 1.f, be = beta ? beta[ch] : 0.f;
+    float sc, sf;
+    if (training) {
+      const double mean = accum[(long long)i * 2] / (double)m;
+      double var = accum[(long long)i * 2 + 1] / (double)m - mean * mean;
+      if (var < 0.0) var = 0.0;
+      sc = ga * (float)(1.0 / sqrt(var + (double)eps));
+      sf = be - (float)mean * sc;
+    } else {
+      sc = ga * (1.f / sqrtf(running_var[ch] + eps));
+      sf = be - running_mean[ch] * sc;
+    }
+    s_scale[i] = sc;
+    s_shift[i] = sf;
+  }
+  if (training && blockIdx.x == 0 && running_mean && running_var) {
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {     // sequential over g: g successive forward calls
+      float rm = running_mean[ch], rv = running_var[ch];
+      for (int gi = 0; gi < g; ++gi) {
+        const double mean = accum[((long long)gi * c + ch) * 2] / (double)m;
+        double var = accum[((long long)gi * c + ch) * 2 + 1] / (double)m - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double unbiased = m > 1 ? var * ((double)m / (double)(m - 1)) : var;
+        rm = (1.f - momentum) * rm + momentum * (float)mean;
+        rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+      }
+      running_mean[ch] = rm;
+      running_var[ch] = rv;
+    }
+  }
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int c4 = c >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const int cc = (int)(i % c4) * 4;
+    const int gi = (int)((i / c4) / m);
+    const float* sc = s_scale + (long long)gi * c + cc;
+    const float* sf = s_shift + (long long)gi * c + cc;
+    float4 v = *(const float4*)(x + i * 4);
+    v.x = fmaf(v.x, sc[0], sf[0]); v.y = fmaf(v.y, sc[1], sf[1]);
+    v.z = fmaf(v.z, sc[2], sf[2]); v.w = fmaf(v.w, sc[3], sf[3]);
+    if (residual) {
+      const float4 r = *(const float4*)(residual + i * 4);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    if (out) *(float4*)(out + i * 4) = v;
+    if (out_hi) {
+      const bool pair = out_lo != nullptr;
+      plane_t h0, l0, h1, l1, h2, l2, h3, l3;
+      split16(v.x, pair, h0, l0); split16(v.y, pair, h1, l1);
+      split16(v.z, pair, h2, l2); split16(v.w, pair, h3, l3);
+      *(uint2*)(out_hi + i * 4) = make_uint2(pack16x2(h0, h1), pack16x2(h2, h3));
+      if (pair) *(uint2*)(out_lo + i * 4) = make_uint2(pack16x2(l0, l1), pack16x2(l2, l3));
+    }
+  }
+}
+
+extern "C" int drb_bn_apply(const float* x, const double* accum, int g, long long m, int c, const float* gamma,
+                            const float* beta, float* running_mean, float* running_var, int training,
+                            float momentum, float eps, const float* residual, int relu, float* out, void* out_hi,
+                            void* out_lo, cudaStream_t stream) {
+  DRB_REQUIRE(x && g > 0 && m > 0 && c > 0 && c % 4 == 0 && (out || out_hi), "drb_bn_apply: bad arguments");
+  DRB_REQUIRE(training ? accum != nullptr : (running_mean && running_var), "drb_bn_apply: missing statistics");
+  const size_t smem = sizeof(float) * 2 * (size_t)g * c;
+  DRB_REQUIRE(smem <= 48 * 1024, "drb_bn_apply: g*c = %d exceeds the shared-memory table", g * c);
+  const long long total4 = (long long)g * m * c / 4;
+  // few, fat blocks: every block recomputes the (g, c) table
+  int grid = (int)((total4 + 256 * 8 - 1) / (256 * 8));
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  bn_apply_kernel<<<grid, 256, smem, stream>>>(x, accum, g, m, c, gamma, beta, running_mean, running_var, training,
+                                               momentum, eps, residual, relu, total4, out, (plane_t*)out_hi,
+                                               (plane_t*)out_lo);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void maxpool_kernel(const float* __restrict__ x, int g, int d, int h, int w, int c,
                                int od, int oh, int ow, float* __restrict__ out,

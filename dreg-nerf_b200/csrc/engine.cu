@@ -331,7 +331,8 @@ static int run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
                      int h, int wd, int cin, int k, const float* bias, const float* residual,
                      int relu, float scale, float* out, plane_t* out_hi, plane_t* out_lo, long long ld,
                      cudaStream_t s, const plane_t* w_hi = nullptr, const plane_t* w_lo = nullptr,
-                     int cout_override = 0, const int* tile_list = nullptr, const int* tile_count = nullptr) {
+                     int cout_override = 0, const int* tile_list = nullptr, const int* tile_count = nullptr,
+                     double* bn_accum = nullptr) {
   drb_conv3d_desc cd;
   memset(&cd, 0, sizeof(cd));
   cd.g = g; cd.d = d; cd.h = h; cd.w = wd;
@@ -346,6 +347,7 @@ static int run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
   cd.out = out; cd.out_hi = out_hi; cd.out_lo = out_lo;
   cd.ld_out = ld;
   cd.tile_list = tile_list; cd.tile_count = tile_count;
+  cd.bn_accum = bn_accum;
   e->launches += 1;
   if (!e->profile) return drb_conv3d_igemm(&cd, s);
   drb_engine::ProfRec r;
@@ -367,9 +369,13 @@ static inline plane_t* off(plane_t* p, long long n) { return p ? p + n : nullptr
 // conv (stride 1 via TMA implicit GEMM, otherwise im2col + 1x1x1 GEMM) into raw fp32 [g][m][cout]
 static int conv_any(drb_engine* e, const ConvW& w, const Act& in, int od, int oh, int ow, float* out,
                     cudaStream_t s) {
+  // Every caller feeds a BatchNorm.  The GEMM epilogue CAN produce the per-channel sums
+  // (drb_conv3d_desc.bn_accum, parity-tested), but its fp64 atomics were measured slower than the separate
+  // HBM-bound pass on B200 (+1.2 ms vs -0.85 ms per pair, round 1), so the engine keeps the separate pass.
+  double* acc = nullptr;
   if (!w.im2col) {
     return run_igemm(e, w, in.hi, in.lo, kG, in.d, in.h, in.w, w.cin, w.k, P(e, w.p_b), nullptr, 0,
-                     1.f, out, nullptr, nullptr, 0, s);
+                     1.f, out, nullptr, nullptr, 0, s, nullptr, nullptr, 0, nullptr, nullptr, acc);
   }
   drb_im2col_desc d;
   memset(&d, 0, sizeof(d));
@@ -381,7 +387,7 @@ static int conv_any(drb_engine* e, const ConvW& w, const Act& in, int od, int oh
   e->launches += 1;
   DRB_TRY(drb_im2col(&d, e->col_hi, e->col_lo, s));
   return run_igemm(e, w, e->col_hi, e->col_lo, kG, od, oh, ow, w.kpad, 1, P(e, w.p_b), nullptr, 0, 1.f,
-                   out, nullptr, nullptr, 0, s);
+                   out, nullptr, nullptr, 0, s, nullptr, nullptr, 0, nullptr, nullptr, acc);
 }
 
 // BatchNorm (+ residual, ReLU) of raw [g][m][c] into out (fp32 and/or planes)
@@ -392,10 +398,9 @@ static int bn_apply(drb_engine* e, const BnP& b, const float* rawp, long long m,
     e->launches += 2;
     DRB_TRY(drb_bn_stats(rawp, kG, m, b.c, e->bn_accum, s));
   }
-  e->launches += 2;
-  DRB_TRY(drb_bn_finalize(e->bn_accum, kG, m, b.c, P(e, b.p_w), P(e, b.p_b), P(e, b.p_rm), P(e, b.p_rv),
-                          training, 0.1f, 1e-5f, b.scale, b.shift, s));
-  return drb_scale_shift_act(rawp, b.scale, b.shift, residual, relu, kG, m, b.c, out, out_hi, out_lo, s);
+  e->launches += 1;
+  return drb_bn_apply(rawp, e->bn_accum, kG, m, b.c, P(e, b.p_w), P(e, b.p_b), P(e, b.p_rm), P(e, b.p_rv), training,
+                      0.1f, 1e-5f, residual, relu, out, out_hi, out_lo, s);
 }
 
 static int run_fpn(drb_engine* e, const drb_pair_io* io, cudaStream_t s) {

@@ -40,6 +40,7 @@ struct IgemmArgs {
   int cs;                // cluster size along M (1, 2 or 4): the weight tile is TMA-multicast
   int splits;            // split-K factor (> 1: partial sums are red.add'ed into a pre-zeroed `out`)
   int kper;              // k-iterations per split (multiple of chunk)
+  double* bn_accum;      // optional [G][Cout][2]: per-channel sum / sum of squares of the output (fused BN stats)
   const int* tile_list;  // optional: compacted list of M-tile indices to compute (output-sparse conv)
   const int* tile_count; // device scalar: number of entries in tile_list
   int relu;
@@ -149,11 +150,30 @@ __device__ __forceinline__ void epilogue_store32(const IgemmArgs& a, float (&f)[
   }
 }
 
+// Fused BatchNorm statistics: column sums of one 32-column block over the warp's 32 rows by a
+// transposing butterfly (31 shuffles; lane l ends up owning one column), then fp64 atomics.
+__device__ __forceinline__ float warp_colsum32(float (&t)[32], int lane, int& col) {
+  col = 0;
+#pragma unroll
+  for (int W = 16, mask = 16; mask >= 1; W >>= 1, mask >>= 1) {
+    const bool upper = (lane & mask) != 0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const float send = upper ? t[j] : t[j + W];
+      const float keep = upper ? t[j + W] : t[j];
+      t[j] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+    if (upper) col += W;
+  }
+  return t[0];
+}
+
 // The tensor core adds every MMA into the fp32 TMEM accumulator with truncation, so a long K chain
 // (K = 6912 -> 1296 MMAs in pair mode) drifts by ~1e-5.  The chain is therefore cut into chunks of
 // `chunk` k-iterations that ping-pong between two TMEM regions; the 8 accumulate warps drain each
 // finished chunk with tcgen05.ld and add it into fp32 registers (round-to-nearest), which also lets
 // the MMA warp start the next tile while the previous tile's epilogue is still storing.
+template <bool kBnStats>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
              const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -362,6 +382,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         tc_fence_before();
         mbar_arrive(tempty_bar(r));
       }
+      if (kBnStats) {
+        // all 32 lanes take part (shuffles); rows outside the volume contribute zeros
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (b * 32 < half) {
+            float tsum[32];
+            int col;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tsum[j] = row_ok ? acc[b * 32 + j] * a.acc_scale : 0.f;
+            const float csum = warp_colsum32(tsum, lane, col);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = row_ok ? acc[b * 32 + j] * a.acc_scale : 0.f;
+              tsum[j] = v * v;
+            }
+            const float csq = warp_colsum32(tsum, lane, col);
+            const int cidx = n0 + colhalf * half + b * 32 + col;
+            if (cidx < a.Cout && g0 < a.G) {
+              double* dst = a.bn_accum + ((long long)g0 * a.Cout + cidx) * 2;
+              atomicAdd(dst, (double)csum);
+              atomicAdd(dst + 1, (double)csq);
+            }
+          }
+        }
+      }
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int n = n0 + colhalf * half + b * 32;
@@ -516,6 +561,16 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   }
   a.tile_list = d->tile_list;
   a.tile_count = d->tile_count;
+  // BatchNorm statistics of the output: fused into the epilogue when a tile never straddles two grids
+  // and the reduction is not split; otherwise a separate pass over the finished output.
+  a.bn_accum = nullptr;
+  bool bn_separate = false;
+  if (d->bn_accum) {
+    DRB_REQUIRE(d->out && !d->bias && !d->residual && !d->relu && !d->tile_list,
+                "drb_conv3d_igemm: bn_accum needs the plain fp32-output epilogue");
+    DRB_CUDA_OK(cudaMemsetAsync(d->bn_accum, 0, sizeof(double) * 2 * (size_t)a.G * a.Cout, stream));
+    if (a.splits == 1 && a.bg == 1) a.bn_accum = d->bn_accum; else bn_separate = true;
+  }
   DRB_REQUIRE((d->tile_list == nullptr) == (d->tile_count == nullptr), "drb_conv3d_igemm: tile_list / tile_count pair");
   if (a.tile_list) { a.splits = 1; a.kper = kiters_h; }
   {
@@ -587,7 +642,9 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    DRB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DRB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+    DRB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024));
     attr_set = true;
   }
@@ -610,7 +667,13 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DRB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel, mA[0], mA[1], mB[0], mB[1], a));
+  // two instantiations: the BatchNorm-statistics epilogue costs registers, the big FPN layers do not pay
+  if (a.bn_accum)
+    DRB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel<true>, mA[0], mA[1], mB[0], mB[1], a));
+  else
+    DRB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel<false>, mA[0], mA[1], mB[0], mB[1], a));
+  if (bn_separate)
+    return drb_bn_stats(a.out, a.G, (long long)a.D * a.H * a.W, a.Cout, d->bn_accum, stream);
   return 0;
 }
 

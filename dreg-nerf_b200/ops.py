@@ -68,7 +68,7 @@ def pack_conv_weight_im2col(w, kpad, pair=True):
 
 
 def conv3d_igemm(x_planes, w_planes, k, planes=2, bias=None, residual=None, relu=False, out_scale=1.0,
-                 want_f32=True, want_planes=False, cout=None, ld_out=0):
+                 want_f32=True, want_planes=False, cout=None, ld_out=0, bn_accum=None):
     """x_planes: (hi, lo) of [g, d, h, w, cin]; w_planes: (hi, lo, scale) of [taps, cout, cin]."""
     x_hi, x_lo = x_planes
     w_hi, w_lo, w_scale = w_planes
@@ -89,7 +89,8 @@ def conv3d_igemm(x_planes, w_planes, k, planes=2, bias=None, residual=None, relu
                            residual=residual.data_ptr() if residual is not None else None,
                            out=out.data_ptr() if out is not None else None,
                            out_hi=o_hi.data_ptr() if o_hi is not None else None,
-                           out_lo=o_lo.data_ptr() if o_lo is not None else None, ld_out=ld)
+                           out_lo=o_lo.data_ptr() if o_lo is not None else None, ld_out=ld,
+                           bn_accum=bn_accum.data_ptr() if bn_accum is not None else None)
     with _dev(x_hi):
         check(_lib.load().drb_conv3d_igemm(C.byref(desc), stream_ptr()), "drb_conv3d_igemm")
     return out, (o_hi, o_lo)
@@ -148,6 +149,24 @@ def batchnorm(x, gamma, beta, running_mean, running_var, training, residual=None
                                   stream_ptr()), "drb_bn_finalize")
         check(lib.drb_scale_shift_act(ptr(x), ptr(scale), ptr(shift), ptr(residual), int(relu), g, m, c,
                                       ptr(out), ptr(o_hi), ptr(o_lo), stream_ptr()), "drb_scale_shift_act")
+    return out, (o_hi, o_lo)
+
+
+def batchnorm_fused(x, gamma, beta, running_mean, running_var, training, residual=None, relu=False,
+                    momentum=0.1, eps=1e-5, want_planes=False):
+    """Same contract as ``batchnorm`` through the single-launch drb_bn_apply."""
+    g, m, c = x.shape
+    lib = _lib.load()
+    accum = torch.empty((g, c, 2), dtype=torch.float64, device=x.device)
+    out = torch.empty_like(x)
+    o_hi = torch.empty_like(x, dtype=torch.float16) if want_planes else None
+    o_lo = torch.empty_like(x, dtype=torch.float16) if want_planes else None
+    with _dev(x):
+        if training:
+            check(lib.drb_bn_stats(ptr(x), g, m, c, ptr(accum), stream_ptr()), "drb_bn_stats")
+        check(lib.drb_bn_apply(ptr(x), ptr(accum), g, m, c, ptr(gamma), ptr(beta), ptr(running_mean),
+                               ptr(running_var), int(training), momentum, eps, ptr(residual), int(relu), ptr(out),
+                               ptr(o_hi), ptr(o_lo), stream_ptr()), "drb_bn_apply")
     return out, (o_hi, o_lo)
 
 

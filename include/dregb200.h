@@ -68,6 +68,9 @@ typedef struct drb_conv3d_desc {
   void* out_hi;            /* 16-bit [m][ld_out] or NULL                                    */
   void* out_lo;            /* fp16 [m][ld_out] or NULL (non-NULL => hi is fp16 too)         */
   long long ld_out;        /* row pitch in elements, 0 -> cout; multiple of 8               */
+  /* Optional fused BatchNorm statistics: double [g][cout][2] receiving per-channel sum and sum of
+   * squares of the fp32 output (zeroed by the call; plain epilogue only: no bias/residual/relu).      */
+  double* bn_accum;
   /* Output-sparse mode (optional, both or neither): only the 128-row output tiles listed in
    * tile_list[0 .. *tile_count) are computed; rows of other tiles are left untouched.  Tile
    * numbering: see drb_conv3d_tile_shape.  Device pointers.                                         */
@@ -124,6 +127,13 @@ int drb_bn_finalize(const double* accum, int g, long long m, int c, const float*
 int drb_scale_shift_act(const float* x, const float* scale, const float* shift,
                         const float* residual, int relu, int g, long long m, int c, float* out,
                         void* out_hi, void* out_lo, drb_stream_t stream);
+
+/* drb_bn_finalize + drb_scale_shift_act in one launch (what the engine uses): statistics from `accum`
+ * (training) or the running buffers (eval), running-statistics update, normalise, residual, ReLU. */
+int drb_bn_apply(const float* x, const double* accum, int g, long long m, int c, const float* gamma,
+                 const float* beta, float* running_mean, float* running_var, int training, float momentum,
+                 float eps, const float* residual, int relu, float* out, void* out_hi, void* out_lo,
+                 drb_stream_t stream);
 
 /* nn.MaxPool3d(3, 2, 1) (resnet3d.py:123) on fp32 [g][d][h][w][c]. */
 int drb_maxpool3d(const float* x, int g, int d, int h, int w, int c, float* out, void* out_hi,

@@ -90,6 +90,26 @@ def test_igemm_split_k(cuda, shape, cin, cout, k):
     assert _rel(out, ref) < 2e-6
 
 
+@pytest.mark.parametrize("shape,cin,cout", [((2, 8, 8, 8), 64, 256), ((2, 6, 10, 12), 128, 64), ((2, 4, 4, 4), 512, 128)])
+def test_igemm_fused_bn_sums(cuda, shape, cin, cout):
+    """Per-channel sum / sum of squares of the conv output from the GEMM epilogue (or the fallback pass
+    when the reduction is split or a tile straddles two grids)."""
+    ops = _ops()
+    g, d, h, w = shape
+    gen = torch.Generator().manual_seed(cin * 3 + cout)
+    x = torch.randn(g, cin, d, h, w, generator=gen)
+    wt = torch.randn(cout, cin, 3, 3, 3, generator=gen) / math.sqrt(cin * 27)
+    xp = ops.split_planes(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda))
+    wp = ops.pack_conv_weight(wt.to(cuda))
+    accum = torch.full((g, cout, 2), 7.0, dtype=torch.float64, device=cuda)
+    out, _ = ops.conv3d_igemm(xp, wp, 3, planes=2, bn_accum=accum)
+    torch.cuda.synchronize()
+    ref = F.conv3d(x.double(), wt.double(), padding=1)
+    assert _rel(out, ref.permute(0, 2, 3, 4, 1).reshape(-1, cout)) < 2e-6
+    assert _rel(accum[:, :, 0], ref.sum(dim=(2, 3, 4))) < 1e-5
+    assert _rel(accum[:, :, 1], (ref * ref).sum(dim=(2, 3, 4))) < 1e-5
+
+
 def test_igemm_epilogue(cuda):
     """out = relu((acc + bias) * scale + residual), fp32 and plane outputs."""
     ops = _ops()
@@ -138,8 +158,9 @@ def test_im2col_stem_matches_generic(cuda):
     assert torch.equal(a_hi, b_hi) and torch.equal(a_lo, b_lo)
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("training", [True, False])
-def test_batchnorm(cuda, training):
+def test_batchnorm(cuda, training, fused):
     ops = _ops()
     gen = torch.Generator().manual_seed(3)
     g, m, c = 2, 1000, 128
@@ -148,8 +169,9 @@ def test_batchnorm(cuda, training):
     rm, rv = torch.randn(c, generator=gen) * 0.1, torch.rand(c, generator=gen) + 0.5
     res = torch.randn(g, m, c, generator=gen)
     rm_d, rv_d = rm.clone().to(cuda), rv.clone().to(cuda)
-    out, (hi, lo) = ops.batchnorm(x.to(cuda), gamma.to(cuda), beta.to(cuda), rm_d, rv_d, training,
-                                  residual=res.to(cuda), relu=True, want_planes=True)
+    fn = ops.batchnorm_fused if fused else ops.batchnorm
+    out, (hi, lo) = fn(x.to(cuda), gamma.to(cuda), beta.to(cuda), rm_d, rv_d, training,
+                       residual=res.to(cuda), relu=True, want_planes=True)
     torch.cuda.synchronize()
     rm_ref, rv_ref = rm.clone(), rv.clone()
     refs = []
