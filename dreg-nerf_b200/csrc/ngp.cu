@@ -379,123 +379,499 @@ __device__ __forceinline__ float dist_to_next_voxel(const MarchArgs& a, const fl
   return fmaxf(t, 0.f);
 }
 
-// Persistent ray queue.  The naive one-thread-per-ray loop ran with 2.9 of 32 lanes active (rays of
-// a warp end at very different times, and the expensive density sample alternates with cheap empty-
-// space skips).  Here every lane owns a ray slot and refills it from a global counter (chunks of 8
-// consecutive rays = neighbouring points of one camera); per iteration each lane first advances its
-// ray through empty space on its own until a sample position inside an occupied cell is pending
-// (phase A, cheap, divergent), then ALL lanes evaluate the hash grid + MLP for their pending sample
-// together (phase B, expensive, convergent).  The per-ray arithmetic (t0/t1/tm updates, skip rule,
-// termination tests) is unchanged, so masks are identical to the scalar oracle.
-__device__ unsigned long long g_march_stats[4];   // rays, skip events, samples, outer iterations (debug)
+// ------------------------------------------------------------------------------------------
+// Compile-time level table (must equal host_levels(); checked once at run time by levels_ok()).
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t lvl_res(int l) {
+  constexpr uint32_t r[kLevels] = {16, 24, 34, 49, 71, 102, 148, 213, 308, 446, 646, 934, 1352, 1956, 2831, 4096};
+  return r[l];
+}
+__host__ __device__ constexpr uint32_t lvl_size(int l) {
+  constexpr uint32_t s[kLevels] = {4096, 13824, 39304, 117656, 357912, 524288, 524288, 524288,
+                                   524288, 524288, 524288, 524288, 524288, 524288, 524288, 524288};
+  return s[l];
+}
+__host__ __device__ constexpr uint32_t lvl_off(int l) {
+  uint32_t o = 0;
+  for (int i = 0; i < l; ++i) o += lvl_size(i);
+  return o;
+}
+__host__ __device__ constexpr bool lvl_dense(int l) {
+  return (uint64_t)lvl_res(l) * lvl_res(l) * lvl_res(l) <= (uint64_t)lvl_size(l);
+}
+static bool levels_ok(const LevelTable& t) {
+  bool ok = true;
+  for (int l = 0; l < kLevels; ++l)
+    ok = ok && t.res[l] == lvl_res(l) && t.size[l] == lvl_size(l) && t.offset[l] == lvl_off(l);
+  return ok;
+}
+
+// One level of the hash encoding with every level constant folded: dense levels index
+// x + y*res + z*res^2 with a conditional wrap (the index stays below 2 * size for points inside the
+// unit cube), hashed levels share the per-axis products between the 8 corners and mask with 2^19 - 1.
+// Same arithmetic and summation order as hash_encode(): identical features for 0 < xn < 1.
+template <int L, int SMEM_LEVELS>
+__device__ __forceinline__ void encode_level(const NgpDev& p, const float2* __restrict__ s_lvl,
+                                             const float xn[3], float& o0, float& o1) {
+  constexpr uint32_t res = lvl_res(L), size = lvl_size(L), off = lvl_off(L);
+  const float scale = p.lv.scale[L];
+  float fr[3];
+  uint32_t g[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float pos = fmaf(xn[d], scale, 0.5f);
+    const float fl = floorf(pos);
+    fr[d] = pos - fl;
+    g[d] = (uint32_t)(int)fl;
+  }
+  uint32_t idx[8];
+  if constexpr (lvl_dense(L)) {
+    const uint32_t base = g[0] + g[1] * res + g[2] * (res * res);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t i = base + ((c & 1) ? 1u : 0u) + ((c & 2) ? res : 0u) + ((c & 4) ? res * res : 0u);
+      idx[c] = i >= size ? i - size : i;
+    }
+  } else {
+    static_assert(lvl_dense(L) || (size & (size - 1)) == 0, "hashed levels are powers of two");
+    const uint32_t hx[2] = {g[0], g[0] + 1u};
+    const uint32_t hy0 = g[1] * 2654435761u, hz0 = g[2] * 805459861u;
+    const uint32_t hy[2] = {hy0, hy0 + 2654435761u};
+    const uint32_t hz[2] = {hz0, hz0 + 805459861u};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) idx[c] = (hx[c & 1] ^ hy[(c >> 1) & 1] ^ hz[c >> 2]) & (size - 1u);
+  }
+  float2 v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if constexpr (L < SMEM_LEVELS) v[c] = s_lvl[off + idx[c]];
+    else v[c] = __ldg(p.table + off + idx[c]);
+  }
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float w = 1.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) w *= (c & (1 << d)) ? fr[d] : 1.f - fr[d];
+    a0 = fmaf(w, v[c].x, a0);
+    a1 = fmaf(w, v[c].y, a1);
+  }
+  o0 = a0;
+  o1 = a1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-level density evaluation of 32 samples (one per lane): hash encoding on the CUDA cores into
+// a 32 x 32 shared-memory tile, then layer 1 (32 -> 64) on the tensor cores as 3xTF32
+// (hi*hi + lo*hi + hi*lo, ~2^-21 relative), ReLU + layer 2 (64 -> 1) + quad shuffle reduction in
+// the accumulator layout.  Tile row pitch 36 words: conflict free for the 128-bit row stores and
+// for the m16n8k8 A-fragment loads; B fragments of W1 (hi, lo) are pre-arranged per (k-step,
+// n-tile, lane) at staging time.  No accumulator is live while the gathers are in flight, so the
+// compiler can keep several levels' loads outstanding.
+// ------------------------------------------------------------------------------------------
+static constexpr int kMarchSmemLevels = 1;           // hash levels staged in shared memory by the marcher
+static constexpr int kTilePitch = 36;                 // words per sample row of the A tile
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct WarpMlp {
+  float* tile;            // [32][kTilePitch] this warp's A tile
+  const float4* bfrag;    // [4 k-steps][8 n-tiles][32 lanes] = (hi b0, hi b1, lo b0, lo b1)
+  const float* w2;        // [64] output row 0 of layer 2
+};
+
+template <int KS>
+__device__ __forceinline__ void encode_group(const NgpDev& p, const float2* __restrict__ s_lvl,
+                                             const float xn[3], float* row) {
+  float f[8];
+  encode_level<4 * KS + 0, kMarchSmemLevels>(p, s_lvl, xn, f[0], f[1]);
+  encode_level<4 * KS + 1, kMarchSmemLevels>(p, s_lvl, xn, f[2], f[3]);
+  encode_level<4 * KS + 2, kMarchSmemLevels>(p, s_lvl, xn, f[4], f[5]);
+  encode_level<4 * KS + 3, kMarchSmemLevels>(p, s_lvl, xn, f[6], f[7]);
+  *(float4*)(row + 8 * KS) = make_float4(f[0], f[1], f[2], f[3]);
+  *(float4*)(row + 8 * KS + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+template <int KS>
+__device__ __forceinline__ void mlp_kstep(const WarpMlp& m, float (&acc)[2][8][4], int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const float* r0 = m.tile + (16 * mt + g) * kTilePitch + 8 * KS + t;
+    const float v[4] = {r0[0], r0[8 * kTilePitch], r0[4], r0[8 * kTilePitch + 4]};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float hi = tf32_hi(v[i]);
+      ahi[mt][i] = __float_as_uint(hi);
+      alo[mt][i] = __float_as_uint(tf32_hi(v[i] - hi));
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const float4 b = m.bfrag[(KS * 8 + nt) * 32 + lane];
+    const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y);
+    const uint32_t bl0 = __float_as_uint(b.z), bl1 = __float_as_uint(b.w);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      mma_tf32(acc[mt][nt], alo[mt], bh0, bh1);
+      mma_tf32(acc[mt][nt], ahi[mt], bl0, bl1);
+      mma_tf32(acc[mt][nt], ahi[mt], bh0, bh1);
+    }
+  }
+}
+
+// Returns layer-2 output 0 (pre-activation of the density) of the calling lane's sample.
+__device__ __forceinline__ float warp_density_raw(const NgpDev& p, const float2* __restrict__ s_lvl,
+                                                  const WarpMlp& m, const float xn[3], int lane) {
+  float* row = m.tile + lane * kTilePitch;
+  __syncwarp();
+  encode_group<0>(p, s_lvl, xn, row);
+  encode_group<1>(p, s_lvl, xn, row);
+  encode_group<2>(p, s_lvl, xn, row);
+  encode_group<3>(p, s_lvl, xn, row);
+  __syncwarp();
+  float acc[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+  mlp_kstep<0>(m, acc, lane);
+  mlp_kstep<1>(m, acc, lane);
+  mlp_kstep<2>(m, acc, lane);
+  mlp_kstep<3>(m, acc, lane);
+  // accumulator layout: acc[mt][nt] = {(row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)} of tile
+  // rows 16*mt.., hidden units 8*nt..
+  const int t = lane & 3;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};                   // rows g, g+8, g+16, g+24
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const float2 w = *(const float2*)(m.w2 + 8 * nt + 2 * t);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      s[2 * mt] = fmaf(w.x, fmaxf(acc[mt][nt][0], 0.f), s[2 * mt]);
+      s[2 * mt] = fmaf(w.y, fmaxf(acc[mt][nt][1], 0.f), s[2 * mt]);
+      s[2 * mt + 1] = fmaf(w.x, fmaxf(acc[mt][nt][2], 0.f), s[2 * mt + 1]);
+      s[2 * mt + 1] = fmaf(w.y, fmaxf(acc[mt][nt][3], 0.f), s[2 * mt + 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s[i] += __shfl_xor_sync(0xffffffffu, s[i], 1);
+    s[i] += __shfl_xor_sync(0xffffffffu, s[i], 2);
+  }
+  // every lane of quad g now holds rows g + 8j; lane t publishes row g + 8t, lane L fetches row L
+  const float mine = t == 0 ? s[0] : (t == 1 ? s[1] : (t == 2 ? s[2] : s[3]));
+  return __shfl_sync(0xffffffffu, mine, 4 * (lane & 7) + (lane >> 3));
+}
+
+// ------------------------------------------------------------------------------------------
+// Surface-field marcher.  One ray per (camera, point); per-ray arithmetic (t0/t1/tm updates, skip
+// rule, termination tests) is the scalar oracle's, so masks are identical.
+//
+// Scheduling.  A ray alternates between cheap, divergent empty-space skipping (phase A) and the
+// expensive density sample (phase B).  Every warp keeps up to 64 rays in shared-memory slots.  In
+// phase A each lane advances one ray (in registers) until its next sample position lies in an
+// occupied cell; the ray is then parked in its slot on the warp's pending list and the lane takes
+// another ray.  As soon as 32 samples are pending the warp evaluates them together - all 32 lanes
+// busy, layer 1 on the tensor cores - and the rays go back to the resume list.  Before this
+// rewrite the kernel ran with 14 of 32 lanes active on average (ncu, round 1).
+//
+// Latency.  Phase A is a chain of dependent occupancy lookups.  A coarse "any voxel occupied"
+// bitmap (cells of cf^3 voxels, <= 64^3 bits = 32 KB) sits in shared memory and answers most
+// lookups of the empty-space approach without leaving the SM; the IEEE divisions by the ROI
+// extent are done as q = x*y, r = fma(-e, q, x), q + r*y with y = RN(1/e), which is the correctly
+// rounded quotient (Markstein) without the MUFU/slow-path sequence.  Camera origins are staged in
+// shared memory as well.
+// ------------------------------------------------------------------------------------------
+__device__ unsigned long long g_march_stats[4];   // rays, skip events, samples, rounds (debug)
 extern "C" int drb_debug_march_stats(unsigned long long* host4, int reset) {
   cudaMemcpyFromSymbol(host4, g_march_stats, sizeof(unsigned long long) * 4);
   if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_march_stats, z, sizeof(z)); }
   return 0;
 }
 
+static constexpr int kMarchThreads = 512;
+static constexpr int kMarchWarps = kMarchThreads / 32;
+static constexpr int kSlots = 64;                    // rays per warp (in flight + pending + resumable)
+static constexpr int kSlotWords = 10;                // dir[3] len t0 t1 tm T best (pi | cam << 22)
+static constexpr int kPiBits = 22;
+static constexpr int kChunk = 8;                     // consecutive rays a lane takes from the global counter
+static constexpr int kCoarseMaxDim = 64;             // coarse occupancy bitmap: at most 64^3 bits
+static constexpr int kCoarseWords = kCoarseMaxDim * kCoarseMaxDim * kCoarseMaxDim / 32;
+static constexpr int kMaxCams = (1 << (32 - kPiBits)) - 1;
+static constexpr size_t kWarpBytes = (size_t)32 * kTilePitch * 4 + (size_t)kSlots * kSlotWords * 4 + 3 * kSlots;
+static_assert(kMarchSmemLevels <= kSmemLevels, "the marcher stages a prefix of the field kernels' levels");
+
 struct RayState {
   float o[3], dir[3], inv[3];
   float len, t0, t1, tm, T, best;
-  int pi;
+  int pi, ci;
 };
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
-surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict__ occ,
+static size_t march_smem_bytes(int ncams) {
+  return (size_t)lvl_off(kMarchSmemLevels) * sizeof(float2) + 64 * sizeof(float) + (size_t)4 * 8 * 32 * 16 +
+         (size_t)kCoarseWords * 4 + (((size_t)ncams * 12 + 15) & ~(size_t)15) + kMarchWarps * kWarpBytes + 16;
+}
+
+// coarse[c] bit = any voxel of the cf^3 cell occupied; cdim = ceil(res / cf) cells per axis.
+__global__ void coarse_occ_kernel(const uint8_t* __restrict__ occ, int res, int shift, int cdim,
+                                  uint32_t* __restrict__ coarse) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = cdim * cdim * cdim;
+  bool any = false;
+  if (c < total) {
+    const int cz = c % cdim, cy = (c / cdim) % cdim, cx = c / (cdim * cdim);
+    const int cf = 1 << shift;
+    for (int dx = 0; dx < cf && !any; ++dx)
+      for (int dy = 0; dy < cf && !any; ++dy)
+        for (int dz = 0; dz < cf; ++dz) {
+          const int x = (cx << shift) + dx, y = (cy << shift) + dy, z = (cz << shift) + dz;
+          if (x < res && y < res && z < res && occ[((long long)x * res + y) * res + z]) { any = true; break; }
+        }
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, any);
+  if ((threadIdx.x & 31) == 0 && c < ((total + 31) & ~31)) coarse[c >> 5] = word;
+}
+
+struct MarchAux {
+  const uint32_t* coarse;   // global copy of the coarse bitmap
+  int coarse_shift, coarse_dim, coarse_words;
+  float roi_rcp[3];         // RN(1 / roi extent)
+};
+
+// correctly rounded a / b given y = RN(1 / b) (no overflow / underflow in this range)
+__device__ __forceinline__ float div_rn_rcp(float a, float b, float y) {
+  const float q = a * y;
+  const float r = fmaf(-b, q, a);
+  return fmaf(r, y, q);
+}
+
+__global__ void __launch_bounds__(kMarchThreads, 1)
+surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const uint8_t* __restrict__ occ,
                     const float* __restrict__ points, int n, const float* __restrict__ cams, int ncams,
                     const int* __restrict__ active_idx, const int* __restrict__ active_count,
                     unsigned long long* __restrict__ counter, uint8_t* __restrict__ surface) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
-  const FieldSmem sm = stage_field(p, smem, &bar);
+  // ---- staging: hash level 0 by bulk TMA, W1 as tf32 hi/lo B fragments, w2 row 0, coarse bitmap, cameras
+  constexpr uint32_t lvl_bytes = lvl_off(kMarchSmemLevels) * (uint32_t)sizeof(float2);
+  float2* s_lvl = (float2*)smem;
+  float* s_w2 = (float*)(smem + lvl_bytes);
+  float4* s_bfrag = (float4*)(smem + lvl_bytes + 64 * sizeof(float));
+  uint32_t* s_coarse = (uint32_t*)(smem + lvl_bytes + 64 * sizeof(float) + (size_t)4 * 8 * 32 * 16);
+  float* s_cams = (float*)(s_coarse + kCoarseWords);
+  uint8_t* s_warp = (uint8_t*)s_cams + (((size_t)ncams * 12 + 15) & ~(size_t)15);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && lvl_bytes > 0) {
+    mbar_expect_tx(smem_u32(&bar), lvl_bytes);
+    for (uint32_t off = 0; off < lvl_bytes; off += 32768u) {
+      const uint32_t nb = lvl_bytes - off < 32768u ? lvl_bytes - off : 32768u;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"(smem_u32(smem + off)), "l"((uint64_t)((const uint8_t*)p.table + off)), "r"(nb),
+            "r"(smem_u32(&bar))
+          : "memory");
+    }
+  }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_w2[i] = p.w2[i];
+  for (int i = threadIdx.x; i < 4 * 8 * 32; i += blockDim.x) {
+    const int ln = i & 31, nt = (i >> 5) & 7, ks = i >> 8;
+    const int nn = 8 * nt + (ln >> 2), k0 = 8 * ks + (ln & 3);
+    const float b0 = p.w1[nn * 32 + k0], b1 = p.w1[nn * 32 + k0 + 4];
+    const float h0 = tf32_hi(b0), h1 = tf32_hi(b1);
+    s_bfrag[i] = make_float4(h0, h1, tf32_hi(b0 - h0), tf32_hi(b1 - h1));
+  }
+  for (int i = threadIdx.x; i < aux.coarse_words; i += blockDim.x) s_coarse[i] = aux.coarse[i];
+  for (int i = threadIdx.x; i < ncams * 3; i += blockDim.x) s_cams[i] = cams[i];
+  if (lvl_bytes > 0) mbar_wait(smem_u32(&bar), 0, nullptr, 0);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* wbase = s_warp + (size_t)warp * kWarpBytes;
+  WarpMlp mlp;
+  mlp.tile = (float*)wbase;
+  mlp.bfrag = s_bfrag;
+  mlp.w2 = s_w2;
+  float* slots = (float*)(wbase + 32 * kTilePitch * 4);            // [kSlotWords][kSlots]
+  uint8_t* l_pend = wbase + 32 * kTilePitch * 4 + kSlots * kSlotWords * 4;
+  uint8_t* l_resume = l_pend + kSlots;
+  uint8_t* l_free = l_resume + kSlots;
+  for (int i = lane; i < kSlots; i += 32) l_free[i] = (uint8_t)i;
+  __syncwarp();
+  int n_pend = 0, n_resume = 0, n_free = kSlots;                   // warp-uniform
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
   const int n_act = active_count ? *active_count : n;
   const unsigned long long total = (unsigned long long)n_act * (unsigned long long)ncams;
-  constexpr unsigned long long kChunk = 8;
   const int kMaxSkips = a.max_skips;
   const bool pow2_res = (a.res & (a.res - 1)) == 0;
   const float inv_res = 1.f / (float)a.res;
-  unsigned long long r_cur = 0, r_end = 0;
-  bool have = false, exhausted = false;
+  const float roi_ext[3] = {a.roi_max[0] - a.roi_min[0], a.roi_max[1] - a.roi_min[1], a.roi_max[2] - a.roi_min[2]};
+
   RayState ray;
+  bool have = false;          // this lane is advancing a ray (state in registers, home slot my_slot)
+  int my_slot = -1;
+  bool global_done = false;   // warp-uniform: the global ray counter is exhausted
+  // lane-local chunk of consecutive rays (same camera, neighbouring points)
+  int ch_left = 0, ch_j = 0, ch_ci = 0;
 #ifdef DRB_MARCH_STATS
-  unsigned long long st_rays = 0, st_skips = 0, st_samples = 0, st_iters = 0;
+  unsigned long long st_rays = 0, st_skips = 0, st_samples = 0, st_rounds = 0;
 #endif
-  while (true) {
+
+  auto store_ray = [&](int s) {
+    slots[0 * kSlots + s] = ray.dir[0]; slots[1 * kSlots + s] = ray.dir[1]; slots[2 * kSlots + s] = ray.dir[2];
+    slots[3 * kSlots + s] = ray.len; slots[4 * kSlots + s] = ray.t0; slots[5 * kSlots + s] = ray.t1;
+    slots[6 * kSlots + s] = ray.tm; slots[7 * kSlots + s] = ray.T; slots[8 * kSlots + s] = ray.best;
+    slots[9 * kSlots + s] = __uint_as_float((uint32_t)ray.pi | ((uint32_t)ray.ci << kPiBits));
+  };
+  // valid == false reads slot 0 / camera 0 into a ray that is never used: the registers are then dead
+  // across phase B for every lane (no state has to survive the tensor-core section in registers)
+  auto load_ray = [&](int s, bool valid) {
+    s = valid ? s : 0;
+    ray.dir[0] = slots[0 * kSlots + s]; ray.dir[1] = slots[1 * kSlots + s]; ray.dir[2] = slots[2 * kSlots + s];
+    ray.len = slots[3 * kSlots + s]; ray.t0 = slots[4 * kSlots + s]; ray.t1 = slots[5 * kSlots + s];
+    ray.tm = slots[6 * kSlots + s]; ray.T = slots[7 * kSlots + s]; ray.best = slots[8 * kSlots + s];
+    const uint32_t pc = valid ? __float_as_uint(slots[9 * kSlots + s]) : 0u;
+    ray.pi = (int)(pc & ((1u << kPiBits) - 1u)); ray.ci = (int)(pc >> kPiBits);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { ray.o[d] = s_cams[ray.ci * 3 + d]; ray.inv[d] = 1.f / ray.dir[d]; }
+  };
+  const long long t_start = clock64();
+
+  for (uint32_t round = 0;; ++round) {
+    // watchdog: a scheduling bug must not hang the GPU box (~30 s at 2 GHz, then give up)
+    if ((round & 0xfffu) == 0xfffu && clock64() - t_start > 60000000000LL) break;
 #ifdef DRB_MARCH_STATS
-    ++st_iters;
+    ++st_rounds;
 #endif
-    // ---------------- phase A: advance until a sample is pending (or no rays are left) -----------
-    // At most kMaxSkips empty-space events per outer iteration: a lane that has just started a ray
-    // (~60 empty voxels before the first occupied one) must not hold back the lanes whose next sample
-    // is already pending; it simply sits out a few of the (expensive, lock-step) phase B rounds.
-    bool pending = false;
-    float x[3];
-    int budget = kMaxSkips;
-    while (!pending && !exhausted && budget > 0) {
-      if (!have) {
-        if (r_cur >= r_end) {
-          r_cur = atomicAdd(counter, kChunk);
-          r_end = r_cur + kChunk < total ? r_cur + kChunk : total;
-          if (r_cur >= total) { exhausted = true; break; }
-        }
-        const unsigned long long r = r_cur++;
-        const int j = (int)(r % (unsigned long long)n_act), ci = (int)(r / (unsigned long long)n_act);
-        const int pi = active_idx ? active_idx[j] : j;
-        if (surface[pi]) continue;               // another camera already saw this point
-        float len = 0.f;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          ray.o[d] = cams[ci * 3 + d];
-          ray.dir[d] = points[pi * 3 + d] - ray.o[d];
-          len += ray.dir[d] * ray.dir[d];
-        }
-        len = sqrtf(len);
-        if (!(len > 0.f)) continue;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) { ray.dir[d] = ray.dir[d] / len; ray.inv[d] = 1.f / ray.dir[d]; }
-        // ray / scene AABB intersection -> t_min (nerfacc ray_aabb_intersect); t_max = |p - o|
-        float tn = -1e30f, tf = 1e30f;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          float ta = (a.scene_min[d] - ray.o[d]) * ray.inv[d], tb = (a.scene_max[d] - ray.o[d]) * ray.inv[d];
-          if (ta > tb) { const float tmp = ta; ta = tb; tb = tmp; }
-          tn = fmaxf(tn, ta); tf = fminf(tf, tb);
-        }
-        if (tn > tf) continue;                    // misses the box
-        ray.len = len; ray.pi = pi;
-        ray.t0 = fmaxf(tn, 0.f); ray.t1 = ray.t0 + a.step; ray.tm = 0.5f * (ray.t0 + ray.t1);
-        ray.T = 1.f; ray.best = 0.f;
+    // ---------------- refill: lanes without a ray take a resumable one, else start new rays ------
+    {
+      const uint32_t need = __ballot_sync(0xffffffffu, !have);
+      // spare slots of lanes whose ray ended in phase A go back to the free list first
+      const uint32_t spare = __ballot_sync(0xffffffffu, !have && my_slot >= 0);
+      if (!have && my_slot >= 0) { l_free[n_free + __popc(spare & lt_mask)] = (uint8_t)my_slot; my_slot = -1; }
+      n_free += __popc(spare);
+      __syncwarp();
+      const int rank = __popc(need & lt_mask);
+      if (!have && rank < n_resume) {
+        my_slot = l_resume[n_resume - 1 - rank];
+        load_ray(my_slot, true);
         have = true;
+      }
+      n_resume -= min(n_resume, __popc(need));
+    }
+    for (int tries = 0; tries < 8; ++tries) {
+      // lanes whose chunk is used up fetch a new one (one atomic per warp)
+      const uint32_t want_chunk = __ballot_sync(0xffffffffu, !have && ch_left == 0);
+      if (want_chunk && !global_done) {
+        const int cnt = __popc(want_chunk);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)cnt * kChunk);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) {
+          global_done = true;
+        } else if (!have && ch_left == 0) {
+          const unsigned long long r0 = base + (unsigned long long)__popc(want_chunk & lt_mask) * kChunk;
+          if (r0 < total) {
+            ch_ci = (int)(r0 / (unsigned long long)n_act);
+            ch_j = (int)(r0 - (unsigned long long)ch_ci * (unsigned long long)n_act);
+            const unsigned long long left = total - r0;
+            ch_left = left < (unsigned long long)kChunk ? (int)left : kChunk;
+          }
+        }
+      }
+      const uint32_t cand = __ballot_sync(0xffffffffu, !have && ch_left > 0);
+      if (cand == 0) break;
+      bool started = false;
+      if (!have && ch_left > 0 && __popc(cand & lt_mask) < n_free) {
+        int j = ch_j, ci = ch_ci;
+        ++ch_j; --ch_left;
+        if (ch_j >= n_act) { ch_j = 0; ++ch_ci; }
+        const int pi = active_idx ? active_idx[j] : j;
+        if (!surface[pi]) {                               // else another camera already saw this point
+          float len = 0.f;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            ray.o[d] = s_cams[ci * 3 + d];
+            ray.dir[d] = points[pi * 3 + d] - ray.o[d];
+            len += ray.dir[d] * ray.dir[d];
+          }
+          len = sqrtf(len);
+          if (len > 0.f) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { ray.dir[d] = ray.dir[d] / len; ray.inv[d] = 1.f / ray.dir[d]; }
+            // ray / scene AABB intersection -> t_min (nerfacc ray_aabb_intersect); t_max = |p - o|
+            float tn = -1e30f, tf = 1e30f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              float ta = (a.scene_min[d] - ray.o[d]) * ray.inv[d], tb = (a.scene_max[d] - ray.o[d]) * ray.inv[d];
+              if (ta > tb) { const float tmp = ta; ta = tb; tb = tmp; }
+              tn = fmaxf(tn, ta); tf = fminf(tf, tb);
+            }
+            if (!(tn > tf)) {                             // else the ray misses the box
+              ray.len = len; ray.pi = pi; ray.ci = ci;
+              ray.t0 = fmaxf(tn, 0.f); ray.t1 = ray.t0 + a.step; ray.tm = 0.5f * (ray.t0 + ray.t1);
+              ray.T = 1.f; ray.best = 0.f;
+              started = true;
+            }
+          }
+        }
+      }
+      // slots for the rays that really started (warp-uniform bookkeeping)
+      const uint32_t st = __ballot_sync(0xffffffffu, started);
+      if (started) { my_slot = l_free[n_free - 1 - __popc(st & lt_mask)]; have = true; }
+      n_free -= __popc(st);
 #ifdef DRB_MARCH_STATS
-        ++st_rays;
+      if (started) ++st_rays;
 #endif
-      }
-      if (!(ray.tm < ray.len)) { have = false; continue; }     // reached the point without a hit
+    }
+
+    // ---------------- phase A: advance until a sample is pending (bounded number of skips) -------
+    bool pending = false;
+    if (have) {
+      int budget = kMaxSkips;
+      while (budget > 0) {
+        if (!(ray.tm < ray.len)) { have = false; break; }       // reached the point without a hit
+        float x[3];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) x[d] = ray.o[d] + ray.tm * ray.dir[d];
-      // occupancy test and distance to the next voxel share u = (x - roi_min) / extent (IEEE division,
-      // as nerfacc's roi_to_unit); res is a power of two in practice, where "/ res" is an exact scaling
-      float u[3];
-      bool in_roi = true;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        u[d] = __fdiv_rn(x[d] - a.roi_min[d], a.roi_max[d] - a.roi_min[d]);
-        in_roi = in_roi && (u[d] >= 0.f) && (u[d] < 1.f);
-      }
-      bool is_occ = false;
-      if (in_roi) {
-        int idx[3];
+        for (int d = 0; d < 3; ++d) x[d] = fmaf(ray.tm, ray.dir[d], ray.o[d]);
+        // occupancy test and distance to the next voxel share u = (x - roi_min) / extent (IEEE division,
+        // as nerfacc's roi_to_unit); res is a power of two in practice, where "/ res" is an exact scaling
+        float u[3];
+        bool in_roi = true;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const int i = (int)(u[d] * (float)a.res);
-          idx[d] = i < 0 ? 0 : (i > a.res - 1 ? a.res - 1 : i);
+          u[d] = div_rn_rcp(x[d] - a.roi_min[d], roi_ext[d], aux.roi_rcp[d]);
+          in_roi = in_roi && (u[d] >= 0.f) && (u[d] < 1.f);
         }
-        is_occ = occ[((long long)idx[0] * a.res + idx[1]) * a.res + idx[2]] != 0;
-      }
-      if (is_occ) {
-        pending = true;
-      } else {
+        bool is_occ = false;
+        if (in_roi) {
+          int idx[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const int i = (int)(u[d] * (float)a.res);
+            idx[d] = i < 0 ? 0 : (i > a.res - 1 ? a.res - 1 : i);
+          }
+          const int cb = ((idx[0] >> aux.coarse_shift) * aux.coarse_dim + (idx[1] >> aux.coarse_shift)) *
+                             aux.coarse_dim + (idx[2] >> aux.coarse_shift);
+          if ((s_coarse[cb >> 5] >> (cb & 31)) & 1u)
+            is_occ = occ[((long long)idx[0] * a.res + idx[1]) * a.res + idx[2]] != 0;
+        }
+        if (is_occ) { pending = true; break; }
         --budget;
         float dist = 1e30f;
 #pragma unroll
@@ -504,7 +880,7 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict
           const float sgn = ray.dir[d] > 0.f ? 1.f : (ray.dir[d] < 0.f ? -1.f : 0.f);
           float td = (floorf(ur + 0.5f + 0.5f * sgn) - ur) * ray.inv[d];
           td = pow2_res ? td * inv_res : __fdiv_rn(td, (float)a.res);
-          dist = fminf(dist, td * (a.roi_max[d] - a.roi_min[d]));
+          dist = fminf(dist, td * roi_ext[d]);
         }
         const float tt = ray.tm + fmaxf(dist, 0.f);
         do { ray.tm += a.step; } while (ray.tm < tt);
@@ -514,49 +890,88 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const uint8_t* __restrict
 #endif
       }
     }
-#ifdef DRB_MARCH_STATS
-    if (pending) ++st_samples;
-#endif
-    // leave only when every lane of the warp is out of rays (a lane without a pending sample may just
-    // have used up its skip budget)
-    if (!__any_sync(0xffffffffu, pending || have || !exhausted)) break;
-    // ---------------- phase B: one density sample per lane, in lock-step -------------------------
-    if (pending) {
-      float xn[3];
-      const bool inside = normalise(p, x, xn);
-      float sigma = 0.f;
-      if (inside) {
-        float f[32], out[1];
-        hash_encode(p, sm, xn, f);
-        density_mlp<1>(sm, f, out);
-        sigma = expf(out[0] - 1.f);
+    // ---------------- park the rays whose sample is pending --------------------------------------
+    {
+      const uint32_t pm = __ballot_sync(0xffffffffu, pending);
+      if (pending) {
+        store_ray(my_slot);
+        l_pend[n_pend + __popc(pm & lt_mask)] = (uint8_t)my_slot;
+        my_slot = -1;
+        have = false;
       }
-      const float alpha = 1.f - expf(-sigma * (ray.t1 - ray.t0));
-      bool done = false;
-      if (ray.T < 1e-4f) {                       // samples past early_stop_eps are dropped (:209)
-        done = true;
-      } else {
-        ray.best = fmaxf(ray.best, alpha * ray.T);
-        if (ray.best >= a.cut_off) {
-          surface[ray.pi] = 1;
+      n_pend += __popc(pm);
+      __syncwarp();
+    }
+    // ---------------- phase B: 32 density samples at a time --------------------------------------
+    const uint32_t busy = __ballot_sync(0xffffffffu, have || ch_left > 0);
+    const bool drain = global_done && busy == 0 && n_resume == 0;
+    if (n_pend == 0 && drain) break;
+    while (n_pend >= 32 || (drain && n_pend > 0)) {
+      // lanes that are in the middle of a ray park it in its home slot (registers are needed below)
+      if (have) store_ray(my_slot);
+      const int nb = min(32, n_pend);
+      const bool valid = lane < nb;
+      const int s = valid ? (int)l_pend[n_pend - nb + lane] : 0;
+      n_pend -= nb;
+      float xn[3] = {0.5f, 0.5f, 0.5f};
+      bool inside = false;
+      if (valid) {
+        const int ci = (int)(__float_as_uint(slots[9 * kSlots + s]) >> kPiBits);
+        const float tm = slots[6 * kSlots + s];
+        float x[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x[d] = fmaf(tm, slots[d * kSlots + s], s_cams[ci * 3 + d]);
+        float xt[3];
+        inside = normalise(p, x, xt);
+        if (inside) { xn[0] = xt[0]; xn[1] = xt[1]; xn[2] = xt[2]; }
+      }
+      const float raw = warp_density_raw(p, s_lvl, mlp, xn, lane);
+      bool resume = false, release = false;
+      if (valid) {
+        const float sigma = inside ? expf(raw - 1.f) : 0.f;
+        float t0 = slots[4 * kSlots + s], t1 = slots[5 * kSlots + s];
+        float T = slots[7 * kSlots + s], best = slots[8 * kSlots + s];
+        const int pi = (int)(__float_as_uint(slots[9 * kSlots + s]) & ((1u << kPiBits) - 1u));
+        const float alpha = 1.f - expf(-sigma * (t1 - t0));
+        bool done = false;
+        if (T < 1e-4f) {                           // samples past early_stop_eps are dropped (:209)
           done = true;
         } else {
-          ray.T *= 1.f - alpha;
-          // exact early out: every later sample contributes alpha * T' <= T' <= T < cut_off
-          if (ray.T < a.cut_off || surface[ray.pi]) done = true;
+          best = fmaxf(best, alpha * T);
+          if (best >= a.cut_off) {
+            surface[pi] = 1;
+            done = true;
+          } else {
+            T *= 1.f - alpha;
+            // exact early out: every later sample contributes alpha * T' <= T' <= T < cut_off
+            if (T < a.cut_off || surface[pi]) done = true;
+          }
         }
+        if (done) {
+          release = true;
+        } else {
+          t0 = t1; t1 = t0 + a.step;
+          slots[4 * kSlots + s] = t0; slots[5 * kSlots + s] = t1; slots[6 * kSlots + s] = 0.5f * (t0 + t1);
+          slots[7 * kSlots + s] = T; slots[8 * kSlots + s] = best;
+          resume = true;
+        }
+#ifdef DRB_MARCH_STATS
+        ++st_samples;
+#endif
       }
-      if (done) {
-        have = false;
-      } else {
-        ray.t0 = ray.t1; ray.t1 = ray.t0 + a.step; ray.tm = 0.5f * (ray.t0 + ray.t1);
-      }
+      const uint32_t rm = __ballot_sync(0xffffffffu, resume), fm = __ballot_sync(0xffffffffu, release);
+      if (resume) l_resume[n_resume + __popc(rm & lt_mask)] = (uint8_t)s;
+      if (release) l_free[n_free + __popc(fm & lt_mask)] = (uint8_t)s;
+      n_resume += __popc(rm);
+      n_free += __popc(fm);
+      __syncwarp();
+      load_ray(my_slot, have);
     }
   }
 #ifdef DRB_MARCH_STATS
   atomicAdd(&g_march_stats[0], st_rays); atomicAdd(&g_march_stats[1], st_skips);
   atomicAdd(&g_march_stats[2], st_samples);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&g_march_stats[3], st_iters);
+  if (lane == 0) atomicAdd(&g_march_stats[3], st_rounds);
 #endif
 }
 
@@ -601,16 +1016,29 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
     if (!skips) { const char* env = getenv("DRB_MARCH_SKIPS"); skips = env ? atoi(env) : 16; if (skips < 1) skips = 16; }
     a.max_skips = skips;
   }
-  const size_t smem = field_smem_bytes(p.lv);
-  static int threads = 0;
-  if (!threads) {
-    const char* env = getenv("DRB_SURFACE_THREADS");
-    threads = env ? atoi(env) : 512;
-    if (threads != 256 && threads != 512 && threads != 768 && threads != 1024) threads = 512;
-    DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DRB_REQUIRE(levels_ok(p.lv), "drb_surface_mask: compile-time level table disagrees with host_levels()");
+  DRB_REQUIRE(n < (1 << kPiBits) && ncams <= kMaxCams,
+              "drb_surface_mask: at most %d points and %d cameras per call", (1 << kPiBits) - 1, kMaxCams);
+  const size_t smem = march_smem_bytes(ncams);
+  DRB_REQUIRE(smem <= 232448, "drb_surface_mask: %d cameras do not fit the shared-memory plan", ncams);
+  static size_t attr = 0;
+  if (attr < smem) {
+    DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  MarchAux aux;
+  aux.coarse_shift = 0;
+  while (((res + (1 << aux.coarse_shift) - 1) >> aux.coarse_shift) > kCoarseMaxDim) ++aux.coarse_shift;
+  aux.coarse_dim = (res + (1 << aux.coarse_shift) - 1) >> aux.coarse_shift;
+  aux.coarse_words = (aux.coarse_dim * aux.coarse_dim * aux.coarse_dim + 31) / 32;
+  for (int d = 0; d < 3; ++d) {
+    const float ext = a.roi_max[d] - a.roi_min[d];
+    DRB_REQUIRE(ext > 0.f, "drb_surface_mask: empty ROI");
+    // the reciprocal-multiply division is exact unless the divisor's significand is all ones
+    uint32_t bits;
+    memcpy(&bits, &ext, 4);
+    DRB_REQUIRE((bits & 0x7fffffu) != 0x7fffffu, "drb_surface_mask: unsupported ROI extent");
+    aux.roi_rcp[d] = (float)(1.0 / (double)ext);
   }
   // scratch: ray counter, active count, compacted (order preserving) list of active points
   keep_async_pool();
@@ -619,7 +1047,8 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
   cub::DeviceSelect::Flagged(nullptr, cub_bytes, (const int*)nullptr, (const uint8_t*)nullptr, (int*)nullptr,
                              (int*)nullptr, n, stream);
   const size_t off_idx = 256, off_iota = off_idx + (((size_t)n * 4 + 255) & ~(size_t)255);
-  const size_t off_cub = off_iota + (((size_t)n * 4 + 255) & ~(size_t)255);
+  const size_t off_coarse = off_iota + (((size_t)n * 4 + 255) & ~(size_t)255);
+  const size_t off_cub = off_coarse + (size_t)kCoarseWords * 4;
   DRB_CUDA_OK(cudaMallocAsync(&scratch, off_cub + cub_bytes + 256, stream));
   DRB_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, stream));
   unsigned long long* counter = (unsigned long long*)scratch;
@@ -632,16 +1061,14 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
     DRB_LAUNCH_OK();
     DRB_CUDA_OK(cub::DeviceSelect::Flagged(scratch + off_cub, cub_bytes, iota, active, idx, count, n, stream));
   }
+  aux.coarse = (const uint32_t*)(scratch + off_coarse);
+  coarse_occ_kernel<<<cdiv(aux.coarse_words * 32, 256), 256, 0, stream>>>(occ_binary, res, aux.coarse_shift,
+                                                                         aux.coarse_dim, (uint32_t*)(scratch + off_coarse));
+  DRB_LAUNCH_OK();
   const int grid = igemm_num_sms();
   const int* cnt = active ? count : nullptr;
-  if (threads == 256)
-    surface_mask_kernel<256><<<grid, 256, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, idx, cnt, counter, surface);
-  else if (threads == 512)
-    surface_mask_kernel<512><<<grid, 512, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, idx, cnt, counter, surface);
-  else if (threads == 768)
-    surface_mask_kernel<768><<<grid, 768, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, idx, cnt, counter, surface);
-  else
-    surface_mask_kernel<1024><<<grid, 1024, smem, stream>>>(p, a, occ_binary, points, n, cam_origins, ncams, idx, cnt, counter, surface);
+  surface_mask_kernel<<<grid, kMarchThreads, smem, stream>>>(p, a, aux, occ_binary, points, n, cam_origins, ncams,
+                                                             idx, cnt, counter, surface);
   DRB_LAUNCH_OK();
   DRB_CUDA_OK(cudaFreeAsync(scratch, stream));
   return 0;
