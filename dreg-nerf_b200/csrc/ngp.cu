@@ -424,28 +424,71 @@ __device__ __forceinline__ void encode_level(const NgpDev& p, const float2* __re
     fr[d] = pos - fl;
     g[d] = (uint32_t)(int)fl;
   }
-  uint32_t idx[8];
+  // x-neighbours (corners c and c^1) are adjacent table entries whenever the x index of the lower
+  // corner is even (dense: idx, idx + 1; hashed: idx, idx ^ 1), i.e. one aligned 16-byte load serves
+  // both.  The load/store unit is bound by wavefronts (one per distinct sector per instruction), so
+  // this removes a quarter of them; odd x indices fetch the upper corner separately.
+  uint32_t idx0[4], idx1[4];              // lower / upper x corner of the 4 (y, z) combinations
   if constexpr (lvl_dense(L)) {
     const uint32_t base = g[0] + g[1] * res + g[2] * (res * res);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uint32_t i = base + ((c & 1) ? 1u : 0u) + ((c & 2) ? res : 0u) + ((c & 4) ? res * res : 0u);
-      idx[c] = i >= size ? i - size : i;
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t i = base + ((c & 1) ? res : 0u) + ((c & 2) ? res * res : 0u);
+      idx0[c] = i >= size ? i - size : i;
+      idx1[c] = i + 1u >= size ? i + 1u - size : i + 1u;
     }
   } else {
     static_assert(lvl_dense(L) || (size & (size - 1)) == 0, "hashed levels are powers of two");
-    const uint32_t hx[2] = {g[0], g[0] + 1u};
     const uint32_t hy0 = g[1] * 2654435761u, hz0 = g[2] * 805459861u;
     const uint32_t hy[2] = {hy0, hy0 + 2654435761u};
     const uint32_t hz[2] = {hz0, hz0 + 805459861u};
 #pragma unroll
-    for (int c = 0; c < 8; ++c) idx[c] = (hx[c & 1] ^ hy[(c >> 1) & 1] ^ hz[c >> 2]) & (size - 1u);
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t hyz = hy[c & 1] ^ hz[c >> 1];
+      idx0[c] = (g[0] ^ hyz) & (size - 1u);
+      idx1[c] = ((g[0] + 1u) ^ hyz) & (size - 1u);
+    }
   }
   float2 v[8];
+  if constexpr (L < SMEM_LEVELS) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    if constexpr (L < SMEM_LEVELS) v[c] = s_lvl[off + idx[c]];
-    else v[c] = __ldg(p.table + off + idx[c]);
+    for (int c = 0; c < 4; ++c) { v[2 * c] = s_lvl[off + idx0[c]]; v[2 * c + 1] = s_lvl[off + idx1[c]]; }
+  } else {
+    static_assert(off % 2 == 0 && size % 2 == 0, "16-byte pairs need even level offsets");
+    const bool paired = (g[0] & 1u) == 0u;          // dense: idx0 parity == g[0] parity only if res is even
+    float4 q[4];
+    if constexpr (lvl_dense(L) && (res & 1u)) {
+      // odd resolution: the parity of idx0 is not that of g[0]; decide per (y, z) combination
+#pragma unroll
+      for (int c = 0; c < 4; ++c) q[c] = __ldg((const float4*)(p.table + off + (idx0[c] & ~1u)));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool odd = idx0[c] & 1u;
+        v[2 * c] = odd ? make_float2(q[c].z, q[c].w) : make_float2(q[c].x, q[c].y);
+        if (!odd && idx1[c] == idx0[c] + 1u) v[2 * c + 1] = make_float2(q[c].z, q[c].w);
+        else v[2 * c + 1] = __ldg(p.table + off + idx1[c]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) q[c] = __ldg((const float4*)(p.table + off + (idx0[c] & ~1u)));
+      if (paired) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          // dense, even res: idx0 even -> idx1 = idx0 + 1 (no wrap between them: size is even);
+          // hashed: idx1 = idx0 ^ 1.  Either way the mate of the aligned pair.
+          const bool odd = idx0[c] & 1u;
+          v[2 * c] = odd ? make_float2(q[c].z, q[c].w) : make_float2(q[c].x, q[c].y);
+          v[2 * c + 1] = odd ? make_float2(q[c].x, q[c].y) : make_float2(q[c].z, q[c].w);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool odd = idx0[c] & 1u;
+          v[2 * c] = odd ? make_float2(q[c].z, q[c].w) : make_float2(q[c].x, q[c].y);
+          v[2 * c + 1] = __ldg(p.table + off + idx1[c]);
+        }
+      }
+    }
   }
   float a0 = 0.f, a1 = 0.f;
 #pragma unroll
@@ -461,16 +504,16 @@ __device__ __forceinline__ void encode_level(const NgpDev& p, const float2* __re
 }
 
 // ------------------------------------------------------------------------------------------
-// Warp-level density evaluation of 32 samples (one per lane): hash encoding on the CUDA cores into
-// a 32 x 32 shared-memory tile, then layer 1 (32 -> 64) on the tensor cores as 3xTF32
-// (hi*hi + lo*hi + hi*lo, ~2^-21 relative), ReLU + layer 2 (64 -> 1) + quad shuffle reduction in
-// the accumulator layout.  Tile row pitch 36 words: conflict free for the 128-bit row stores and
-// for the m16n8k8 A-fragment loads; B fragments of W1 (hi, lo) are pre-arranged per (k-step,
-// n-tile, lane) at staging time.  No accumulator is live while the gathers are in flight, so the
-// compiler can keep several levels' loads outstanding.
+// Warp-level density evaluation of 32 samples (one per lane): hash encoding on the CUDA cores, four
+// levels (8 features = one K-step) at a time through a 32 x 8 shared-memory tile, layer 1 (32 -> 64)
+// on the tensor cores as 3xTF32 (hi*hi + lo*hi + hi*lo, ~2^-21 relative), ReLU + layer 2 (64 -> 1)
+// + quad shuffle reduction in the accumulator layout.  Tile row pitch 12 words: conflict free for
+// the 128-bit row stores and for the m16n8k8 A-fragment loads; B fragments of W1 (hi, lo) are
+// pre-arranged per (k-step, n-tile, lane) at staging time.  The tile is kept this small on purpose:
+// every KB of shared memory is a KB less L1 for the table gathers, which bound the kernel.
 // ------------------------------------------------------------------------------------------
 static constexpr int kMarchSmemLevels = 1;           // hash levels staged in shared memory by the marcher
-static constexpr int kTilePitch = 36;                 // words per sample row of the A tile
+static constexpr int kTilePitch = 12;                 // words per sample row of the A tile (one K-step)
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
@@ -489,23 +532,24 @@ struct WarpMlp {
 
 template <int KS>
 __device__ __forceinline__ void encode_group(const NgpDev& p, const float2* __restrict__ s_lvl,
-                                             const float xn[3], float* row) {
-  float f[8];
+                                             const float xn[3], float f[8]) {
   encode_level<4 * KS + 0, kMarchSmemLevels>(p, s_lvl, xn, f[0], f[1]);
   encode_level<4 * KS + 1, kMarchSmemLevels>(p, s_lvl, xn, f[2], f[3]);
   encode_level<4 * KS + 2, kMarchSmemLevels>(p, s_lvl, xn, f[4], f[5]);
   encode_level<4 * KS + 3, kMarchSmemLevels>(p, s_lvl, xn, f[6], f[7]);
-  *(float4*)(row + 8 * KS) = make_float4(f[0], f[1], f[2], f[3]);
-  *(float4*)(row + 8 * KS + 4) = make_float4(f[4], f[5], f[6], f[7]);
 }
 
 template <int KS>
-__device__ __forceinline__ void mlp_kstep(const WarpMlp& m, float (&acc)[2][8][4], int lane) {
+__device__ __forceinline__ void mlp_kstep(const WarpMlp& m, const float f[8], float (&acc)[2][8][4], int lane) {
   const int g = lane >> 2, t = lane & 3;
+  __syncwarp();                                        // the previous K-step's fragment loads are done
+  *(float4*)(m.tile + lane * kTilePitch) = make_float4(f[0], f[1], f[2], f[3]);
+  *(float4*)(m.tile + lane * kTilePitch + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  __syncwarp();
   uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
-    const float* r0 = m.tile + (16 * mt + g) * kTilePitch + 8 * KS + t;
+    const float* r0 = m.tile + (16 * mt + g) * kTilePitch + t;
     const float v[4] = {r0[0], r0[8 * kTilePitch], r0[4], r0[8 * kTilePitch + 4]};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -531,13 +575,6 @@ __device__ __forceinline__ void mlp_kstep(const WarpMlp& m, float (&acc)[2][8][4
 // Returns layer-2 output 0 (pre-activation of the density) of the calling lane's sample.
 __device__ __forceinline__ float warp_density_raw(const NgpDev& p, const float2* __restrict__ s_lvl,
                                                   const WarpMlp& m, const float xn[3], int lane) {
-  float* row = m.tile + lane * kTilePitch;
-  __syncwarp();
-  encode_group<0>(p, s_lvl, xn, row);
-  encode_group<1>(p, s_lvl, xn, row);
-  encode_group<2>(p, s_lvl, xn, row);
-  encode_group<3>(p, s_lvl, xn, row);
-  __syncwarp();
   float acc[2][8][4];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -545,10 +582,11 @@ __device__ __forceinline__ float warp_density_raw(const NgpDev& p, const float2*
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-  mlp_kstep<0>(m, acc, lane);
-  mlp_kstep<1>(m, acc, lane);
-  mlp_kstep<2>(m, acc, lane);
-  mlp_kstep<3>(m, acc, lane);
+  float f[8];
+  encode_group<0>(p, s_lvl, xn, f); mlp_kstep<0>(m, f, acc, lane);
+  encode_group<1>(p, s_lvl, xn, f); mlp_kstep<1>(m, f, acc, lane);
+  encode_group<2>(p, s_lvl, xn, f); mlp_kstep<2>(m, f, acc, lane);
+  encode_group<3>(p, s_lvl, xn, f); mlp_kstep<3>(m, f, acc, lane);
   // accumulator layout: acc[mt][nt] = {(row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)} of tile
   // rows 16*mt.., hidden units 8*nt..
   const int t = lane & 3;
@@ -605,11 +643,13 @@ static constexpr int kMarchWarps = kMarchThreads / 32;
 static constexpr int kSlots = 64;                    // rays per warp (in flight + pending + resumable)
 static constexpr int kSlotWords = 10;                // dir[3] len t0 t1 tm T best (pi | cam << 22)
 static constexpr int kPiBits = 22;
-static constexpr int kChunk = 8;                     // consecutive rays a lane takes from the global counter
-static constexpr int kCoarseMaxDim = 64;             // coarse occupancy bitmap: at most 64^3 bits
+static constexpr int kWindow = 128;                  // consecutive rays a warp takes from the global counter per fetch
+static constexpr int kCandCap = 32 + kWindow;        // per-warp queue of rays that passed the "not yet seen" test
+static constexpr int kCoarseMaxDim = 64;             // coarse occupancy bitmap: at most 64^3 bits (32 KB)
 static constexpr int kCoarseWords = kCoarseMaxDim * kCoarseMaxDim * kCoarseMaxDim / 32;
 static constexpr int kMaxCams = (1 << (32 - kPiBits)) - 1;
-static constexpr size_t kWarpBytes = (size_t)32 * kTilePitch * 4 + (size_t)kSlots * kSlotWords * 4 + 3 * kSlots;
+static constexpr size_t kWarpBytes = (size_t)32 * kTilePitch * 4 + (size_t)kSlots * kSlotWords * 4 + 3 * kSlots +
+                                     (size_t)kCandCap * 4;
 static_assert(kMarchSmemLevels <= kSmemLevels, "the marcher stages a prefix of the field kernels' levels");
 
 struct RayState {
@@ -710,9 +750,10 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
   uint8_t* l_pend = wbase + 32 * kTilePitch * 4 + kSlots * kSlotWords * 4;
   uint8_t* l_resume = l_pend + kSlots;
   uint8_t* l_free = l_resume + kSlots;
+  uint32_t* l_cand = (uint32_t*)(l_free + kSlots);                 // (pi | cam << 22) of rays waiting to start
   for (int i = lane; i < kSlots; i += 32) l_free[i] = (uint8_t)i;
   __syncwarp();
-  int n_pend = 0, n_resume = 0, n_free = kSlots;                   // warp-uniform
+  int n_pend = 0, n_resume = 0, n_free = kSlots, n_cand = 0;       // warp-uniform
   const uint32_t lt_mask = (1u << lane) - 1u;
 
   const int n_act = active_count ? *active_count : n;
@@ -726,8 +767,6 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
   bool have = false;          // this lane is advancing a ray (state in registers, home slot my_slot)
   int my_slot = -1;
   bool global_done = false;   // warp-uniform: the global ray counter is exhausted
-  // lane-local chunk of consecutive rays (same camera, neighbouring points)
-  int ch_left = 0, ch_j = 0, ch_ci = 0;
 #ifdef DRB_MARCH_STATS
   unsigned long long st_rays = 0, st_skips = 0, st_samples = 0, st_rounds = 0;
 #endif
@@ -774,67 +813,75 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
       }
       n_resume -= min(n_resume, __popc(need));
     }
-    for (int tries = 0; tries < 8; ++tries) {
-      // lanes whose chunk is used up fetch a new one (one atomic per warp)
-      const uint32_t want_chunk = __ballot_sync(0xffffffffu, !have && ch_left == 0);
-      if (want_chunk && !global_done) {
-        const int cnt = __popc(want_chunk);
+    {
+      // New rays.  The warp takes windows of kWindow consecutive rays (one camera, points that are
+      // neighbours in Morton order), drops the ones whose point another camera already saw, and queues
+      // the rest; lanes without a ray start the queued candidates.  All rays of a warp therefore stay
+      // spatially close: their hash-grid and occupancy lookups share cache lines.
+      const uint32_t need = __ballot_sync(0xffffffffu, !have);
+      const int nn = min(__popc(need), n_free);
+      for (int tries = 0; n_cand < nn && !global_done && tries < 4; ++tries) {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(counter, (unsigned long long)cnt * kChunk);
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)kWindow);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= total) {
-          global_done = true;
-        } else if (!have && ch_left == 0) {
-          const unsigned long long r0 = base + (unsigned long long)__popc(want_chunk & lt_mask) * kChunk;
-          if (r0 < total) {
-            ch_ci = (int)(r0 / (unsigned long long)n_act);
-            ch_j = (int)(r0 - (unsigned long long)ch_ci * (unsigned long long)n_act);
-            const unsigned long long left = total - r0;
-            ch_left = left < (unsigned long long)kChunk ? (int)left : kChunk;
+        if (base >= total) { global_done = true; break; }
+        const int ci0 = (int)(base / (unsigned long long)n_act);
+        const int j0 = (int)(base - (unsigned long long)ci0 * (unsigned long long)n_act);
+#pragma unroll
+        for (int k = 0; k < kWindow / 32; ++k) {
+          bool ok = base + (unsigned long long)(k * 32 + lane) < total;
+          int j = j0 + k * 32 + lane, ci = ci0;
+          while (ok && j >= n_act) { j -= n_act; ++ci; }
+          int pi = 0;
+          if (ok) {
+            pi = active_idx ? active_idx[j] : j;
+            ok = surface[pi] == 0;                          // else another camera already saw this point
           }
+          const uint32_t m = __ballot_sync(0xffffffffu, ok);
+          if (ok) l_cand[n_cand + __popc(m & lt_mask)] = (uint32_t)pi | ((uint32_t)ci << kPiBits);
+          n_cand += __popc(m);
         }
+        __syncwarp();
       }
-      const uint32_t cand = __ballot_sync(0xffffffffu, !have && ch_left > 0);
-      if (cand == 0) break;
+      const int take = min(nn, n_cand);
+      const int rank = __popc(need & lt_mask);
       bool started = false;
-      if (!have && ch_left > 0 && __popc(cand & lt_mask) < n_free) {
-        int j = ch_j, ci = ch_ci;
-        ++ch_j; --ch_left;
-        if (ch_j >= n_act) { ch_j = 0; ++ch_ci; }
-        const int pi = active_idx ? active_idx[j] : j;
-        if (!surface[pi]) {                               // else another camera already saw this point
-          float len = 0.f;
+      if (!have && rank < take) {
+        const uint32_t pc = l_cand[n_cand - take + rank];
+        const int pi = (int)(pc & ((1u << kPiBits) - 1u)), ci = (int)(pc >> kPiBits);
+        float len = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          ray.o[d] = s_cams[ci * 3 + d];
+          ray.dir[d] = points[pi * 3 + d] - ray.o[d];
+          len += ray.dir[d] * ray.dir[d];
+        }
+        len = sqrtf(len);
+        if (len > 0.f) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) { ray.dir[d] = ray.dir[d] / len; ray.inv[d] = 1.f / ray.dir[d]; }
+          // ray / scene AABB intersection -> t_min (nerfacc ray_aabb_intersect); t_max = |p - o|
+          float tn = -1e30f, tf = 1e30f;
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
-            ray.o[d] = s_cams[ci * 3 + d];
-            ray.dir[d] = points[pi * 3 + d] - ray.o[d];
-            len += ray.dir[d] * ray.dir[d];
+            float ta = (a.scene_min[d] - ray.o[d]) * ray.inv[d], tb = (a.scene_max[d] - ray.o[d]) * ray.inv[d];
+            if (ta > tb) { const float tmp = ta; ta = tb; tb = tmp; }
+            tn = fmaxf(tn, ta); tf = fminf(tf, tb);
           }
-          len = sqrtf(len);
-          if (len > 0.f) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) { ray.dir[d] = ray.dir[d] / len; ray.inv[d] = 1.f / ray.dir[d]; }
-            // ray / scene AABB intersection -> t_min (nerfacc ray_aabb_intersect); t_max = |p - o|
-            float tn = -1e30f, tf = 1e30f;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              float ta = (a.scene_min[d] - ray.o[d]) * ray.inv[d], tb = (a.scene_max[d] - ray.o[d]) * ray.inv[d];
-              if (ta > tb) { const float tmp = ta; ta = tb; tb = tmp; }
-              tn = fmaxf(tn, ta); tf = fminf(tf, tb);
-            }
-            if (!(tn > tf)) {                             // else the ray misses the box
-              ray.len = len; ray.pi = pi; ray.ci = ci;
-              ray.t0 = fmaxf(tn, 0.f); ray.t1 = ray.t0 + a.step; ray.tm = 0.5f * (ray.t0 + ray.t1);
-              ray.T = 1.f; ray.best = 0.f;
-              started = true;
-            }
+          if (!(tn > tf)) {                             // else the ray misses the box
+            ray.len = len; ray.pi = pi; ray.ci = ci;
+            ray.t0 = fmaxf(tn, 0.f); ray.t1 = ray.t0 + a.step; ray.tm = 0.5f * (ray.t0 + ray.t1);
+            ray.T = 1.f; ray.best = 0.f;
+            started = true;
           }
         }
       }
+      n_cand -= take;
       // slots for the rays that really started (warp-uniform bookkeeping)
       const uint32_t st = __ballot_sync(0xffffffffu, started);
       if (started) { my_slot = l_free[n_free - 1 - __popc(st & lt_mask)]; have = true; }
       n_free -= __popc(st);
+      __syncwarp();
 #ifdef DRB_MARCH_STATS
       if (started) ++st_rays;
 #endif
@@ -903,8 +950,8 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
       __syncwarp();
     }
     // ---------------- phase B: 32 density samples at a time --------------------------------------
-    const uint32_t busy = __ballot_sync(0xffffffffu, have || ch_left > 0);
-    const bool drain = global_done && busy == 0 && n_resume == 0;
+    const uint32_t busy = __ballot_sync(0xffffffffu, have);
+    const bool drain = global_done && busy == 0 && n_resume == 0 && n_cand == 0;
     if (n_pend == 0 && drain) break;
     while (n_pend >= 32 || (drain && n_pend > 0)) {
       // lanes that are in the middle of a ray park it in its home slot (registers are needed below)
@@ -990,9 +1037,38 @@ static void keep_async_pool() {
   done = true;
 }
 
-__global__ void iota_kernel(int* __restrict__ v, int n) {
+struct MortonArgs { float roi_min[3], roi_inv[3]; };
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {      // 10 bits -> every third bit
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+// key = 30-bit Morton code of the point inside the ROI for active points, all ones otherwise (sorts last);
+// *count = number of active points.  Only the ORDER of the rays depends on it, never a result.
+__global__ void morton_key_kernel(const MortonArgs m, const float* __restrict__ points, int n,
+                                  const uint8_t* __restrict__ active, uint32_t* __restrict__ keys,
+                                  int* __restrict__ vals, int* __restrict__ count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) v[i] = i;
+  bool act = false;
+  if (i < n) {
+    act = active ? active[i] != 0 : true;
+    uint32_t key = 0xffffffffu;
+    if (act) {
+      uint32_t q[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float u = (points[i * 3 + d] - m.roi_min[d]) * m.roi_inv[d];
+        q[d] = (uint32_t)fminf(fmaxf(u * 1024.f, 0.f), 1023.f);
+      }
+      key = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
+    }
+    keys[i] = key;
+    vals[i] = i;
+  }
+  const uint32_t mask = __ballot_sync(0xffffffffu, act);
+  if ((threadIdx.x & 31) == 0 && mask) atomicAdd(count, __popc(mask));
 }
 
 static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary, int res,
@@ -1017,6 +1093,7 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
     a.max_skips = skips;
   }
   DRB_REQUIRE(levels_ok(p.lv), "drb_surface_mask: compile-time level table disagrees with host_levels()");
+  DRB_REQUIRE(((uintptr_t)pp->hash_table & 15) == 0, "drb_surface_mask: hash table must be 16-byte aligned");
   DRB_REQUIRE(n < (1 << kPiBits) && ncams <= kMaxCams,
               "drb_surface_mask: at most %d points and %d cameras per call", (1 << kPiBits) - 1, kMaxCams);
   const size_t smem = march_smem_bytes(ncams);
@@ -1040,33 +1117,38 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
     DRB_REQUIRE((bits & 0x7fffffu) != 0x7fffffu, "drb_surface_mask: unsupported ROI extent");
     aux.roi_rcp[d] = (float)(1.0 / (double)ext);
   }
-  // scratch: ray counter, active count, compacted (order preserving) list of active points
+  // scratch: ray counter, active count, the active points in Morton order (rays of neighbouring points
+  // run together in one warp), coarse occupancy bitmap, CUB temporaries
   keep_async_pool();
   uint8_t* scratch = nullptr;
   size_t cub_bytes = 0;
-  cub::DeviceSelect::Flagged(nullptr, cub_bytes, (const int*)nullptr, (const uint8_t*)nullptr, (int*)nullptr,
-                             (int*)nullptr, n, stream);
-  const size_t off_idx = 256, off_iota = off_idx + (((size_t)n * 4 + 255) & ~(size_t)255);
-  const size_t off_coarse = off_iota + (((size_t)n * 4 + 255) & ~(size_t)255);
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const int*)nullptr, (int*)nullptr, n, 0, 32, stream);
+  const size_t arr = ((size_t)n * 4 + 255) & ~(size_t)255;
+  const size_t off_kin = 256, off_kout = off_kin + arr, off_vin = off_kout + arr, off_vout = off_vin + arr;
+  const size_t off_coarse = off_vout + arr;
   const size_t off_cub = off_coarse + (size_t)kCoarseWords * 4;
   DRB_CUDA_OK(cudaMallocAsync(&scratch, off_cub + cub_bytes + 256, stream));
   DRB_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, stream));
   unsigned long long* counter = (unsigned long long*)scratch;
   int* count = (int*)(scratch + 64);
-  int* idx = nullptr;
-  if (active) {
-    idx = (int*)(scratch + off_idx);
-    int* iota = (int*)(scratch + off_iota);
-    iota_kernel<<<cdiv(n, 256), 256, 0, stream>>>(iota, n);
+  int* idx = (int*)(scratch + off_vout);
+  {
+    MortonArgs ma;
+    for (int d = 0; d < 3; ++d) { ma.roi_min[d] = a.roi_min[d]; ma.roi_inv[d] = 1.f / (a.roi_max[d] - a.roi_min[d]); }
+    morton_key_kernel<<<cdiv(n, 256), 256, 0, stream>>>(ma, points, n, active, (uint32_t*)(scratch + off_kin),
+                                                        (int*)(scratch + off_vin), count);
     DRB_LAUNCH_OK();
-    DRB_CUDA_OK(cub::DeviceSelect::Flagged(scratch + off_cub, cub_bytes, iota, active, idx, count, n, stream));
+    DRB_CUDA_OK(cub::DeviceRadixSort::SortPairs(scratch + off_cub, cub_bytes, (const uint32_t*)(scratch + off_kin),
+                                                (uint32_t*)(scratch + off_kout), (const int*)(scratch + off_vin),
+                                                idx, n, 0, 32, stream));
   }
   aux.coarse = (const uint32_t*)(scratch + off_coarse);
   coarse_occ_kernel<<<cdiv(aux.coarse_words * 32, 256), 256, 0, stream>>>(occ_binary, res, aux.coarse_shift,
                                                                          aux.coarse_dim, (uint32_t*)(scratch + off_coarse));
   DRB_LAUNCH_OK();
   const int grid = igemm_num_sms();
-  const int* cnt = active ? count : nullptr;
+  const int* cnt = count;
   surface_mask_kernel<<<grid, kMarchThreads, smem, stream>>>(p, a, aux, occ_binary, points, n, cam_origins, ncams,
                                                              idx, cnt, counter, surface);
   DRB_LAUNCH_OK();

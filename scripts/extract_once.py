@@ -8,7 +8,8 @@ occ, poses = pkg.synthetic.extract_scene(128, 50)
 meta = dict(pkg.synthetic.extract_meta(poses), camera_poses=poses.to(dev))
 sg = pkg.SampleGrid(list(pkg.synthetic.AABB), 128)
 occ_d = occ.to(dev)
-f = pkg.synthetic.make_ngp_field(seed=500).to(dev)
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 500
+f = pkg.synthetic.make_ngp_field(seed=seed).to(dev)
 for rep in range(reps):
     torch.cuda.synchronize(); t = time.time()
     g, m = pkg.extract_block(f, sg, occ_d, meta, dev)

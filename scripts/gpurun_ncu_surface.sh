@@ -1,6 +1,5 @@
 cd /root/repo
 mkdir -p gpurun_out
-python scripts/extract_once.py 4
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/extract_launches.csv python scripts/extract_once.py 3 > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:surface_mask -s 2 -c 1 -f -o gpurun_out/surface_full python scripts/extract_once.py 3 > gpurun_out/ncu_surface.log 2>&1
+SEED=${SEED:-501}
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:surface_mask -s 2 -c 1 -f -o gpurun_out/surface_full python scripts/extract_once.py 3 $SEED > gpurun_out/ncu_surface.log 2>&1
 tail -3 gpurun_out/ncu_surface.log
