@@ -322,19 +322,6 @@ def run_ours(args):
                 stage_ms["n"] += 1
             return pose
 
-        def surface_kernel_ms(i):
-            """device time of the two surface-field launches of one step (event-bracketed in the library)"""
-            import ctypes
-            lib = pkg.load_library()
-            tot = 0.0
-            with torch.no_grad():
-                for f in dev_fields[i % N_RESIDENT_PAIRS]:
-                    pkg.extract_block(f, sgrid, occ_dev, meta, dev)
-                    ms_ = ctypes.c_float(0.0)
-                    lib.drb_extract_last_surface_ms(ctypes.byref(ms_))
-                    tot += ms_.value
-            return tot
-
         # e2e: the NeRF parameters of step i+1 are copied on a side stream while step i computes
         side = torch.cuda.Stream()
         slot_fields = [[pkg.synthetic.make_ngp_field(seed=900 + s_ * 2 + side_).to(dev) for side_ in (0, 1)]
@@ -377,11 +364,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    import ctypes
+    lib = pkg.load_library()
+    surf_prof = {"ms": 0.0, "launches": 0, "stats": [0, 0, 0, 0]}
+
     def timed(fn, steps, profile=False):
         barrier()
         model.set_profile(profile)
         if profile:
             model.read_profile()
+            if full:                      # surface-field kernel: events + work counters over the timed steps
+                st = (ctypes.c_ulonglong * 4)()
+                lib.drb_march_stats(st, 1)
+                lib.drb_extract_set_profile(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = model.launch_count()
         e0.record()
@@ -395,6 +390,13 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         prof = model.read_profile() if profile else None
         model.set_profile(False)
+        if profile and full:
+            ms_, n_ = ctypes.c_float(0.0), ctypes.c_int(0)
+            lib.drb_extract_read_profile(ctypes.byref(ms_), ctypes.byref(n_))
+            lib.drb_extract_set_profile(0)
+            st = (ctypes.c_ulonglong * 4)()
+            lib.drb_march_stats(st, 1)
+            surf_prof.update(ms=ms_.value, launches=n_.value, stats=[int(v) for v in st])
         return float(t.item()), model.launch_count() - l0, prof
 
     for i in range(max(args.warmup, 3)):
@@ -407,11 +409,9 @@ def run_ours(args):
     for i in range(2):
         step_e2e(i)
     ms_e2e, _, _ = timed(step_e2e, args.steps)
-    surf_ms = 0.0
     if full:
         for i in range(min(args.steps, 3)):          # untimed extra steps: per-stage split
             step_resident(i, timed_stages=True)
-        surf_ms = sum(surface_kernel_ms(i) for i in range(N_RESIDENT_PAIRS)) / N_RESIDENT_PAIRS
 
     if rank == 0:
         peaks = _peaks()
@@ -456,22 +456,35 @@ def run_ours(args):
                          "mma_flops_factor": mma_factor, "tensor_pipe_frac_est": mma_factor * achieved / peak},
         }
         if full:
-            # In the full path the surface-field ray marcher is the dominant kernel: a gather/latency-bound
-            # kernel (DRAM idle, L2 hit rate 99 %), reported against the HBM roofline as the contract asks.
+            # In the full path the surface-field ray marcher is the dominant kernel.  DRAM is idle (the 48 MB
+            # table is L2 resident); the kernel is bound by the rate at which an SM can miss 32-byte sectors
+            # of the hash table into L2 (random 8-byte gathers, 128 per density sample).  Reported against
+            # the HBM roofline as the contract asks: `achieved` = algorithmic bytes (every input read once),
+            # `issued_*` = the gather traffic the algorithm issues (samples x 128 corners x 8 B).
             n_cand = int(occ.sum())
-            table_b = int(pkg.load_library().drb_ngp_table_entries()) * 8
-            alg_bytes = 2 * (table_b + RES ** 3 + n_cand * (12 + 1 + 1) + args.cams * 12)   # two launches
+            table_b = int(lib.drb_ngp_table_entries()) * 8
+            n_l = max(surf_prof["launches"], 1)
+            surf_ms = surf_prof["ms"] / n_l                                   # per launch, inside the timed steps
+            alg_bytes = table_b + RES ** 3 + n_cand * (12 + 1 + 1) + args.cams * 12   # one launch
             hb = alg_bytes / (surf_ms / 1e3) / 1e9 if surf_ms > 0 else 0.0
+            rays, skips, samples, rounds = surf_prof["stats"]
+            issued = samples * 1024.0 / n_l
             line["roofline_register"] = line["roofline"]
             line["roofline"] = {
-                "bound": "hbm", "kernel": "surface_mask_kernel<512> (occupancy-grid ray marcher + fused hash-grid/MLP "
-                                          "density), the 2 launches of a step",
+                "bound": "hbm", "kernel": "surface_mask_kernel (occupancy-grid ray marcher + fused hash-grid / tensor-core "
+                                          "MLP density), the %d launches of the timed steps" % surf_prof["launches"],
                 "achieved": hb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hb / peaks["hbm_gbs"],
-                "peak_source": peaks["source"], "traffic": 57.3e6,
-                "traffic_note": "dram read+write of one launch, ncu --set full (profiles/r01_ncu_full_surface_summary.csv)",
-                "kernel_ms_per_step": surf_ms, "kernel_share_of_step": surf_ms / (ms / args.steps),
-                "note": "algorithmic bytes = hash table + occupancy grid + points + masks, each read once; the kernel "
-                        "is L2-gather / latency bound (128 table gathers per density sample), not bandwidth bound"}
+                "peak_source": peaks["source"], "traffic": 45.3e6,
+                "traffic_note": "dram read+write of one launch, ncu --set full (profiles/r01_v4_ncu_surface_summary.txt)",
+                "kernel_ms_per_launch": surf_ms, "launches": surf_prof["launches"],
+                "kernel_ms_per_step": surf_prof["ms"] / args.steps,
+                "kernel_share_of_step": surf_prof["ms"] / ms,
+                "per_launch": {"rays": rays / n_l, "skip_events": skips / n_l, "density_samples": samples / n_l},
+                "issued_gather_bytes_per_launch": issued,
+                "issued_gather_gbs": issued / (surf_ms / 1e3) / 1e9 if surf_ms > 0 else 0.0,
+                "density_samples_per_s": samples / (surf_prof["ms"] / 1e3) if surf_prof["ms"] > 0 else 0.0,
+                "note": "algorithmic bytes = hash table + occupancy grid + points + masks + cameras, each read once per "
+                        "launch; the kernel is L1-miss / L2-gather bound (DRAM idle), not bandwidth bound"}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(pkg, model, args.stage, args.cams)
         print(json.dumps(line), flush=True)

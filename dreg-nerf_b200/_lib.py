@@ -114,6 +114,9 @@ SIGNATURES = {
     "drb_extract_block": (c_int, [C.POINTER(NgpParams), C.POINTER(ExtractDesc), c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "drb_extract_last_surface_ms": (c_int, [C.POINTER(c_float)]),
+    "drb_march_stats": (c_int, [C.POINTER(C.c_ulonglong), c_int]),
+    "drb_extract_set_profile": (c_int, [c_int]),
+    "drb_extract_read_profile": (c_int, [C.POINTER(c_float), C.POINTER(c_int)]),
     "drb_engine_create": (c_int, [C.POINTER(EngineConfig), C.POINTER(c_void_p)]),
     "drb_engine_destroy": (None, [c_void_p]),
     "drb_engine_num_params": (c_int, [c_void_p]),

@@ -12,9 +12,6 @@ SOURCES = ["igemm.cu", "elementwise.cu", "points.cu", "transformer.cu", "procrus
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]   # IEEE math on purpose
-for _flag in ("DRB_MARCH_STATS",):      # experiment switches (never set in production)
-    if os.environ.get(_flag):
-        NVCC_FLAGS.append("-D" + _flag)
 if os.environ.get("DRB_SMEM_LEVELS"):
     NVCC_FLAGS.append("-DDRB_SMEM_LEVELS=" + os.environ["DRB_SMEM_LEVELS"])
 

@@ -17,6 +17,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <vector>
+
 namespace drb {
 
 int igemm_num_sms();
@@ -270,17 +272,60 @@ __device__ __forceinline__ void sh4(float x, float y, float z, float o[16]) {
 static constexpr int kMaxDirs = 32;
 struct DirTable { float d[kMaxDirs][3]; int n; };
 
-__global__ void __launch_bounds__(256)
+// Tensor-core version: one warp owns 32 points (two m16 tiles).  Layer 1's feature part
+// (15 -> 64) and layer 2 (64 -> 64, once per direction) run as 3xTF32 mma.sync m16n8k8
+// (hi*hi + lo*hi + hi*lo, fp32 accumulate, ~2^-21 relative).  The accumulator layout of one layer
+// is fed straight back as the A operand of the next one: within every block of 8 hidden units the
+// K index is permuted (fragment column t <-> unit 2t, t+4 <-> 2t+1), and the B fragments are
+// pre-arranged with the same permutation, so no shuffle or shared-memory round trip is needed.
+// Layer 3 (64 -> 3) + sigmoid + mean over the directions happen in the accumulator layout with one
+// quad reduction per direction.
+static constexpr int kRgbThreads = 256;
+struct RgbSmem {
+  float4 b2[8 * 8 * 32];      // layer 2 B fragments [ks][nt][lane] = (hi b0, hi b1, lo b0, lo b1)
+  float4 b1[2 * 8 * 32];      // layer 1 (feature columns 16..30 of c1, column 31 handled in dir[])
+  float dir[kMaxDirs][64];    // SH (+ padded-one column) contribution of layer 1 per direction
+  float c3[3][64];
+};
+
+__device__ __forceinline__ uint32_t f2u(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ void mma_1688(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// acc (+)= A(hi, lo) x B(hi, lo) for one k-step / n-tile, small terms first
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], const float4& b) {
+  mma_1688(c, alo, f2u(b.x), f2u(b.y));
+  mma_1688(c, ahi, f2u(b.z), f2u(b.w));
+  mma_1688(c, ahi, f2u(b.x), f2u(b.y));
+}
+
+__global__ void __launch_bounds__(kRgbThreads, 1)
 ngp_rgb_kernel(const NgpDev p, const float* __restrict__ feat, int n, const DirTable dirs,
                float* __restrict__ rgb) {
-  __shared__ float s_c1[64][32];
-  __shared__ float s_c2[64][64];
-  __shared__ float s_c3[3][64];
-  __shared__ float s_dir[kMaxDirs][64];     // SH (+ padded-one column) contribution per direction
-  for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) s_c1[i / 32][i % 32] = p.c1[i];
-  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) s_c2[i / 64][i % 64] = p.c2[i];
-  for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) s_c3[i / 64][i % 64] = p.c3[i];
-  __syncthreads();
+  extern __shared__ __align__(16) uint8_t rgb_smem_raw[];
+  RgbSmem& sm = *(RgbSmem*)rgb_smem_raw;
+  // ---- staging: B fragments with the permuted K order, per-direction SH contributions ----
+  for (int i = threadIdx.x; i < 8 * 8 * 32; i += blockDim.x) {
+    const int ln = i & 31, nt = (i >> 5) & 7, ks = i >> 8;
+    const int nn = 8 * nt + (ln >> 2), k0 = 8 * ks + 2 * (ln & 3);
+    const float w0 = p.c2[nn * 64 + k0], w1 = p.c2[nn * 64 + k0 + 1];
+    const float h0 = tf32_trunc(w0), h1 = tf32_trunc(w1);
+    sm.b2[i] = make_float4(h0, h1, tf32_trunc(w0 - h0), tf32_trunc(w1 - h1));
+  }
+  for (int i = threadIdx.x; i < 2 * 8 * 32; i += blockDim.x) {
+    const int ln = i & 31, nt = (i >> 5) & 7, ks = i >> 8;
+    const int nn = 8 * nt + (ln >> 2), k0 = 8 * ks + 2 * (ln & 3);
+    // feature q sits in column 16 + q of c1; q = 15 is the padding column (its input is the constant 1,
+    // folded into dir[] below), so it contributes nothing here
+    const float w0 = p.c1[nn * 32 + 16 + k0], w1 = (k0 + 1 < 15) ? p.c1[nn * 32 + 16 + k0 + 1] : 0.f;
+    const float h0 = tf32_trunc(w0), h1 = tf32_trunc(w1);
+    sm.b1[i] = make_float4(h0, h1, tf32_trunc(w0 - h0), tf32_trunc(w1 - h1));
+  }
+  for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) sm.c3[i / 64][i % 64] = p.c3[i];
   for (int i = threadIdx.x; i < dirs.n * 64; i += blockDim.x) {
     const int k = i / 64, j = i % 64;
     // (dir + 1) / 2 -> tcnn maps back to [-1, 1] before evaluating the basis (ngp.py:181)
@@ -289,39 +334,118 @@ ngp_rgb_kernel(const NgpDev p, const float* __restrict__ feat, int n, const DirT
     const float dz = ((dirs.d[k][2] + 1.f) * 0.5f) * 2.f - 1.f;
     float sh[16];
     sh4(dx, dy, dz, sh);
-    float acc = s_c1[j][31];                 // width padding column is fed with 1 (tcnn Identity pad)
+    float acc = p.c1[j * 32 + 31];           // width padding column is fed with 1 (tcnn Identity pad)
 #pragma unroll
-    for (int q = 0; q < 16; ++q) acc = fmaf(s_c1[j][q], sh[q], acc);
-    s_dir[k][j] = acc;
+    for (int q = 0; q < 16; ++q) acc = fmaf(p.c1[j * 32 + q], sh[q], acc);
+    sm.dir[k][j] = acc;
   }
   __syncthreads();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float e[15];
+
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int n_batches = (n + 31) / 32;
+  for (int batch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); batch < n_batches; batch += warps_total) {
+    const int row0 = batch * 32;
+    // ---- layer 1, feature part: h1[32 x 64] = E[32 x 16] * C1f^T, accumulator layout ----
+    float h1[2][8][4];
 #pragma unroll
-    for (int q = 0; q < 15; ++q) e[q] = feat[(long long)i * 15 + q];
-    float h1[64];
-#pragma unroll 8
-    for (int j = 0; j < 64; ++j) {
-      float acc = 0.f;
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int q = 0; q < 15; ++q) acc = fmaf(s_c1[j][16 + q], e[q], acc);
-      h1[j] = acc;
-    }
-    float r = 0.f, g = 0.f, b = 0.f;
-    for (int k = 0; k < dirs.n; ++k) {
-      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-#pragma unroll 4
-      for (int j2 = 0; j2 < 64; ++j2) {
-        float acc = 0.f;
+      for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-        for (int j = 0; j < 64; ++j) acc = fmaf(s_c2[j2][j], fmaxf(h1[j] + s_dir[k][j], 0.f), acc);
-        acc = fmaxf(acc, 0.f);
-        o0 = fmaf(s_c3[0][j2], acc, o0); o1 = fmaf(s_c3[1][j2], acc, o1); o2 = fmaf(s_c3[2][j2], acc, o2);
+        for (int i = 0; i < 4; ++i) h1[mt][nt][i] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          // fragment (row g + 8*(i&1), column t + 4*(i>>1)) <-> feature 8*ks + 2t + (i>>1)
+          const int r = row0 + 16 * mt + g + 8 * (i & 1), q = 8 * ks + 2 * t + (i >> 1);
+          const float v = (r < n && q < 15) ? feat[(long long)r * 15 + q] : 0.f;
+          const float hi = tf32_trunc(v);
+          ahi[mt][i] = f2u(hi);
+          alo[mt][i] = f2u(tf32_trunc(v - hi));
+        }
       }
-      r += 1.f / (1.f + expf(-o0)); g += 1.f / (1.f + expf(-o1)); b += 1.f / (1.f + expf(-o2));
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float4 b = sm.b1[(ks * 8 + nt) * 32 + lane];
+        mma3(h1[0][nt], ahi[0], alo[0], b);
+        mma3(h1[1][nt], ahi[1], alo[1], b);
+      }
     }
-    const float inv = 1.f / (float)dirs.n;
-    rgb[(long long)i * 3] = r * inv; rgb[(long long)i * 3 + 1] = g * inv; rgb[(long long)i * 3 + 2] = b * inv;
+    // ---- per direction: layer 2 on the tensor cores, layer 3 + sigmoid in the accumulator layout ----
+    float sum[3] = {0.f, 0.f, 0.f};          // lane (g, t) accumulates the colour of row g + 8t
+    for (int k = 0; k < dirs.n; ++k) {
+      float acc[2][8][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        // A fragment of k-step ks = relu(h1 + dir) of hidden units 8*ks + {2t, 2t+1}: exactly what this lane
+        // holds in h1[mt][ks][*] (accumulator (g, 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1))
+        const float2 dv = *(const float2*)&sm.dir[k][8 * ks + 2 * t];
+        uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const float v[4] = {fmaxf(h1[mt][ks][0] + dv.x, 0.f), fmaxf(h1[mt][ks][2] + dv.x, 0.f),
+                              fmaxf(h1[mt][ks][1] + dv.y, 0.f), fmaxf(h1[mt][ks][3] + dv.y, 0.f)};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float hi = tf32_trunc(v[i]);
+            ahi[mt][i] = f2u(hi);
+            alo[mt][i] = f2u(tf32_trunc(v[i] - hi));
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const float4 b = sm.b2[(ks * 8 + nt) * 32 + lane];
+          mma3(acc[0][nt], ahi[0], alo[0], b);
+          mma3(acc[1][nt], ahi[1], alo[1], b);
+        }
+      }
+      // layer 3: o[c] = sum_j2 c3[c][j2] * relu(h2[j2]); this lane holds units 8*nt + {2t, 2t+1}
+      float o[4][3];                           // rows g, g+8, g+16, g+24
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { o[r][0] = 0.f; o[r][1] = 0.f; o[r][2] = 0.f; }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float2 w = *(const float2*)&sm.c3[c][8 * nt + 2 * t];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            o[2 * mt][c] = fmaf(w.x, fmaxf(acc[mt][nt][0], 0.f), o[2 * mt][c]);
+            o[2 * mt][c] = fmaf(w.y, fmaxf(acc[mt][nt][1], 0.f), o[2 * mt][c]);
+            o[2 * mt + 1][c] = fmaf(w.x, fmaxf(acc[mt][nt][2], 0.f), o[2 * mt + 1][c]);
+            o[2 * mt + 1][c] = fmaf(w.y, fmaxf(acc[mt][nt][3], 0.f), o[2 * mt + 1][c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          o[r][c] += __shfl_xor_sync(0xffffffffu, o[r][c], 1);
+          o[r][c] += __shfl_xor_sync(0xffffffffu, o[r][c], 2);
+        }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float mine = t == 0 ? o[0][c] : (t == 1 ? o[1][c] : (t == 2 ? o[2][c] : o[3][c]));
+        sum[c] += 1.f / (1.f + expf(-mine));
+      }
+    }
+    const int r = row0 + g + 8 * t;
+    if (r < n) {
+      const float inv = 1.f / (float)dirs.n;
+      rgb[(long long)r * 3] = sum[0] * inv; rgb[(long long)r * 3 + 1] = sum[1] * inv; rgb[(long long)r * 3 + 2] = sum[2] * inv;
+    }
   }
 }
 
@@ -335,9 +459,15 @@ extern "C" int drb_ngp_rgb_mean(const drb_ngp_params* pp, const float* feat, int
   dt.n = ndirs;
   for (int k = 0; k < ndirs; ++k)
     for (int d = 0; d < 3; ++d) dt.d[k][d] = host_dirs[k * 3 + d];
-  int grid = cdiv(n, 256);
-  if (grid > 148 * 4) grid = 148 * 4;
-  ngp_rgb_kernel<<<grid, 256, 0, stream>>>(p, feat, n, dt, rgb);
+  static bool attr = false;
+  if (!attr) {
+    DRB_CUDA_OK(cudaFuncSetAttribute(ngp_rgb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RgbSmem)));
+    attr = true;
+  }
+  const int warps = kRgbThreads / 32;
+  int grid = cdiv(cdiv(n, 32), warps);
+  if (grid > igemm_num_sms()) grid = igemm_num_sms();
+  ngp_rgb_kernel<<<grid, kRgbThreads, sizeof(RgbSmem), stream>>>(p, feat, n, dt, rgb);
   DRB_LAUNCH_OK();
   return 0;
 }
@@ -427,7 +557,8 @@ __device__ __forceinline__ void encode_level(const NgpDev& p, const float2* __re
   // x-neighbours (corners c and c^1) are adjacent table entries whenever the x index of the lower
   // corner is even (dense: idx, idx + 1; hashed: idx, idx ^ 1), i.e. one aligned 16-byte load serves
   // both.  The load/store unit is bound by wavefronts (one per distinct sector per instruction), so
-  // this removes a quarter of them; odd x indices fetch the upper corner separately.
+  // this removes a quarter of them; odd x indices fetch the upper corner separately.  (Reading the fine
+  // levels with L1::no_allocate was measured 10 % slower on B200 and is not used.)
   uint32_t idx0[4], idx1[4];              // lower / upper x corner of the 4 (y, z) combinations
   if constexpr (lvl_dense(L)) {
     const uint32_t base = g[0] + g[1] * res + g[2] * (res * res);
@@ -512,7 +643,10 @@ __device__ __forceinline__ void encode_level(const NgpDev& p, const float2* __re
 // pre-arranged per (k-step, n-tile, lane) at staging time.  The tile is kept this small on purpose:
 // every KB of shared memory is a KB less L1 for the table gathers, which bound the kernel.
 // ------------------------------------------------------------------------------------------
-static constexpr int kMarchSmemLevels = 1;           // hash levels staged in shared memory by the marcher
+#ifndef DRB_MARCH_SMEM_LEVELS
+#define DRB_MARCH_SMEM_LEVELS 1
+#endif
+static constexpr int kMarchSmemLevels = DRB_MARCH_SMEM_LEVELS;           // hash levels staged in shared memory by the marcher
 static constexpr int kTilePitch = 12;                 // words per sample row of the A tile (one K-step)
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
@@ -631,10 +765,14 @@ __device__ __forceinline__ float warp_density_raw(const NgpDev& p, const float2*
 // rounded quotient (Markstein) without the MUFU/slow-path sequence.  Camera origins are staged in
 // shared memory as well.
 // ------------------------------------------------------------------------------------------
-__device__ unsigned long long g_march_stats[4];   // rays, skip events, samples, rounds (debug)
-extern "C" int drb_debug_march_stats(unsigned long long* host4, int reset) {
-  cudaMemcpyFromSymbol(host4, g_march_stats, sizeof(unsigned long long) * 4);
-  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_march_stats, z, sizeof(z)); }
+__device__ unsigned long long g_march_stats[4];   // rays, skip events, density samples, warp rounds
+extern "C" int drb_march_stats(unsigned long long* host4, int reset) {
+  DRB_REQUIRE(host4, "drb_march_stats: null argument");
+  DRB_CUDA_OK(cudaMemcpyFromSymbol(host4, g_march_stats, sizeof(unsigned long long) * 4));
+  if (reset) {
+    const unsigned long long z[4] = {0, 0, 0, 0};
+    DRB_CUDA_OK(cudaMemcpyToSymbol(g_march_stats, z, sizeof(z)));
+  }
   return 0;
 }
 
@@ -767,9 +905,7 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
   bool have = false;          // this lane is advancing a ray (state in registers, home slot my_slot)
   int my_slot = -1;
   bool global_done = false;   // warp-uniform: the global ray counter is exhausted
-#ifdef DRB_MARCH_STATS
-  unsigned long long st_rays = 0, st_skips = 0, st_samples = 0, st_rounds = 0;
-#endif
+  uint32_t st_rays = 0, st_skips = 0, st_samples = 0, st_rounds = 0;   // roofline accounting
 
   auto store_ray = [&](int s) {
     slots[0 * kSlots + s] = ray.dir[0]; slots[1 * kSlots + s] = ray.dir[1]; slots[2 * kSlots + s] = ray.dir[2];
@@ -794,9 +930,7 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
   for (uint32_t round = 0;; ++round) {
     // watchdog: a scheduling bug must not hang the GPU box (~30 s at 2 GHz, then give up)
     if ((round & 0xfffu) == 0xfffu && clock64() - t_start > 60000000000LL) break;
-#ifdef DRB_MARCH_STATS
     ++st_rounds;
-#endif
     // ---------------- refill: lanes without a ray take a resumable one, else start new rays ------
     {
       const uint32_t need = __ballot_sync(0xffffffffu, !have);
@@ -882,9 +1016,7 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
       if (started) { my_slot = l_free[n_free - 1 - __popc(st & lt_mask)]; have = true; }
       n_free -= __popc(st);
       __syncwarp();
-#ifdef DRB_MARCH_STATS
       if (started) ++st_rays;
-#endif
     }
 
     // ---------------- phase A: advance until a sample is pending (bounded number of skips) -------
@@ -932,9 +1064,7 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
         const float tt = ray.tm + fmaxf(dist, 0.f);
         do { ray.tm += a.step; } while (ray.tm < tt);
         ray.t0 = ray.tm - 0.5f * a.step; ray.t1 = ray.tm + 0.5f * a.step;
-#ifdef DRB_MARCH_STATS
         ++st_skips;
-#endif
       }
     }
     // ---------------- park the rays whose sample is pending --------------------------------------
@@ -1002,9 +1132,7 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
           slots[7 * kSlots + s] = T; slots[8 * kSlots + s] = best;
           resume = true;
         }
-#ifdef DRB_MARCH_STATS
         ++st_samples;
-#endif
       }
       const uint32_t rm = __ballot_sync(0xffffffffu, resume), fm = __ballot_sync(0xffffffffu, release);
       if (resume) l_resume[n_resume + __popc(rm & lt_mask)] = (uint8_t)s;
@@ -1015,11 +1143,14 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
       load_ray(my_slot, have);
     }
   }
-#ifdef DRB_MARCH_STATS
-  atomicAdd(&g_march_stats[0], st_rays); atomicAdd(&g_march_stats[1], st_skips);
-  atomicAdd(&g_march_stats[2], st_samples);
-  if (lane == 0) atomicAdd(&g_march_stats[3], st_rounds);
-#endif
+  {
+    const unsigned long long r = __reduce_add_sync(0xffffffffu, st_rays), k = __reduce_add_sync(0xffffffffu, st_skips);
+    const unsigned long long m = __reduce_add_sync(0xffffffffu, st_samples);
+    if (lane == 0) {
+      atomicAdd(&g_march_stats[0], r); atomicAdd(&g_march_stats[1], k);
+      atomicAdd(&g_march_stats[2], m); atomicAdd(&g_march_stats[3], (unsigned long long)st_rounds);
+    }
+  }
 }
 
 // The stream-ordered allocator gives memory back to the OS at every synchronisation unless a release
@@ -1210,16 +1341,42 @@ __global__ void finish_extract_kernel(const long long* __restrict__ occupied, in
   }
 }
 
-// Roofline instrumentation: device time of the surface-field kernel of the most recent
-// drb_extract_block on this thread (CUDA events on the launching stream).  Synchronises on the event.
+// Roofline instrumentation: device time of the surface-field kernel (CUDA events on the launching
+// stream).  drb_extract_last_surface_ms: the calling thread's most recent drb_extract_block.
+// Profile mode: every drb_extract_block of this thread appends an event pair; drb_extract_read_profile
+// synchronises on them once, returns the summed kernel time and the launch count, and clears the list
+// (this is how bench.py times the kernel INSIDE its timed steps without a sync per call).
 static thread_local cudaEvent_t g_surf_ev[2] = {nullptr, nullptr};
 static thread_local bool g_surf_valid = false;
+static thread_local bool g_surf_profile = false;
+static thread_local std::vector<cudaEvent_t>* g_surf_list = nullptr;
 extern "C" int drb_extract_last_surface_ms(float* host_ms) {
   DRB_REQUIRE(host_ms, "drb_extract_last_surface_ms: null argument");
   *host_ms = 0.f;
   if (!g_surf_valid) return 0;
   DRB_CUDA_OK(cudaEventSynchronize(g_surf_ev[1]));
   DRB_CUDA_OK(cudaEventElapsedTime(host_ms, g_surf_ev[0], g_surf_ev[1]));
+  return 0;
+}
+extern "C" int drb_extract_set_profile(int on) {
+  g_surf_profile = on != 0;
+  if (g_surf_profile && !g_surf_list) g_surf_list = new std::vector<cudaEvent_t>();
+  return 0;
+}
+extern "C" int drb_extract_read_profile(float* total_ms, int* launches) {
+  DRB_REQUIRE(total_ms && launches, "drb_extract_read_profile: null argument");
+  *total_ms = 0.f;
+  *launches = 0;
+  if (!g_surf_list) return 0;
+  for (size_t i = 0; i + 1 < g_surf_list->size(); i += 2) {
+    float ms = 0.f;
+    DRB_CUDA_OK(cudaEventSynchronize((*g_surf_list)[i + 1]));
+    DRB_CUDA_OK(cudaEventElapsedTime(&ms, (*g_surf_list)[i], (*g_surf_list)[i + 1]));
+    *total_ms += ms;
+    ++*launches;
+  }
+  for (cudaEvent_t e : *g_surf_list) cudaEventDestroy(e);
+  g_surf_list->clear();
   return 0;
 }
 
@@ -1251,11 +1408,14 @@ extern "C" int drb_extract_block(const drb_ngp_params* pp, const drb_extract_des
   if (!rc) rc = drb_ngp_rgb_mean(pp, feat, n, e->host_dirs, e->ndirs, rgb, stream);
   if (!rc) {
     if (!g_surf_ev[0]) { cudaEventCreate(&g_surf_ev[0]); cudaEventCreate(&g_surf_ev[1]); }
+    cudaEvent_t pe[2] = {nullptr, nullptr};
+    if (g_surf_profile) { cudaEventCreate(&pe[0]); cudaEventCreate(&pe[1]); cudaEventRecord(pe[0], stream); }
     cudaEventRecord(g_surf_ev[0], stream);
     rc = surface_mask_impl(pp, e->occ_binary, e->res, e->roi_aabb, e->scene_aabb, points, n, e->cam_origins,
                            e->ncams, e->render_step_size, e->cut_off,
                            e->surface_only_where_dense ? density_mask : nullptr, surface_mask, stream);
     cudaEventRecord(g_surf_ev[1], stream);
+    if (g_surf_profile) { cudaEventRecord(pe[1], stream); g_surf_list->push_back(pe[0]); g_surf_list->push_back(pe[1]); }
     g_surf_valid = true;
   }
   if (!rc) {

@@ -260,6 +260,17 @@ int drb_extract_block(const drb_ngp_params* p, const drb_extract_desc* e, float*
  * drb_extract_block (roofline instrumentation; waits for that kernel). */
 int drb_extract_last_surface_ms(float* host_ms);
 
+/* Profile mode (per calling thread): while on, every drb_extract_block records the surface-field
+ * kernel's start/stop events; drb_extract_read_profile waits for them, returns the summed kernel time
+ * and the number of launches, and clears the record. */
+int drb_extract_set_profile(int on);
+int drb_extract_read_profile(float* total_ms, int* launches);
+
+/* Work counters of the surface-field kernel accumulated on the current device since the last reset:
+ * host4 = {rays marched, empty-space skip events, density samples, warp scheduling rounds}.
+ * Synchronises the device (roofline instrumentation: issued gather bytes = samples * 1024). */
+int drb_march_stats(unsigned long long* host4, int reset);
+
 /* ------------------------------------------------------------------------------------------
  * Whole-path engine: NeRFRegTr.forward (conerf/register/nerf_regtr.py:112-248) without Python in
  * the loop.  Parameters are addressed by the reference's state-dict key.
