@@ -758,8 +758,13 @@ __device__ __forceinline__ float warp_density_raw(const NgpDev& p, const float2*
 // busy, layer 1 on the tensor cores - and the rays go back to the resume list.  Before this
 // rewrite the kernel ran with 14 of 32 lanes active on average (ncu, round 1).
 //
+// Shared-memory diet.  Phase B is bound by the rate at which an SM can miss table sectors into L2, so
+// L1 capacity matters more than anything kept in shared memory: the plan below (hash level 0, B
+// fragments, coarse bitmap, 16 x (A tile + 64 ray slots + lists)) stays under 132 KB, which leaves a
+// 96 KB L1 (measured: 29 -> 26 ms on the heaviest synthetic block against the 164 KB carve-out).
+//
 // Latency.  Phase A is a chain of dependent occupancy lookups.  A coarse "any voxel occupied"
-// bitmap (cells of cf^3 voxels, <= 64^3 bits = 32 KB) sits in shared memory and answers most
+// bitmap (cells of cf^3 voxels, <= 32^3 bits = 4 KB) sits in shared memory and answers most
 // lookups of the empty-space approach without leaving the SM; the IEEE divisions by the ROI
 // extent are done as q = x*y, r = fma(-e, q, x), q + r*y with y = RN(1/e), which is the correctly
 // rounded quotient (Markstein) without the MUFU/slow-path sequence.  Camera origins are staged in
@@ -781,9 +786,15 @@ static constexpr int kMarchWarps = kMarchThreads / 32;
 static constexpr int kSlots = 64;                    // rays per warp (in flight + pending + resumable)
 static constexpr int kSlotWords = 10;                // dir[3] len t0 t1 tm T best (pi | cam << 22)
 static constexpr int kPiBits = 22;
-static constexpr int kWindow = 128;                  // consecutive rays a warp takes from the global counter per fetch
+#ifndef DRB_WINDOW
+#define DRB_WINDOW 64
+#endif
+static constexpr int kWindow = DRB_WINDOW;                  // consecutive rays a warp takes from the global counter per fetch
 static constexpr int kCandCap = 32 + kWindow;        // per-warp queue of rays that passed the "not yet seen" test
-static constexpr int kCoarseMaxDim = 64;             // coarse occupancy bitmap: at most 64^3 bits (32 KB)
+#ifndef DRB_COARSE_DIM
+#define DRB_COARSE_DIM 32
+#endif
+static constexpr int kCoarseMaxDim = DRB_COARSE_DIM;             // coarse occupancy bitmap: at most DRB_COARSE_DIM^3 bits (32^3 = 4 KB)
 static constexpr int kCoarseWords = kCoarseMaxDim * kCoarseMaxDim * kCoarseMaxDim / 32;
 static constexpr int kMaxCams = (1 << (32 - kPiBits)) - 1;
 static constexpr size_t kWarpBytes = (size_t)32 * kTilePitch * 4 + (size_t)kSlots * kSlotWords * 4 + 3 * kSlots +
