@@ -120,3 +120,41 @@ def test_extract_then_register_128(pkg, cuda):
     with torch.no_grad():
         out = model(data)
     assert out["pose"].shape == (6, 1, 3, 4) and torch.isfinite(out["pose"]).all()
+
+
+def test_surface_mask_schedule_independent_128(pkg, cuda):
+    """Full-size (128^3, 50 cameras) property test of the ray scheduler: the surface-field mask is an OR
+    over (camera, point) rays, so it must not depend on the order in which rays are scheduled.  Marching
+    all candidate cells vs only the dense ones (different Morton windows, different warp batches) and a
+    permuted camera list must give bit-identical voxel masks; the work counters must add up."""
+    import ctypes
+    res = 128
+    occ, poses = pkg.synthetic.extract_scene(res, 50)
+    meta = dict(pkg.synthetic.extract_meta(poses), camera_poses=poses.to(cuda))
+    sg = pkg.SampleGrid(list(pkg.synthetic.AABB), res)
+    sg.set_binary_fields(occ.to(cuda))
+    f = pkg.synthetic.make_ngp_field(seed=500).to(cuda)
+    k = int(occ.sum())
+    jitter = torch.rand((k, 3), generator=torch.Generator().manual_seed(3))
+    lib = pkg.load_library()
+    st = (ctypes.c_ulonglong * 4)()
+    lib.drb_march_stats(st, 1)
+    full = sg.query_radiance_and_density_from_camera(f, occ.to(cuda), meta, cuda, jitter=jitter)
+    lib.drb_march_stats(st, 1)
+    rays_full, samples_full = int(st[0]), int(st[2])
+    fused = sg.query_radiance_and_density_from_camera(f, occ.to(cuda), meta, cuda, jitter=jitter,
+                                                      surface_only_where_dense=True)
+    lib.drb_march_stats(st, 1)
+    rays_fused = int(st[0])
+    keep_full = (full[4] & full[5]).cpu()
+    keep_fused = (fused[4] & fused[5]).cpu()
+    assert torch.equal(keep_full, keep_fused)
+    assert not bool((fused[5] & ~fused[4]).any())            # no rays where the density test fails
+    perm = torch.randperm(50, generator=torch.Generator().manual_seed(4))
+    meta_p = dict(meta, camera_poses=poses[perm].to(cuda))
+    shuffled = sg.query_radiance_and_density_from_camera(f, occ.to(cuda), meta_p, cuda, jitter=jitter,
+                                                         surface_only_where_dense=True)
+    assert torch.equal((shuffled[4] & shuffled[5]).cpu(), keep_fused)
+    print("kept %d of %d cells; rays marched: all cells %d, dense only %d; samples %d"
+          % (int(keep_fused.sum()), k, rays_full, rays_fused, samples_full))
+    assert 0 < rays_fused < rays_full <= k * 50 and samples_full > 0

@@ -83,3 +83,34 @@ def test_seeded_state_dict_is_reproducible(pkg):
     assert all(torch.equal(a[k], b[k]) for k in a)
     m.load_state_dict(a)
     assert (a["fpn3d.backbone_net.bn1.running_var"] > 0).all()
+
+
+def test_reciprocal_fma_division_is_correctly_rounded():
+    """The marcher replaces the IEEE divisions by the ROI extent (nerfacc roi_to_unit) with
+    q = a*y, r = fma(-b, q, a), q + r*y, y = RN(1/b) (csrc/ngp.cu div_rn_rcp).  Checked here against
+    exact rational arithmetic: the result must equal RN(a / b) bit for bit."""
+    from fractions import Fraction
+    import numpy as np
+
+    def rn32(fr):
+        f = np.float32(float(fr))
+        best = None
+        for c in (f, np.nextafter(f, np.float32(np.inf)), np.nextafter(f, np.float32(-np.inf))):
+            d = abs(Fraction(float(c)) - fr)
+            even = (int(np.float32(c).view(np.uint32)) & 1) == 0
+            if best is None or d < best[0] or (d == best[0] and even):
+                best = (d, c)
+        return np.float32(best[1])
+
+    def fma(a, b, c):
+        return rn32(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))
+
+    rng = np.random.default_rng(0)
+    for b in (3.0, 2.5, 1.7, 0.3, 10.0, 3.2):
+        b = np.float32(b)
+        y = rn32(Fraction(1) / Fraction(float(b)))
+        assert y == np.float32(1.0 / float(b))                  # what the host computes
+        for a in np.concatenate([rng.uniform(-4, 4, 700), rng.uniform(-1e-3, 1e-3, 100)]).astype(np.float32):
+            q = rn32(Fraction(float(a)) * Fraction(float(y)))
+            r = fma(-b, q, a)
+            assert fma(r, y, q) == rn32(Fraction(float(a)) / Fraction(float(b)))
