@@ -72,46 +72,76 @@ extern "C" int drb_layernorm256(const float* x, int n, const float* gamma, const
 }
 
 // ------------------------------------------------------------------------------------------
-// Attention core, head dim 32, fp32.  Block = 4 warps = 32 queries of one head; every lane owns one
-// query (q and o in registers), the 4 warps split each 64-key shared-memory tile, partial
-// (max, sum, o) are merged through shared memory at the end.  All lanes of a warp read the same
-// K/V row (broadcast float4 loads).
+// Attention core, head dim 32: flash-attention style on the tensor cores.  Block = 4 warps = one
+// 16-query tile of one head; K / V go through shared memory in 64-key tiles (row pitch 36 words:
+// conflict-free fragment reads), every warp owns a quarter (16 keys) of each tile with its own online
+// soft-max state, and the four partial (max, sum, O) are merged through shared memory at the end.
+// Both products run as 3xTF32 mma.sync m16n8k8 (hi*hi + lo*hi + hi*lo, fp32 accumulate, ~2^-21
+// relative - the fp32-grade contract of the register path): S = (Q * scale) K^T, then P = exp2(S - m)
+// in the accumulator layout is fed straight back as the A operand of P V by permuting the key index
+// inside each block of 8 (fragment column t <-> key 2t, t+4 <-> key 2t+1; the V fragments are read
+// with the same permutation), so P never leaves registers.
 // ------------------------------------------------------------------------------------------
 static constexpr int kHd = 32;
 static constexpr int kKeyTile = 64;
+static constexpr int kKvPitch = 36;
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  const float h = tf32_hi(x);
+  hi = __float_as_uint(h);
+  lo = __float_as_uint(tf32_hi(x - h));
+}
+__device__ __forceinline__ void mma_1688(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4],
+                                     float b0, float b1) {
+  uint32_t h0, l0, h1, l1;
+  split_tf32(b0, h0, l0);
+  split_tf32(b1, h1, l1);
+  mma_1688(c, alo, h0, h1);
+  mma_1688(c, ahi, l0, l1);
+  mma_1688(c, ahi, h0, h1);
+}
 
 __global__ void __launch_bounds__(128)
 mha_core_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
                 const float* __restrict__ v, int ldv, int nq, int nk, float scale_log2,
                 float* __restrict__ out, plane_t* __restrict__ out_hi, plane_t* __restrict__ out_lo,
                 int ld_out) {
-  __shared__ __align__(16) float sk[kKeyTile][kHd];
-  __shared__ __align__(16) float sv[kKeyTile][kHd];
-  __shared__ float sm[4][32], sl[4][32];
-  __shared__ float so[4][32][kHd + 1];
+  __shared__ __align__(16) float sk[kKeyTile][kKvPitch];
+  __shared__ __align__(16) float sv[kKeyTile][kKvPitch];
+  __shared__ float sm[4][16], sl[4][16];
+  __shared__ float so[4][16][kHd + 1];
 
   const int head = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qi = blockIdx.x * 32 + lane;
-  const bool q_ok = qi < nq;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * 16;
 
-  float qr[kHd], o[kHd];
-  {
-    const float* qp = q + (long long)(q_ok ? qi : 0) * ldq + head * kHd;
+  // Q fragments (scaled): rows g / g+8 of the tile, columns 8*ks + t / + t + 4
+  uint32_t qhi[4][4], qlo[4][4];
 #pragma unroll
-    for (int d = 0; d < kHd; d += 4) {
-      const float4 t = *(const float4*)(qp + d);
-      qr[d] = t.x * scale_log2; qr[d + 1] = t.y * scale_log2;
-      qr[d + 2] = t.z * scale_log2; qr[d + 3] = t.w * scale_log2;
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = q0 + g + 8 * (i & 1), c = 8 * ks + t + 4 * (i >> 1);
+      const float x = r < nq ? q[(long long)r * ldq + head * kHd + c] * scale_log2 : 0.f;
+      split_tf32(x, qhi[ks][i], qlo[ks][i]);
     }
+  float o[4][4];                         // O tile: 4 n-tiles of 8 dims, accumulator layout
 #pragma unroll
-    for (int d = 0; d < kHd; ++d) o[d] = 0.f;
-  }
-  float m = -INFINITY, l = 0.f;
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[nt][i] = 0.f;
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};     // rows g, g + 8 (l: this lane's share)
 
   for (int k0 = 0; k0 < nk; k0 += kKeyTile) {
     __syncthreads();
-    // cooperative tile load: 64 rows x 32 floats for K and V
     for (int i = threadIdx.x; i < kKeyTile * (kHd / 4); i += 128) {
       const int r = i / (kHd / 4), c = (i % (kHd / 4)) * 4;
       float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
@@ -123,51 +153,79 @@ mha_core_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ 
       *(float4*)&sv[r][c] = vv;
     }
     __syncthreads();
-    const int jend = min(kKeyTile, nk - k0);
-    // this warp's quarter of the tile, 4 keys at a time
-    for (int j0 = warp * 16; j0 < min(jend, warp * 16 + 16); j0 += 4) {
-      float s[4];
+    const int kb = warp * 16;                         // this warp's 16 keys of the tile
+    if (k0 + kb >= nk) continue;                      // (warp-uniform) nothing valid in this quarter
+    // ---- S = Q K^T for 2 n-tiles of 8 keys ----
+    float sacc[2][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float acc = 0.f;
+    for (int j = 0; j < 2; ++j) {
 #pragma unroll
-        for (int d = 0; d < kHd; d += 4) {
-          const float4 kk = *(const float4*)&sk[j0 + u][d];
-          acc = fmaf(qr[d], kk.x, acc); acc = fmaf(qr[d + 1], kk.y, acc);
-          acc = fmaf(qr[d + 2], kk.z, acc); acc = fmaf(qr[d + 3], kk.w, acc);
-        }
-        s[u] = (j0 + u < jend) ? acc : -INFINITY;
+      for (int i = 0; i < 4; ++i) sacc[j][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const float* kr = &sk[kb + 8 * j + g][8 * ks + t];    // B fragment: (k = dim, n = key g)
+        mma3(sacc[j], qhi[ks], qlo[ks], kr[0], kr[4]);
       }
-      const float mx = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), m);
-      const float corr = exp2f(m - mx);   // m == -inf on the first group -> 0
-      l *= corr;
+      // accumulator (row g | g+8, key 2t | 2t+1): mask keys beyond nk
+      const int key = k0 + kb + 8 * j + 2 * t;
+      if (key >= nk) { sacc[j][0] = -INFINITY; sacc[j][2] = -INFINITY; }
+      if (key + 1 >= nk) { sacc[j][1] = -INFINITY; sacc[j][3] = -INFINITY; }
+    }
+    // ---- online soft-max over the 16 keys, rows g (regs 0, 1) and g + 8 (regs 2, 3) ----
+    float corr[2];
 #pragma unroll
-      for (int d = 0; d < kHd; ++d) o[d] *= corr;
+    for (int r = 0; r < 2; ++r) {
+      float mx = fmaxf(fmaxf(sacc[0][2 * r], sacc[0][2 * r + 1]), fmaxf(sacc[1][2 * r], sacc[1][2 * r + 1]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      mx = fmaxf(mx, m[r]);                           // finite: the first key of the quarter is valid
+      corr[r] = exp2f(m[r] - mx);                     // m == -inf on the first group -> 0
+      m[r] = mx;
+      l[r] *= corr[r];
+    }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float p = exp2f(s[u] - mx);
-        l += p;
+    for (int nt = 0; nt < 4; ++nt) {
+      o[nt][0] *= corr[0]; o[nt][1] *= corr[0];
+      o[nt][2] *= corr[1]; o[nt][3] *= corr[1];
+    }
+    // ---- O += P V, P straight from the accumulator (keys permuted inside each block of 8) ----
 #pragma unroll
-        for (int d = 0; d < kHd; d += 4) {
-          const float4 vv = *(const float4*)&sv[j0 + u][d];
-          o[d] = fmaf(p, vv.x, o[d]); o[d + 1] = fmaf(p, vv.y, o[d + 1]);
-          o[d + 2] = fmaf(p, vv.z, o[d + 2]); o[d + 3] = fmaf(p, vv.w, o[d + 3]);
-        }
-      }
-      m = mx;
+    for (int j = 0; j < 2; ++j) {
+      const float p0 = exp2f(sacc[j][0] - m[0]), p1 = exp2f(sacc[j][1] - m[0]);
+      const float p2 = exp2f(sacc[j][2] - m[1]), p3 = exp2f(sacc[j][3] - m[1]);
+      l[0] += p0 + p1;
+      l[1] += p2 + p3;
+      uint32_t phi[4], plo[4];
+      split_tf32(p0, phi[0], plo[0]);                 // a0 = (row g,   key 2t)
+      split_tf32(p2, phi[1], plo[1]);                 // a1 = (row g+8, key 2t)
+      split_tf32(p1, phi[2], plo[2]);                 // a2 = (row g,   key 2t+1)
+      split_tf32(p3, phi[3], plo[3]);                 // a3 = (row g+8, key 2t+1)
+      const float* v0 = &sv[kb + 8 * j + 2 * t][g];   // B fragment: (k = key 2t | 2t+1, n = dim 8*nt + g)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma3(o[nt], phi, plo, v0[8 * nt], v0[kKvPitch + 8 * nt]);
     }
   }
-  // merge the 4 key splits
-  sm[warp][lane] = m;
-  sl[warp][lane] = l;
+  // ---- merge the 4 key splits ----
 #pragma unroll
-  for (int d = 0; d < kHd; ++d) so[warp][lane][d] = o[d];
+  for (int r = 0; r < 2; ++r) {
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+  }
+  if (t == 0) {
+    sm[warp][g] = m[0]; sm[warp][g + 8] = m[1];
+    sl[warp][g] = l[0]; sl[warp][g + 8] = l[1];
+  }
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    so[warp][g][8 * nt + 2 * t] = o[nt][0]; so[warp][g][8 * nt + 2 * t + 1] = o[nt][1];
+    so[warp][g + 8][8 * nt + 2 * t] = o[nt][2]; so[warp][g + 8][8 * nt + 2 * t + 1] = o[nt][3];
+  }
   __syncthreads();
-  // thread t: query = t / 4, dims (t % 4) * 8 .. + 8
-  const int mq = threadIdx.x >> 2, md = (threadIdx.x & 3) * 8;
-  const int oq = blockIdx.x * 32 + mq;
+  // thread: query row = tid / 8, dims (tid % 8) * 4 .. + 4
+  const int mq = threadIdx.x >> 3, md = (threadIdx.x & 7) * 4;
+  const int oq = q0 + mq;
   if (oq < nq) {
-    float mm = fmaxf(fmaxf(sm[0][mq], sm[1][mq]), fmaxf(sm[2][mq], sm[3][mq]));
+    const float mm = fmaxf(fmaxf(sm[0][mq], sm[1][mq]), fmaxf(sm[2][mq], sm[3][mq]));
     float w[4], lt = 0.f;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -175,29 +233,23 @@ mha_core_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ 
       lt += w[u] * sl[u][mq];
     }
     const float inv = 1.f / lt;
-    float r[8];
+    float r[4];
 #pragma unroll
-    for (int d = 0; d < 8; ++d) {
+    for (int d = 0; d < 4; ++d) {
       float acc = 0.f;
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc += w[u] * so[u][mq][md + d];
       r[d] = acc * inv;
     }
     const long long off = (long long)oq * ld_out + head * kHd + md;
-    if (out) {
-      *(float4*)(out + off) = make_float4(r[0], r[1], r[2], r[3]);
-      *(float4*)(out + off + 4) = make_float4(r[4], r[5], r[6], r[7]);
-    }
+    if (out) *(float4*)(out + off) = make_float4(r[0], r[1], r[2], r[3]);
     if (out_hi) {
       const bool pair = out_lo != nullptr;
-      plane_t h[8], lo8[8];
+      plane_t h[4], lo4[4];
 #pragma unroll
-      for (int d = 0; d < 8; ++d) split16(r[d], pair, h[d], lo8[d]);
-      *(uint4*)(out_hi + off) = make_uint4(pack16x2(h[0], h[1]), pack16x2(h[2], h[3]),
-                                           pack16x2(h[4], h[5]), pack16x2(h[6], h[7]));
-      if (out_lo)
-        *(uint4*)(out_lo + off) = make_uint4(pack16x2(lo8[0], lo8[1]), pack16x2(lo8[2], lo8[3]),
-                                             pack16x2(lo8[4], lo8[5]), pack16x2(lo8[6], lo8[7]));
+      for (int d = 0; d < 4; ++d) split16(r[d], pair, h[d], lo4[d]);
+      *(uint2*)(out_hi + off) = make_uint2(pack16x2(h[0], h[1]), pack16x2(h[2], h[3]));
+      if (out_lo) *(uint2*)(out_lo + off) = make_uint2(pack16x2(lo4[0], lo4[1]), pack16x2(lo4[2], lo4[3]));
     }
   }
 }
@@ -211,7 +263,7 @@ extern "C" int drb_mha_core(const float* q, int ldq, const float* k, int ldk, co
   DRB_REQUIRE(nk > 0, "drb_mha_core: empty key set");
   if (nq == 0) return 0;
   const float scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid((unsigned)cdiv(nq, 32), (unsigned)heads);
+  dim3 grid((unsigned)cdiv(nq, 16), (unsigned)heads);
   mha_core_kernel<<<grid, 128, 0, stream>>>(q, ldq, k, ldk, v, ldv, nq, nk, scale_log2, out,
                                             (plane_t*)out_hi, (plane_t*)out_lo, ld_out);
   DRB_LAUNCH_OK();
