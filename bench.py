@@ -483,6 +483,15 @@ def run_ours(args):
                 "issued_gather_bytes_per_launch": issued,
                 "issued_gather_gbs": issued / (surf_ms / 1e3) / 1e9 if surf_ms > 0 else 0.0,
                 "density_samples_per_s": samples / (surf_prof["ms"] / 1e3) if surf_prof["ms"] > 0 else 0.0,
+                # The limit that actually binds: an SM retires ~1.02 random table gathers per clock whatever the
+                # occupancy or ILP (scripts/ubench/gather.cu on this pool's B200: 287 G gathers/s, halved when
+                # the shared-memory carve-out leaves < ~64 KB of L1).  Per sample the kernel issues 15 levels x
+                # (4 aligned 16-byte pairs + 4 single corners for odd x indices, i.e. 6 on average) = 90 requests
+                # (level 0 is served from shared memory).
+                "gather_roofline": {"requests_per_sample": 90,
+                                    "achieved_g_per_s": 90.0 * samples / (surf_prof["ms"] / 1e3) / 1e9 if surf_prof["ms"] > 0 else 0.0,
+                                    "peak_g_per_s": 287.0, "peak_source": "measured, scripts/ubench/gather.cu (profiles/r01_ubench_gather.txt)",
+                                    "frac": 90.0 * samples / (surf_prof["ms"] / 1e3) / 287e9 if surf_prof["ms"] > 0 else 0.0},
                 "note": "algorithmic bytes = hash table + occupancy grid + points + masks + cameras, each read once per "
                         "launch; the kernel is L1-miss / L2-gather bound (DRAM idle), not bandwidth bound"}
         if not args.no_cpu_baseline and world == 1:
