@@ -786,6 +786,12 @@ static constexpr int kMarchWarps = kMarchThreads / 32;
 static constexpr int kSlots = 64;                    // rays per warp (in flight + pending + resumable)
 static constexpr int kSlotWords = 10;                // dir[3] len t0 t1 tm T best (pi | cam << 22)
 static constexpr int kPiBits = 22;
+#ifndef DRB_SPEC
+#define DRB_SPEC 4
+#endif
+static constexpr int kSpec = DRB_SPEC;               // consecutive samples of one ray evaluated in one batch
+static constexpr int kRaysPerBatch = 32 / kSpec;
+static_assert(kSpec == 1 || kSpec == 2 || kSpec == 4 || kSpec == 8, "group size");
 #ifndef DRB_WINDOW
 #define DRB_WINDOW 64
 #endif
@@ -797,7 +803,7 @@ static constexpr int kCandCap = 32 + kWindow;        // per-warp queue of rays t
 static constexpr int kCoarseMaxDim = DRB_COARSE_DIM;             // coarse occupancy bitmap: at most DRB_COARSE_DIM^3 bits (32^3 = 4 KB)
 static constexpr int kCoarseWords = kCoarseMaxDim * kCoarseMaxDim * kCoarseMaxDim / 32;
 static constexpr int kMaxCams = (1 << (32 - kPiBits)) - 1;
-static constexpr size_t kWarpBytes = (size_t)32 * kTilePitch * 4 + (size_t)kSlots * kSlotWords * 4 + 3 * kSlots +
+static constexpr size_t kWarpBytes = (size_t)32 * kTilePitch * 4 + (size_t)kSlots * kSlotWords * 4 + 4 * kSlots +
                                      (size_t)kCandCap * 4;
 static_assert(kMarchSmemLevels <= kSmemLevels, "the marcher stages a prefix of the field kernels' levels");
 
@@ -896,8 +902,8 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
   mlp.bfrag = s_bfrag;
   mlp.w2 = s_w2;
   float* slots = (float*)(wbase + 32 * kTilePitch * 4);            // [kSlotWords][kSlots]
-  uint8_t* l_pend = wbase + 32 * kTilePitch * 4 + kSlots * kSlotWords * 4;
-  uint8_t* l_resume = l_pend + kSlots;
+  uint16_t* l_pend = (uint16_t*)(wbase + 32 * kTilePitch * 4 + kSlots * kSlotWords * 4);   // slot | (nspec-1) << 6
+  uint8_t* l_resume = (uint8_t*)(l_pend + kSlots);
   uint8_t* l_free = l_resume + kSlots;
   uint32_t* l_cand = (uint32_t*)(l_free + kSlots);                 // (pi | cam << 22) of rays waiting to start
   for (int i = lane; i < kSlots; i += 32) l_free[i] = (uint8_t)i;
@@ -1031,38 +1037,38 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
     }
 
     // ---------------- phase A: advance until a sample is pending (bounded number of skips) -------
+    // occupancy of the cell that contains o + tm * dir; u = (x - roi_min) / extent (IEEE division, as
+    // nerfacc's roi_to_unit) is handed back for the distance-to-next-voxel rule
+    auto occupied_at = [&](float tm, float (&u)[3]) -> bool {
+      bool in_roi = true;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float x = fmaf(tm, ray.dir[d], ray.o[d]);
+        u[d] = div_rn_rcp(x - a.roi_min[d], roi_ext[d], aux.roi_rcp[d]);
+        in_roi = in_roi && (u[d] >= 0.f) && (u[d] < 1.f);
+      }
+      if (!in_roi) return false;
+      int idx[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int i = (int)(u[d] * (float)a.res);
+        idx[d] = i < 0 ? 0 : (i > a.res - 1 ? a.res - 1 : i);
+      }
+      const int cb = ((idx[0] >> aux.coarse_shift) * aux.coarse_dim + (idx[1] >> aux.coarse_shift)) *
+                         aux.coarse_dim + (idx[2] >> aux.coarse_shift);
+      if (!((s_coarse[cb >> 5] >> (cb & 31)) & 1u)) return false;
+      return occ[((long long)idx[0] * a.res + idx[1]) * a.res + idx[2]] != 0;
+    };
     bool pending = false;
+    int nspec = 1;
     if (have) {
       int budget = kMaxSkips;
       while (budget > 0) {
         if (!(ray.tm < ray.len)) { have = false; break; }       // reached the point without a hit
-        float x[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) x[d] = fmaf(ray.tm, ray.dir[d], ray.o[d]);
-        // occupancy test and distance to the next voxel share u = (x - roi_min) / extent (IEEE division,
-        // as nerfacc's roi_to_unit); res is a power of two in practice, where "/ res" is an exact scaling
         float u[3];
-        bool in_roi = true;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          u[d] = div_rn_rcp(x[d] - a.roi_min[d], roi_ext[d], aux.roi_rcp[d]);
-          in_roi = in_roi && (u[d] >= 0.f) && (u[d] < 1.f);
-        }
-        bool is_occ = false;
-        if (in_roi) {
-          int idx[3];
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const int i = (int)(u[d] * (float)a.res);
-            idx[d] = i < 0 ? 0 : (i > a.res - 1 ? a.res - 1 : i);
-          }
-          const int cb = ((idx[0] >> aux.coarse_shift) * aux.coarse_dim + (idx[1] >> aux.coarse_shift)) *
-                             aux.coarse_dim + (idx[2] >> aux.coarse_shift);
-          if ((s_coarse[cb >> 5] >> (cb & 31)) & 1u)
-            is_occ = occ[((long long)idx[0] * a.res + idx[1]) * a.res + idx[2]] != 0;
-        }
-        if (is_occ) { pending = true; break; }
+        if (occupied_at(ray.tm, u)) { pending = true; break; }
         --budget;
+        // res is a power of two in practice, where "/ res" is an exact scaling
         float dist = 1e30f;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -1077,73 +1083,107 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
         ray.t0 = ray.tm - 0.5f * a.step; ray.t1 = ray.tm + 0.5f * a.step;
         ++st_skips;
       }
+      if (pending && kSpec > 1) {
+        // Speculation along the ray: if the next sample positions (the chain t0 = t1, t1 = t0 + step,
+        // tm = (t0 + t1) / 2 the marcher follows after a non-terminating sample) also lie in occupied
+        // cells before the end of the ray, they are certain to be the next samples unless the ray
+        // terminates first.  They are evaluated in the same batch: consecutive samples of one ray are
+        // 1 step apart and share table sectors (the density phase is bound by distinct sectors per
+        // load instruction), at the price of a few wasted samples when a ray terminates early.
+        float t1s = ray.t1;
+        for (int j = 1; j < kSpec; ++j) {
+          const float t0s = t1s;
+          t1s = t0s + a.step;
+          const float tms = 0.5f * (t0s + t1s);
+          float u[3];
+          if (!(tms < ray.len) || !occupied_at(tms, u)) break;
+          ++nspec;
+        }
+      }
     }
     // ---------------- park the rays whose sample is pending --------------------------------------
     {
       const uint32_t pm = __ballot_sync(0xffffffffu, pending);
       if (pending) {
         store_ray(my_slot);
-        l_pend[n_pend + __popc(pm & lt_mask)] = (uint8_t)my_slot;
+        l_pend[n_pend + __popc(pm & lt_mask)] = (uint16_t)(my_slot | ((nspec - 1) << 6));
         my_slot = -1;
         have = false;
       }
       n_pend += __popc(pm);
       __syncwarp();
     }
-    // ---------------- phase B: 32 density samples at a time --------------------------------------
+    // ---------------- phase B: kRaysPerBatch rays x up to kSpec consecutive samples at a time -----
     const uint32_t busy = __ballot_sync(0xffffffffu, have);
     const bool drain = global_done && busy == 0 && n_resume == 0 && n_cand == 0;
     if (n_pend == 0 && drain) break;
-    while (n_pend >= 32 || (drain && n_pend > 0)) {
+    while (n_pend >= kRaysPerBatch || (drain && n_pend > 0)) {
       // lanes that are in the middle of a ray park it in its home slot (registers are needed below)
       if (have) store_ray(my_slot);
-      const int nb = min(32, n_pend);
-      const bool valid = lane < nb;
-      const int s = valid ? (int)l_pend[n_pend - nb + lane] : 0;
+      const int nb = min(kRaysPerBatch, n_pend);
+      const int br = lane / kSpec, bj = lane % kSpec;          // ray of the batch, sample along the ray
+      const uint32_t entry = br < nb ? (uint32_t)l_pend[n_pend - nb + br] : 0u;
+      const int s = (int)(entry & 63u);
+      const int ns = (int)(entry >> 6) + 1;                    // samples of this ray in the batch
+      const bool valid = br < nb && bj < ns;
       n_pend -= nb;
       float xn[3] = {0.5f, 0.5f, 0.5f};
       bool inside = false;
+      float dt = 0.f;
       if (valid) {
         const int ci = (int)(__float_as_uint(slots[9 * kSlots + s]) >> kPiBits);
-        const float tm = slots[6 * kSlots + s];
+        // sample bj of the chain: the stored (t0, t1, tm) for bj = 0, then t0 = t1, t1 = t0 + step
+        float t0 = slots[4 * kSlots + s], t1 = slots[5 * kSlots + s], tm = slots[6 * kSlots + s];
+        for (int jj = 0; jj < bj; ++jj) { t0 = t1; t1 = t0 + a.step; tm = 0.5f * (t0 + t1); }
+        dt = t1 - t0;
         float x[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) x[d] = fmaf(tm, slots[d * kSlots + s], s_cams[ci * 3 + d]);
         float xt[3];
         inside = normalise(p, x, xt);
         if (inside) { xn[0] = xt[0]; xn[1] = xt[1]; xn[2] = xt[2]; }
+        ++st_samples;
       }
       const float raw = warp_density_raw(p, s_lvl, mlp, xn, lane);
+      const float sigma = (valid && inside) ? expf(raw - 1.f) : 0.f;
+      const float alpha_mine = 1.f - expf(-sigma * dt);
+      float alphas[kSpec];
+#pragma unroll
+      for (int jj = 0; jj < kSpec; ++jj) alphas[jj] = __shfl_sync(0xffffffffu, alpha_mine, (lane & ~(kSpec - 1)) + jj);
       bool resume = false, release = false;
-      if (valid) {
-        const float sigma = inside ? expf(raw - 1.f) : 0.f;
+      if (br < nb && bj == 0) {
+        // the ray's samples in order, exactly as the sequential marcher would take them
         float t0 = slots[4 * kSlots + s], t1 = slots[5 * kSlots + s];
         float T = slots[7 * kSlots + s], best = slots[8 * kSlots + s];
         const int pi = (int)(__float_as_uint(slots[9 * kSlots + s]) & ((1u << kPiBits) - 1u));
-        const float alpha = 1.f - expf(-sigma * (t1 - t0));
         bool done = false;
-        if (T < 1e-4f) {                           // samples past early_stop_eps are dropped (:209)
-          done = true;
-        } else {
-          best = fmaxf(best, alpha * T);
-          if (best >= a.cut_off) {
-            surface[pi] = 1;
-            done = true;
-          } else {
-            T *= 1.f - alpha;
-            // exact early out: every later sample contributes alpha * T' <= T' <= T < cut_off
-            if (T < a.cut_off || surface[pi]) done = true;
+#pragma unroll
+        for (int jj = 0; jj < kSpec; ++jj) {
+          if (jj < ns && !done) {
+            const float alpha = alphas[jj];
+            if (T < 1e-4f) {                         // samples past early_stop_eps are dropped (:209)
+              done = true;
+            } else {
+              best = fmaxf(best, alpha * T);
+              if (best >= a.cut_off) {
+                surface[pi] = 1;
+                done = true;
+              } else {
+                T *= 1.f - alpha;
+                // exact early out: every later sample contributes alpha * T' <= T' <= T < cut_off
+                if (T < a.cut_off || surface[pi]) done = true;
+              }
+            }
+            if (!done) { t0 = t1; t1 = t0 + a.step; }
           }
         }
         if (done) {
           release = true;
         } else {
-          t0 = t1; t1 = t0 + a.step;
           slots[4 * kSlots + s] = t0; slots[5 * kSlots + s] = t1; slots[6 * kSlots + s] = 0.5f * (t0 + t1);
           slots[7 * kSlots + s] = T; slots[8 * kSlots + s] = best;
           resume = true;
         }
-        ++st_samples;
       }
       const uint32_t rm = __ballot_sync(0xffffffffu, resume), fm = __ballot_sync(0xffffffffu, release);
       if (resume) l_resume[n_resume + __popc(rm & lt_mask)] = (uint8_t)s;
