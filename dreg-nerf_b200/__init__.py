@@ -7,4 +7,4 @@ interfaces (``NeRFRegTr``, ``NGPradianceField`` / ``SampleGrid`` extract).
 from ._lib import DrbError, load as load_library  # noqa: F401
 from .nerf_regtr import NeRFRegTr  # noqa: F401
 from .ngp import NGPradianceField, SampleGrid, extract_block  # noqa: F401
-from . import synthetic  # noqa: F401
+from . import blockio, synthetic  # noqa: F401

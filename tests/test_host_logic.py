@@ -114,3 +114,50 @@ def test_reciprocal_fma_division_is_correctly_rounded():
             q = rn32(Fraction(float(a)) * Fraction(float(y)))
             r = fma(-b, q, a)
             assert fma(r, y, q) == rn32(Fraction(float(a)) / Fraction(float(b)))
+
+
+def test_block_files_round_trip(tmp_path, pkg):
+    """voxel_grid.pt / voxel_mask.pt written by blockio.save_block are what the reference's dataset reads
+    (dataset.py:244-248): same tensors, same permute, and the mask addresses the (X, Y, Z) C-order rows."""
+    import os
+    import torch
+    g = torch.Generator().manual_seed(3)
+    grid = torch.zeros(16, 16, 16, 7)
+    mask = torch.randperm(16 ** 3, generator=g)[:200].sort().values
+    grid.reshape(-1, 7)[mask] = torch.rand(200, 7, generator=g)
+    d0, d1 = str(tmp_path / "block_0"), str(tmp_path / "block_1")
+    pkg.blockio.save_block(d0, grid, mask)
+    pkg.blockio.save_block(d1, grid.flip(0).contiguous(), mask)
+    assert sorted(os.listdir(d0)) == ["voxel_grid.pt", "voxel_mask.pt"]
+    # the reference's reader, verbatim
+    ref_xyz_rgba = torch.load(os.path.join(d0, "voxel_grid.pt")).permute(3, 2, 0, 1).unsqueeze(dim=0)
+    ref_mask = torch.load(os.path.join(d0, "voxel_mask.pt"))
+    data = pkg.blockio.load_pair(d0, d1, src_transform=torch.eye(4), tgt_transform=torch.eye(4), scene="s")
+    assert torch.equal(data["src_xyz_rgba"], ref_xyz_rgba) and torch.equal(data["src_mask"], ref_mask)
+    assert data["src_xyz_rgba"].shape == (1, 7, 16, 16, 16) and data["pose"].shape == (1, 4, 4)
+    assert data["src_nerf_path"].endswith("block_0/model.pth") and data["scene"] == "s"
+    # rows selected the way NeRFRegTr.forward does (nerf_regtr.py:144-147) are the stored rows
+    rows = data["src_xyz_rgba"].permute(0, 3, 4, 2, 1).reshape(1, -1, 7)[0, data["src_mask"]]
+    assert torch.equal(rows, grid.reshape(-1, 7)[mask])
+    import pytest
+    with pytest.raises(ValueError):
+        pkg.blockio.save_block(d0, grid.permute(3, 0, 1, 2), mask)
+
+
+def test_field_checkpoint_round_trip(tmp_path, pkg):
+    """A checkpoint in the CheckPointManager layout ({'model': state_dict}) with tiny-cuda-nn's flat
+    params loads into NGPradianceField; a wrong-size table is rejected."""
+    import torch
+    import pytest
+    f = pkg.NGPradianceField(aabb=[-1.5] * 3 + [1.5] * 3)
+    f.reset_parameters(table_std=2.0)
+    path = str(tmp_path / "model.pth")
+    torch.save({"model": f.state_dict(), "step": 7}, path)
+    g = pkg.blockio.load_field(path)
+    assert torch.equal(g.mlp_base.params, f.mlp_base.params) and torch.equal(g.color_mlp.params, f.color_mlp.params)
+    assert torch.equal(g.aabb, f.aabb)
+    bad = dict(f.state_dict())
+    bad["mlp_base.params"] = bad["mlp_base.params"][:-8]
+    torch.save(bad, path)
+    with pytest.raises(ValueError):
+        pkg.blockio.load_field(path)
