@@ -110,3 +110,27 @@ def test_forward_bf16_mode_runs(pkg, cuda):
     assert out["pose"].shape == (6, 1, 3, 4)
     assert torch.isfinite(out["pose"]).all()
     assert _relerr(out["src_feats"][0], ref["src_feats"][0]) < 0.15
+
+
+def test_256_cube_plumbing(pkg, cuda):
+    """BASELINE.json configs[4] shape: a 256^3 block goes through extract and a 256^3 pair through
+    NeRFRegTr.forward (index arithmetic beyond 2^24 cells, coarse occupancy bitmap with 8^3-voxel cells,
+    engine buffers 8x the 128^3 ones).  Plumbing and finiteness; parity is covered at 32^3 / 64^3."""
+    res = 256
+    occ, poses = pkg.synthetic.extract_scene(res, 8)
+    meta = dict(pkg.synthetic.extract_meta(poses), camera_poses=poses.to(cuda))
+    sg = pkg.SampleGrid(list(pkg.synthetic.AABB), res)
+    f = pkg.synthetic.make_ngp_field(seed=500).to(cuda)
+    grid, mask = pkg.extract_block(f, sg, occ.to(cuda), meta, cuda)
+    assert grid.shape == (res, res, res, 7) and mask.numel() > 1000
+    rows = grid.reshape(-1, 7)
+    assert bool((rows[mask].abs().sum(dim=1) > 0).all())
+    assert int((rows.abs().sum(dim=1) > 0).sum()) == mask.numel()        # zeros outside the mask
+    del grid, rows
+    torch.manual_seed(0)
+    model = pkg.NeRFRegTr().to(cuda).eval()
+    data = pkg.synthetic.to_device(pkg.synthetic.make_pair(res=res, pair_id=0), cuda)
+    with torch.no_grad():
+        out = model(data)
+    assert out["pose"].shape == (6, 1, 3, 4) and torch.isfinite(out["pose"]).all()
+    assert all(torch.isfinite(t).all() for t in out["src_feats"])
