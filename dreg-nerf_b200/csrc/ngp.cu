@@ -664,22 +664,116 @@ struct WarpMlp {
   const float* w2;        // [64] output row 0 of layer 2
 };
 
-template <int KS>
-__device__ __forceinline__ void encode_group(const NgpDev& p, const float2* __restrict__ s_lvl,
-                                             const float xn[3], float f[8]) {
-  encode_level<4 * KS + 0, kMarchSmemLevels>(p, s_lvl, xn, f[0], f[1]);
-  encode_level<4 * KS + 1, kMarchSmemLevels>(p, s_lvl, xn, f[2], f[3]);
-  encode_level<4 * KS + 2, kMarchSmemLevels>(p, s_lvl, xn, f[4], f[5]);
-  encode_level<4 * KS + 3, kMarchSmemLevels>(p, s_lvl, xn, f[6], f[7]);
+// Hashed level with run-time level index: levels 5..15 differ only in scale and table offset, so one
+// copy of this body serves all eleven from a rolled loop.  The unrolled form was 5.1 k SASS instructions
+// (80 KB) walked once per batch by 16 warps at different places: 33 % of the stall samples were
+// instruction-fetch misses (ncu, round 1).  Same arithmetic and summation order as encode_level<L>.
+#ifndef DRB_HASH_UNROLL
+#define DRB_HASH_UNROLL 1
+#endif
+static constexpr int kHashUnroll = DRB_HASH_UNROLL;
+__device__ __forceinline__ void encode_hashed(const NgpDev& p, int l, const float xn[3], float& o0, float& o1) {
+  constexpr uint32_t size = 1u << 19;
+  const float scale = p.lv.scale[l];
+  const float2* __restrict__ tab = p.table + p.lv.offset[l];
+  float fr[3];
+  uint32_t g[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float pos = fmaf(xn[d], scale, 0.5f);
+    const float fl = floorf(pos);
+    fr[d] = pos - fl;
+    g[d] = (uint32_t)(int)fl;
+  }
+  const uint32_t hy0 = g[1] * 2654435761u, hz0 = g[2] * 805459861u;
+  const uint32_t hy[2] = {hy0, hy0 + 2654435761u};
+  const uint32_t hz[2] = {hz0, hz0 + 805459861u};
+  uint32_t idx0[4], idx1[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t hyz = hy[c & 1] ^ hz[c >> 1];
+    idx0[c] = (g[0] ^ hyz) & (size - 1u);
+    idx1[c] = ((g[0] + 1u) ^ hyz) & (size - 1u);
+  }
+  float4 q[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) q[c] = __ldg((const float4*)(tab + (idx0[c] & ~1u)));
+  float2 v[8];
+  if ((g[0] & 1u) == 0u) {                     // idx1 = idx0 ^ 1: the mate of the aligned pair
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool odd = idx0[c] & 1u;
+      v[2 * c] = odd ? make_float2(q[c].z, q[c].w) : make_float2(q[c].x, q[c].y);
+      v[2 * c + 1] = odd ? make_float2(q[c].x, q[c].y) : make_float2(q[c].z, q[c].w);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool odd = idx0[c] & 1u;
+      v[2 * c] = odd ? make_float2(q[c].z, q[c].w) : make_float2(q[c].x, q[c].y);
+      v[2 * c + 1] = __ldg(tab + idx1[c]);
+    }
+  }
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float w = 1.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) w *= (c & (1 << d)) ? fr[d] : 1.f - fr[d];
+    a0 = fmaf(w, v[c].x, a0);
+    a1 = fmaf(w, v[c].y, a1);
+  }
+  o0 = a0;
+  o1 = a1;
 }
 
-template <int KS>
-__device__ __forceinline__ void mlp_kstep(const WarpMlp& m, const float f[8], float (&acc)[2][8][4], int lane) {
+// Dense level with run-time level index (levels 1..4 of the marcher; level 0 lives in shared memory):
+// index x + y*res + z*res^2 with the conditional wrap, aligned 16-byte pair when the lower x corner
+// is even and its x-neighbour is the next entry.  Same arithmetic as encode_level<L>.
+__device__ __forceinline__ void encode_dense(const NgpDev& p, int l, const float xn[3], float& o0, float& o1) {
+  const float scale = p.lv.scale[l];
+  const uint32_t res = p.lv.res[l], size = p.lv.size[l];
+  const float2* __restrict__ tab = p.table + p.lv.offset[l];
+  float fr[3];
+  uint32_t g[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float pos = fmaf(xn[d], scale, 0.5f);
+    const float fl = floorf(pos);
+    fr[d] = pos - fl;
+    g[d] = (uint32_t)(int)fl;
+  }
+  const uint32_t res2 = res * res;
+  const uint32_t base = g[0] + g[1] * res + g[2] * res2;
+  float2 v[8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t i = base + ((c & 1) ? res : 0u) + ((c & 2) ? res2 : 0u);
+    const uint32_t i0 = i >= size ? i - size : i;
+    const uint32_t i1 = i + 1u >= size ? i + 1u - size : i + 1u;
+    const float4 q = __ldg((const float4*)(tab + (i0 & ~1u)));
+    const bool odd = i0 & 1u;
+    v[2 * c] = odd ? make_float2(q.z, q.w) : make_float2(q.x, q.y);
+    if (!odd && i1 == i0 + 1u) v[2 * c + 1] = make_float2(q.z, q.w);
+    else v[2 * c + 1] = __ldg(tab + i1);
+  }
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float w = 1.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) w *= (c & (1 << d)) ? fr[d] : 1.f - fr[d];
+    a0 = fmaf(w, v[c].x, a0);
+    a1 = fmaf(w, v[c].y, a1);
+  }
+  o0 = a0;
+  o1 = a1;
+}
+
+// One K-step of layer 1: the 32 x 8 tile (this warp's rows are complete) -> A fragments -> 48 MMAs.
+__device__ __forceinline__ void mlp_kstep(const WarpMlp& m, int ks, float (&acc)[2][8][4], int lane) {
   const int g = lane >> 2, t = lane & 3;
-  __syncwarp();                                        // the previous K-step's fragment loads are done
-  *(float4*)(m.tile + lane * kTilePitch) = make_float4(f[0], f[1], f[2], f[3]);
-  *(float4*)(m.tile + lane * kTilePitch + 4) = make_float4(f[4], f[5], f[6], f[7]);
-  __syncwarp();
+  __syncwarp();                                        // every lane's features of this K-step are in the tile
   uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
@@ -692,9 +786,11 @@ __device__ __forceinline__ void mlp_kstep(const WarpMlp& m, const float f[8], fl
       alo[mt][i] = __float_as_uint(tf32_hi(v[i] - hi));
     }
   }
+  __syncwarp();                                        // fragment loads done: the tile may be overwritten
+  const float4* bf = m.bfrag + ks * 8 * 32 + lane;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    const float4 b = m.bfrag[(KS * 8 + nt) * 32 + lane];
+    const float4 b = bf[nt * 32];
     const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y);
     const uint32_t bl0 = __float_as_uint(b.z), bl1 = __float_as_uint(b.w);
 #pragma unroll
@@ -716,11 +812,28 @@ __device__ __forceinline__ float warp_density_raw(const NgpDev& p, const float2*
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-  float f[8];
-  encode_group<0>(p, s_lvl, xn, f); mlp_kstep<0>(m, f, acc, lane);
-  encode_group<1>(p, s_lvl, xn, f); mlp_kstep<1>(m, f, acc, lane);
-  encode_group<2>(p, s_lvl, xn, f); mlp_kstep<2>(m, f, acc, lane);
-  encode_group<3>(p, s_lvl, xn, f); mlp_kstep<3>(m, f, acc, lane);
+  float* row = m.tile + lane * kTilePitch;
+  static_assert(kMarchSmemLevels <= 1, "levels 1.. are read through L1 by the rolled loops");
+  {
+    float f0, f1;
+    encode_level<0, kMarchSmemLevels>(p, s_lvl, xn, f0, f1);       // level 0: shared memory (or L1)
+    *(float2*)row = make_float2(f0, f1);
+  }
+#pragma unroll 1
+  for (int l = 1; l < 5; ++l) {
+    float f0, f1;
+    encode_dense(p, l, xn, f0, f1);
+    *(float2*)(row + 2 * (l & 3)) = make_float2(f0, f1);
+    if ((l & 3) == 3) mlp_kstep(m, l >> 2, acc, lane);
+  }
+  static_assert(!lvl_dense(5) && lvl_dense(4), "levels 5..15 are the hashed ones");
+#pragma unroll kHashUnroll
+  for (int l = 5; l < kLevels; ++l) {
+    float f0, f1;
+    encode_hashed(p, l, xn, f0, f1);
+    *(float2*)(row + 2 * (l & 3)) = make_float2(f0, f1);
+    if ((l & 3) == 3) mlp_kstep(m, l >> 2, acc, lane);
+  }
   // accumulator layout: acc[mt][nt] = {(row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)} of tile
   // rows 16*mt.., hidden units 8*nt..
   const int t = lane & 3;
