@@ -894,7 +894,10 @@ extern "C" int drb_march_stats(unsigned long long* host4, int reset) {
   return 0;
 }
 
-static constexpr int kMarchThreads = 512;
+#ifndef DRB_MARCH_THREADS
+#define DRB_MARCH_THREADS 512
+#endif
+static constexpr int kMarchThreads = DRB_MARCH_THREADS;
 static constexpr int kMarchWarps = kMarchThreads / 32;
 static constexpr int kSlots = 64;                    // rays per warp (in flight + pending + resumable)
 static constexpr int kSlotWords = 10;                // dir[3] len t0 t1 tm T best (pi | cam << 22)

@@ -158,3 +158,7 @@ def test_surface_mask_schedule_independent_128(pkg, cuda):
     print("kept %d of %d cells; rays marched: all cells %d, dense only %d; samples %d"
           % (int(keep_fused.sum()), k, rays_full, rays_fused, samples_full))
     assert 0 < rays_fused < rays_full <= k * 50 and samples_full > 0
+    # run-to-run determinism on a heavy block (many samples per ray): identical masks, bit for bit
+    f2 = pkg.synthetic.make_ngp_field(seed=505).to(cuda)
+    runs = [pkg.extract_block(f2, sg, occ.to(cuda), meta, cuda, jitter=jitter)[1].cpu() for _ in range(3)]
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
