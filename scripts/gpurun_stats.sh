@@ -14,11 +14,11 @@ for seed in (500, 501, 502, 505):
     g, m = pkg.extract_block(f, sg, occ_d, meta, dev)
     torch.cuda.synchronize()
     st = (ctypes.c_ulonglong * 4)()
-    lib.drb_debug_march_stats(st, 1)
+    lib.drb_march_stats(st, 1)
     torch.cuda.synchronize(); t = time.time()
     g, m = pkg.extract_block(f, sg, occ_d, meta, dev)
     torch.cuda.synchronize(); dt = (time.time() - t) * 1e3
-    lib.drb_debug_march_stats(st, 1)
+    lib.drb_march_stats(st, 1)
     rays, skips, samples, rounds = [int(v) for v in st]
     pts = torch.rand(200000, 3, device=dev) * 3 - 1.5
     d = f.query_density(pts)
