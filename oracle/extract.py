@@ -43,11 +43,15 @@ def _occupied(x, occ, res, roi):
     return bool(occ[idx[0], idx[1], idx[2]])
 
 
-def surface_mask(points, cam_origins, occ, res, roi_aabb, scene_aabb, step, cut_off, density_fn):
-    """sample_grid.py:245-318: surface[p] = any camera sees max_s(alpha_s * T_s) >= cut_off."""
+def surface_mask(points, cam_origins, occ, res, roi_aabb, scene_aabb, step, cut_off, density_fn,
+                 return_best=False):
+    """sample_grid.py:245-318: surface[p] = any camera sees max_s(alpha_s * T_s) >= cut_off.
+    ``return_best``: also return, per point, the largest surface-field value any marched ray reached
+    (tests use it to set aside decisions that hang on the last bits of the density)."""
     roi = torch.as_tensor(roi_aabb, dtype=torch.float32)
     scene = torch.as_tensor(scene_aabb, dtype=torch.float32)
     out = torch.zeros(points.shape[0], dtype=torch.bool)
+    best_of = torch.zeros(points.shape[0], dtype=torch.float64)
     f32 = torch.float32
     step = torch.tensor(step, dtype=f32)
     for pi in range(points.shape[0]):
@@ -95,9 +99,10 @@ def surface_mask(points, cam_origins, occ, res, roi_aabb, scene_aabb, step, cut_
                         if not float(tm) < float(tt):
                             break
                     t0, t1 = tm - 0.5 * step, tm + 0.5 * step
+            best_of[pi] = max(float(best_of[pi]), best)
             if best >= cut_off:
                 out[pi] = True
-    return out
+    return (out, best_of) if return_best else out
 
 
 def surface_mask_vectorized(points, cam_origins, occ, res, roi_aabb, scene_aabb, step, cut_off, density_fn,

@@ -115,6 +115,33 @@ def extract_case():
         int(o["density_mask"].sum()), sub.numel(), int(o["surface_mask"].sum()), o["mask"].numel()))
 
 
+def visibility_case():
+    """compute_visibility_score fixture (conerf/loss/confidence_loss.py:56-160): arbitrary query points -
+    on and around the occupied shell, some outside the AABB - scored by the scalar oracle marcher, with
+    the best surface-field value per point so that decisions within 1e-3 of the cut-off can be set aside."""
+    import math
+    import dreg_nerf_b200 as pkg
+    from oracle import extract, ngp
+    res, n_cam, seed, table_std = 32, 4, 7, 8.0
+    step = 3.0 * math.sqrt(3) / 256
+    ref = make_field(pkg, seed, table_std)[1]
+    occ, cams = extract_scene(res, n_cam)
+    roi = [-1.5, -1.5, -1.5, 1.5, 1.5, 1.5]
+    g = torch.Generator().manual_seed(5)
+    idx = torch.nonzero(occ.flatten())[:, 0]
+    pick = idx[torch.randperm(idx.numel(), generator=g)[:360]]
+    cell = torch.stack([pick // (res * res), (pick // res) % res, pick % res], dim=1).float()
+    pts = (cell + torch.rand(360, 3, generator=g)) / res * 3.0 - 1.5
+    pts = torch.cat([pts, torch.rand(40, 3, generator=g) * 3.6 - 1.8])
+    dens_fn = lambda x: ngp.query_density(x, ref["aabb"], ref["table"], ref["w1"], ref["w2"])[0]
+    want, best = extract.surface_mask(pts, cams, occ, res, roi, roi, step, 0.5, dens_fn, return_best=True)
+    fix = {"res": res, "n_cam": n_cam, "seed": seed, "table_std": table_std, "step": step, "points": pts,
+           "visible": want, "best": best.float(), "density": dens_fn(pts)}
+    torch.save(fix, os.path.join(GOLDEN, "visibility_32.pt"))
+    print("wrote visibility_32: %d of %d visible, %d within 1e-3 of the cut-off"
+          % (int(want.sum()), pts.shape[0], int(((best - 0.5).abs() < 1e-3).sum())))
+
+
 def make_field(pkg, seed, table_std):
     """(module, oracle parameter dict) of a seeded random-weight NGP field."""
     from importlib import import_module
@@ -137,6 +164,10 @@ def extract_scene(res, n_cam):
 
 
 if __name__ == "__main__":
+    if "--visibility-only" in sys.argv:
+        visibility_case()
+        sys.exit(0)
     if "--extract-only" not in sys.argv:
         main()
     extract_case()
+    visibility_case()

@@ -162,3 +162,33 @@ def test_surface_mask_schedule_independent_128(pkg, cuda):
     f2 = pkg.synthetic.make_ngp_field(seed=505).to(cuda)
     runs = [pkg.extract_block(f2, sg, occ.to(cuda), meta, cuda, jitter=jitter)[1].cpu() for _ in range(3)]
     assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+
+
+def test_compute_visibility_score(pkg, cuda):
+    """compute_visibility_score (conerf/loss/confidence_loss.py:56-160) on arbitrary query points - decoder
+    key points, not voxel samples; some outside the AABB - against the fixture the scalar oracle marcher
+    produced in the build container (oracle/make_goldens.py visibility_case)."""
+    import os
+    fix = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "visibility_32.pt"))
+    res, step, pts = fix["res"], fix["step"], fix["points"]
+    f, _ = _field(pkg, cuda, seed=fix["seed"], table_std=fix["table_std"])
+    occ, cams = _scene(res, fix["n_cam"])
+    roi = [-1.5, -1.5, -1.5, 1.5, 1.5, 1.5]
+    poses = torch.eye(4).repeat(cams.shape[0], 1, 1)
+    poses[:, :3, 3] = cams
+    meta = {"aabb": roi, "render_step_size": step, "camera_poses": poses.to(cuda)}
+    n = pts.shape[0]
+    # points whose best surface-field value lies within 1e-3 of the cut-off: the decision hangs on the
+    # last bits of the density (fp32 summation order, 3xTF32); set aside like the 0.7 density band
+    band = (fix["best"] - 0.5).abs() < 1e-3
+    xyz = pts.reshape(2, n // 2, 3).to(cuda)                      # [num_layers, N, 3]
+    got = pkg.compute_visibility_score([xyz], f, occ, meta)[0]
+    assert got.shape == (2, n // 2, 1) and got.dtype == torch.float32
+    got_b = got.cpu().reshape(-1).bool()
+    mism = (got_b != fix["visible"]) & ~band
+    print("visibility: %d of %d points visible, %d within 1e-3 of the cut-off, mismatches elsewhere %d"
+          % (int(fix["visible"].sum()), n, int(band.sum()), int(mism.sum())))
+    assert int(mism.sum()) == 0 and 0 < int(fix["visible"].sum()) < n and int(band.sum()) < 8
+    dens = pkg.compute_visibility_score([xyz], f, occ, meta, score_type="density_field")[0]
+    want_alpha = torch.clip(1 - torch.exp(-1e-2 * fix["density"]), 0, 1)
+    assert (dens.cpu().reshape(-1) - want_alpha).abs().max() < 2e-5

@@ -132,3 +132,20 @@ def test_vectorized_surface_mask_equals_scalar_oracle(pkg):
     d, feat = ngp.query_density(pts, ref["aabb"], ref["table"], ref["w1"], ref["w2"])
     assert torch.allclose(d, fix["density"], rtol=1e-5, atol=1e-6)
     assert torch.equal(d > 0.7, fix["density_mask"])
+
+
+def test_visibility_fixture_lockstep_oracle(pkg):
+    """The lock-step CPU marcher (bench.py's cpu_baseline for the extract half) reproduces the scalar
+    oracle's visibility fixture wherever the decision is not within 1e-3 of the cut-off."""
+    import os
+    from oracle import extract, ngp
+    from oracle.make_goldens import extract_scene, make_field
+    fix = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "visibility_32.pt"))
+    ref = make_field(pkg, fix["seed"], fix["table_std"])[1]
+    occ, cams = extract_scene(fix["res"], fix["n_cam"])
+    roi = [-1.5, -1.5, -1.5, 1.5, 1.5, 1.5]
+    dens_fn = lambda x: ngp.query_density(x, ref["aabb"], ref["table"], ref["w1"], ref["w2"])[0]
+    assert (dens_fn(fix["points"]) - fix["density"]).abs().max() <= 1e-5 * fix["density"].abs().max()
+    got = extract.surface_mask_vectorized(fix["points"], cams, occ, fix["res"], roi, roi, fix["step"], 0.5, dens_fn)
+    band = (fix["best"] - 0.5).abs() < 1e-3
+    assert int(((got != fix["visible"]) & ~band).sum()) == 0
