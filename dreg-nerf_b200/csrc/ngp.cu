@@ -909,7 +909,7 @@ static constexpr int kSpec = DRB_SPEC;               // consecutive samples of o
 static constexpr int kRaysPerBatch = 32 / kSpec;
 static_assert(kSpec == 1 || kSpec == 2 || kSpec == 4 || kSpec == 8, "group size");
 #ifndef DRB_WINDOW
-#define DRB_WINDOW 64
+#define DRB_WINDOW 32
 #endif
 static constexpr int kWindow = DRB_WINDOW;                  // consecutive rays a warp takes from the global counter per fetch
 static constexpr int kCandCap = 32 + kWindow;        // per-warp queue of rays that passed the "not yet seen" test
