@@ -867,12 +867,15 @@ __device__ __forceinline__ float warp_density_raw(const NgpDev& p, const float2*
 // expensive density sample (phase B).  Every warp keeps up to 64 rays in shared-memory slots.  In
 // phase A each lane advances one ray (in registers) until its next sample position lies in an
 // occupied cell; the ray is then parked in its slot on the warp's pending list and the lane takes
-// another ray.  As soon as 32 samples are pending the warp evaluates them together - all 32 lanes
-// busy, layer 1 on the tensor cores - and the rays go back to the resume list.  Before this
-// rewrite the kernel ran with 14 of 32 lanes active on average (ncu, round 1).
+// another ray.  As soon as 8 rays are pending the warp evaluates them together - up to 4 consecutive
+// samples per ray (see "speculation" in phase A), 32 lanes, layer 1 on the tensor cores - and the rays
+// go back to the resume list.  New rays come in windows of 32 consecutive (camera, point) pairs with
+// the points in Morton order, so the rays a warp holds are spatial neighbours.  Before this rewrite
+// the kernel ran with 14 of 32 lanes active on average (ncu, round 1).
 //
-// Shared-memory diet.  Phase B is bound by the rate at which an SM can miss table sectors into L2, so
-// L1 capacity matters more than anything kept in shared memory: the plan below (hash level 0, B
+// Shared-memory diet.  Phase B is bound by the rate at which an SM's L1 retires distinct 32-byte
+// sectors (one per load instruction per clock, halved when the carve-out leaves ~28 KB of L1:
+// scripts/ubench/gather*.cu), so L1 capacity matters more than anything kept in shared memory: the plan below (hash level 0, B
 // fragments, coarse bitmap, 16 x (A tile + 64 ray slots + lists)) stays under 132 KB, which leaves a
 // 96 KB L1 (measured: 29 -> 26 ms on the heaviest synthetic block against the 164 KB carve-out).
 //
