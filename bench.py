@@ -76,10 +76,11 @@ def _state(pkg, model):
 def cpu_extract_seconds(pkg, cams, ray_sample=20000):
     """CPU time of ONE block's extract (oracle port: the reference's own extract is CUDA-only, tcnn +
     nerfacc, so no reference CPU implementation exists).  Density / colour over all candidate cells is
-    timed in full; the surface-field ray march is timed on a bounded sample of rays and scaled by the
-    ray count (every (camera, point) ray is marched, as sample_grid.py:245-318 does)."""
+    timed in full (torch CPU ops); the surface-field ray march runs in the C / OpenMP restatement
+    (oracle/extract_c.c, all host threads) on a bounded sample of points - every camera's ray to each of
+    them, as sample_grid.py:245-318 marches them - and is scaled by the ray count."""
     import torch
-    from oracle import extract, ngp
+    from oracle import extract, extract_c, ngp
     from oracle.make_goldens import make_field
     occ, poses = pkg.synthetic.extract_scene(RES, cams)
     meta = pkg.synthetic.extract_meta(poses)
@@ -94,14 +95,16 @@ def cpu_extract_seconds(pkg, cams, ray_sample=20000):
     ngp.query_rgb_mean(ngp.fixed_viewing_directions(), feat, ref["c1"], ref["c2"], ref["c3"])
     t_field = time.perf_counter() - t0
     total_rays = idx.numel() * cams
-    sample = torch.randperm(total_rays, generator=gen)[:min(ray_sample, total_rays)]
-    dens_fn = lambda x: ngp.query_density(x, ref["aabb"], ref["table"], ref["w1"], ref["w2"])[0]
+    n_pts = max(1, min(idx.numel(), ray_sample // max(cams, 1)))
+    pick = torch.randperm(idx.numel(), generator=gen)[:n_pts]
+    extract_c.load()
     t0 = time.perf_counter()
-    extract.surface_mask_vectorized(pts, poses[:, :3, 3].contiguous(), occ, RES, roi, roi, meta["render_step_size"],
-                                    0.5, dens_fn, ray_subset=sample)
-    t_rays = (time.perf_counter() - t0) * (total_rays / sample.numel())
+    _, _, n_samples = extract_c.surface_mask(pts[pick], poses[:, :3, 3].contiguous(), occ, RES, roi, roi,
+                                             meta["render_step_size"], 0.5, ref, all_rays=True)
+    t_rays = (time.perf_counter() - t0) * (total_rays / (n_pts * cams))
     return t_field + t_rays, {"field_s": t_field, "rays_s_extrapolated": t_rays, "rays_total": int(total_rays),
-                              "rays_sampled": int(sample.numel())}
+                              "rays_sampled": int(n_pts * cams), "density_samples_in_sample": int(n_samples),
+                              "marcher": "oracle/extract_c.c (C, OpenMP, %d threads)" % (os.cpu_count() or 1)}
 
 
 def run_reference(args):
@@ -136,7 +139,7 @@ def run_reference(args):
 
     extract_s, extract_info = (0.0, None)
     if full:
-        one_block, extract_info = cpu_extract_seconds(pkg, args.cams)
+        one_block, extract_info = cpu_extract_seconds(pkg, args.cams, ray_sample=400000)
         extract_s = 2.0 * one_block
     t0 = time.perf_counter()
     full_step()
@@ -517,7 +520,7 @@ def cpu_baseline(pkg, model, stage, cams):
     dt = time.perf_counter() - t0
     sample = "1 pair, 128^3, NeRFRegTr.forward, fp32 torch CPU ops, %d threads, single cold run (%.1f s)" % (cores, dt)
     if stage == "full":
-        one_block, info = cpu_extract_seconds(pkg, cams, ray_sample=10000)
+        one_block, info = cpu_extract_seconds(pkg, cams, ray_sample=200000)
         dt += 2.0 * one_block
         sample += ("; + extract of 2 blocks by the oracle port (%.1f s; ray march extrapolated from %d of %d rays)"
                    % (2.0 * one_block, info["rays_sampled"], info["rays_total"]))

@@ -149,3 +149,39 @@ def test_visibility_fixture_lockstep_oracle(pkg):
     got = extract.surface_mask_vectorized(fix["points"], cams, occ, fix["res"], roi, roi, fix["step"], 0.5, dens_fn)
     band = (fix["best"] - 0.5).abs() < 1e-3
     assert int(((got != fix["visible"]) & ~band).sum()) == 0
+
+
+def test_c_oracle_matches_python_oracle(pkg):
+    """oracle/extract_c.c (C / OpenMP restatement of A1 + A5, used for full-size checks and as the timed CPU
+    baseline) against the pure-Python oracles: density to fp32 summation-order noise, the scalar marcher's
+    fixtures bit for bit (extract_32) / off the 1e-3 band around the cut-off (visibility_32; the C code keeps
+    the transmittance in fp32 like nerfacc, the Python oracle in doubles)."""
+    import os
+    from oracle import extract_c, ngp
+    from oracle.make_goldens import extract_scene, make_field
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    _, ref = make_field(pkg, 0, 1.0)
+    x = torch.rand(3000, 3, generator=torch.Generator().manual_seed(1)) * 3.2 - 1.6
+    d_py = ngp.query_density(x, ref["aabb"], ref["table"], ref["w1"], ref["w2"])[0]
+    d_c = extract_c.query_density(x, ref["aabb"], ref["table"], ref["w1"], ref["w2"])
+    inside = d_py > 0
+    assert bool(((d_c == 0) == (d_py == 0)).all())
+    assert float(((d_c - d_py).abs()[inside] / d_py[inside]).max()) < 5e-6
+    roi = [-1.5, -1.5, -1.5, 1.5, 1.5, 1.5]
+    fix = torch.load(os.path.join(golden, "extract_32.pt"))
+    ref = make_field(pkg, fix["seed"], fix["table_std"])[1]
+    occ, cams = extract_scene(fix["res"], fix["n_cam"])
+    m, _, n_samples = extract_c.surface_mask(fix["points"], cams, occ, fix["res"], roi, roi, fix["step"], 0.5, ref)
+    assert torch.equal(m, fix["surface_mask"]) and n_samples > 0
+    fix = torch.load(os.path.join(golden, "visibility_32.pt"))
+    ref = make_field(pkg, fix["seed"], fix["table_std"])[1]
+    occ, cams = extract_scene(fix["res"], fix["n_cam"])
+    m, best, _ = extract_c.surface_mask(fix["points"], cams, occ, fix["res"], roi, roi, fix["step"], 0.5, ref)
+    band = (fix["best"] - 0.5).abs() < 1e-3
+    assert int(((m != fix["visible"]) & ~band).sum()) == 0
+    # restricting the rays to flagged points / marching every camera does not change the flagged points' answer
+    act = torch.zeros(m.numel(), dtype=torch.bool)
+    act[::3] = True
+    m2, _, _ = extract_c.surface_mask(fix["points"], cams, occ, fix["res"], roi, roi, fix["step"], 0.5, ref,
+                                      active=act, all_rays=True)
+    assert torch.equal(m2[act], m[act]) and not bool(m2[~act].any())
