@@ -18,4 +18,8 @@ Parity status (also recorded in DESIGN.md):
     installable here; the restatements follow the published algorithms and the
     reference's call sites.  The only in-repo golden vector (transmittance
     docstring, conerf/utils/nerfacc_utils.py:56-63) is checked.
+  * ``oracle/extract_c.c`` (``make -C oracle`` -> ``oracle/_c/``): the A1 / A5
+    arithmetic once more in C with OpenMP (fp32, no early outs), tied to the
+    Python oracles' fixtures by ``tests/test_oracle_golden.py``; used for the
+    full-size 128^3 parity test and as bench.py's timed CPU marcher.
 """
