@@ -134,3 +134,13 @@ def test_256_cube_plumbing(pkg, cuda):
         out = model(data)
     assert out["pose"].shape == (6, 1, 3, 4) and torch.isfinite(out["pose"]).all()
     assert all(torch.isfinite(t).all() for t in out["src_feats"])
+
+
+def test_forward_128_train_bn(pkg, cuda):
+    """BASELINE.json configs[1] size: the full 128^3 pair, batch-statistics BatchNorm (what the bench runs),
+    against the CPU oracle (bit-identical to the reference's modules) - key points bit exact, features /
+    correspondences / overlap / pose within the 1e-3 bar."""
+    model, sd, data, out, ref, _ = _run(pkg, cuda, 128, training=True)
+    assert out["pose"].shape == (6, 1, 3, 4)
+    print("tokens", model.last_token_counts, "masked voxels", data["src_mask"].numel(), data["tgt_mask"].numel())
+    _check(out, ref)
