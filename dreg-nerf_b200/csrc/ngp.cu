@@ -483,32 +483,6 @@ struct MarchArgs {
   int max_skips;      // empty-space events a lane may take per outer iteration
 };
 
-__device__ __forceinline__ bool occupied_at(const MarchArgs& a, const uint8_t* occ, const float x[3]) {
-  int idx[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    const float u = (x[d] - a.roi_min[d]) / (a.roi_max[d] - a.roi_min[d]);
-    if (!(u >= 0.f && u < 1.f)) return false;
-    int i = (int)(u * (float)a.res);
-    idx[d] = i < 0 ? 0 : (i > a.res - 1 ? a.res - 1 : i);
-  }
-  return occ[((long long)idx[0] * a.res + idx[1]) * a.res + idx[2]] != 0;
-}
-
-__device__ __forceinline__ float dist_to_next_voxel(const MarchArgs& a, const float x[3], const float dir[3],
-                                                    const float inv_dir[3]) {
-  float t = 1e30f;
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    const float ext = a.roi_max[d] - a.roi_min[d];
-    const float u = (x[d] - a.roi_min[d]) / ext * (float)a.res;
-    const float sgn = dir[d] > 0.f ? 1.f : (dir[d] < 0.f ? -1.f : 0.f);
-    const float td = (floorf(u + 0.5f + 0.5f * sgn) - u) * inv_dir[d] / (float)a.res * ext;
-    t = fminf(t, td);
-  }
-  return fmaxf(t, 0.f);
-}
-
 // ------------------------------------------------------------------------------------------
 // Compile-time level table (must equal host_levels(); checked once at run time by levels_ok()).
 // ------------------------------------------------------------------------------------------
