@@ -90,6 +90,53 @@ def main():
               "oracle == reference bit-exact")
 
 
+def training_loss(out):
+    """A fixed scalar of every output of NeRFRegTr.forward (stand-in for the training losses of
+    train_nerf_regtr.py:171-256, which need NeRF checkpoints): used only to pin gradients."""
+    loss = (out["pose"][-1] ** 2).mean()
+    for side in ("src", "tgt"):
+        loss = loss + (out[side + "_feats"][0][-1] ** 2).mean() + (out[side + "_kp_warped"][0] ** 2).mean() \
+            + out[side + "_overlap"][0].mean()
+    return loss
+
+
+def gradient_case():
+    """Backward fixture for the round that builds the backward kernels: gradients of ``training_loss`` w.r.t.
+    every parameter, computed by autograd through the REFERENCE's own modules (32^3, running-statistics
+    BatchNorm), asserted equal for the functional oracle, stored as per-parameter digests + a few samples."""
+    import dreg_nerf_b200 as pkg
+    ref = import_reference()
+    torch.manual_seed(0)
+    model = ref.NeRFRegTr()
+    sd = pkg.synthetic.seeded_state_dict(model, seed=0, attn_gain=4.0)
+    model.load_state_dict(sd)
+    model.train(False)
+    data = pkg.synthetic.make_pair(res=32, pair_id=0)
+    out = model({k: (v.clone() if torch.is_tensor(v) else v) for k, v in data.items()})
+    loss = training_loss(out)
+    loss.backward()
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    # the functional oracle on leaf copies of the same weights
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k in grads else v) for k, v in sd.items()}
+    out_or = regtr.forward(leaf, data, training=False)
+    loss_or = training_loss(out_or)
+    loss_or.backward()
+    assert torch.equal(loss_or.detach(), loss.detach()), (float(loss_or), float(loss))
+    worst = 0.0
+    for k, g in grads.items():
+        go = leaf[k].grad
+        assert go is not None, k
+        worst = max(worst, float((go - g).abs().max() / (g.abs().max() + 1e-30)))
+    assert worst < 1e-5, worst
+    fix = {"loss": loss.detach(), "res": 32, "pair_id": 0, "gain": 4.0, "seed": 0,
+           "digests": {k: _digest(g) for k, g in grads.items()},
+           "samples": {k: grads[k].reshape(-1)[:64].clone() for k in list(grads)[:3] + list(grads)[-6:]},
+           "oracle_vs_reference_max_rel": worst}
+    torch.save(fix, os.path.join(GOLDEN, "grad_32_eval.pt"))
+    print("wrote grad_32_eval: loss %.6f, %d parameter gradients, oracle vs reference max rel %.2e"
+          % (float(loss), len(grads), worst))
+
+
 def extract_case():
     """Extract fixture: a 32^3 block of a seeded random-weight field, evaluated by the (slow, pure
     Python) oracle here so that the GPU box only has to load the result."""
@@ -164,6 +211,9 @@ def extract_scene(res, n_cam):
 
 
 if __name__ == "__main__":
+    if "--gradient-only" in sys.argv:
+        gradient_case()
+        sys.exit(0)
     if "--visibility-only" in sys.argv:
         visibility_case()
         sys.exit(0)
@@ -171,3 +221,4 @@ if __name__ == "__main__":
         main()
     extract_case()
     visibility_case()
+    gradient_case()

@@ -185,3 +185,32 @@ def test_c_oracle_matches_python_oracle(pkg):
     m2, _, _ = extract_c.surface_mask(fix["points"], cams, occ, fix["res"], roi, roi, fix["step"], 0.5, ref,
                                       active=act, all_rays=True)
     assert torch.equal(m2[act], m[act]) and not bool(m2[~act].any())
+
+
+def test_oracle_gradients_match_reference(pkg):
+    """Backward pin for the round that builds the backward kernels: autograd through the functional oracle
+    reproduces the gradients the REFERENCE's own modules produced (tests/golden/grad_32_eval.pt, written by
+    oracle/make_goldens.py gradient_case with /root/reference imported)."""
+    import os
+    from oracle import regtr
+    from oracle.make_goldens import training_loss
+    fix = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grad_32_eval.pt"))
+    torch.manual_seed(0)
+    model = pkg.NeRFRegTr()
+    sd = pkg.synthetic.seeded_state_dict(model, seed=fix["seed"], attn_gain=fix["gain"])
+    leaf = {k: (v.clone().requires_grad_(True) if k in fix["digests"] else v) for k, v in sd.items()}
+    data = pkg.synthetic.make_pair(res=fix["res"], pair_id=fix["pair_id"])
+    loss = training_loss(regtr.forward(leaf, data, training=False))
+    assert abs(float(loss) - float(fix["loss"])) < 1e-6 * abs(float(fix["loss"]))
+    loss.backward()
+    assert len(fix["digests"]) == 293
+    for k, want in fix["digests"].items():
+        g = leaf[k].grad.double()
+        got = torch.stack([g.sum(), g.abs().sum(), (g * g).sum()])
+        scale = float(want[1]) + 1e-30
+        assert abs(float(got[0] - want[0])) < 1e-4 * scale, k
+        assert abs(float(got[1] - want[1])) < 1e-4 * scale, k
+        assert abs(float(got[2] - want[2])) < 1e-4 * (float(want[2]) + 1e-30), k
+    for k, want in fix["samples"].items():
+        got = leaf[k].grad.reshape(-1)[:64]
+        assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max() + 1e-12), k
