@@ -21,7 +21,21 @@ class Conv3dDesc(C.Structure):
                 ("x_hi", c_void_p), ("x_lo", c_void_p), ("w_hi", c_void_p), ("w_lo", c_void_p),
                 ("bias", c_void_p), ("residual", c_void_p),
                 ("out", c_void_p), ("out_hi", c_void_p), ("out_lo", c_void_p),
-                ("ld_out", c_ll), ("bn_accum", c_void_p), ("tile_list", c_void_p), ("tile_count", c_void_p)]
+                ("ld_out", c_ll), ("bn_accum", c_void_p), ("tile_list", c_void_p), ("tile_count", c_void_p),
+                ("acc_scale_dev", c_void_p * 2)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("g", c_int), ("d", c_int), ("h", c_int), ("w", c_int), ("cout", c_int), ("cin", c_int),
+                ("kd", c_int), ("kh", c_int), ("kw", c_int), ("planes", c_int),
+                ("dy_hi", c_void_p), ("dy_lo", c_void_p), ("x_hi", c_void_p), ("x_lo", c_void_p),
+                ("scale", c_float), ("scale_dev", c_void_p), ("dw", c_void_p),
+                ("c_real", c_int), ("taps_real", c_int), ("tile_list", c_void_p), ("tile_count", c_void_p)]
+
+
+class PairGrad(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("d_src_feats", "d_tgt_feats", "d_src_corr", "d_tgt_corr",
+                                        "d_src_overlap", "d_tgt_overlap", "d_pose")]
 
 
 class Im2colDesc(C.Structure):
@@ -117,6 +131,55 @@ SIGNATURES = {
     "drb_march_stats": (c_int, [C.POINTER(C.c_ulonglong), c_int]),
     "drb_extract_set_profile": (c_int, [c_int]),
     "drb_extract_read_profile": (c_int, [C.POINTER(c_float), C.POINTER(c_int)]),
+    "drb_conv3d_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
+    "drb_grad_split": (c_int, [c_void_p, c_ll, c_int, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "drb_add_inplace": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+    "drb_relu_mask_plane": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+    "drb_colsum_add": (c_int, [c_void_p, c_ll, c_int, c_ll, c_void_p, c_void_p]),
+    "drb_bn_save_stats": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "drb_bn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                c_int, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "drb_maxpool3d_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "drb_upsample2_add_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                           c_void_p]),
+    "drb_trilinear_gather_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                              c_void_p, c_int, c_void_p, c_void_p]),
+    "drb_col2im": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                           c_void_p]),
+    "drb_layernorm256_backward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                          c_void_p]),
+    "drb_overlap_sigmoid_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p]),
+    "drb_softmax_rows": (c_int, [c_void_p, c_ll, c_int, c_int, c_float, c_void_p]),
+    "drb_softmax_backward_rows": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_void_p]),
+    "drb_softmax_weighted_xyz_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "drb_sgemm_strided": (c_int, [c_void_p, c_ll, c_ll, c_ll, c_void_p, c_ll, c_ll, c_ll, c_void_p, c_ll, c_ll, c_int,
+                                  c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "drb_mha_backward_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "drb_mha_core_backward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                      c_int, c_float, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                      c_size_t, c_void_p]),
+    "drb_procrustes_backward": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int,
+                                        c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "drb_segment_mean_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "drb_hierarchical_downsample_tape": (c_int, [c_void_p, c_int, c_int, c_int, c_int, C.c_double, c_int, c_void_p,
+                                                 c_size_t, c_void_p, C.POINTER(c_int), C.POINTER(c_int), c_void_p, c_ll,
+                                                 C.POINTER(c_int), C.POINTER(c_int), c_void_p]),
+    "drb_fpn_dilated_tiles": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "drb_adamw_create": (c_int, [c_int, C.POINTER(c_void_p), C.POINTER(c_ll), C.POINTER(c_void_p)]),
+    "drb_adamw_destroy": (None, [c_void_p]),
+    "drb_adamw_step": (c_int, [c_void_p, C.POINTER(c_void_p), c_float, c_float, c_float, c_float, c_float, c_float,
+                               c_void_p]),
+    "drb_adamw_grad_norm": (c_int, [c_void_p, C.POINTER(C.c_double), c_void_p]),
+    "drb_adamw_copy_state": (c_int, [c_void_p, c_int, c_void_p, c_void_p, C.POINTER(c_ll), c_void_p]),
+    "drb_adamw_set_step": (c_int, [c_void_p, c_ll]),
+    "drb_engine_set_grad_mode": (c_int, [c_void_p, c_int]),
+    "drb_engine_param_trainable": (c_int, [c_void_p, c_int]),
+    "drb_engine_bind_grad": (c_int, [c_void_p, c_int, c_void_p]),
+    "drb_engine_backward": (c_int, [c_void_p, C.POINTER(PairIO), C.POINTER(PairOut), C.POINTER(PairGrad), c_void_p]),
+    "drb_engine_set_max_tokens": (c_int, [c_void_p, c_int]),
     "drb_engine_create": (c_int, [C.POINTER(EngineConfig), C.POINTER(c_void_p)]),
     "drb_engine_destroy": (None, [c_void_p]),
     "drb_engine_num_params": (c_int, [c_void_p]),
@@ -150,7 +213,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.drb_abi_version() != 1:
+    if lib.drb_abi_version() != 2:
         raise DrbError("libdregb200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -39,6 +39,14 @@ void set_error(const char* fmt, ...);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// host helpers shared by the tensor-core kernels (igemm.cu)
+int igemm_num_sms();                 // SM count of the current device
+int* igemm_err_flag();               // per-device pipeline watchdog flag (device int), lazily allocated
+void igemm_clear_err_flag();
+void igemm_choose_box(int G, int D, int H, int W, int& bg, int& bd, int& bh, int& bw);
+int igemm_make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, bool is_bf16);
+
 // 16-bit operand "planes" of the tensor-core GEMM (raw storage).
 //   pair mode   (lo plane present): x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significand
 //               bits survive as long as |x| stays inside fp16's normal range (weights are pre-scaled by a

@@ -5,135 +5,9 @@
 // Network topology restated from conerf/model/resnet3d.py:116-172 (ResNet-50, Bottleneck
 // [3,4,6,3], conv1 5^3 s2, maxpool 3 s2) and conerf/model/feature_pyramid_net.py:39-108 (FPN v1),
 // conerf/register/transformer.py:225-299 (pre-LN cross encoder), nerf_regtr.py:350-394 (decoder).
-#include "common.cuh"
-
-#include <string>
-#include <vector>
-
-namespace drb {
-
-static constexpr int kG = 2;            // src + tgt
-static constexpr int kRowLd = 260;      // [x y z 0 | 256 features]
-static constexpr int kLayers = 6;
-static constexpr int kD = 256;
-
-struct Act {                 // channels-last activation [g][d][h][w][c]
-  float* f = nullptr;
-  plane_t* hi = nullptr;
-  plane_t* lo = nullptr;
-  int d = 0, h = 0, w = 0, c = 0;
-  long long m() const { return (long long)d * h * w; }          // voxels per grid
-  long long numel() const { return (long long)kG * m() * c; }
-};
-
-enum ParamKind { PK_CONV, PK_VEC };
-
-struct Param {
-  std::string name;
-  long long numel = 0;
-  float* ptr = nullptr;
-};
-
-struct ConvW {               // packed weight planes
-  int p_w = -1, p_b = -1;    // param indices (bias optional)
-  int cout = 0, cin = 0, k = 1, stride = 1;
-  float scale = 1.f;         // power-of-two pre-scale applied when packing (pair mode)
-  bool im2col = false;       // lowered through an explicit im2col buffer
-  int kpad = 0;              // im2col K (multiple of 64)
-  plane_t* hi = nullptr;
-  plane_t* lo = nullptr;
-};
-
-struct BnP {
-  int p_w = -1, p_b = -1, p_rm = -1, p_rv = -1;
-  int c = 0;
-  float* scale = nullptr;    // [g][c]
-  float* shift = nullptr;
-};
-
-struct Block {
-  ConvW conv1, conv2, conv3, down;
-  BnP bn1, bn2, bn3, bnd;
-  bool has_down = false;
-  int stride = 1;
-};
-
-struct AttnW { ConvW in_proj, out_proj; };
-struct TLayer {
-  AttnW self_attn, cross_attn;
-  ConvW lin1, lin2;
-  int n1w, n1b, n2w, n2b, n3w, n3b;
-};
-
-}  // namespace drb
+#include "engine.cuh"
 
 using namespace drb;
-
-struct drb_engine {
-  drb_engine_config cfg;
-  std::vector<Param> params;
-  std::vector<void*> allocs;
-  long long launches = 0;
-  bool committed = false;
-  bool profile = false;
-  struct ProfRec { cudaEvent_t a, b; double flops; int list_id; double flops_per_tile; };
-  std::vector<ProfRec> prof;
-  std::string fail;
-
-  // topology
-  ConvW conv1; BnP bn1;
-  std::vector<Block> blocks[4];
-  ConvW pyr[5], ups[4];
-  TLayer tl[kLayers];
-  int fin_w, fin_b;                 // transformer_encoder.norm
-  ConvW q_proj, k_proj;
-  int conf_w, conf_b;
-
-  // FPN buffers
-  int D, H, W;                      // conv volume axes: D = Z, H = X, W = Y
-  plane_t *col_hi = nullptr, *col_lo = nullptr;   // shared im2col scratch
-  long long col_elems = 0;
-  float* raw = nullptr;             // shared raw conv output scratch (largest BN'd conv)
-  long long raw_elems = 0;
-  float* raw2 = nullptr;            // second scratch (downsample branch)
-  double* bn_accum = nullptr;
-  Act c1, x0, c[4];                 // c[0..3] = c2..c5
-  std::vector<Act> tmp;             // per-block temporaries
-  Act lat[5], sum[4], p[5];         // p[0] = p1 ... p[4] = p5
-  // output-sparse evaluation of the two level-1 FPN convolutions
-  bool sparse_fpn = true;
-  uint8_t* need = nullptr;
-  int *tiles_out = nullptr, *tiles_in = nullptr, *tile_counts = nullptr;
-  unsigned long long* tile_totals = nullptr;   // running sums of the list lengths (profiling)
-  // point stage
-  float* rows = nullptr;            // [2*max_mask][260]
-  float* rows_ds = nullptr;
-  void* ds_ws = nullptr; size_t ds_ws_bytes = 0;
-  int n_src = 0, n_tgt = 0;         // tokens after down-sampling
-  // transformer buffers (capacity tok_cap rows)
-  int tok_cap = 0;
-  float *x = nullptr, *pos = nullptr, *qkv = nullptr, *kp_xyz = nullptr, *sbuf = nullptr;
-  plane_t *xn_hi = nullptr, *xn_lo = nullptr, *att_hi = nullptr, *att_lo = nullptr;
-  plane_t *ffn_hi = nullptr, *ffn_lo = nullptr, *dec_hi = nullptr, *dec_lo = nullptr;
-  plane_t *qp_hi = nullptr, *qp_lo = nullptr, *kp_hi = nullptr, *kp_lo = nullptr;
-  std::vector<void*> tok_allocs;
-
-  template <typename T> T* alloc(long long n) {
-    void* p = nullptr;
-    if (n <= 0) n = 1;
-    if (cudaMalloc(&p, (size_t)n * sizeof(T)) != cudaSuccess) {
-      fail = "cudaMalloc failed";
-      return nullptr;
-    }
-    allocs.push_back(p);
-    return (T*)p;
-  }
-  int add_param(const std::string& name, long long numel) {
-    Param q; q.name = name; q.numel = numel;
-    params.push_back(q);
-    return (int)params.size() - 1;
-  }
-};
 
 namespace drb {
 
@@ -141,8 +15,8 @@ static ConvW make_conv(drb_engine* e, const std::string& name, int cout, int cin
                        bool bias) {
   ConvW w;
   w.cout = cout; w.cin = cin; w.k = k; w.stride = stride;
-  w.p_w = e->add_param(name + ".weight", (long long)cout * cin * k * k * k);
-  if (bias) w.p_b = e->add_param(name + ".bias", cout);
+  w.p_w = e->add_param(name + ".weight", (long long)cout * cin * k * k * k, true);
+  if (bias) w.p_b = e->add_param(name + ".bias", cout, true);
   const int taps = k * k * k;
   w.im2col = (stride != 1) || (cin % 64 != 0);
   if (w.im2col) {
@@ -159,12 +33,14 @@ static ConvW make_conv(drb_engine* e, const std::string& name, int cout, int cin
 static BnP make_bn(drb_engine* e, const std::string& name, int c) {
   BnP b;
   b.c = c;
-  b.p_w = e->add_param(name + ".weight", c);
-  b.p_b = e->add_param(name + ".bias", c);
-  b.p_rm = e->add_param(name + ".running_mean", c);
-  b.p_rv = e->add_param(name + ".running_var", c);
+  b.p_w = e->add_param(name + ".weight", c, true);
+  b.p_b = e->add_param(name + ".bias", c, true);
+  b.p_rm = e->add_param(name + ".running_mean", c, false);
+  b.p_rv = e->add_param(name + ".running_var", c, false);
   b.scale = e->alloc<float>((long long)kG * c);
   b.shift = e->alloc<float>((long long)kG * c);
+  b.mean = e->alloc<float>((long long)kG * c);
+  b.rstd = e->alloc<float>((long long)kG * c);
   return b;
 }
 
@@ -223,9 +99,9 @@ static int build(drb_engine* e) {
     TLayer& t = e->tl[l];
     auto attn = [&](const std::string& an) {
       AttnW a;
-      a.in_proj.cout = 768; a.in_proj.cin = 256;
-      a.in_proj.p_w = e->add_param(pn + "." + an + ".in_proj_weight", 768 * 256);
-      a.in_proj.p_b = e->add_param(pn + "." + an + ".in_proj_bias", 768);
+      a.in_proj.cout = 768; a.in_proj.cin = 256; a.in_proj.k = 1; a.in_proj.stride = 1;
+      a.in_proj.p_w = e->add_param(pn + "." + an + ".in_proj_weight", 768 * 256, true);
+      a.in_proj.p_b = e->add_param(pn + "." + an + ".in_proj_bias", 768, true);
       a.in_proj.hi = e->alloc<plane_t>(768 * 256);
       if (e->cfg.planes == 2) a.in_proj.lo = e->alloc<plane_t>(768 * 256);
       a.out_proj = make_conv(e, pn + "." + an + ".out_proj", 256, 256, 1, 1, true);
@@ -235,16 +111,16 @@ static int build(drb_engine* e) {
     t.cross_attn = attn("cross_attn");
     t.lin1 = make_conv(e, pn + ".linear1", 1024, 256, 1, 1, true);
     t.lin2 = make_conv(e, pn + ".linear2", 256, 1024, 1, 1, true);
-    t.n1w = e->add_param(pn + ".norm1.weight", 256); t.n1b = e->add_param(pn + ".norm1.bias", 256);
-    t.n2w = e->add_param(pn + ".norm2.weight", 256); t.n2b = e->add_param(pn + ".norm2.bias", 256);
-    t.n3w = e->add_param(pn + ".norm3.weight", 256); t.n3b = e->add_param(pn + ".norm3.bias", 256);
+    t.n1w = e->add_param(pn + ".norm1.weight", 256, true); t.n1b = e->add_param(pn + ".norm1.bias", 256, true);
+    t.n2w = e->add_param(pn + ".norm2.weight", 256, true); t.n2b = e->add_param(pn + ".norm2.bias", 256, true);
+    t.n3w = e->add_param(pn + ".norm3.weight", 256, true); t.n3b = e->add_param(pn + ".norm3.bias", 256, true);
   }
-  e->fin_w = e->add_param("transformer_encoder.norm.weight", 256);
-  e->fin_b = e->add_param("transformer_encoder.norm.bias", 256);
+  e->fin_w = e->add_param("transformer_encoder.norm.weight", 256, true);
+  e->fin_b = e->add_param("transformer_encoder.norm.bias", 256, true);
   e->q_proj = make_conv(e, "correspondence_decoder.q_proj", 256, 256, 1, 1, true);
   e->k_proj = make_conv(e, "correspondence_decoder.k_proj", 256, 256, 1, 1, true);
-  e->conf_w = e->add_param("correspondence_decoder.conf_logits_decoder.weight", 256);
-  e->conf_b = e->add_param("correspondence_decoder.conf_logits_decoder.bias", 1);
+  e->conf_w = e->add_param("correspondence_decoder.conf_logits_decoder.weight", 256, true);
+  e->conf_b = e->add_param("correspondence_decoder.conf_logits_decoder.bias", 1, true);
 
   // ---------------- activation buffers ----------------
   const int d1 = conv_out(e->D, 5, 2, 2), h1 = conv_out(e->H, 5, 2, 2), w1 = conv_out(e->W, 5, 2, 2);
@@ -304,7 +180,8 @@ static int build(drb_engine* e) {
     e->need = e->alloc<uint8_t>((long long)kG * e->c1.m());
     e->tiles_out = e->alloc<int>(nt);
     e->tiles_in = e->alloc<int>(nt);
-    e->tile_counts = e->alloc<int>(2);
+    e->tiles_in2 = e->alloc<int>(nt);
+    e->tile_counts = e->alloc<int>(3);
     e->tile_totals = e->alloc<unsigned long long>(2);
     cudaMemset(e->tile_totals, 0, 2 * sizeof(unsigned long long));
     // rows of tiles that are skipped keep whatever they held: start from zeros, not from garbage
@@ -317,22 +194,43 @@ static int build(drb_engine* e) {
   e->rows_ds = e->alloc<float>((long long)2 * cfg.max_mask * kRowLd);
   e->ds_ws_bytes = drb_downsample_workspace_bytes(2 * cfg.max_mask, kRowLd);
   e->ds_ws = e->alloc<uint8_t>((long long)e->ds_ws_bytes);
+  // every packed weight, in one table (the vectors above are final: the pointers stay valid)
+  e->conv1.need_dgrad = false;
+  e->all_convs.push_back(&e->conv1);
+  for (int li = 0; li < 4; ++li)
+    for (Block& b : e->blocks[li]) {
+      e->all_convs.push_back(&b.conv1); e->all_convs.push_back(&b.conv2); e->all_convs.push_back(&b.conv3);
+      if (b.has_down) e->all_convs.push_back(&b.down);
+    }
+  for (int i = 0; i < 5; ++i) e->all_convs.push_back(&e->pyr[i]);
+  for (int i = 0; i < 4; ++i) e->all_convs.push_back(&e->ups[i]);
+  for (int l = 0; l < kLayers; ++l) {
+    TLayer& t = e->tl[l];
+    e->all_convs.push_back(&t.self_attn.in_proj); e->all_convs.push_back(&t.self_attn.out_proj);
+    e->all_convs.push_back(&t.cross_attn.in_proj); e->all_convs.push_back(&t.cross_attn.out_proj);
+    e->all_convs.push_back(&t.lin1); e->all_convs.push_back(&t.lin2);
+  }
+  e->all_convs.push_back(&e->q_proj); e->all_convs.push_back(&e->k_proj);
+  const int nw = (int)e->all_convs.size();
+  e->n_slots = nw + 64;                                   // one per weight + a ring for gradient tensors
+  e->slots = e->alloc<float>(2LL * e->n_slots);
+  if (e->slots) cudaMemset(e->slots, 0, sizeof(float) * 2 * e->n_slots);
+  e->d_pack = e->alloc<PackDesc>(nw);
+  for (int i = 0; i < nw; ++i) {
+    e->all_convs[i]->pack_index = i;
+    e->all_convs[i]->slot = e->slots ? e->slots + 2 * i : nullptr;
+  }
   return e->fail.empty() ? 0 : DRB_ENOMEM;
 }
 
 // --------------------------------------------------------------------------------------------
-#define DRB_TRY(expr)            \
-  do {                           \
-    int _rc = (expr);            \
-    if (_rc != 0) return _rc;    \
-  } while (0)
 
-static int run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const plane_t* x_lo, int g, int d,
+int engine_run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const plane_t* x_lo, int g, int d,
                      int h, int wd, int cin, int k, const float* bias, const float* residual,
                      int relu, float scale, float* out, plane_t* out_hi, plane_t* out_lo, long long ld,
-                     cudaStream_t s, const plane_t* w_hi = nullptr, const plane_t* w_lo = nullptr,
-                     int cout_override = 0, const int* tile_list = nullptr, const int* tile_count = nullptr,
-                     double* bn_accum = nullptr) {
+                     cudaStream_t s, const plane_t* w_hi, const plane_t* w_lo, int cout_override,
+                     const int* tile_list, const int* tile_count, const float* scale_dev0,
+                     const float* scale_dev1) {
   drb_conv3d_desc cd;
   memset(&cd, 0, sizeof(cd));
   cd.g = g; cd.d = d; cd.h = h; cd.w = wd;
@@ -340,14 +238,16 @@ static int run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
   cd.kd = cd.kh = cd.kw = k;
   cd.planes = e->cfg.planes;
   cd.relu = relu; cd.out_scale = scale;
-  cd.acc_scale = w_hi ? 1.f : 1.f / w.scale;
+  cd.acc_scale = 1.f;
   cd.x_hi = x_hi; cd.x_lo = x_lo;
   cd.w_hi = w_hi ? w_hi : w.hi; cd.w_lo = w_lo ? w_lo : w.lo;
   cd.bias = bias; cd.residual = residual;
   cd.out = out; cd.out_hi = out_hi; cd.out_lo = out_lo;
   cd.ld_out = ld;
   cd.tile_list = tile_list; cd.tile_count = tile_count;
-  cd.bn_accum = bn_accum;
+  // the weight pre-scale lives on the device (drb_engine_commit_params never synchronises)
+  cd.acc_scale_dev[0] = scale_dev0;
+  cd.acc_scale_dev[1] = scale_dev1;
   e->launches += 1;
   if (!e->profile) return drb_conv3d_igemm(&cd, s);
   drb_engine::ProfRec r;
@@ -363,20 +263,20 @@ static int run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
   return rc;
 }
 
-static inline float* P(drb_engine* e, int idx) { return idx >= 0 ? e->params[idx].ptr : nullptr; }
-static inline plane_t* off(plane_t* p, long long n) { return p ? p + n : nullptr; }
+// forward GEMM with the layer's own packed weights (their inverse pre-scale is slot + 1)
+static int run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const plane_t* x_lo, int g, int d,
+                     int h, int wd, int cin, int k, const float* bias, const float* residual,
+                     int relu, float scale, float* out, plane_t* out_hi, plane_t* out_lo, long long ld,
+                     cudaStream_t s, const plane_t* w_hi = nullptr, const plane_t* w_lo = nullptr,
+                     int cout_override = 0, const int* tile_list = nullptr, const int* tile_count = nullptr) {
+  const float* wscale = (w_hi == nullptr && e->cfg.planes == 2 && w.slot) ? w.slot + 1 : nullptr;
+  return engine_run_igemm(e, w, x_hi, x_lo, g, d, h, wd, cin, k, bias, residual, relu, scale, out, out_hi, out_lo, ld,
+                          s, w_hi, w_lo, cout_override, tile_list, tile_count, wscale, nullptr);
+}
 
-// conv (stride 1 via TMA implicit GEMM, otherwise im2col + 1x1x1 GEMM) into raw fp32 [g][m][cout]
-static int conv_any(drb_engine* e, const ConvW& w, const Act& in, int od, int oh, int ow, float* out,
-                    cudaStream_t s) {
-  // Every caller feeds a BatchNorm.  The GEMM epilogue CAN produce the per-channel sums
-  // (drb_conv3d_desc.bn_accum, parity-tested), but its fp64 atomics were measured slower than the separate
-  // HBM-bound pass on B200 (+1.2 ms vs -0.85 ms per pair, round 1), so the engine keeps the separate pass.
-  double* acc = nullptr;
-  if (!w.im2col) {
-    return run_igemm(e, w, in.hi, in.lo, kG, in.d, in.h, in.w, w.cin, w.k, P(e, w.p_b), nullptr, 0,
-                     1.f, out, nullptr, nullptr, 0, s, nullptr, nullptr, 0, nullptr, nullptr, acc);
-  }
+
+// im2col of `in` for the strided / narrow convolution `w` into the shared column planes
+int engine_im2col(drb_engine* e, const ConvW& w, const Act& in, cudaStream_t s) {
   drb_im2col_desc d;
   memset(&d, 0, sizeof(d));
   d.x = in.f;
@@ -385,9 +285,21 @@ static int conv_any(drb_engine* e, const ConvW& w, const Act& in, int od, int oh
   d.g = kG; d.c = in.c; d.d = in.d; d.h = in.h; d.w = in.w;
   d.k = w.k; d.stride = w.stride; d.pad = w.k / 2; d.kpad = w.kpad;
   e->launches += 1;
-  DRB_TRY(drb_im2col(&d, e->col_hi, e->col_lo, s));
+  return drb_im2col(&d, e->col_hi, e->col_lo, s);
+}
+
+// conv (stride 1 via TMA implicit GEMM, otherwise im2col + 1x1x1 GEMM) into raw fp32 [g][m][cout].
+// Every caller feeds a BatchNorm.  The GEMM epilogue CAN produce the per-channel sums
+// (drb_conv3d_desc.bn_accum, parity-tested), but its fp64 atomics were measured slower than the separate
+// HBM-bound pass on B200 (+1.2 ms vs -0.85 ms per pair, round 1), so the engine keeps the separate pass.
+static int conv_any(drb_engine* e, const ConvW& w, const Act& in, int od, int oh, int ow, float* out,
+                    cudaStream_t s) {
+  if (!w.im2col)
+    return run_igemm(e, w, in.hi, in.lo, kG, in.d, in.h, in.w, w.cin, w.k, P(e, w.p_b), nullptr, 0,
+                     1.f, out, nullptr, nullptr, 0, s);
+  DRB_TRY(engine_im2col(e, w, in, s));
   return run_igemm(e, w, e->col_hi, e->col_lo, kG, od, oh, ow, w.kpad, 1, P(e, w.p_b), nullptr, 0, 1.f,
-                   out, nullptr, nullptr, 0, s, nullptr, nullptr, 0, nullptr, nullptr, acc);
+                   out, nullptr, nullptr, 0, s);
 }
 
 // BatchNorm (+ residual, ReLU) of raw [g][m][c] into out (fp32 and/or planes)
@@ -398,27 +310,42 @@ static int bn_apply(drb_engine* e, const BnP& b, const float* rawp, long long m,
     e->launches += 2;
     DRB_TRY(drb_bn_stats(rawp, kG, m, b.c, e->bn_accum, s));
   }
+  if (e->grad_mode) {   // what the backward pass needs: the statistics the apply below is about to use
+    e->launches += 1;
+    DRB_TRY(drb_bn_save_stats(e->bn_accum, kG, m, b.c, P(e, b.p_w), P(e, b.p_b), P(e, b.p_rm), P(e, b.p_rv), training,
+                              1e-5f, b.mean, b.rstd, b.scale, b.shift, s));
+  }
   e->launches += 1;
   return drb_bn_apply(rawp, e->bn_accum, kG, m, b.c, P(e, b.p_w), P(e, b.p_b), P(e, b.p_rm), P(e, b.p_rv), training,
                       0.1f, 1e-5f, residual, relu, out, out_hi, out_lo, s);
 }
 
+// conv1 (5^3 s2, Cin 4 = rgba channels 3..6 of the [1,7,Z,X,Y] grid): im2col of both grids into the shared
+// column planes
+int engine_stem_im2col(drb_engine* e, const drb_pair_io* io, cudaStream_t s) {
+  const ConvW& w = e->conv1;
+  const long long per_grid = e->c1.m() * w.kpad;
+  for (int g = 0; g < kG; ++g) {
+    const float* base = g == 0 ? io->src_grid : io->tgt_grid;
+    const long long sc = g == 0 ? io->s_ch : io->t_ch;
+    e->launches += 2;
+    DRB_TRY(drb_im2col_stem(base + 3 * sc, sc, g == 0 ? io->s_z : io->t_z, g == 0 ? io->s_x : io->t_x,
+                            g == 0 ? io->s_y : io->t_y, e->D, e->H, e->W, e->raw2,
+                            e->col_hi + g * per_grid, off(e->col_lo, g * per_grid), s));
+  }
+  return 0;
+}
+
 static int run_fpn(drb_engine* e, const drb_pair_io* io, cudaStream_t s) {
-  // ---- conv1 (5^3 s2, Cin 4 = rgba channels 3..6 of the [1,7,Z,X,Y] grid) through im2col ----
+  // in grad mode every BatchNorm keeps the convolution output it normalised; otherwise one scratch is reused
+  auto rawbuf = [&](const BnP& b, float* shared) { return e->grad_mode ? b.raw_keep : shared; };
   {
     const ConvW& w = e->conv1;
-    const long long per_grid = e->c1.m() * w.kpad;
-    for (int g = 0; g < kG; ++g) {
-      const float* base = g == 0 ? io->src_grid : io->tgt_grid;
-      const long long sc = g == 0 ? io->s_ch : io->t_ch;
-      e->launches += 2;
-      DRB_TRY(drb_im2col_stem(base + 3 * sc, sc, g == 0 ? io->s_z : io->t_z, g == 0 ? io->s_x : io->t_x,
-                              g == 0 ? io->s_y : io->t_y, e->D, e->H, e->W, e->raw2,
-                              e->col_hi + g * per_grid, off(e->col_lo, g * per_grid), s));
-    }
+    DRB_TRY(engine_stem_im2col(e, io, s));
+    float* r0 = rawbuf(e->bn1, e->raw);
     DRB_TRY(run_igemm(e, w, e->col_hi, e->col_lo, kG, e->c1.d, e->c1.h, e->c1.w, w.kpad, 1, nullptr,
-                      nullptr, 0, 1.f, e->raw, nullptr, nullptr, 0, s));
-    DRB_TRY(bn_apply(e, e->bn1, e->raw, e->c1.m(), nullptr, 1, e->c1.f, e->c1.hi, e->c1.lo, s));
+                      nullptr, 0, 1.f, r0, nullptr, nullptr, 0, s));
+    DRB_TRY(bn_apply(e, e->bn1, r0, e->c1.m(), nullptr, 1, e->c1.f, e->c1.hi, e->c1.lo, s));
     e->launches += 1;
     DRB_TRY(drb_maxpool3d(e->c1.f, kG, e->c1.d, e->c1.h, e->c1.w, 64, e->x0.f, e->x0.hi, e->x0.lo, s));
   }
@@ -430,18 +357,22 @@ static int run_fpn(drb_engine* e, const drb_pair_io* io, cudaStream_t s) {
       const Block& b = e->blocks[li][bi];
       const Act& t1 = e->tmp[ti]; const Act& t2 = e->tmp[ti + 1]; const Act& out = e->tmp[ti + 2];
       ti += 3;
-      DRB_TRY(conv_any(e, b.conv1, *x, x->d, x->h, x->w, e->raw, s));
-      DRB_TRY(bn_apply(e, b.bn1, e->raw, t1.m(), nullptr, 1, t1.f, t1.hi, t1.lo, s));
-      DRB_TRY(conv_any(e, b.conv2, t1, t2.d, t2.h, t2.w, e->raw, s));
-      DRB_TRY(bn_apply(e, b.bn2, e->raw, t2.m(), nullptr, 1, nullptr, t2.hi, t2.lo, s));
+      float* r1 = rawbuf(b.bn1, e->raw);
+      DRB_TRY(conv_any(e, b.conv1, *x, x->d, x->h, x->w, r1, s));
+      DRB_TRY(bn_apply(e, b.bn1, r1, t1.m(), nullptr, 1, t1.f, t1.hi, t1.lo, s));
+      float* r2 = rawbuf(b.bn2, e->raw);
+      DRB_TRY(conv_any(e, b.conv2, t1, t2.d, t2.h, t2.w, r2, s));
+      DRB_TRY(bn_apply(e, b.bn2, r2, t2.m(), nullptr, 1, nullptr, t2.hi, t2.lo, s));
       const float* res = x->f;
       if (b.has_down) {
-        DRB_TRY(conv_any(e, b.down, *x, out.d, out.h, out.w, e->raw2, s));
-        DRB_TRY(bn_apply(e, b.bnd, e->raw2, out.m(), nullptr, 0, e->raw2, nullptr, nullptr, s));
+        float* rd = rawbuf(b.bnd, e->raw2);
+        DRB_TRY(conv_any(e, b.down, *x, out.d, out.h, out.w, rd, s));
+        DRB_TRY(bn_apply(e, b.bnd, rd, out.m(), nullptr, 0, e->raw2, nullptr, nullptr, s));
         res = e->raw2;
       }
-      DRB_TRY(conv_any(e, b.conv3, t2, out.d, out.h, out.w, e->raw, s));
-      DRB_TRY(bn_apply(e, b.bn3, e->raw, out.m(), res, 1, out.f, out.hi, out.lo, s));
+      float* r3 = rawbuf(b.bn3, e->raw);
+      DRB_TRY(conv_any(e, b.conv3, t2, out.d, out.h, out.w, r3, s));
+      DRB_TRY(bn_apply(e, b.bn3, r3, out.m(), res, 1, out.f, out.hi, out.lo, s));
       x = &out;
     }
   }
@@ -479,14 +410,16 @@ __global__ void unpack_rows_kernel(const float* __restrict__ rows, int n, float*
   if (c4 == 0) { kp[row * 3] = r[0]; kp[row * 3 + 1] = r[1]; kp[row * 3 + 2] = r[2]; }
 }
 
-static int ensure_tokens(drb_engine* e, int m) {
-  if (m <= e->tok_cap) return 0;
+int engine_ensure_tokens(drb_engine* e, int m) {
+  if (m <= e->tok_cap && (!e->grad_mode || e->tok_grad)) return 0;
   for (void* p : e->tok_allocs) cudaFree(p);
   e->tok_allocs.clear();
+  if (m < e->tok_cap) m = e->tok_cap;
   const long long cap = ((m + 127) / 128) * 128 + 128;
+  bool ok = true;
   auto A = [&](long long bytes) -> void* {
     void* p = nullptr;
-    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { ok = false; return nullptr; }
     e->tok_allocs.push_back(p);
     return p;
   };
@@ -495,22 +428,121 @@ static int ensure_tokens(drb_engine* e, int m) {
   e->qkv = (float*)A(cap * 768 * 4); e->kp_xyz = (float*)A(cap * 3 * 4 + 64);
   e->sbuf = (float*)A(cap * cap_ld * 4);
   const bool pair = e->cfg.planes == 2;
-  auto AL = [&](long long bytes) -> plane_t* { return pair ? (plane_t*)A(bytes) : nullptr; };
-  e->xn_hi = (plane_t*)A(cap * kD * 2); e->xn_lo = AL(cap * kD * 2);
-  e->att_hi = (plane_t*)A(cap * kD * 2); e->att_lo = AL(cap * kD * 2);
-  e->ffn_hi = (plane_t*)A(cap * 1024 * 2); e->ffn_lo = AL(cap * 1024 * 2);
-  e->dec_hi = (plane_t*)A(kLayers * cap * kD * 2); e->dec_lo = AL(kLayers * cap * kD * 2);
-  e->qp_hi = (plane_t*)A(kLayers * cap * kD * 2); e->qp_lo = AL(kLayers * cap * kD * 2);
-  e->kp_hi = (plane_t*)A(kLayers * cap * kD * 2); e->kp_lo = AL(kLayers * cap * kD * 2);
-  const bool lo_ok = !pair || (e->xn_lo && e->att_lo && e->ffn_lo && e->dec_lo && e->qp_lo && e->kp_lo);
-  if (!e->x || !e->pos || !e->qkv || !e->kp_xyz || !e->sbuf || !e->xn_hi || !e->att_hi || !e->ffn_hi ||
-      !e->dec_hi || !e->qp_hi || !e->kp_hi || !lo_ok) {
+  auto AP = [&](long long elems) -> plane_t* { return (plane_t*)A(elems * 2); };
+  auto AL = [&](long long elems) -> plane_t* { return pair ? (plane_t*)A(elems * 2) : nullptr; };
+  e->xn_hi = AP(cap * kD); e->xn_lo = AL(cap * kD);
+  e->att_hi = AP(cap * kD); e->att_lo = AL(cap * kD);
+  e->ffn_hi = AP(cap * 1024); e->ffn_lo = AL(cap * 1024);
+  e->dec_hi = AP(kLayers * cap * kD); e->dec_lo = AL(kLayers * cap * kD);
+  e->qp_hi = AP(kLayers * cap * kD); e->qp_lo = AL(kLayers * cap * kD);
+  e->kp_hi = AP(kLayers * cap * kD); e->kp_lo = AL(kLayers * cap * kD);
+  e->tok_grad = e->grad_mode;
+  if (e->grad_mode) {
+    // the training graph: per-layer copies of everything the backward pass re-reads, plus its scratch
+    for (int l = 0; l <= kLayers; ++l) e->xs[l] = (float*)A(cap * kD * 4);
+    for (int l = 0; l < kLayers; ++l) {
+      TSave& t = e->ts[l];
+      t.x1 = (float*)A(cap * kD * 4); t.x2 = (float*)A(cap * kD * 4);
+      t.xn1_hi = AP(cap * kD); t.xn1_lo = AL(cap * kD);
+      t.xn2_hi = AP(cap * kD); t.xn2_lo = AL(cap * kD);
+      t.xn3_hi = AP(cap * kD); t.xn3_lo = AL(cap * kD);
+      t.qkv_s = (float*)A(cap * 768 * 4); t.qkv_c = (float*)A(cap * 768 * 4);
+      t.att_s_hi = AP(cap * kD); t.att_s_lo = AL(cap * kD);
+      t.att_c_hi = AP(cap * kD); t.att_c_lo = AL(cap * kD);
+      t.ffn_hi = AP(cap * 1024); t.ffn_lo = AL(cap * 1024);
+    }
+    e->qf = (float*)A(kLayers * cap * kD * 4); e->kf = (float*)A(kLayers * cap * kD * 4);
+    e->t_dx = (float*)A(cap * kD * 4); e->t_dy = (float*)A(cap * kD * 4);
+    e->t_dh = (float*)A(cap * 1024 * 4); e->t_dqkv = (float*)A(cap * 768 * 4);
+    e->t_datt = (float*)A(cap * kD * 4); e->t_dxn = (float*)A(cap * kD * 4);
+    e->t_ddec = (float*)A(kLayers * cap * kD * 4);
+    e->t_dqf = (float*)A(kLayers * cap * kD * 4); e->t_dkf = (float*)A(kLayers * cap * kD * 4);
+    e->t_dcorr = (float*)A(kLayers * cap * 3 * 4 + 64); e->t_dov = (float*)A(kLayers * cap * 4 + 64);
+    e->t_ph = AP(kLayers * cap * 1024 / 4 + cap * 1024); e->t_pl = AL(kLayers * cap * 1024 / 4 + cap * 1024);
+    e->mha_ws_bytes = drb_mha_backward_workspace_bytes((int)cap, (int)cap, 8);
+    e->mha_ws = A((long long)e->mha_ws_bytes);
+  } else {
+    for (int l = 0; l <= kLayers; ++l) e->xs[l] = e->x;
+    for (int l = 0; l < kLayers; ++l) {
+      TSave& t = e->ts[l];
+      t.x1 = t.x2 = e->x;
+      t.xn1_hi = t.xn2_hi = t.xn3_hi = e->xn_hi; t.xn1_lo = t.xn2_lo = t.xn3_lo = e->xn_lo;
+      t.qkv_s = t.qkv_c = e->qkv;
+      t.att_s_hi = t.att_c_hi = e->att_hi; t.att_s_lo = t.att_c_lo = e->att_lo;
+      t.ffn_hi = e->ffn_hi; t.ffn_lo = e->ffn_lo;
+    }
+    e->qf = e->kf = nullptr;
+  }
+  if (!ok) {
     set_error("drb_engine: out of device memory for %d tokens", m);
     e->tok_cap = 0;
     return DRB_ENOMEM;
   }
   e->tok_cap = (int)cap;
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-tensor weight packing: one absmax launch + one pack launch for all ~150 weights, pre-scales kept
+// on the device (no host synchronisation; a training step repacks after every optimiser update).
+//   forward layout   [tap][cout][cin]            (im2col: [cout][kpad], k = tap * cin + c)
+//   data-grad layout [taps-1-tap][cin][cout]     (im2col: [kpad][cout])  - the same implicit GEMM then
+//                    computes dX = dY (*) flip(W)^T, respectively dcol = dY W.
+// ------------------------------------------------------------------------------------------
+__global__ void pack_absmax_kernel(const PackDesc* __restrict__ descs) {
+  const PackDesc d = descs[blockIdx.y];
+  const long long n = (long long)d.cout * d.cin * d.taps;
+  float m = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(d.w[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax((unsigned int*)d.slot, __float_as_uint(m));
+}
+
+__global__ void pack_all_kernel(const PackDesc* __restrict__ descs, int pair) {
+  const PackDesc d = descs[blockIdx.y];
+  float scale = 1.f;
+  if (pair) {
+    const float mx = __uint_as_float(*(const unsigned int*)d.slot);
+    if (mx > 0.f && isfinite(mx)) {
+      int ex = 0;
+      frexpf(mx, &ex);
+      scale = ldexpf(1.f, 9 - ex);          // max |w| * scale in [256, 512): fp16-normal hi AND lo
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) d.slot[1] = 1.f / scale;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int cin = d.cin, cout = d.cout, taps = d.taps, kpad = d.kpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d.fwd_elems; i += stride) {
+    float v = 0.f;
+    if (kpad > 0) {
+      const int k = (int)(i % kpad), o = (int)(i / kpad);
+      if (k < taps * cin) v = d.w[((long long)o * cin + k % cin) * taps + k / cin];
+    } else {
+      const int c = (int)(i % cin), o = (int)((i / cin) % cout), t = (int)(i / ((long long)cin * cout));
+      v = d.w[((long long)o * cin + c) * taps + t];
+    }
+    plane_t h, l;
+    split16(v * scale, pair != 0, h, l);
+    d.hi[i] = h;
+    if (pair) d.lo[i] = l;
+  }
+  if (!d.thi) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d.bwd_elems; i += stride) {
+    float v = 0.f;
+    const int o = (int)(i % cout);
+    if (kpad > 0) {
+      const int k = (int)(i / cout);
+      if (k < taps * cin) v = d.w[((long long)o * cin + k % cin) * taps + k / cin];
+    } else {
+      const int c = (int)((i / cout) % cin), t = (int)(i / ((long long)cin * cout));
+      v = d.w[((long long)o * cin + c) * taps + (taps - 1 - t)];
+    }
+    plane_t h, l;
+    split16(v * scale, pair != 0, h, l);
+    d.thi[i] = h;
+    if (pair) d.tlo[i] = l;
+  }
 }
 
 }  // namespace drb
@@ -602,32 +634,54 @@ extern "C" int drb_engine_commit_params(drb_engine* e, cudaStream_t s) {
   DRB_REQUIRE(e, "drb_engine_commit_params: null engine");
   for (const Param& p : e->params)
     DRB_REQUIRE(p.ptr != nullptr, "drb_engine_commit_params: parameter %s is not bound", p.name.c_str());
+  if (e->grad_mode) DRB_TRY(engine_ensure_grad_buffers(e));
   const bool pair = e->cfg.planes == 2;
-  auto pack = [&](ConvW& w) -> int {
+  const int nw = (int)e->all_convs.size();
+  std::vector<PackDesc> table((size_t)nw);
+  for (int i = 0; i < nw; ++i) {
+    const ConvW& w = *e->all_convs[i];
+    PackDesc& d = table[(size_t)i];
     const int taps = w.k * w.k * w.k;
-    w.scale = 1.f;
-    if (pair) DRB_TRY(drb_weight_scale(P(e, w.p_w), (long long)w.cout * w.cin * taps, &w.scale, s));
-    plane_t* lo = pair ? w.lo : nullptr;
-    if (w.im2col)
-      return drb_pack_conv_weight_im2col(P(e, w.p_w), w.cout, w.cin, taps, w.kpad, w.scale, w.hi, lo, s);
-    return drb_pack_conv_weight(P(e, w.p_w), w.cout, w.cin, taps, w.cin, w.scale, w.hi, lo, s);
-  };
-  DRB_TRY(pack(e->conv1));
-  for (int li = 0; li < 4; ++li)
-    for (Block& b : e->blocks[li]) {
-      DRB_TRY(pack(b.conv1)); DRB_TRY(pack(b.conv2)); DRB_TRY(pack(b.conv3));
-      if (b.has_down) DRB_TRY(pack(b.down));
-    }
-  for (int i = 0; i < 5; ++i) DRB_TRY(pack(e->pyr[i]));
-  for (int i = 0; i < 4; ++i) DRB_TRY(pack(e->ups[i]));
-  for (int l = 0; l < kLayers; ++l) {
-    TLayer& t = e->tl[l];
-    DRB_TRY(pack(t.self_attn.in_proj)); DRB_TRY(pack(t.self_attn.out_proj));
-    DRB_TRY(pack(t.cross_attn.in_proj)); DRB_TRY(pack(t.cross_attn.out_proj));
-    DRB_TRY(pack(t.lin1)); DRB_TRY(pack(t.lin2));
+    d.w = P(e, w.p_w);
+    d.cout = w.cout; d.cin = w.cin; d.taps = taps; d.kpad = w.im2col ? w.kpad : 0;
+    d.hi = w.hi; d.lo = pair ? w.lo : nullptr;
+    d.thi = w.thi; d.tlo = pair ? w.tlo : nullptr;
+    d.slot = w.slot;
+    d.fwd_elems = w.im2col ? (long long)w.cout * w.kpad : (long long)taps * w.cout * w.cin;
+    d.bwd_elems = d.fwd_elems;
   }
-  DRB_TRY(pack(e->q_proj)); DRB_TRY(pack(e->k_proj));
+  DRB_CUDA_OK(cudaMemcpyAsync(e->d_pack, table.data(), sizeof(PackDesc) * (size_t)nw, cudaMemcpyHostToDevice, s));
+  DRB_CUDA_OK(cudaMemsetAsync(e->slots, 0, sizeof(float) * 2 * (size_t)nw, s));
+  e->launches += 2;
+  if (pair) {
+    pack_absmax_kernel<<<dim3(16, (unsigned)nw), 256, 0, s>>>(e->d_pack);
+    DRB_LAUNCH_OK();
+  }
+  pack_all_kernel<<<dim3(64, (unsigned)nw), 256, 0, s>>>(e->d_pack, pair ? 1 : 0);
+  DRB_LAUNCH_OK();
   e->committed = true;
+  return 0;
+}
+
+extern "C" int drb_engine_set_grad_mode(drb_engine* e, int on) {
+  DRB_REQUIRE(e, "drb_engine_set_grad_mode: null engine");
+  const bool want = on != 0;
+  if (want && !e->grad_allocated) e->committed = false;   // the data-gradient weight planes must be packed
+  e->grad_mode = want;
+  if (!want) e->graph_valid = false;
+  return 0;
+}
+extern "C" int drb_engine_param_trainable(const drb_engine* e, int i) {
+  return (e && i >= 0 && i < (int)e->params.size() && e->params[i].trainable) ? 1 : 0;
+}
+extern "C" int drb_engine_bind_grad(drb_engine* e, int i, float* device_ptr) {
+  DRB_REQUIRE(e && i >= 0 && i < (int)e->params.size(), "drb_engine_bind_grad: bad arguments");
+  e->params[i].grad = device_ptr;
+  return 0;
+}
+extern "C" int drb_engine_set_max_tokens(drb_engine* e, int max_total) {
+  DRB_REQUIRE(e && max_total > 0, "drb_engine_set_max_tokens: bad arguments");
+  e->max_tokens = max_total;
   return 0;
 }
 
@@ -641,12 +695,21 @@ extern "C" int drb_engine_encode(drb_engine* e, const drb_pair_io* io, int* host
               "drb_engine_encode: mask larger than max_mask=%d", e->cfg.max_mask);
   const Act& p1 = e->p[0];
   const int X = e->cfg.res_x, Y = e->cfg.res_y, Z = e->cfg.res_z;
+  if (e->grad_mode) {
+    DRB_TRY(engine_ensure_grad_buffers(e));
+    DRB_REQUIRE(e->committed, "drb_engine_encode: parameters not committed after grad mode was switched on");
+  }
+  e->graph_valid = false;
   if (e->sparse_fpn) {
     const long long* masks[2] = {io->src_mask, io->tgt_mask};
     const int ks[2] = {io->n_src_mask, io->n_tgt_mask};
     e->launches += 4;
     DRB_TRY(drb_fpn_need_tiles(masks, ks, kG, X, Y, Z, p1.d, p1.h, p1.w, e->need, e->tiles_out, e->tiles_in,
                                e->tile_counts, e->profile ? e->tile_totals : nullptr, s));
+    if (e->grad_mode) {   // the backward pass of pyramid_transformation_1 reaches one voxel further
+      e->launches += 1;
+      DRB_TRY(drb_fpn_dilated_tiles(e->need, kG, p1.d, p1.h, p1.w, 2, e->tiles_in2, e->tile_counts + 2, s));
+    }
   }
   DRB_TRY(run_fpn(e, io, s));
   e->launches += 2;
@@ -658,8 +721,36 @@ extern "C" int drb_engine_encode(drb_engine* e, const drb_pair_io* io, int* host
   // dl0 = 2 * (0.025 * 2.75) / 2.75 computed in double like grid_downsample.py:68,77
   const double dl0 = 2.0 * (0.025 * 2.75) / 2.75;
   e->launches += 6 * e->cfg.num_downsample;
-  DRB_TRY(drb_hierarchical_downsample(e->rows, io->n_src_mask, io->n_tgt_mask, kRowLd, e->cfg.num_downsample,
-                                      dl0, 3000, e->ds_ws, e->ds_ws_bytes, e->rows_ds, &e->n_src, &e->n_tgt, s));
+  e->n_src_mask = io->n_src_mask; e->n_tgt_mask = io->n_tgt_mask;
+  e->ds_tape.clear();
+  if (e->grad_mode) {
+    int info[64], rounds = 0;
+    DRB_REQUIRE(e->cfg.num_downsample <= 32, "drb_engine_encode: num_downsample > 32");
+    DRB_TRY(drb_hierarchical_downsample_tape(e->rows, io->n_src_mask, io->n_tgt_mask, kRowLd, e->cfg.num_downsample,
+                                             dl0, e->max_tokens, e->ds_ws, e->ds_ws_bytes, e->rows_ds, &e->n_src,
+                                             &e->n_tgt, e->ds_tape_buf, e->ds_tape_cap, info, &rounds, s));
+    long long used = 0;
+    for (int r = 0; r < rounds; ++r) {
+      DsRound d;
+      d.n_in = info[2 * r]; d.n_seg = info[2 * r + 1];
+      d.sorted_rows = e->ds_tape_buf + used;
+      d.seg_start = d.sorted_rows + d.n_in;
+      used += (long long)d.n_in + d.n_seg + 1;
+      e->ds_tape.push_back(d);
+    }
+  } else {
+    DRB_TRY(drb_hierarchical_downsample(e->rows, io->n_src_mask, io->n_tgt_mask, kRowLd, e->cfg.num_downsample,
+                                        dl0, e->max_tokens, e->ds_ws, e->ds_ws_bytes, e->rows_ds, &e->n_src,
+                                        &e->n_tgt, s));
+  }
+  // the down-sampler synchronised: the mask range check of the gather kernels is readable for free
+  int flag = 0;
+  DRB_TRY(drb_igemm_error_flag(&flag));
+  if (flag == 21) {
+    igemm_clear_err_flag();
+    set_error("drb_engine_encode: a mask index is outside [0, X*Y*Z) (mask of another resolution?)");
+    return DRB_EINVAL;
+  }
   *host_n_src = e->n_src;
   *host_n_tgt = e->n_tgt;
   return 0;
@@ -672,9 +763,10 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
               "drb_engine_decode: null output");
   const int ns = e->n_src, nt = e->n_tgt, m = ns + nt;
   DRB_REQUIRE(ns > 0 && nt > 0, "drb_engine_decode: encode() produced no tokens (%d, %d)", ns, nt);
-  DRB_TRY(ensure_tokens(e, m));
+  DRB_TRY(engine_ensure_tokens(e, m));
   e->launches += 2;
-  unpack_rows_kernel<<<cdiv((long long)m * 64, 256), 256, 0, s>>>(e->rows_ds, m, e->kp_xyz, e->x);
+  // in grad mode every layer keeps its own copies (TSave / xs); otherwise they all alias one scratch set
+  unpack_rows_kernel<<<cdiv((long long)m * 64, 256), 256, 0, s>>>(e->rows_ds, m, e->kp_xyz, e->xs[0]);
   DRB_LAUNCH_OK();
   DRB_TRY(drb_pos_embed_sine(e->kp_xyz, 3, m, e->cfg.pos_emb_scaling, e->pos, s));
   const float att_scale = 1.f / sqrtf(32.f);
@@ -684,51 +776,54 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
   };
   for (int l = 0; l < kLayers; ++l) {
     TLayer& t = e->tl[l];
+    TSave& v = e->ts[l];
+    float* x0 = e->xs[l];
+    float* x3 = e->xs[l + 1];
     // self attention (shared weights for src and tgt)
     e->launches += 1;
-    DRB_TRY(drb_layernorm256(e->x, m, P(e, t.n1w), P(e, t.n1b), e->pos, nullptr, e->xn_hi, e->xn_lo, s));
-    DRB_TRY(linear(t.self_attn.in_proj, e->xn_hi, e->xn_lo, m, 256, nullptr, 0, 1.f, e->qkv, nullptr, nullptr));
+    DRB_TRY(drb_layernorm256(x0, m, P(e, t.n1w), P(e, t.n1b), e->pos, nullptr, v.xn1_hi, v.xn1_lo, s));
+    DRB_TRY(linear(t.self_attn.in_proj, v.xn1_hi, v.xn1_lo, m, 256, nullptr, 0, 1.f, v.qkv_s, nullptr, nullptr));
     e->launches += 2;
-    DRB_TRY(drb_mha_core(e->qkv, 768, e->qkv + 256, 768, e->qkv + 512, 768, ns, ns, 8, att_scale, nullptr,
-                         e->att_hi, e->att_lo, 256, s));
-    DRB_TRY(drb_mha_core(e->qkv + (long long)ns * 768, 768, e->qkv + (long long)ns * 768 + 256, 768,
-                         e->qkv + (long long)ns * 768 + 512, 768, nt, nt, 8, att_scale, nullptr,
-                         e->att_hi + (long long)ns * 256, off(e->att_lo, (long long)ns * 256), 256, s));
-    DRB_TRY(linear(t.self_attn.out_proj, e->att_hi, e->att_lo, m, 256, e->x, 0, 1.f, e->x, nullptr, nullptr));
+    DRB_TRY(drb_mha_core(v.qkv_s, 768, v.qkv_s + 256, 768, v.qkv_s + 512, 768, ns, ns, 8, att_scale, nullptr,
+                         v.att_s_hi, v.att_s_lo, 256, s));
+    DRB_TRY(drb_mha_core(v.qkv_s + (long long)ns * 768, 768, v.qkv_s + (long long)ns * 768 + 256, 768,
+                         v.qkv_s + (long long)ns * 768 + 512, 768, nt, nt, 8, att_scale, nullptr,
+                         v.att_s_hi + (long long)ns * 256, off(v.att_s_lo, (long long)ns * 256), 256, s));
+    DRB_TRY(linear(t.self_attn.out_proj, v.att_s_hi, v.att_s_lo, m, 256, x0, 0, 1.f, v.x1, nullptr, nullptr));
     // cross attention, both directions from the same pre-update normalised features
     e->launches += 1;
-    DRB_TRY(drb_layernorm256(e->x, m, P(e, t.n2w), P(e, t.n2b), e->pos, nullptr, e->xn_hi, e->xn_lo, s));
-    DRB_TRY(linear(t.cross_attn.in_proj, e->xn_hi, e->xn_lo, m, 256, nullptr, 0, 1.f, e->qkv, nullptr, nullptr));
+    DRB_TRY(drb_layernorm256(v.x1, m, P(e, t.n2w), P(e, t.n2b), e->pos, nullptr, v.xn2_hi, v.xn2_lo, s));
+    DRB_TRY(linear(t.cross_attn.in_proj, v.xn2_hi, v.xn2_lo, m, 256, nullptr, 0, 1.f, v.qkv_c, nullptr, nullptr));
     e->launches += 2;
-    DRB_TRY(drb_mha_core(e->qkv, 768, e->qkv + (long long)ns * 768 + 256, 768,
-                         e->qkv + (long long)ns * 768 + 512, 768, ns, nt, 8, att_scale, nullptr, e->att_hi,
-                         e->att_lo, 256, s));
-    DRB_TRY(drb_mha_core(e->qkv + (long long)ns * 768, 768, e->qkv + 256, 768, e->qkv + 512, 768, nt, ns, 8,
-                         att_scale, nullptr, e->att_hi + (long long)ns * 256, off(e->att_lo, (long long)ns * 256),
+    DRB_TRY(drb_mha_core(v.qkv_c, 768, v.qkv_c + (long long)ns * 768 + 256, 768,
+                         v.qkv_c + (long long)ns * 768 + 512, 768, ns, nt, 8, att_scale, nullptr, v.att_c_hi,
+                         v.att_c_lo, 256, s));
+    DRB_TRY(drb_mha_core(v.qkv_c + (long long)ns * 768, 768, v.qkv_c + 256, 768, v.qkv_c + 512, 768, nt, ns, 8,
+                         att_scale, nullptr, v.att_c_hi + (long long)ns * 256, off(v.att_c_lo, (long long)ns * 256),
                          256, s));
-    DRB_TRY(linear(t.cross_attn.out_proj, e->att_hi, e->att_lo, m, 256, e->x, 0, 1.f, e->x, nullptr, nullptr));
+    DRB_TRY(linear(t.cross_attn.out_proj, v.att_c_hi, v.att_c_lo, m, 256, v.x1, 0, 1.f, v.x2, nullptr, nullptr));
     // feed forward
     e->launches += 1;
-    DRB_TRY(drb_layernorm256(e->x, m, P(e, t.n3w), P(e, t.n3b), nullptr, nullptr, e->xn_hi, e->xn_lo, s));
-    DRB_TRY(linear(t.lin1, e->xn_hi, e->xn_lo, m, 256, nullptr, 1, 1.f, nullptr, e->ffn_hi, e->ffn_lo));
-    DRB_TRY(linear(t.lin2, e->ffn_hi, e->ffn_lo, m, 1024, e->x, 0, 1.f, e->x, nullptr, nullptr));
+    DRB_TRY(drb_layernorm256(v.x2, m, P(e, t.n3w), P(e, t.n3b), nullptr, nullptr, v.xn3_hi, v.xn3_lo, s));
+    DRB_TRY(linear(t.lin1, v.xn3_hi, v.xn3_lo, m, 256, nullptr, 1, 1.f, nullptr, v.ffn_hi, v.ffn_lo));
+    DRB_TRY(linear(t.lin2, v.ffn_hi, v.ffn_lo, m, 1024, v.x2, 0, 1.f, x3, nullptr, nullptr));
     // shared final norm -> per-layer outputs (transformer.py:69-84)
     float* sf = o->src_feats + (long long)l * ns * kD;
     float* tf = o->tgt_feats + (long long)l * nt * kD;
     e->launches += 5;
-    DRB_TRY(drb_layernorm256(e->x, ns, P(e, e->fin_w), P(e, e->fin_b), nullptr, sf, nullptr, nullptr, s));
-    DRB_TRY(drb_layernorm256(e->x + (long long)ns * kD, nt, P(e, e->fin_w), P(e, e->fin_b), nullptr, tf, nullptr,
+    DRB_TRY(drb_layernorm256(x3, ns, P(e, e->fin_w), P(e, e->fin_b), nullptr, sf, nullptr, nullptr, s));
+    DRB_TRY(drb_layernorm256(x3 + (long long)ns * kD, nt, P(e, e->fin_w), P(e, e->fin_b), nullptr, tf, nullptr,
                              nullptr, s));
-    DRB_TRY(drb_layernorm256(e->x, m, P(e, e->fin_w), P(e, e->fin_b), e->pos, nullptr,
+    DRB_TRY(drb_layernorm256(x3, m, P(e, e->fin_w), P(e, e->fin_b), e->pos, nullptr,
                              e->dec_hi + (long long)l * m * kD, off(e->dec_lo, (long long)l * m * kD), s));
     DRB_TRY(drb_overlap_sigmoid(sf, ns, P(e, e->conf_w), P(e, e->conf_b), o->src_overlap + (long long)l * ns, s));
     DRB_TRY(drb_overlap_sigmoid(tf, nt, P(e, e->conf_w), P(e, e->conf_b), o->tgt_overlap + (long long)l * nt, s));
   }
   // decoder: q / k projections for all layers at once, then per layer soft correspondences
   const int m6 = kLayers * m;
-  DRB_TRY(linear(e->q_proj, e->dec_hi, e->dec_lo, m6, 256, nullptr, 0, 1.f / sqrtf((float)kD), nullptr, e->qp_hi,
+  DRB_TRY(linear(e->q_proj, e->dec_hi, e->dec_lo, m6, 256, nullptr, 0, 1.f / sqrtf((float)kD), e->qf, e->qp_hi,
                  e->qp_lo));
-  DRB_TRY(linear(e->k_proj, e->dec_hi, e->dec_lo, m6, 256, nullptr, 0, 1.f, nullptr, e->kp_hi, e->kp_lo));
+  DRB_TRY(linear(e->k_proj, e->dec_hi, e->dec_lo, m6, 256, nullptr, 0, 1.f, e->kf, e->kp_hi, e->kp_lo));
   e->launches += 1;
   DRB_CUDA_OK(cudaMemcpyAsync(o->src_kp, e->kp_xyz, (size_t)ns * 3 * 4, cudaMemcpyDeviceToDevice, s));
   DRB_CUDA_OK(cudaMemcpyAsync(o->tgt_kp, e->kp_xyz + (long long)ns * 3, (size_t)nt * 3 * 4,
@@ -754,6 +849,7 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
   e->launches += 1;
   DRB_TRY(drb_procrustes(o->src_kp, 0, o->src_corr, (long long)ns * 3, o->src_overlap, ns, ns, o->tgt_corr,
                          (long long)nt * 3, o->tgt_kp, 0, o->tgt_overlap, nt, nt, 3, kLayers, o->pose, s));
+  e->graph_valid = e->grad_mode;
   return 0;
 }
 

@@ -45,6 +45,8 @@ struct IgemmArgs {
   const int* tile_count; // device scalar: number of entries in tile_list
   int relu;
   float acc_scale;         // multiplies the raw accumulator (undoes the weight pre-scale)
+  const float* acc_scale_dev0;   // optional device scalars multiplied into acc_scale (gradient / weight
+  const float* acc_scale_dev1;   // pre-scales that only exist on the device)
   float out_scale;
   const float* bias;       // [Cout] or null
   const float* residual;   // [M, ld] fp32 or null; out = relu((acc*acc_scale + bias)*out_scale + residual)
@@ -57,11 +59,11 @@ struct IgemmArgs {
 
 // Fused epilogue of 32 consecutive output channels of one row.
 __device__ __forceinline__ void epilogue_store32(const IgemmArgs& a, float (&f)[32], long long m, int n,
-                                                 int split) {
+                                                 int split, float acc_scale) {
   const long long off = m * a.ld + n;
   const bool full = (n + 32 <= a.Cout);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] *= a.acc_scale;
+  for (int j = 0; j < 32; ++j) f[j] *= acc_scale;
   if (a.splits > 1) {
     // split-K: partial sums of the K slices meet in a pre-zeroed fp32 output (bias joins slice 0)
 #pragma unroll
@@ -347,6 +349,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     const int colhalf = (warp - 2) >> 2;     // warps 2-5: first half of the columns, 6-9: second
     const int half = a.BN >> 1;              // columns per warp (multiple of 32)
     const int row = q * 32 + lane;           // accumulator row == tile-local voxel
+    float acc_scale = a.acc_scale;
+    if (a.acc_scale_dev0) acc_scale *= *a.acc_scale_dev0;
+    if (a.acc_scale_dev1) acc_scale *= *a.acc_scale_dev1;
     float acc[128];
     uint32_t cc = 0;
     for (int it = cluster_id; it < total_items; it += num_clusters) {
@@ -390,11 +395,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             float tsum[32];
             int col;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) tsum[j] = row_ok ? acc[b * 32 + j] * a.acc_scale : 0.f;
+            for (int j = 0; j < 32; ++j) tsum[j] = row_ok ? acc[b * 32 + j] * acc_scale : 0.f;
             const float csum = warp_colsum32(tsum, lane, col);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float v = row_ok ? acc[b * 32 + j] * a.acc_scale : 0.f;
+              const float v = row_ok ? acc[b * 32 + j] * acc_scale : 0.f;
               tsum[j] = v * v;
             }
             const float csq = warp_colsum32(tsum, lane, col);
@@ -414,7 +419,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = acc[b * 32 + j];
-          epilogue_store32(a, f, m, n, sp);
+          epilogue_store32(a, f, m, n, sp, acc_scale);
         }
       }
     }
@@ -448,8 +453,8 @@ static int ensure_encode() {
 }
 
 // 16-bit float tensor map, 128-byte swizzle, zero OOB fill.  dims/box are innermost-first.
-static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, bool is_bf16) {
+int igemm_make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, bool is_bf16) {
   int rc = ensure_encode();
   if (rc) return rc;
   cuuint64_t gdim[5];
@@ -474,22 +479,49 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t
   return 0;
 }
 
-int igemm_num_sms();
-static int g_num_sms = 0;
-static int* g_err_flag = nullptr;   // device int, lazily allocated
+// Per-device state (a process may drive several GPUs: NeRFRegTr keys its engines by device index).
+static constexpr int kMaxDevices = 64;
+struct DeviceState {
+  int num_sms = 0;
+  int* err_flag = nullptr;
+  bool attr_set = false;
+};
+static DeviceState g_dev[kMaxDevices];
+
+static DeviceState& device_state() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  return g_dev[dev];
+}
 
 int igemm_num_sms() {
-  if (!g_num_sms) {
+  DeviceState& st = device_state();
+  if (!st.num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+    cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (st.num_sms <= 0) st.num_sms = 148;
   }
-  return g_num_sms;
+  return st.num_sms;
+}
+
+void igemm_clear_err_flag() {
+  DeviceState& st = device_state();
+  if (st.err_flag) cudaMemset(st.err_flag, 0, sizeof(int));
+}
+
+int* igemm_err_flag() {
+  DeviceState& st = device_state();
+  if (!st.err_flag) {
+    if (cudaMalloc(&st.err_flag, sizeof(int)) != cudaSuccess) { st.err_flag = nullptr; return nullptr; }
+    cudaMemset(st.err_flag, 0, sizeof(int));
+  }
+  return st.err_flag;
 }
 
 // Chooses the 128-row spatial box (bg, bd, bh, bw) for an output volume.
-static void choose_box(int G, int D, int H, int W, int& bg, int& bd, int& bh, int& bw) {
+void igemm_choose_box(int G, int D, int H, int W, int& bg, int& bd, int& bh, int& bw) {
   int rem = kBM;
   auto take = [&](int extent) {
     int b = 1;
@@ -529,7 +561,7 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   a.Cin = d->cin; a.Cout = d->cout;
   a.kd = d->kd; a.kh = d->kh; a.kw = d->kw;
   a.pd = d->kd / 2; a.ph = d->kh / 2; a.pw = d->kw / 2;
-  choose_box(a.G, a.D, a.H, a.W, a.bg, a.bd, a.bh, a.bw);
+  igemm_choose_box(a.G, a.D, a.H, a.W, a.bg, a.bd, a.bh, a.bw);
   a.chunk = d->planes == 2 ? 2 : 4;
   const int nsm = igemm_num_sms();
   const long long tiles_m_h = (long long)cdiv(a.W, a.bw) * cdiv(a.H, a.bh) * cdiv(a.D, a.bd) * cdiv(a.G, a.bg);
@@ -599,6 +631,8 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   a.relu = d->relu;
   a.out_scale = d->out_scale == 0.f ? 1.f : d->out_scale;
   a.acc_scale = d->acc_scale == 0.f ? 1.f : d->acc_scale;
+  a.acc_scale_dev0 = d->acc_scale_dev[0];
+  a.acc_scale_dev1 = d->acc_scale_dev[1];
   a.bias = d->bias; a.residual = d->residual; a.out = d->out; a.out_hi = (plane_t*)d->out_hi; a.out_lo = (plane_t*)d->out_lo;
   a.ld = ld;
   // vector stores in the epilogue need 16-byte aligned rows
@@ -612,11 +646,8 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   a.stages = stages;
   const size_t smem = 1024 + stages * stage_bytes + (2 * kMaxStages + 4) * 8 + 16;
 
-  if (!g_err_flag) {
-    DRB_CUDA_OK(cudaMalloc(&g_err_flag, sizeof(int)));
-    DRB_CUDA_OK(cudaMemset(g_err_flag, 0, sizeof(int)));
-  }
-  a.err = g_err_flag;
+  a.err = igemm_err_flag();
+  DRB_REQUIRE(a.err != nullptr, "drb_conv3d_igemm: could not allocate the device error flag");
 
   CUtensorMap mA[2], mB[2];
   memset(mA, 0, sizeof(mA));
@@ -630,17 +661,17 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   const uint64_t bstr[2] = {(uint64_t)a.Cin * 2, (uint64_t)a.Cout * a.Cin * 2};
   const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)(a.BN / a.cs), 1u};
   int rc;
-  if ((rc = make_map(&mA[0], d->x_hi, 5, adims, astr, abox, a.planes == 1))) return rc;
-  if ((rc = make_map(&mB[0], d->w_hi, 3, bdims, bstr, bbox, a.planes == 1))) return rc;
+  if ((rc = igemm_make_map(&mA[0], d->x_hi, 5, adims, astr, abox, a.planes == 1))) return rc;
+  if ((rc = igemm_make_map(&mB[0], d->w_hi, 3, bdims, bstr, bbox, a.planes == 1))) return rc;
   if (a.planes == 2) {
-    if ((rc = make_map(&mA[1], d->x_lo, 5, adims, astr, abox, false))) return rc;
-    if ((rc = make_map(&mB[1], d->w_lo, 3, bdims, bstr, bbox, false))) return rc;
+    if ((rc = igemm_make_map(&mA[1], d->x_lo, 5, adims, astr, abox, false))) return rc;
+    if ((rc = igemm_make_map(&mB[1], d->w_lo, 3, bdims, bstr, bbox, false))) return rc;
   } else {
     mA[1] = mA[0];
     mB[1] = mB[0];
   }
 
-  static bool attr_set = false;
+  bool& attr_set = device_state().attr_set;
   if (!attr_set) {
     DRB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024));
@@ -680,7 +711,7 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
 extern "C" int drb_conv3d_tile_shape(int g, int d, int h, int w, int box[4], int tiles[4]) {
   DRB_REQUIRE(box && tiles && g > 0 && d > 0 && h > 0 && w > 0, "drb_conv3d_tile_shape: bad arguments");
   int bg, bd, bh, bw;
-  choose_box(g, d, h, w, bg, bd, bh, bw);
+  igemm_choose_box(g, d, h, w, bg, bd, bh, bw);
   box[0] = bg; box[1] = bd; box[2] = bh; box[3] = bw;
   tiles[0] = cdiv(g, bg); tiles[1] = cdiv(d, bd); tiles[2] = cdiv(h, bh); tiles[3] = cdiv(w, bw);
   return 0;
@@ -689,8 +720,9 @@ extern "C" int drb_conv3d_tile_shape(int g, int d, int h, int w, int box[4], int
 extern "C" int drb_igemm_error_flag(int* host_value) {
   if (!host_value) return DRB_EINVAL;
   *host_value = 0;
-  if (!g_err_flag) return 0;
-  DRB_CUDA_OK(cudaMemcpy(host_value, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  int* flag = device_state().err_flag;
+  if (!flag) return 0;
+  DRB_CUDA_OK(cudaMemcpy(host_value, flag, sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
 

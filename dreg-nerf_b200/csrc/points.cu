@@ -16,11 +16,15 @@ __global__ void trilinear_gather_kernel(const float* __restrict__ p1, int dc, in
                                         const float* __restrict__ grid, long long s_ch,
                                         long long s_z, long long s_x, long long s_y, int X, int Y,
                                         int Z, const long long* __restrict__ mask, int k,
-                                        float* __restrict__ rows, int ld) {
+                                        float* __restrict__ rows, int ld, int* __restrict__ err) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= k) return;
   const long long idx = mask[warp];
+  if (idx < 0 || idx >= (long long)X * Y * Z) {      // stale mask of another resolution: flag, do not touch memory
+    if (lane == 0 && err) atomicExch(err, 21);
+    return;
+  }
   const int z = (int)(idx % Z);
   const int y = (int)((idx / Z) % Y);
   const int x = (int)(idx / ((long long)Z * Y));
@@ -70,7 +74,7 @@ extern "C" int drb_trilinear_gather(const float* p1, int dc, int hc, int wc, int
   if (k == 0) return 0;
   const int warps_per_block = 8;
   trilinear_gather_kernel<<<cdiv(k, warps_per_block), warps_per_block * 32, 0, stream>>>(
-      p1, dc, hc, wc, c, grid, s_ch, s_z, s_x, s_y, X, Y, Z, mask, k, rows_out, ld_rows);
+      p1, dc, hc, wc, c, grid, s_ch, s_z, s_x, s_y, X, Y, Z, mask, k, rows_out, ld_rows, igemm_err_flag());
   DRB_LAUNCH_OK();
   return 0;
 }
@@ -83,10 +87,14 @@ extern "C" int drb_trilinear_gather(const float* p1, int dc, int hc, int wc, int
 // trilinear_gather_kernel).  list: tiles whose (optionally 1-dilated) box contains a needed voxel.
 // ------------------------------------------------------------------------------------------
 __global__ void mark_need_kernel(const long long* __restrict__ mask, int k, int X, int Y, int Z, int dc,
-                                 int hc, int wc, uint8_t* __restrict__ need) {
+                                 int hc, int wc, uint8_t* __restrict__ need, int* __restrict__ err) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= k) return;
   const long long idx = mask[i];
+  if (idx < 0 || idx >= (long long)X * Y * Z) {
+    if (err) atomicExch(err, 21);
+    return;
+  }
   const int z = (int)(idx % Z);
   const int y = (int)((idx / Z) % Y);
   const int x = (int)(idx / ((long long)Z * Y));
@@ -146,7 +154,7 @@ extern "C" int drb_fpn_need_tiles(const long long* const* masks_host, const int*
   for (int i = 0; i < g; ++i) {
     if (ks_host[i] == 0) continue;
     mark_need_kernel<<<cdiv(ks_host[i], 256), 256, 0, stream>>>(masks_host[i], ks_host[i], X, Y, Z, dc, hc, wc,
-                                                              need + i * vol);
+                                                              need + i * vol, igemm_err_flag());
     DRB_LAUNCH_OK();
   }
   int box[4], tiles[4];
@@ -158,6 +166,22 @@ extern "C" int drb_fpn_need_tiles(const long long* const* masks_host, const int*
   DRB_LAUNCH_OK();
   tile_list_kernel<<<nt, 128, 0, stream>>>(need, g, dc, hc, wc, box[0], box[1], box[2], box[3], tiles[0],
                                            tiles[1], tiles[2], tiles[3], 1, list_in, counts + 1, totals ? totals + 1 : nullptr);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+// Extra tile list for the backward pass: tiles within `dilate` voxels of a needed voxel (need as left by
+// drb_fpn_need_tiles).  count: device int, zeroed by the call.
+extern "C" int drb_fpn_dilated_tiles(const uint8_t* need, int g, int dc, int hc, int wc, int dilate, int* list,
+                                     int* count, cudaStream_t stream) {
+  DRB_REQUIRE(need && list && count && g > 0 && dilate >= 0, "drb_fpn_dilated_tiles: bad arguments");
+  DRB_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(int), stream));
+  int box[4], tiles[4];
+  int rc = drb_conv3d_tile_shape(g, dc, hc, wc, box, tiles);
+  if (rc) return rc;
+  const int nt = tiles[0] * tiles[1] * tiles[2] * tiles[3];
+  tile_list_kernel<<<nt, 128, 0, stream>>>(need, g, dc, hc, wc, box[0], box[1], box[2], box[3], tiles[0], tiles[1],
+                                           tiles[2], tiles[3], dilate, list, count, nullptr);
   DRB_LAUNCH_OK();
   return 0;
 }
@@ -261,13 +285,17 @@ extern "C" size_t drb_downsample_workspace_bytes(int n_rows, int ld) {
   return ds_layout(n_rows, ld).total;
 }
 
-extern "C" int drb_hierarchical_downsample(const float* rows, int n_src, int n_tgt, int ld,
-                                           int num_rounds, double dl0, int max_total,
-                                           void* workspace, size_t workspace_bytes, float* rows_out,
-                                           int* host_n_src_out, int* host_n_tgt_out,
-                                           cudaStream_t stream) {
+extern "C" int drb_hierarchical_downsample_tape(const float* rows, int n_src, int n_tgt, int ld,
+                                                int num_rounds, double dl0, int max_total,
+                                                void* workspace, size_t workspace_bytes, float* rows_out,
+                                                int* host_n_src_out, int* host_n_tgt_out, int* tape,
+                                                long long tape_capacity, int* host_round_info,
+                                                int* host_rounds, cudaStream_t stream) {
   DRB_REQUIRE(rows && rows_out && workspace && host_n_src_out && host_n_tgt_out,
               "drb_hierarchical_downsample: null argument");
+  DRB_REQUIRE(!tape || (host_round_info && host_rounds), "drb_hierarchical_downsample_tape: tape needs the host arrays");
+  long long tape_used = 0;
+  int rounds_done = 0;
   DRB_REQUIRE(ld % 4 == 0 && ld >= 4, "drb_hierarchical_downsample: pitch must be a multiple of 4");
   const int n0 = n_src + n_tgt;
   const DsLayout L = ds_layout(n0, ld);
@@ -312,6 +340,17 @@ extern "C" int drb_hierarchical_downsample(const float* rows, int n_src, int n_t
     float* dst = bufs[which];
     segment_mean_kernel<<<cdiv(n_seg, 8), 256, 0, stream>>>(cur, ld, vals_b, seg_start, n_seg, dst);
     DRB_LAUNCH_OK();
+    if (tape) {
+      // record this round for the backward pass: the sort permutation and the segment boundaries
+      DRB_REQUIRE(tape_used + n + n_seg + 1 <= tape_capacity, "drb_hierarchical_downsample_tape: tape too small");
+      DRB_CUDA_OK(cudaMemcpyAsync(tape + tape_used, vals_b, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+      DRB_CUDA_OK(cudaMemcpyAsync(tape + tape_used + n, seg_start, sizeof(int) * (size_t)(n_seg + 1),
+                                  cudaMemcpyDeviceToDevice, stream));
+      host_round_info[2 * rounds_done] = n;
+      host_round_info[2 * rounds_done + 1] = n_seg;
+      tape_used += (long long)n + n_seg + 1;
+      ++rounds_done;
+    }
     cur = dst;
     which ^= 1;
     cur_src = host_counts[0];
@@ -325,7 +364,18 @@ extern "C" int drb_hierarchical_downsample(const float* rows, int n_src, int n_t
                               cudaMemcpyDeviceToDevice, stream));
   *host_n_src_out = cur_src;
   *host_n_tgt_out = cur_tgt;
+  if (host_rounds) *host_rounds = rounds_done;
   return 0;
+}
+
+extern "C" int drb_hierarchical_downsample(const float* rows, int n_src, int n_tgt, int ld,
+                                           int num_rounds, double dl0, int max_total,
+                                           void* workspace, size_t workspace_bytes, float* rows_out,
+                                           int* host_n_src_out, int* host_n_tgt_out,
+                                           cudaStream_t stream) {
+  return drb_hierarchical_downsample_tape(rows, n_src, n_tgt, ld, num_rounds, dl0, max_total, workspace,
+                                          workspace_bytes, rows_out, host_n_src_out, host_n_tgt_out, nullptr, 0,
+                                          nullptr, nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------

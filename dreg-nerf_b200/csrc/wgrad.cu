@@ -1,0 +1,373 @@
+// Weight gradient of every Conv3d / Linear on the registration path as ONE tcgen05 kernel:
+//   dW[tap][co][ci] = sum over voxels m of dY[m][co] * X[m + off(tap)][ci]
+// (autograd's conv3d weight gradient for conerf/model/resnet3d.py:81-86,120, feature_pyramid_net.py:24,33
+// and the Linear layers of conerf/register/transformer.py:128-138, nerf_regtr.py:268-270).
+//
+// The reduction runs over voxels, which is the slow axis of the channels-last activations, so both
+// operands are fed to the tensor core MN-major: the TMA boxes are exactly the forward's
+// [spatial rows][64 channels] boxes (SWIZZLE_128B, zero fill out of bounds == the convolution halo), and the
+// shared-memory descriptors declare "64-element MN groups LBO apart, 8-row K groups SBO = 1024 B apart"
+// with the a_major / b_major bits of the instruction descriptor set.  No transposed copies of dY or X exist.
+//
+//   warp 0   : TMA producer - per K step one 64-voxel box of dY (2 x 64 channels) and the tap-shifted box of X
+//   warp 1   : TMEM allocator + tcgen05.mma issuer (128 x BN x 16, 4 per box and operand product)
+//   warps 2-9: drain each finished chunk from TMEM into fp32 registers (the tensor core accumulates with
+//              truncation, see igemm.cu), then red.add the tile into the fp32 gradient in torch's
+//              [co][ci][tap] layout
+// Work item = (tap, 128-wide co tile, BN-wide ci tile, K split).  With a tile list (output-sparse level-1
+// FPN convolutions) only the listed 128-voxel tiles are reduced over.
+#include "common.cuh"
+
+#include <stdlib.h>
+
+namespace drb {
+
+static constexpr int kWM = 128;        // co tile = TMEM lanes
+static constexpr int kWK = 64;         // voxels per K step (one box)
+static constexpr int kWMaxStages = 8;
+static constexpr int kWAccWarps = 8;
+static constexpr int kWThreads = 64 + kWAccWarps * 32;
+
+struct WgradArgs {
+  int G, D, H, W;
+  int Cout, Cin;
+  int kd, kh, kw, pd, ph, pw;
+  int fbg, fbd, fbh, fbw;   // the forward's 128-voxel box (tile numbering of tile_list)
+  int bg, bd, bh, bw;       // 64-voxel half box
+  int sdim;                 // axis halved to form the half box: 0 g, 1 d, 2 h, 3 w
+  int BN, planes, stages, chunk, splits;
+  int desc_swap;            // debug: swap LBO / SBO
+  const int* tile_list;
+  const int* tile_count;
+  float scale;
+  const float* scale_dev;
+  float* out;
+  int c_real, taps_real;
+  int* err;
+};
+
+// MN-major, SWIZZLE_128B shared-memory matrix descriptor: rows (K) of 128 B = 64 MN elements, 8-row groups
+// `sbo` bytes apart, the next 64 MN elements `lbo` bytes away.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kWThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+             const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+             const WgradArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t sub_bytes = kWK * 64 * 2;                 // one [64 voxels][64 channels] box: 8 KB
+  const uint32_t a_bytes = 2 * sub_bytes;                  // 128 co
+  const uint32_t b_bytes = (uint32_t)(a.BN / 64) * sub_bytes;
+  const uint32_t stage_bytes = (uint32_t)a.planes * (a_bytes + b_bytes);
+
+  uint64_t* bars = (uint64_t*)(smem + (size_t)a.stages * stage_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kWMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kWMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kWMaxStages + 2 + s); };
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kWMaxStages + 4);
+
+  const int ftw = (a.W + a.fbw - 1) / a.fbw, fth = (a.H + a.fbh - 1) / a.fbh;
+  const int ftd = (a.D + a.fbd - 1) / a.fbd, ftg = (a.G + a.fbg - 1) / a.fbg;
+  const int ftiles = ftw * fth * ftd * ftg;
+  const int ntiles = a.tile_list ? *a.tile_count : ftiles;
+  const int nboxes = 2 * ntiles;
+  const int per = (nboxes + a.splits - 1) / a.splits;
+  const int tiles_mo = (a.Cout + kWM - 1) / kWM;
+  const int tiles_n = (a.Cin + a.BN - 1) / a.BN;
+  const int taps = a.kd * a.kh * a.kw;
+  const int total_items = taps * tiles_mo * tiles_n * a.splits;
+  const uint32_t tmem_cols = (2 * a.BN <= 128) ? 128 : (2 * a.BN <= 256) ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), kWAccWarps * 32);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (a.planes == 2) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode_item = [&](int it, int& tap, int& mt, int& nt, int& j0, int& j1) {
+    const int sp = it % a.splits;
+    int r = it / a.splits;
+    nt = r % tiles_n; r /= tiles_n;
+    mt = r % tiles_mo;
+    tap = r / tiles_mo;
+    j0 = sp * per;
+    j1 = min(nboxes, j0 + per);
+  };
+  auto decode_box = [&](int j, int& w0, int& h0, int& d0, int& g0) {
+    int m = a.tile_list ? a.tile_list[j >> 1] : (j >> 1);
+    const int u = j & 1;
+    const int tw = m % ftw; m /= ftw;
+    const int th = m % fth; m /= fth;
+    const int td = m % ftd; m /= ftd;
+    w0 = tw * a.fbw; h0 = th * a.fbh; d0 = td * a.fbd; g0 = m * a.fbg;
+    if (u) {
+      if (a.sdim == 0) g0 += a.bg;
+      else if (a.sdim == 1) d0 += a.bd;
+      else if (a.sdim == 2) h0 += a.bh;
+      else w0 += a.bw;
+    }
+  };
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+        int tap, mt, nt, j0, j1;
+        decode_item(it, tap, mt, nt, j0, j1);
+        const int tw = tap % a.kw, th = (tap / a.kw) % a.kh, td = tap / (a.kw * a.kh);
+        for (int j = j0; j < j1; ++j) {
+          int w0, h0, d0, g0;
+          decode_box(j, w0, h0, d0, g0);
+          mbar_wait(empty_bar(s), ph ^ 1u, a.err, 11);
+          const uint32_t fb = full_bar(s);
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + (uint32_t)a.planes * a_bytes;
+          for (int p = 0; p < a.planes; ++p) {
+            const CUtensorMap* mA = p ? &tmA1 : &tmA0;
+            const CUtensorMap* mB = p ? &tmB1 : &tmB0;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+              tma_load_5d(sa + p * a_bytes + u * sub_bytes, mA, fb, mt * kWM + 64 * u, w0, h0, d0, g0);
+            for (int v = 0; v < a.BN / 64; ++v)
+              tma_load_5d(sb + p * b_bytes + v * sub_bytes, mB, fb, nt * a.BN + 64 * v, w0 + tw - a.pw,
+                          h0 + th - a.ph, d0 + td - a.pd, g0);
+          }
+          if (++s == a.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ----------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_16(kWM, a.BN, a.planes == 1) | (1u << 15) | (1u << 16);   // A, B MN-major
+      const uint32_t lbo = a.desc_swap ? 1024u : sub_bytes;
+      const uint32_t sbo = a.desc_swap ? sub_bytes : 1024u;
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t cc = 0;
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+        int tap, mt, nt, j0, j1;
+        decode_item(it, tap, mt, nt, j0, j1);
+        for (int k0 = j0; k0 < j1; k0 += a.chunk, ++cc) {
+          const uint32_t r = cc & 1u, rph = (cc >> 1) & 1u;
+          mbar_wait(tempty_bar(r), rph ^ 1u, a.err, 12);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + r * (uint32_t)a.BN;
+          const int kend = min(k0 + a.chunk, j1);
+          for (int ki = k0; ki < kend; ++ki) {
+            mbar_wait(full_bar(s), ph, a.err, 13);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t sb = sa + (uint32_t)a.planes * a_bytes;
+#pragma unroll
+            for (int k = 0; k < kWK / 16; ++k) {
+              const uint32_t koff = (uint32_t)k * 16u * 128u;          // 16 voxel rows of 128 B
+              const uint64_t da0 = umma_desc_sw128_mn(sa + koff, lbo, sbo);
+              const uint64_t db0 = umma_desc_sw128_mn(sb + koff, lbo, sbo);
+              umma_f16(tmem_d, da0, db0, idesc, (ki != k0 || k != 0) ? 1u : 0u);
+              if (a.planes == 2) {
+                const uint64_t da1 = umma_desc_sw128_mn(sa + a_bytes + koff, lbo, sbo);
+                const uint64_t db1 = umma_desc_sw128_mn(sb + b_bytes + koff, lbo, sbo);
+                umma_f16(tmem_d, da0, db1, idesc, 1u);
+                umma_f16(tmem_d, da1, db0, idesc, 1u);
+              }
+            }
+            umma_commit(empty_bar(s));
+            if (++s == a.stages) { s = 0; ph ^= 1u; }
+          }
+          umma_commit(tfull_bar(r));
+        }
+      }
+    }
+  } else {
+    // ------------------------------- accumulate + epilogue ------------------------------------
+    const int q = warp & 3;
+    const int colhalf = (warp - 2) >> 2;
+    const int half = a.BN >> 1;
+    const int row = q * 32 + lane;           // accumulator row == co within the tile
+    float sc = a.scale;
+    if (a.scale_dev) sc *= *a.scale_dev;
+    float acc[128];
+    uint32_t cc = 0;
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      int tap, mt, nt, j0, j1;
+      decode_item(it, tap, mt, nt, j0, j1);
+      if (j0 >= j1) continue;
+#pragma unroll
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      for (int k0 = j0; k0 < j1; k0 += a.chunk, ++cc) {
+        const uint32_t r = cc & 1u, rph = (cc >> 1) & 1u;
+        mbar_wait(tfull_bar(r), rph, a.err, 14);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + r * (uint32_t)a.BN + (uint32_t)(colhalf * half);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (b * 32 < half) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + (uint32_t)(b * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[b * 32 + j] += __uint_as_float(v[j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(r));
+      }
+      const int co = mt * kWM + row;
+      if (co < a.Cout) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (b * 32 < half) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int ci = nt * a.BN + colhalf * half + b * 32 + j;
+              if (ci < a.Cin) {
+                const long long klin = (long long)tap * a.Cin + ci;
+                const int tp = (int)(klin / a.c_real);
+                const int c = (int)(klin - (long long)tp * a.c_real);
+                if (tp < a.taps_real)
+                  atomicAdd(a.out + ((long long)co * a.c_real + c) * a.taps_real + tp, acc[b * 32 + j] * sc);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+extern "C" int drb_conv3d_wgrad(const drb_wgrad_desc* d, cudaStream_t stream) {
+  DRB_REQUIRE(d != nullptr, "drb_conv3d_wgrad: null descriptor");
+  DRB_REQUIRE(d->planes == 1 || d->planes == 2, "drb_conv3d_wgrad: planes must be 1 or 2");
+  DRB_REQUIRE(d->cin > 0 && d->cin % 64 == 0, "drb_conv3d_wgrad: Cin=%d must be a multiple of 64", d->cin);
+  DRB_REQUIRE(d->cout > 0 && d->cout % 8 == 0, "drb_conv3d_wgrad: Cout=%d must be a multiple of 8", d->cout);
+  DRB_REQUIRE(d->dy_hi && d->x_hi && d->dw, "drb_conv3d_wgrad: null operand");
+  DRB_REQUIRE(d->planes == 1 || (d->dy_lo && d->x_lo), "drb_conv3d_wgrad: planes==2 needs lo planes");
+  DRB_REQUIRE(d->kd >= 1 && d->kh >= 1 && d->kw >= 1 && (d->kd & 1) && (d->kh & 1) && (d->kw & 1),
+              "drb_conv3d_wgrad: kernel extents must be odd");
+  DRB_REQUIRE((d->tile_list == nullptr) == (d->tile_count == nullptr), "drb_conv3d_wgrad: tile_list / tile_count pair");
+
+  WgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.G = d->g; a.D = d->d; a.H = d->h; a.W = d->w;
+  a.Cout = d->cout; a.Cin = d->cin;
+  a.kd = d->kd; a.kh = d->kh; a.kw = d->kw;
+  a.pd = d->kd / 2; a.ph = d->kh / 2; a.pw = d->kw / 2;
+  igemm_choose_box(a.G, a.D, a.H, a.W, a.fbg, a.fbd, a.fbh, a.fbw);
+  a.bg = a.fbg; a.bd = a.fbd; a.bh = a.fbh; a.bw = a.fbw;
+  if (a.fbg > 1) { a.sdim = 0; a.bg = a.fbg / 2; }
+  else if (a.fbd > 1) { a.sdim = 1; a.bd = a.fbd / 2; }
+  else if (a.fbh > 1) { a.sdim = 2; a.bh = a.fbh / 2; }
+  else { a.sdim = 3; a.bw = a.fbw / 2; }
+  a.planes = d->planes;
+  a.chunk = d->planes == 2 ? 2 : 4;
+  a.BN = d->cin >= 256 ? 256 : (d->cin >= 128 ? 128 : 64);
+  const int taps = a.kd * a.kh * a.kw;
+  a.c_real = d->c_real > 0 ? d->c_real : d->cin;
+  a.taps_real = d->taps_real > 0 ? d->taps_real : taps;
+  DRB_REQUIRE((long long)a.c_real * a.taps_real <= (long long)taps * d->cin,
+              "drb_conv3d_wgrad: c_real * taps_real exceeds the GEMM's K extent");
+  a.scale = d->scale == 0.f ? 1.f : d->scale;
+  a.scale_dev = d->scale_dev;
+  a.out = d->dw;
+  a.tile_list = d->tile_list;
+  a.tile_count = d->tile_count;
+  {
+    static int swap = -1;
+    if (swap < 0) { const char* env = getenv("DRB_WGRAD_DESC_SWAP"); swap = env ? atoi(env) : 0; }
+    a.desc_swap = swap;
+  }
+  const int nsm = igemm_num_sms();
+  const long long ftiles = (long long)cdiv(a.W, a.fbw) * cdiv(a.H, a.fbh) * cdiv(a.D, a.fbd) * cdiv(a.G, a.fbg);
+  const long long nboxes = 2 * ftiles;
+  const long long base_items = (long long)taps * cdiv(a.Cout, kWM) * cdiv(a.Cin, a.BN);
+  long long splits = (2LL * nsm + base_items - 1) / base_items;
+  long long max_splits = nboxes / (2 * a.chunk);
+  if (max_splits < 1) max_splits = 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  a.splits = (int)splits;
+
+  const size_t stage_bytes = (size_t)a.planes * ((size_t)kWM * kWK * 2 + (size_t)a.BN * kWK * 2);
+  const size_t budget = 200 * 1024;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > kWMaxStages) stages = kWMaxStages;
+  DRB_REQUIRE(stages >= 2, "drb_conv3d_wgrad: tile does not fit shared memory");
+  a.stages = stages;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * kWMaxStages + 4) * 8 + 16;
+  a.err = igemm_err_flag();
+  DRB_REQUIRE(a.err != nullptr, "drb_conv3d_wgrad: could not allocate the device error flag");
+
+  CUtensorMap mA[2], mB[2];
+  memset(mA, 0, sizeof(mA));
+  memset(mB, 0, sizeof(mB));
+  const uint64_t adims[5] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.D, (uint64_t)a.G};
+  const uint64_t astr[4] = {(uint64_t)a.Cout * 2, (uint64_t)a.W * a.Cout * 2, (uint64_t)a.H * a.W * a.Cout * 2,
+                            (uint64_t)a.D * a.H * a.W * a.Cout * 2};
+  const uint64_t bdims[5] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.D, (uint64_t)a.G};
+  const uint64_t bstr[4] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2,
+                            (uint64_t)a.D * a.H * a.W * a.Cin * 2};
+  const uint32_t box[5] = {64u, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bd, (uint32_t)a.bg};
+  int rc;
+  if ((rc = igemm_make_map(&mA[0], d->dy_hi, 5, adims, astr, box, a.planes == 1))) return rc;
+  if ((rc = igemm_make_map(&mB[0], d->x_hi, 5, bdims, bstr, box, a.planes == 1))) return rc;
+  if (a.planes == 2) {
+    if ((rc = igemm_make_map(&mA[1], d->dy_lo, 5, adims, astr, box, false))) return rc;
+    if ((rc = igemm_make_map(&mB[1], d->x_lo, 5, bdims, bstr, box, false))) return rc;
+  } else {
+    mA[1] = mA[0];
+    mB[1] = mB[0];
+  }
+  DRB_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const long long items = base_items * a.splits;
+  const int grid = (int)(items < nsm ? items : nsm);
+  wgrad_kernel<<<grid, kWThreads, smem, stream>>>(mA[0], mA[1], mB[0], mB[1], a);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace drb

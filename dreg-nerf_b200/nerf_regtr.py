@@ -9,7 +9,6 @@ reference's layout; all arithmetic happens in the C-ABI engine.  There is no PyT
 """
 import copy
 import ctypes as C
-import warnings
 
 import torch
 from torch import nn
@@ -149,7 +148,7 @@ class NeRFRegTr(nn.Module):
         self._engines = {}
         # evaluate the two level-1 FPN convolutions only where the masked gather reads p1 (exact)
         self.sparse_fpn = True
-        self._warned_grad = False
+        self.max_tokens = 3000
         self.last_token_counts = (0, 0)
 
     # -------------------------------------------------------------------------------------------
@@ -177,6 +176,14 @@ class NeRFRegTr(nn.Module):
             _lib.check(lib.drb_engine_create(C.byref(cfg), C.byref(handle)), "drb_engine_create")
         names = [lib.drb_engine_param_name(handle, i).decode() for i in range(lib.drb_engine_num_params(handle))]
         ent = {"handle": handle, "names": names, "max_mask": cap, "sig": None, "device": device}
+        idx = [i for i in range(len(names)) if lib.drb_engine_param_trainable(handle, i)]
+        numels = [int(lib.drb_engine_param_numel(handle, i)) for i in idx]
+        offs, total = [], 0
+        for n in numels:
+            offs.append(total)
+            total += (n + 3) // 4 * 4          # 16-byte aligned views (vector loads / stores in the kernels)
+        ent.update(train_idx=idx, train_names=[names[i] for i in idx], train_numels=numels,
+                   train_offsets=offs, train_total=total)
         if getattr(self, "_profile", False):
             _lib.check(lib.drb_engine_set_profile(handle, 1))
         self._engines[key] = ent
@@ -231,8 +238,101 @@ class NeRFRegTr(nn.Module):
             pass
 
     # -------------------------------------------------------------------------------------------
+    def set_max_tokens(self, max_total):
+        """Stopping rule of the down-sampler (grid_downsample.py:70,91 hard-code 3000 points for the pair);
+        BASELINE.json's 8k-token configuration raises it."""
+        self.max_tokens = int(max_total)
+
+    def _pair_io(self, src, tgt, src_mask, tgt_mask):
+        return _lib.PairIO(
+            src_grid=src.data_ptr(), tgt_grid=tgt.data_ptr(),
+            s_ch=src.stride(1), s_z=src.stride(2), s_x=src.stride(3), s_y=src.stride(4),
+            t_ch=tgt.stride(1), t_z=tgt.stride(2), t_x=tgt.stride(3), t_y=tgt.stride(4),
+            src_mask=src_mask.data_ptr(), n_src_mask=src_mask.numel(),
+            tgt_mask=tgt_mask.data_ptr(), n_tgt_mask=tgt_mask.numel())
+
+    @staticmethod
+    def _pair_out(outs):
+        src_feats, tgt_feats, src_kp, tgt_kp, src_corr, tgt_corr, src_ov, tgt_ov, pose = outs
+        return _lib.PairOut(src_feats=src_feats.data_ptr(), tgt_feats=tgt_feats.data_ptr(),
+                            src_kp=src_kp.data_ptr(), tgt_kp=tgt_kp.data_ptr(),
+                            src_corr=src_corr.data_ptr(), tgt_corr=tgt_corr.data_ptr(),
+                            src_overlap=src_ov.data_ptr(), tgt_overlap=tgt_ov.data_ptr(),
+                            pose=pose.data_ptr())
+
+    def _run_engine(self, ent, src, tgt, src_mask, tgt_mask, grad_mode):
+        """encode + decode through the C ABI -> the nine output tensors."""
+        lib = _lib.load()
+        device = src.device
+        with torch.cuda.device(device):
+            handle = ent["handle"]
+            _lib.check(lib.drb_engine_set_grad_mode(handle, 1 if grad_mode else 0))
+            if grad_mode and not ent.get("grad_ready"):
+                ent["sig"] = None            # the data-gradient weight planes are packed by the next commit
+                ent["grad_ready"] = True
+            self._sync_params(ent)
+            _lib.check(lib.drb_engine_set_training(handle, 1 if self.training else 0))
+            _lib.check(lib.drb_engine_set_sparse_fpn(handle, 1 if self.sparse_fpn else 0))
+            _lib.check(lib.drb_engine_set_max_tokens(handle, int(getattr(self, "max_tokens", 3000))))
+            io = self._pair_io(src, tgt, src_mask, tgt_mask)
+            ns, nt = C.c_int(0), C.c_int(0)
+            stream = _lib.stream_ptr()
+            _lib.check(lib.drb_engine_encode(handle, C.byref(io), C.byref(ns), C.byref(nt), stream),
+                       "drb_engine_encode")
+            ns, nt = ns.value, nt.value
+            self.last_token_counts = (ns, nt)
+            f32 = dict(dtype=torch.float32, device=device)
+            outs = (torch.empty((6, ns, 256), **f32), torch.empty((6, nt, 256), **f32),
+                    torch.empty((ns, 3), **f32), torch.empty((nt, 3), **f32),
+                    torch.empty((6, ns, 3), **f32), torch.empty((6, nt, 3), **f32),
+                    torch.empty((6, ns, 1), **f32), torch.empty((6, nt, 1), **f32),
+                    torch.empty((6, 1, 3, 4), **f32))
+            out = self._pair_out(outs)
+            _lib.check(lib.drb_engine_decode(handle, C.byref(out), stream), "drb_engine_decode")
+            if self.training:
+                # nn.BatchNorm3d bookkeeping: two training-mode calls (src, tgt) per forward
+                if getattr(self, "_nbt", None) is None or self._nbt[0].device != device:
+                    self._nbt = [b for n, b in self.named_buffers() if n.endswith("num_batches_tracked")]
+                torch._foreach_add_(self._nbt, 2)
+        return outs
+
+    def _run_backward(self, ent, inputs, outs, grads_out, need):
+        """drb_engine_backward -> one gradient tensor (or None) per entry of ent['train_names']."""
+        lib = _lib.load()
+        src, tgt, src_mask, tgt_mask = inputs
+        device = src.device
+        with torch.cuda.device(device):
+            handle = ent["handle"]
+            numels = ent["train_numels"]
+            offs = ent["train_offsets"]
+            flat = torch.zeros(ent["train_total"], dtype=torch.float32, device=device)
+            views = []
+            for j, i in enumerate(ent["train_idx"]):
+                v = flat[offs[j]:offs[j] + numels[j]]
+                views.append(v)
+                _lib.check(lib.drb_engine_bind_grad(handle, i, _lib.ptr(v) if need[j] else None))
+
+            def g(t, shape):
+                if t is None:
+                    return None
+                t = t.contiguous().float()
+                assert tuple(t.shape) == tuple(shape), (t.shape, shape)
+                return t
+            d_sf, d_tf, _, _, d_sc, d_tc, d_so, d_to, d_pose = grads_out
+            keep = [g(d_sf, outs[0].shape), g(d_tf, outs[1].shape), g(d_sc, outs[4].shape), g(d_tc, outs[5].shape),
+                    g(d_so, outs[6].shape), g(d_to, outs[7].shape), g(d_pose, outs[8].shape)]
+            pg = _lib.PairGrad(*[(t.data_ptr() if t is not None else None) for t in keep])
+            io = self._pair_io(src, tgt, src_mask, tgt_mask)
+            out = self._pair_out(outs)
+            _lib.check(lib.drb_engine_backward(handle, C.byref(io), C.byref(out), C.byref(pg), _lib.stream_ptr()),
+                       "drb_engine_backward")
+            tensors = self._named_tensors()
+            return [views[j].view(tensors[n].shape) if need[j] else None for j, n in enumerate(ent["train_names"])]
+
     def forward(self, data):
-        """Same contract as conerf/register/nerf_regtr.py:112-248 (one pair per call)."""
+        """Same contract as conerf/register/nerf_regtr.py:112-248 (one pair per call).  When gradients are
+        enabled and a parameter requires them, the outputs carry an autograd node whose backward runs the
+        engine's backward pass (train_nerf_regtr.py:229)."""
         if len(data["src_xyz_rgba"].shape) == 6:
             data["src_xyz_rgba"] = data["src_xyz_rgba"].squeeze(0)
             data["tgt_xyz_rgba"] = data["tgt_xyz_rgba"].squeeze(0)
@@ -254,49 +354,19 @@ class NeRFRegTr(nn.Module):
             raise _lib.DrbError("grids must be float32")
         if src.shape != tgt.shape or src.shape[1] != 7:
             raise _lib.DrbError("expected two [1, 7, Z, X, Y] grids of equal resolution")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not self._warned_grad:
-            warnings.warn("libdregb200 round 1 implements the forward pass only; outputs carry no autograd graph")
-            self._warned_grad = True
         device = src.device
         src_mask = data["src_mask"].reshape(-1).to(device=device, dtype=torch.int64).contiguous()
         tgt_mask = data["tgt_mask"].reshape(-1).to(device=device, dtype=torch.int64).contiguous()
         _, _, Z, X, Y = src.shape
-        lib = _lib.load()
         with torch.cuda.device(device):
             ent = self._get_engine((X, Y, Z), device, max(src_mask.numel(), tgt_mask.numel()))
-            self._sync_params(ent)
-            _lib.check(lib.drb_engine_set_training(ent["handle"], 1 if self.training else 0))
-            _lib.check(lib.drb_engine_set_sparse_fpn(ent["handle"], 1 if self.sparse_fpn else 0))
-            io = _lib.PairIO(
-                src_grid=src.data_ptr(), tgt_grid=tgt.data_ptr(),
-                s_ch=src.stride(1), s_z=src.stride(2), s_x=src.stride(3), s_y=src.stride(4),
-                t_ch=tgt.stride(1), t_z=tgt.stride(2), t_x=tgt.stride(3), t_y=tgt.stride(4),
-                src_mask=src_mask.data_ptr(), n_src_mask=src_mask.numel(),
-                tgt_mask=tgt_mask.data_ptr(), n_tgt_mask=tgt_mask.numel())
-            ns, nt = C.c_int(0), C.c_int(0)
-            stream = _lib.stream_ptr()
-            _lib.check(lib.drb_engine_encode(ent["handle"], C.byref(io), C.byref(ns), C.byref(nt), stream),
-                       "drb_engine_encode")
-            ns, nt = ns.value, nt.value
-            self.last_token_counts = (ns, nt)
-            f32 = dict(dtype=torch.float32, device=device)
-            src_feats = torch.empty((6, ns, 256), **f32)
-            tgt_feats = torch.empty((6, nt, 256), **f32)
-            src_kp, tgt_kp = torch.empty((ns, 3), **f32), torch.empty((nt, 3), **f32)
-            src_corr, tgt_corr = torch.empty((6, ns, 3), **f32), torch.empty((6, nt, 3), **f32)
-            src_ov, tgt_ov = torch.empty((6, ns, 1), **f32), torch.empty((6, nt, 1), **f32)
-            pose = torch.empty((6, 1, 3, 4), **f32)
-            out = _lib.PairOut(src_feats=src_feats.data_ptr(), tgt_feats=tgt_feats.data_ptr(),
-                               src_kp=src_kp.data_ptr(), tgt_kp=tgt_kp.data_ptr(),
-                               src_corr=src_corr.data_ptr(), tgt_corr=tgt_corr.data_ptr(),
-                               src_overlap=src_ov.data_ptr(), tgt_overlap=tgt_ov.data_ptr(),
-                               pose=pose.data_ptr())
-            _lib.check(lib.drb_engine_decode(ent["handle"], C.byref(out), stream), "drb_engine_decode")
-            if self.training:
-                # nn.BatchNorm3d bookkeeping: two training-mode calls (src, tgt) per forward
-                if getattr(self, "_nbt", None) is None or self._nbt[0].device != device:
-                    self._nbt = [b for n, b in self.named_buffers() if n.endswith("num_batches_tracked")]
-                torch._foreach_add_(self._nbt, 2)
+        tensors = self._named_tensors()
+        train_params = [tensors[n] for n in ent["train_names"]]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in train_params):
+            outs = _RegistrationFn.apply(self, ent, src, tgt, src_mask, tgt_mask, *train_params)
+        else:
+            outs = self._run_engine(ent, src, tgt, src_mask, tgt_mask, grad_mode=False)
+        src_feats, tgt_feats, src_kp, tgt_kp, src_corr, tgt_corr, src_ov, tgt_ov, pose = outs
         return {
             "src_feats": [src_feats], "tgt_feats": [tgt_feats],
             "src_kp": [src_kp], "src_kp_warped": [src_corr],
@@ -316,3 +386,24 @@ class NeRFRegTr(nn.Module):
                                       _lib.stream_ptr()), "drb_engine_tap")
         torch.cuda.synchronize()
         return buf[:n.value].clone()
+
+
+class _RegistrationFn(torch.autograd.Function):
+    """Autograd node of one NeRFRegTr.forward: forward = drb_engine_encode + decode with the training graph
+    kept inside the engine, backward = drb_engine_backward (one backward per forward)."""
+
+    @staticmethod
+    def forward(ctx, module, ent, src, tgt, src_mask, tgt_mask, *params):
+        outs = module._run_engine(ent, src, tgt, src_mask, tgt_mask, grad_mode=True)
+        ctx.module, ctx.ent = module, ent
+        ctx.need = [bool(p.requires_grad) for p in params]
+        ctx.save_for_backward(src, tgt, src_mask, tgt_mask, *outs)
+        ctx.mark_non_differentiable(outs[2], outs[3])       # key points depend on the inputs only
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grads_out):
+        saved = ctx.saved_tensors
+        inputs, outs = saved[:4], saved[4:]
+        grads = ctx.module._run_backward(ctx.ent, inputs, outs, grads_out, ctx.need)
+        return (None, None, None, None, None, None) + tuple(grads)

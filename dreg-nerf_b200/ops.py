@@ -280,3 +280,228 @@ def procrustes(a, b, w):
         check(_lib.load().drb_procrustes(ptr(a), n * 3, ptr(b), n * 3, ptr(w), n, n, None, 0, None, 0, None, 0, 0,
                                          3, L, ptr(out), stream_ptr()), "drb_procrustes")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# backward-pass primitives (train_nerf_regtr.py:229)
+# ------------------------------------------------------------------------------------------------
+def grad_split(x, pair=True, ld_out=None):
+    """fp32 [rows, cols] -> (hi, lo, inv_scale device scalar or None): gradient planes with the power-of-two
+    pre-scale of the fp16 pair mode."""
+    x = x.contiguous().float()
+    rows, cols = x.shape
+    ld_out = ld_out or cols
+    hi = torch.empty((rows, ld_out), dtype=_plane_dtype(pair), device=x.device)
+    lo = torch.empty_like(hi) if pair else None
+    slot = torch.zeros(2, dtype=torch.float32, device=x.device)
+    with _dev(x):
+        check(_lib.load().drb_grad_split(ptr(x), rows, cols, cols, ld_out, ptr(hi), ptr(lo), ptr(slot), stream_ptr()),
+              "drb_grad_split")
+    return hi, lo, (slot[1:] if pair else None)
+
+
+def conv3d_wgrad(dy_planes, x_planes, k, cout, cin, planes=2, c_real=0, taps_real=0, tile_list=None,
+                 tile_count=None, scale=1.0):
+    """dy_planes: (hi, lo, inv_scale) of [g, d, h, w, cout]; x_planes: (hi, lo) of [g, d, h, w, cin]
+    -> dw fp32 [cout, c_real or cin, taps_real or k^3]."""
+    dy_hi, dy_lo, inv = dy_planes
+    x_hi, x_lo = x_planes
+    g, d, h, w, _ = x_hi.shape
+    cr, tr = (c_real or cin), (taps_real or k ** 3)
+    dw = torch.zeros((cout, cr, tr), dtype=torch.float32, device=x_hi.device)
+    desc = _lib.WgradDesc(g=g, d=d, h=h, w=w, cout=cout, cin=cin, kd=k, kh=k, kw=k, planes=planes,
+                          dy_hi=dy_hi.data_ptr(), dy_lo=dy_lo.data_ptr() if dy_lo is not None else None,
+                          x_hi=x_hi.data_ptr(), x_lo=x_lo.data_ptr() if x_lo is not None else None,
+                          scale=scale, scale_dev=inv.data_ptr() if inv is not None else None,
+                          dw=dw.data_ptr(), c_real=c_real, taps_real=taps_real,
+                          tile_list=tile_list.data_ptr() if tile_list is not None else None,
+                          tile_count=tile_count.data_ptr() if tile_count is not None else None)
+    with _dev(x_hi):
+        check(_lib.load().drb_conv3d_wgrad(C.byref(desc), stream_ptr()), "drb_conv3d_wgrad")
+    return dw
+
+
+def conv3d_tile_shape(g, d, h, w):
+    box, tiles = (C.c_int * 4)(), (C.c_int * 4)()
+    check(_lib.load().drb_conv3d_tile_shape(g, d, h, w, C.byref(box), C.byref(tiles)), "drb_conv3d_tile_shape")
+    return list(box), list(tiles)
+
+
+def bn_forward_stats(x, gamma, beta, running_mean, running_var, training, eps=1e-5):
+    """-> (mean, rstd, scale, shift) [g, c] exactly as the forward derives them."""
+    g, m, c = x.shape
+    lib = _lib.load()
+    accum = torch.zeros((g, c, 2), dtype=torch.float64, device=x.device)
+    outs = [torch.empty((g, c), dtype=torch.float32, device=x.device) for _ in range(4)]
+    with _dev(x):
+        if training:
+            check(lib.drb_bn_stats(ptr(x), g, m, c, ptr(accum), stream_ptr()), "drb_bn_stats")
+        check(lib.drb_bn_save_stats(ptr(accum), g, m, c, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                                    int(training), eps, ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]),
+                                    stream_ptr()), "drb_bn_save_stats")
+    return outs
+
+
+def bn_backward(dy, raw, stats, gamma, training, relu=False, post=None):
+    """dy / raw fp32 [g, m, c]; stats from bn_forward_stats -> (dx, dgamma, dbeta); dy is masked in place."""
+    g, m, c = raw.shape
+    mean, rstd, scale, shift = stats
+    sums = torch.empty((g, c, 2), dtype=torch.float64, device=raw.device)
+    dx = torch.empty_like(raw)
+    dgamma = torch.zeros(c, dtype=torch.float32, device=raw.device)
+    dbeta = torch.zeros_like(dgamma)
+    with _dev(raw):
+        check(_lib.load().drb_bn_backward(ptr(dy), ptr(raw), ptr(post), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+                                          ptr(gamma), int(relu), int(training), g, m, c, ptr(sums), ptr(dx),
+                                          ptr(dgamma), ptr(dbeta), stream_ptr()), "drb_bn_backward")
+    return dx, dgamma, dbeta
+
+
+def maxpool3d_backward(x, dout):
+    g, d, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    with _dev(x):
+        check(_lib.load().drb_maxpool3d_backward(ptr(x), ptr(dout), g, d, h, w, c, ptr(dx), stream_ptr()),
+              "drb_maxpool3d_backward")
+    return dx
+
+
+def upsample2_add_backward(dsum, coarse_shape):
+    g, d, h, w, c = dsum.shape
+    _, dc, hc, wc, _ = coarse_shape
+    out = torch.empty(coarse_shape, dtype=torch.float32, device=dsum.device)
+    with _dev(dsum):
+        check(_lib.load().drb_upsample2_add_backward(ptr(dsum), g, d, h, w, c, dc, hc, wc, ptr(out), stream_ptr()),
+              "drb_upsample2_add_backward")
+    return out
+
+
+def trilinear_gather_backward(drows, p1_shape, grid_res, mask):
+    """drows fp32 [K, c]; -> dp1 [dc, hc, wc, c]."""
+    dc, hc, wc, c = p1_shape
+    X, Y, Z = grid_res
+    dp1 = torch.zeros(p1_shape, dtype=torch.float32, device=drows.device)
+    with _dev(drows):
+        check(_lib.load().drb_trilinear_gather_backward(ptr(drows), drows.stride(0), 0, dc, hc, wc, c, X, Y, Z,
+                                                        ptr(mask), mask.numel(), ptr(dp1), stream_ptr()),
+              "drb_trilinear_gather_backward")
+    return dp1
+
+
+def col2im(dcol, x_shape, k, stride, pad, residual=None):
+    """dcol fp32 [g, do, ho, wo, kpad] -> dx [g, d, h, w, c]."""
+    g, d, h, w, c = x_shape
+    kpad = dcol.shape[-1]
+    dx = torch.empty(x_shape, dtype=torch.float32, device=dcol.device)
+    with _dev(dcol):
+        check(_lib.load().drb_col2im(ptr(dcol), g, c, d, h, w, k, stride, pad, kpad, ptr(residual), ptr(dx),
+                                     stream_ptr()), "drb_col2im")
+    return dx
+
+
+def layernorm256_backward(x, dy, gamma, dx_accum=None):
+    n = x.shape[0]
+    dx = dx_accum if dx_accum is not None else torch.empty_like(x)
+    dg = torch.zeros(256, dtype=torch.float32, device=x.device)
+    db = torch.zeros_like(dg)
+    with _dev(x):
+        check(_lib.load().drb_layernorm256_backward(ptr(x), ptr(dy), n, ptr(gamma), ptr(dx),
+                                                    0 if dx_accum is not None else 1, ptr(dg), ptr(db), stream_ptr()),
+              "drb_layernorm256_backward")
+    return dx, dg, db
+
+
+def overlap_sigmoid_backward(feat, ov, dov, w):
+    n = feat.shape[0]
+    dfeat = torch.zeros_like(feat)
+    dw = torch.zeros(256, dtype=torch.float32, device=feat.device)
+    db = torch.zeros(1, dtype=torch.float32, device=feat.device)
+    with _dev(feat):
+        check(_lib.load().drb_overlap_sigmoid_backward(ptr(feat), ptr(ov), ptr(dov), n, ptr(w), ptr(dfeat), ptr(dw),
+                                                       ptr(db), stream_ptr()), "drb_overlap_sigmoid_backward")
+    return dfeat, dw, db
+
+
+def softmax_weighted_xyz_backward(s, nk, xyz, dcorr):
+    """s fp32 [nq, ld] logits -> dS (new tensor, same shape)."""
+    ds = s.clone()
+    with _dev(s):
+        check(_lib.load().drb_softmax_weighted_xyz_backward(ptr(ds), ds.stride(0), ds.shape[0], nk, ptr(xyz),
+                                                            xyz.stride(0), ptr(dcorr), stream_ptr()),
+              "drb_softmax_weighted_xyz_backward")
+    return ds
+
+
+def sgemm_strided(A, a_strides, B, b_strides, Cm, c_strides, M, N, K, batch=1, alpha=1.0, accumulate=False):
+    with _dev(A):
+        check(_lib.load().drb_sgemm_strided(ptr(A), *a_strides, ptr(B), *b_strides, ptr(Cm), *c_strides, M, N, K, batch,
+                                            alpha, int(accumulate), stream_ptr()), "drb_sgemm_strided")
+    return Cm
+
+
+def mha_core_backward(q, k, v, dout, heads=8, scale=None):
+    """Row matrices [n, 256] (may be strided row views) -> (dq, dk, dv)."""
+    nq, nk = q.shape[0], k.shape[0]
+    scale = scale if scale is not None else (q.shape[1] // heads) ** -0.5
+    lib = _lib.load()
+    nbytes = lib.drb_mha_backward_workspace_bytes(nq, nk, heads)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    dq = torch.empty((nq, 256), dtype=torch.float32, device=q.device)
+    dk = torch.empty((nk, 256), dtype=torch.float32, device=q.device)
+    dv = torch.empty_like(dk)
+    with _dev(q):
+        check(lib.drb_mha_core_backward(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(dout),
+                                        dout.stride(0), nq, nk, heads, scale, ptr(dq), 256, ptr(dk), 256, ptr(dv), 256,
+                                        ptr(ws), nbytes, stream_ptr()), "drb_mha_core_backward")
+    return dq, dk, dv
+
+
+def procrustes_backward(a, b, w, dpose):
+    """a, b [L, n, 3], w [L, n], dpose [L, 3, 4] -> (da, db, dw)."""
+    a, b, w, dpose = [t.contiguous().float() for t in (a, b, w, dpose)]
+    L, n, _ = a.shape
+    da, db, dw = torch.zeros_like(a), torch.zeros_like(b), torch.zeros_like(w)
+    with _dev(a):
+        check(_lib.load().drb_procrustes_backward(ptr(a), n * 3, ptr(b), n * 3, ptr(w), n, n, None, 0, None, 0, None, 0,
+                                                  0, 3, L, ptr(dpose), ptr(da), ptr(db), ptr(dw), None, None, None,
+                                                  stream_ptr()), "drb_procrustes_backward")
+    return da, db, dw
+
+
+def hierarchical_downsample_tape(rows, n_src, n_tgt, num_rounds=6, dl0=None, max_total=3000):
+    """-> (rows_out, n_src_out, n_tgt_out, tape, [(n_in, n_seg), ...])."""
+    lib = _lib.load()
+    ld = rows.shape[1]
+    n = n_src + n_tgt
+    if dl0 is None:
+        dl0 = 2.0 * (0.025 * 2.75) / 2.75
+    nbytes = lib.drb_downsample_workspace_bytes(n, ld)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=rows.device)
+    out = torch.empty_like(rows)
+    cap = num_rounds * (2 * n + 2)
+    tape = torch.zeros(cap, dtype=torch.int32, device=rows.device)
+    info = (C.c_int * (2 * num_rounds))()
+    rounds = C.c_int(0)
+    a, b = C.c_int(0), C.c_int(0)
+    with _dev(rows):
+        check(lib.drb_hierarchical_downsample_tape(ptr(rows), n_src, n_tgt, ld, num_rounds, dl0, max_total, ptr(ws),
+                                                   nbytes, ptr(out), C.byref(a), C.byref(b), ptr(tape), cap, info,
+                                                   C.byref(rounds), stream_ptr()), "drb_hierarchical_downsample_tape")
+    return out[:a.value + b.value], a.value, b.value, tape, [(info[2 * r], info[2 * r + 1]) for r in range(rounds.value)]
+
+
+def downsample_backward(dout, tape, rounds, c):
+    """Replays the tape in reverse: dout fp32 [n_out, c] -> gradient of the input rows [n_in0, c]."""
+    lib = _lib.load()
+    offs, used = [], 0
+    for n_in, n_seg in rounds:
+        offs.append(used)
+        used += n_in + n_seg + 1
+    cur = dout.contiguous()
+    for (n_in, n_seg), o in reversed(list(zip(rounds, offs))):
+        din = torch.empty((n_in, c), dtype=torch.float32, device=dout.device)
+        with _dev(dout):
+            check(lib.drb_segment_mean_backward(ptr(cur), c, ptr(tape[o:]), ptr(tape[o + n_in:]), n_seg, c, ptr(din), c,
+                                                stream_ptr()), "drb_segment_mean_backward")
+        cur = din
+    return cur

@@ -34,7 +34,7 @@ extern "C" {
 #define DRB_ENOMEM (-3)
 #define DRB_ESTATE (-4)
 
-#define DRB_ABI_VERSION 1
+#define DRB_ABI_VERSION 2
 
 typedef struct CUstream_st* drb_stream_t; /* == cudaStream_t */
 
@@ -76,6 +76,9 @@ typedef struct drb_conv3d_desc {
    * numbering: see drb_conv3d_tile_shape.  Device pointers.                                         */
   const int* tile_list;
   const int* tile_count;
+  /* Optional device scalars multiplied into acc_scale inside the kernel (pre-scales that only exist on the
+   * device: packed weights, gradient planes of drb_grad_split); NULL = 1.                               */
+  const float* acc_scale_dev[2];
 } drb_conv3d_desc;
 /* Geometry of the 128-row output tiles drb_conv3d_igemm uses for a [g][d][h][w] volume: box extents
  * (bg, bd, bh, bw) and tile counts (tg, td, th, tw); tile index = ((ig*td + id)*th + ih)*tw + iw. */
@@ -161,6 +164,11 @@ int drb_fpn_need_tiles(const long long* const* masks_host, const int* ks_host, i
                        int dc, int hc, int wc, uint8_t* need, int* list_out, int* list_in, int* counts,
                        unsigned long long* totals /* optional running totals [2] */, drb_stream_t stream);
 
+/* Tiles within `dilate` voxels of a voxel marked by drb_fpn_need_tiles (backward pass: the data gradient of
+ * a 3^3 convolution spreads one voxel per layer).  count: device int, zeroed by the call. */
+int drb_fpn_dilated_tiles(const uint8_t* need, int g, int dc, int hc, int wc, int dilate, int* list, int* count,
+                          drb_stream_t stream);
+
 /* R4: hierarchical voxel-average down-sampling (conerf/register/grid_downsample.py:6-94).
  * rows [n_src + n_tgt][ld] = [x y z 0 | 256 features]; cells of size dl0 * 2^round; rows of one
  * cloud are emitted in ascending (cx, cy, cz) order; stops after the first round that leaves
@@ -171,6 +179,15 @@ int drb_hierarchical_downsample(const float* rows, int n_src, int n_tgt, int ld,
                                 double dl0, int max_total, void* workspace, size_t workspace_bytes,
                                 float* rows_out, int* host_n_src_out, int* host_n_tgt_out,
                                 drb_stream_t stream);
+
+/* Same, recording every round for the backward pass: tape receives, per round, the sort permutation
+ * (n_in ints) followed by the segment starts (n_seg + 1 ints); host_round_info[2 r] = n_in,
+ * [2 r + 1] = n_seg; *host_rounds = rounds run.  Replay in reverse with drb_segment_mean_backward. */
+int drb_hierarchical_downsample_tape(const float* rows, int n_src, int n_tgt, int ld, int num_rounds,
+                                     double dl0, int max_total, void* workspace, size_t workspace_bytes,
+                                     float* rows_out, int* host_n_src_out, int* host_n_tgt_out, int* tape,
+                                     long long tape_capacity, int* host_round_info, int* host_rounds,
+                                     drb_stream_t stream);
 
 /* R5: PositionEmbeddingCoordsSine (conerf/register/position_embedding.py:30-53), d_model 256. */
 int drb_pos_embed_sine(const float* xyz, int ld_xyz, int n, float scale, float* out,
@@ -272,6 +289,106 @@ int drb_extract_read_profile(float* total_ms, int* launches);
 int drb_march_stats(unsigned long long* host4, int reset);
 
 /* ------------------------------------------------------------------------------------------
+ * Backward pass (train_nerf_regtr.py:229 `loss.backward()`; the reference relies on torch autograd
+ * through the modules cited next to each forward entry point above).
+ * ---------------------------------------------------------------------------------------- */
+/* Weight gradient of a stride-1 "same" Conv3d / Linear: dw[co][c][tap] += scale * sum_m dy[m][co] *
+ * x[m + off(tap)][ci] with k = tap * cin + ci re-read as (tap', c) = (k / c_real, k % c_real) - identity
+ * for a direct convolution, the im2col unpacking when x is an im2col buffer (kd = kh = kw = 1,
+ * cin = kpad, c_real = channels, taps_real = K^3).  Both operands are 16-bit planes [g][d][h][w][c]
+ * (tcgen05, MN-major operands).  tile_list: reduce only over the listed 128-voxel tiles
+ * (numbering of drb_conv3d_tile_shape). */
+typedef struct drb_wgrad_desc {
+  int g, d, h, w;
+  int cout, cin;             /* cin multiple of 64, cout multiple of 8                          */
+  int kd, kh, kw;
+  int planes;
+  const void* dy_hi; const void* dy_lo;    /* [g][d][h][w][cout]                               */
+  const void* x_hi; const void* x_lo;      /* [g][d][h][w][cin]                                */
+  float scale;                             /* 0 is read as 1                                   */
+  const float* scale_dev;                  /* optional device scalar multiplied into scale     */
+  float* dw;                               /* fp32 [cout][c_real][taps_real], accumulated      */
+  int c_real, taps_real;                   /* 0 -> cin, kd*kh*kw                               */
+  const int* tile_list;
+  const int* tile_count;
+} drb_wgrad_desc;
+int drb_conv3d_wgrad(const drb_wgrad_desc* desc, drb_stream_t stream);
+
+/* fp32 [rows][cols] (pitch ld_in) -> planes (pitch ld_out, padding columns zeroed).  Pair mode (lo != NULL):
+ * the tensor is multiplied by the power of two that maps max|x| into [256, 512) first; slot (2 device
+ * floats of scratch) receives {bits of max|x|, 1 / scale} - pass slot + 1 as acc_scale_dev / scale_dev. */
+int drb_grad_split(const float* x, long long rows, int cols, long long ld_in, long long ld_out, void* hi,
+                   void* lo, float* slot, drb_stream_t stream);
+int drb_add_inplace(float* dst, const float* src, long long n, drb_stream_t stream);
+/* dy[i] = 0 where the saved ReLU output plane is zero. */
+int drb_relu_mask_plane(float* dy, const void* hi, long long n, drb_stream_t stream);
+/* out[c] += sum_r x[r][c]  (bias gradients). */
+int drb_colsum_add(const float* x, long long rows, int c, long long ld, float* out, drb_stream_t stream);
+/* BatchNorm3d: per-(g, c) mean / rstd / scale / shift exactly as drb_bn_apply derives them. */
+int drb_bn_save_stats(const double* accum, int g, long long m, int c, const float* gamma, const float* beta,
+                      const float* running_mean, const float* running_var, int training, float eps,
+                      float* mean, float* rstd, float* scale, float* shift, drb_stream_t stream);
+/* BatchNorm3d (+ fused ReLU) backward.  dy [g][m][c] is masked IN PLACE when relu != 0 (post > 0 if post is
+ * given, else fma(raw, scale, shift) > 0); dx may alias dy; sums: [g][c][2] doubles of scratch;
+ * dgamma / dbeta (optional) are accumulated. */
+int drb_bn_backward(float* dy, const float* raw, const float* post, const float* scale, const float* shift,
+                    const float* mean, const float* rstd, const float* gamma, int relu, int training, int g,
+                    long long m, int c, double* sums, float* dx, float* dgamma, float* dbeta,
+                    drb_stream_t stream);
+int drb_maxpool3d_backward(const float* x, const float* dout, int g, int d, int h, int w, int c, float* dx,
+                           drb_stream_t stream);
+int drb_upsample2_add_backward(const float* dsum, int g, int d, int h, int w, int c, int dc, int hc, int wc,
+                               float* dcoarse, drb_stream_t stream);
+/* drows [k][ld] with the feature gradient at columns [col0, col0 + c); dp1 must be zeroed by the caller. */
+int drb_trilinear_gather_backward(const float* drows, int ld, int col0, int dc, int hc, int wc, int c, int X,
+                                  int Y, int Z, const long long* mask, int k, float* dp1, drb_stream_t stream);
+/* Adjoint of drb_im2col: dx[g][d][h][w][c] = residual + sum over taps of dcol. */
+int drb_col2im(const float* dcol, int g, int c, int d, int h, int w, int k, int stride, int pad, int kpad,
+               const float* residual, float* dx, drb_stream_t stream);
+/* dx (+)= dLayerNorm/dx; dgamma / dbeta (optional) accumulated. */
+int drb_layernorm256_backward(const float* x, const float* dy, int n, const float* gamma, float* dx,
+                              int overwrite, float* dgamma, float* dbeta, drb_stream_t stream);
+int drb_overlap_sigmoid_backward(const float* feat, const float* ov, const float* dov, int n, const float* w,
+                                 float* dfeat, float* dw, float* db, drb_stream_t stream);
+int drb_softmax_rows(float* s, long long rows, int nk, int ld, float scale, drb_stream_t stream);
+int drb_softmax_backward_rows(const float* p, float* dp, long long rows, int nk, int ld, float scale,
+                              drb_stream_t stream);
+/* s [nq][ld] (logits) -> dS of corr = softmax(s) xyz given dcorr [nq][3], in place. */
+int drb_softmax_weighted_xyz_backward(float* s, int ld, int nq, int nk, const float* xyz, int ld_xyz,
+                                      const float* dcorr, drb_stream_t stream);
+/* C[b](m, n) (+)= alpha sum_k A[b](m, k) B[b](k, n), arbitrary element strides, fp32 CUDA cores. */
+int drb_sgemm_strided(const float* A, long long a_b, long long a_m, long long a_k, const float* B,
+                      long long b_b, long long b_k, long long b_n, float* C, long long c_b, long long c_m, int M,
+                      int N, int K, int batch, float alpha, int accumulate, drb_stream_t stream);
+size_t drb_mha_backward_workspace_bytes(int nq, int nk, int heads);
+int drb_mha_core_backward(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                          const float* dout, int ld_do, int nq, int nk, int heads, float scale, float* dq,
+                          int ld_dq, float* dk, int ld_dk, float* dv, int ld_dv, void* workspace,
+                          size_t workspace_bytes, drb_stream_t stream);
+/* Gradients of drb_procrustes w.r.t. its point / weight operands (accumulated; NULL = not needed). */
+int drb_procrustes_backward(const float* a1, long long a1_ls, const float* b1, long long b1_ls,
+                            const float* w1, long long w1_ls, int n1, const float* a2, long long a2_ls,
+                            const float* b2, long long b2_ls, const float* w2, long long w2_ls, int n2,
+                            int ld_pts, int layers, const float* dpose, float* da1, float* db1, float* dw1,
+                            float* da2, float* db2, float* dw2, drb_stream_t stream);
+int drb_segment_mean_backward(const float* dout, int ld_out, const int* sorted_rows, const int* seg_start,
+                              int n_seg, int c, float* din, int ld_in, drb_stream_t stream);
+
+/* Fused clip_grad_norm_ + AdamW (train_nerf_regtr.py:96-102,232-239) over a fixed set of tensors. */
+typedef struct drb_adamw drb_adamw;
+int drb_adamw_create(int n, float* const* params_host, const long long* numels_host, drb_adamw** out);
+void drb_adamw_destroy(drb_adamw* o);
+/* max_grad_norm <= 0: no clipping.  No host synchronisation. */
+int drb_adamw_step(drb_adamw* o, const float* const* grads_host, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, float max_grad_norm, drb_stream_t stream);
+/* Total gradient norm seen by the last step (synchronous). */
+int drb_adamw_grad_norm(drb_adamw* o, double* host_norm, drb_stream_t stream);
+/* Copies exp_avg / exp_avg_sq of tensor i into caller storage (device, same numel); *step = steps taken. */
+int drb_adamw_copy_state(drb_adamw* o, int i, float* exp_avg_out, float* exp_avg_sq_out, long long* step,
+                         drb_stream_t stream);
+int drb_adamw_set_step(drb_adamw* o, long long step);
+
+/* ------------------------------------------------------------------------------------------
  * Whole-path engine: NeRFRegTr.forward (conerf/register/nerf_regtr.py:112-248) without Python in
  * the loop.  Parameters are addressed by the reference's state-dict key.
  * ---------------------------------------------------------------------------------------- */
@@ -325,6 +442,25 @@ typedef struct drb_pair_out {
   float* pose;
 } drb_pair_out;
 int drb_engine_decode(drb_engine* e, const drb_pair_out* out, drb_stream_t stream);
+/* Training: with grad mode on, encode / decode keep what the backward pass needs (per-layer convolution
+ * outputs, BatchNorm statistics, transformer states) and drb_engine_backward accumulates the gradient of
+ * every trainable parameter into the storage bound with drb_engine_bind_grad (zeroed by the caller).
+ * One forward may be outstanding per engine. */
+int drb_engine_set_grad_mode(drb_engine* e, int on);
+int drb_engine_param_trainable(const drb_engine* e, int i);
+int drb_engine_bind_grad(drb_engine* e, int i, float* device_ptr);
+typedef struct drb_pair_grad {            /* gradients of the drb_pair_out tensors; NULL = zero */
+  const float* d_src_feats; const float* d_tgt_feats;
+  const float* d_src_corr; const float* d_tgt_corr;
+  const float* d_src_overlap; const float* d_tgt_overlap;
+  const float* d_pose;
+} drb_pair_grad;
+/* io / out: the arguments of the forward (same tensors, still alive). */
+int drb_engine_backward(drb_engine* e, const drb_pair_io* io, const drb_pair_out* out,
+                        const drb_pair_grad* grad, drb_stream_t stream);
+/* Caps the down-sampler's stopping rule (grid_downsample.py:70,91; default 3000 tokens). */
+int drb_engine_set_max_tokens(drb_engine* e, int max_total);
+
 /* Debug / parity taps: copies a named intermediate ("c1".."c5", "p1".."p5", "rows") of grid
  * `which` (0 src, 1 tgt) as fp32 channels-last into dst; returns element count via *numel. */
 int drb_engine_tap(drb_engine* e, const char* name, int which, float* dst, long long capacity,

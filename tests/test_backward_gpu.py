@@ -1,0 +1,414 @@
+"""Backward-pass kernels against torch autograd on identical inputs, then the whole NeRFRegTr backward against
+autograd through the CPU oracle (oracle/regtr.py == the reference's modules, tests/test_oracle_golden.py) and
+the reference-pinned gradient fixture tests/golden/grad_32_eval.pt.
+
+Tolerance: 1e-3 relative (max |diff| / max |reference| per tensor), BASELINE.json north_star."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def _ops():
+    from importlib import import_module
+    return import_module("dreg-nerf_b200.ops")
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core weight gradient
+# ------------------------------------------------------------------------------------------------
+def _wgrad_ref(dy, x, k):
+    """dy [g,d,h,w,co], x [g,d,h,w,ci] (fp64, channels-last) -> dw [co, ci, k^3] of a stride-1 'same' conv."""
+    xc = x.permute(0, 4, 1, 2, 3).contiguous().requires_grad_(False)
+    dyc = dy.permute(0, 4, 1, 2, 3).contiguous()
+    w = torch.zeros(dy.shape[-1], x.shape[-1], k, k, k, dtype=torch.float64, requires_grad=True)
+    y = F.conv3d(xc, w, padding=k // 2)
+    (y * dyc).sum().backward()
+    return w.grad.reshape(dy.shape[-1], x.shape[-1], k ** 3)
+
+
+@pytest.mark.parametrize("case", [
+    dict(g=1, d=1, h=1, w=1000, cin=256, cout=768, k=1),       # a Linear over 1000 tokens (in_proj)
+    dict(g=2, d=8, h=8, w=8, cin=64, cout=128, k=3),           # 3^3 conv, two grids
+    dict(g=2, d=1, h=1, w=1, cin=512, cout=512, k=3),          # deepest level at 32^3: one voxel per grid
+    dict(g=2, d=4, h=4, w=4, cin=64, cout=64, k=1),            # Cout below the 128-lane tile
+    dict(g=1, d=1, h=1, w=300, cin=1024, cout=256, k=1),       # linear2
+])
+@pytest.mark.parametrize("planes", [2, 1])
+def test_wgrad_tcgen05(pkg, cuda, case, planes):
+    ops = _ops()
+    torch.manual_seed(3)
+    g, d, h, w, cin, cout, k = [case[n] for n in ("g", "d", "h", "w", "cin", "cout", "k")]
+    x = torch.randn(g, d, h, w, cin)
+    dy = torch.randn(g, d, h, w, cout) * 1e-4            # gradients are small: exercises the power-of-two pre-scale
+    ref = _wgrad_ref(dy.double(), x.double(), k)
+    pair = planes == 2
+    xh, xl = ops.split_planes(x.to(cuda).reshape(-1, cin), want_lo=pair)
+    dyp = ops.grad_split(dy.to(cuda).reshape(-1, cout), pair=pair)
+    xh = xh.view(g, d, h, w, cin)
+    xl = xl.view(g, d, h, w, cin) if xl is not None else None
+    dw = ops.conv3d_wgrad(dyp, (xh, xl), k, cout, cin, planes=planes)
+    torch.cuda.synchronize()
+    assert ops.igemm_error_flag() == 0
+    err = _rel(dw, ref)
+    print("wgrad", case, "planes", planes, "rel err %.2e" % err)
+    assert err < (2e-5 if pair else 2e-2)
+
+
+def test_wgrad_im2col_unpack_and_tile_list(pkg, cuda):
+    ops = _ops()
+    torch.manual_seed(4)
+    # (a) im2col unpacking: x is a [rows][kpad] column buffer with k = tap * c + ch
+    rows, c, taps, cout = 512, 4, 125, 64
+    kpad = 512
+    col = torch.zeros(rows, kpad)
+    col[:, :c * taps] = torch.randn(rows, c * taps)
+    dy = torch.randn(rows, cout)
+    ref = (dy.double().t() @ col.double())[:, :c * taps].reshape(cout, taps, c).permute(0, 2, 1)
+    xh, xl = ops.split_planes(col.to(cuda))
+    dyp = ops.grad_split(dy.to(cuda))
+    dw = ops.conv3d_wgrad(dyp, (xh.view(1, 1, 1, rows, kpad), xl.view(1, 1, 1, rows, kpad)), 1, cout, kpad,
+                          c_real=c, taps_real=taps)
+    err = _rel(dw, ref)
+    print("wgrad im2col rel err %.2e" % err)
+    assert err < 2e-5
+    # (b) tile list: only voxels of the listed 128-voxel tiles contribute
+    g, d, h, w, cin, cout, k = 2, 16, 16, 16, 64, 64, 3
+    box, tiles = ops.conv3d_tile_shape(g, d, h, w)
+    nt = tiles[0] * tiles[1] * tiles[2] * tiles[3]
+    pick = torch.randperm(nt)[: nt // 3].sort().values.int()
+    x = torch.randn(g, d, h, w, cin)
+    dy = torch.randn(g, d, h, w, cout)
+    keep = torch.zeros(g, d, h, w, dtype=torch.bool)
+    for t in pick.tolist():
+        iw = t % tiles[3]; ih = (t // tiles[3]) % tiles[2]; idd = (t // (tiles[3] * tiles[2])) % tiles[1]
+        ig = t // (tiles[3] * tiles[2] * tiles[1])
+        keep[ig * box[0]:(ig + 1) * box[0], idd * box[1]:(idd + 1) * box[1], ih * box[2]:(ih + 1) * box[2],
+             iw * box[3]:(iw + 1) * box[3]] = True
+    ref = _wgrad_ref((dy * keep[..., None]).double(), x.double(), k)
+    xh, xl = ops.split_planes(x.to(cuda).reshape(-1, cin))
+    dyp = ops.grad_split(dy.to(cuda).reshape(-1, cout))
+    cnt = torch.tensor([pick.numel()], dtype=torch.int32, device=cuda)
+    dw = ops.conv3d_wgrad(dyp, (xh.view(g, d, h, w, cin), xl.view(g, d, h, w, cin)), k, cout, cin,
+                          tile_list=pick.to(cuda), tile_count=cnt)
+    err = _rel(dw, ref)
+    print("wgrad tile-list rel err %.2e" % err)
+    assert err < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# element-wise / reduction backward kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("relu", [True, False])
+def test_bn_backward(pkg, cuda, training, relu):
+    ops = _ops()
+    torch.manual_seed(5)
+    g, m, c = 2, 700, 96
+    raw = torch.randn(g, m, c) * 2 + 0.5
+    gamma, beta = torch.rand(c) + 0.5, torch.randn(c) * 0.1
+    rm, rv = torch.randn(c) * 0.1, torch.rand(c) + 0.5
+    dy = torch.randn(g, m, c)
+    x = raw.double().requires_grad_(True)
+    ga, be = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    ys = []
+    for gi in range(g):     # the reference runs one grid per call
+        xi = x[gi].t().reshape(1, c, m, 1, 1)
+        y = F.batch_norm(xi, rm.double().clone(), rv.double().clone(), ga, be, training, 0.1, 1e-5)
+        ys.append(F.relu(y) if relu else y)
+    loss = sum((ys[gi].reshape(c, m).t() * dy[gi].double()).sum() for gi in range(g))
+    loss.backward()
+    dev = lambda t: t.to(cuda).contiguous()
+    stats = ops.bn_forward_stats(dev(raw), dev(gamma), dev(beta), dev(rm), dev(rv), training)
+    dx, dg, db = ops.bn_backward(dev(dy), dev(raw), stats, dev(gamma), training, relu=relu)
+    errs = (_rel(dx, x.grad), _rel(dg, ga.grad), _rel(db, be.grad))
+    print("bn backward training=%s relu=%s" % (training, relu), ["%.2e" % e for e in errs])
+    assert max(errs) < 1e-4
+
+
+def test_maxpool_upsample_col2im_backward(pkg, cuda):
+    ops = _ops()
+    torch.manual_seed(6)
+    g, d, h, w, c = 2, 9, 8, 7, 8
+    x = torch.relu(torch.randn(g, d, h, w, c))                  # zeros -> ties, as after the stem's ReLU
+    xt = x.permute(0, 4, 1, 2, 3).double().requires_grad_(True)
+    y = F.max_pool3d(xt, 3, 2, 1)
+    dout = torch.randn_like(y)
+    (y * dout).sum().backward()
+    got = ops.maxpool3d_backward(x.to(cuda), dout.permute(0, 2, 3, 4, 1).contiguous().float().to(cuda))
+    # ties at 0 may route differently; compare where the input is positive (the ReLU mask removes the rest)
+    pos = (x > 0)
+    err = _rel(got.cpu() * pos, xt.grad.permute(0, 2, 3, 4, 1) * pos)
+    print("maxpool backward rel err %.2e" % err)
+    assert err < 1e-6
+    # nearest-upsample + add (with the reference's crop for odd sizes)
+    dsum = torch.randn(g, 5, 4, 3, 8)
+    top = torch.zeros(g, 8, 3, 2, 2, dtype=torch.float64, requires_grad=True)
+    up = F.interpolate(top, scale_factor=2)[:, :, :5, :4, :3]
+    (up * dsum.permute(0, 4, 1, 2, 3).double()).sum().backward()
+    got = ops.upsample2_add_backward(dsum.to(cuda), (g, 3, 2, 2, 8))
+    err = _rel(got, top.grad.permute(0, 2, 3, 4, 1))
+    print("upsample-add backward rel err %.2e" % err)
+    assert err < 1e-6
+    # col2im = adjoint of im2col (3^3 stride 2 pad 1, and 1^3 stride 2)
+    for k, s, p in ((3, 2, 1), (1, 2, 0)):
+        cc = 4
+        xin = torch.zeros(g, cc, d, h, w, dtype=torch.float64, requires_grad=True)
+        od, oh, ow = [(n + 2 * p - k) // s + 1 for n in (d, h, w)]
+        kpad = 128
+        dcol = torch.randn(g, od, oh, ow, kpad)
+        wsel = torch.zeros(k ** 3 * cc, cc, k, k, k, dtype=torch.float64)    # conv whose outputs ARE the columns
+        for t in range(k ** 3):
+            for ch in range(cc):
+                wsel[t * cc + ch, ch, t // (k * k), (t // k) % k, t % k] = 1
+        col = F.conv3d(xin, wsel, stride=s, padding=p)                         # [g, k^3*c, od, oh, ow]
+        (col * dcol[..., :k ** 3 * cc].permute(0, 4, 1, 2, 3).double()).sum().backward()
+        got = ops.col2im(dcol.to(cuda), (g, d, h, w, cc), k, s, p)
+        err = _rel(got, xin.grad.permute(0, 2, 3, 4, 1))
+        print("col2im k=%d s=%d rel err %.2e" % (k, s, err))
+        assert err < 1e-6
+
+
+def test_trilinear_gather_backward(pkg, cuda):
+    ops = _ops()
+    torch.manual_seed(7)
+    R, c = 16, 256
+    p1 = torch.zeros(1, c, R // 2, R // 2, R // 2, dtype=torch.float64, requires_grad=True)
+    mask = torch.randperm(R ** 3)[:500].sort().values
+    up = F.interpolate(p1, size=(R, R, R), mode="trilinear", align_corners=True)
+    feats = up.permute(0, 3, 4, 2, 1).reshape(1, -1, c)[0, mask]
+    drows = torch.randn(500, c)
+    (feats * drows.double()).sum().backward()
+    got = ops.trilinear_gather_backward(drows.to(cuda), (R // 2, R // 2, R // 2, c), (R, R, R), mask.to(cuda))
+    ref = p1.grad[0].permute(1, 2, 3, 0)       # [d, h, w, c]
+    err = _rel(got, ref)
+    print("trilinear gather backward rel err %.2e" % err)
+    assert err < 1e-5
+
+
+def test_layernorm_overlap_backward(pkg, cuda):
+    ops = _ops()
+    torch.manual_seed(8)
+    n = 777
+    x = torch.randn(n, 256) * 3
+    gamma, beta = torch.rand(256) + 0.5, torch.randn(256)
+    dy = torch.randn(n, 256)
+    xd, gd, bd = x.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    (F.layer_norm(xd, (256,), gd, bd, 1e-5) * dy.double()).sum().backward()
+    prev = torch.randn(n, 256)
+    dx, dg, db = ops.layernorm256_backward(x.to(cuda), dy.to(cuda), gamma.to(cuda), dx_accum=prev.clone().to(cuda))
+    errs = (_rel(dx.cpu() - prev, xd.grad), _rel(dg, gd.grad), _rel(db, bd.grad))
+    print("layernorm backward", ["%.2e" % e for e in errs])
+    assert max(errs) < 1e-4
+    w, b = torch.randn(256) * 0.1, torch.randn(1)
+    f = x.double().requires_grad_(True)
+    wd, bdd = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    ov = torch.sigmoid(f @ wd + bdd)
+    dov = torch.randn(n)
+    (ov * dov.double()).sum().backward()
+    dfeat, dw, dbb = ops.overlap_sigmoid_backward(x.to(cuda), ov.detach().float().to(cuda), dov.to(cuda), w.to(cuda))
+    errs = (_rel(dfeat, f.grad), _rel(dw, wd.grad), _rel(dbb, bdd.grad))
+    print("overlap backward", ["%.2e" % e for e in errs])
+    assert max(errs) < 1e-4
+
+
+def test_attention_backward(pkg, cuda):
+    ops = _ops()
+    torch.manual_seed(9)
+    nq, nk = 333, 257
+    qkv_q = torch.randn(nq, 768)
+    qkv_k = torch.randn(nk, 768)
+    dout = torch.randn(nq, 256)
+    q = qkv_q[:, :256].double().requires_grad_(True)
+    k = qkv_k[:, 256:512].double().requires_grad_(True)
+    v = qkv_k[:, 512:].double().requires_grad_(True)
+    qh = q.view(nq, 8, 32).transpose(0, 1) / math.sqrt(32)
+    att = torch.softmax(qh @ k.view(nk, 8, 32).transpose(0, 1).transpose(1, 2), dim=-1)
+    o = (att @ v.view(nk, 8, 32).transpose(0, 1)).transpose(0, 1).reshape(nq, 256)
+    (o * dout.double()).sum().backward()
+    gq, gk = qkv_q.to(cuda), qkv_k.to(cuda)
+    dq, dk, dv = ops.mha_core_backward(gq[:, :256], gk[:, 256:512], gk[:, 512:], dout.to(cuda))
+    errs = (_rel(dq, q.grad), _rel(dk, k.grad), _rel(dv, v.grad))
+    print("mha backward", ["%.2e" % e for e in errs])
+    assert max(errs) < 1e-4
+    # decoder: corr = softmax(s) xyz
+    ld = 264
+    s = torch.randn(nq, ld) * 2
+    xyz = torch.randn(nk, 3)
+    dcorr = torch.randn(nq, 3)
+    sd = s[:, :nk].double().requires_grad_(True)
+    (torch.softmax(sd, -1) @ xyz.double() * dcorr.double()).sum().backward()
+    ds = ops.softmax_weighted_xyz_backward(s.to(cuda), nk, xyz.to(cuda), dcorr.to(cuda))
+    err = _rel(ds[:, :nk], sd.grad)
+    print("soft-correspondence backward rel err %.2e" % err)
+    assert err < 1e-4
+    assert float(ds[:, nk:].abs().max()) == 0.0
+
+
+def test_procrustes_backward(pkg, cuda):
+    from oracle import regtr
+    ops = _ops()
+    torch.manual_seed(10)
+    L, n = 6, 300
+    a = torch.randn(L, n, 3)
+    rot = torch.linalg.qr(torch.randn(3, 3))[0]
+    if torch.det(rot) < 0:
+        rot[:, 0] *= -1
+    b = a @ rot.t() + 0.05 * torch.randn(L, n, 3) + torch.randn(3)
+    b[1] = b[1] * torch.tensor([1.0, 1.0, -1.0])           # a reflected problem: exercises the det < 0 branch
+    w = torch.rand(L, n)
+    dpose = torch.randn(L, 3, 4)
+    ad, bd, wd = [t.double().requires_grad_(True) for t in (a, b, w)]
+    (regtr.compute_rigid_transform(ad, bd, wd) * dpose.double()).sum().backward()
+    da, db, dw = ops.procrustes_backward(a.to(cuda), b.to(cuda), w.to(cuda), dpose.to(cuda))
+    errs = (_rel(da, ad.grad), _rel(db, bd.grad), _rel(dw, wd.grad))
+    print("procrustes backward", ["%.2e" % e for e in errs])
+    assert max(errs) < 1e-4
+
+
+def test_downsample_backward(pkg, cuda):
+    ops = _ops()
+    from oracle.downsample import hierarchical_grid_subsample
+    torch.manual_seed(11)
+    n_src, n_tgt = 3000, 2500
+    xyz = torch.rand(n_src + n_tgt, 3) * 2.5 - 1.25
+    feats = torch.randn(n_src + n_tgt, 256)
+    fd = feats.double().requires_grad_(True)
+    lengths = torch.tensor([n_src, n_tgt])
+    pts, f_out, ds_len = hierarchical_grid_subsample(xyz, fd.float(), lengths, 6)
+    rows = torch.cat([xyz, torch.zeros(n_src + n_tgt, 1), feats], dim=1).contiguous()
+    out, a, b, tape, rounds = ops.hierarchical_downsample_tape(rows.to(cuda), n_src, n_tgt)
+    assert (a, b) == (int(ds_len[0]), int(ds_len[1]))
+    dout = torch.randn(a + b, 256)
+    fref = feats.clone().requires_grad_(True)
+    _, f2, _ = hierarchical_grid_subsample(xyz, fref, lengths, 6)
+    (f2 * dout).sum().backward()
+    got = ops.downsample_backward(dout.to(cuda), tape, rounds, 256)
+    err = _rel(got, fref.grad)
+    print("down-sampling backward rel err %.2e (rounds %s)" % (err, rounds))
+    assert err < 1e-5
+
+
+def test_fused_adamw_matches_torch(pkg, cuda):
+    torch.manual_seed(12)
+    shapes = [(300, 77), (5,), (64, 64, 3, 3, 3), (1,)]
+    ps = [torch.randn(s, device=cuda).requires_grad_(True) for s in shapes]
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    opt = pkg.FusedAdamW(ps, lr=1e-2, weight_decay=1e-2, max_grad_norm=0.1)
+    ref = torch.optim.AdamW(qs, lr=1e-2, weight_decay=1e-2)
+    for it in range(3):
+        gs = [torch.randn_like(p) * (0.01 if it == 1 else 1.0) for p in ps]
+        for p, q, g in zip(ps, qs, gs):
+            p.grad = g.clone()
+            q.grad = g.clone()
+        norm = torch.nn.utils.clip_grad_norm_(qs, 0.1)
+        ref.step()
+        opt.step()
+        assert abs(opt.grad_norm() - float(norm)) < 1e-4 * float(norm)
+    for p, q in zip(ps, qs):
+        assert _rel(p, q) < 1e-5
+    assert ps[0]._version > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole backward pass
+# ------------------------------------------------------------------------------------------------
+def _grad_case(pkg, cuda, res, training, precision="fp32"):
+    from oracle import regtr
+    from oracle.make_goldens import training_loss
+    torch.manual_seed(0)
+    model = pkg.NeRFRegTr(precision=precision)
+    sd = pkg.synthetic.seeded_state_dict(model, seed=0, attn_gain=4.0)
+    model.load_state_dict(sd)
+    model = model.to(cuda).train(training)
+    data = pkg.synthetic.make_pair(res=res, pair_id=0)
+    out = model(pkg.synthetic.to_device(data, cuda))
+    loss = training_loss(out)
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k in grads else v) for k, v in sd.items()}
+    out_or = regtr.forward(leaf, data, training=training)
+    loss_or = training_loss(out_or)
+    loss_or.backward()
+    return model, float(loss), float(loss_or), grads, {k: leaf[k].grad for k in grads}
+
+
+def _report(grads, ref):
+    worst = []
+    for k in grads:
+        assert ref[k] is not None, k
+        worst.append((_rel(grads[k], ref[k]), k))
+    worst.sort(reverse=True)
+    print("worst parameter gradients:")
+    for e, k in worst[:12]:
+        print("   %.3e  %s" % (e, k))
+    return worst
+
+
+def test_backward_32_eval_matches_reference_fixture(pkg, cuda):
+    """All 293 parameter gradients at 32^3 (running-statistics BatchNorm) against autograd through the oracle,
+    and the reference-pinned digests of tests/golden/grad_32_eval.pt."""
+    model, loss, loss_or, grads, ref = _grad_case(pkg, cuda, 32, training=False)
+    fix = torch.load(os.path.join(GOLDEN, "grad_32_eval.pt"))
+    assert abs(loss_or - float(fix["loss"])) < 1e-6
+    assert abs(loss - float(fix["loss"])) < 1e-3 * abs(float(fix["loss"]))
+    assert set(grads) == set(fix["digests"]), set(fix["digests"]) ^ set(grads)
+    assert len(grads) == 293
+    worst = _report(grads, ref)
+    assert worst[0][0] < TOL, worst[0]
+    for k, d in fix["digests"].items():       # sum, sum |.|, sum of squares of the reference's gradient
+        g = grads[k].double()
+        got = torch.stack([g.sum(), g.abs().sum(), (g * g).sum()])
+        assert abs(got[1] - d[1]) <= 2e-3 * abs(d[1]) + 1e-12, (k, got, d)
+        assert abs(got[2] - d[2]) <= 4e-3 * abs(d[2]) + 1e-18, (k, got, d)
+    for k, smp in fix["samples"].items():
+        assert _rel(grads[k].reshape(-1)[:64], smp) < TOL, k
+
+
+def test_backward_64_train_bn(pkg, cuda):
+    """Batch-statistics BatchNorm backward (the training configuration) at 64^3."""
+    model, loss, loss_or, grads, ref = _grad_case(pkg, cuda, 64, training=True)
+    assert abs(loss - loss_or) < 1e-3 * abs(loss_or)
+    worst = _report(grads, ref)
+    assert worst[0][0] < TOL, worst[0]
+
+
+def test_training_steps_run(pkg, cuda):
+    """train_nerf_regtr.py:171-239 step sequence: forward, loss, backward, clip 0.1, AdamW; twice, bf16 operands."""
+    from oracle.make_goldens import training_loss
+    torch.manual_seed(0)
+    model = pkg.NeRFRegTr(precision="bf16")
+    model.load_state_dict(pkg.synthetic.seeded_state_dict(model, seed=0, attn_gain=4.0))
+    model = model.to(cuda).train(True)
+    model.correspondence_decoder.q_norm.requires_grad_(False)
+    opt = pkg.FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4,
+                         max_grad_norm=0.1)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=34000, gamma=0.5)
+    data = pkg.synthetic.to_device(pkg.synthetic.make_pair(res=64, pair_id=3), cuda)
+    losses = []
+    before = model.fpn3d.backbone_net.conv1.weight.detach().clone()
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        out = model(dict(data))
+        loss = training_loss(out)
+        loss.backward()
+        opt.step()
+        sched.step()
+        losses.append(float(loss))
+    print("losses", losses, "grad norm", opt.grad_norm())
+    assert all(math.isfinite(v) for v in losses)
+    assert not torch.equal(before, model.fpn3d.backbone_net.conv1.weight)
+    assert losses[-1] < losses[0]
