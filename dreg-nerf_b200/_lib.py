@@ -82,6 +82,7 @@ SIGNATURES = {
     "drb_abi_version": (c_int, []),
     "drb_last_error": (C.c_char_p, []),
     "drb_igemm_error_flag": (c_int, [C.POINTER(c_int)]),
+    "drb_error_flag_clear": (c_int, []),
     "drb_conv3d_igemm": (c_int, [C.POINTER(Conv3dDesc), c_void_p]),
     "drb_conv3d_tile_shape": (c_int, [c_int, c_int, c_int, c_int, C.POINTER(c_int * 4), C.POINTER(c_int * 4)]),
     "drb_split_planes": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
@@ -224,6 +225,20 @@ def check(rc, what=""):
         msg = load().drb_last_error()
         raise DrbError("%s failed with code %d: %s" % (what or "libdregb200 call", rc,
                                                       msg.decode(errors="replace") if msg else ""))
+
+
+_FLAG_TEXT = {21: "a mask index is outside the grid", 31: "the surface-field marcher hit its watchdog: result truncated"}
+
+
+def check_device_flag(what=""):
+    """Reads the current device's sticky error flag (synchronises); raises and clears it when set."""
+    lib = load()
+    v = C.c_int(0)
+    check(lib.drb_igemm_error_flag(C.byref(v)), "drb_igemm_error_flag")
+    if v.value != 0:
+        lib.drb_error_flag_clear()
+        raise DrbError("%s: device error flag %d (%s)" % (what or "libdregb200", v.value,
+                                                          _FLAG_TEXT.get(v.value, "tensor-core pipeline watchdog")))
 
 
 def ptr(t):

@@ -38,6 +38,7 @@ def surface_field_mask(radiance_field, occupancy_binary, points, cam_origins, ro
         _lib.check(lib.drb_surface_mask(C.byref(ps), _lib.ptr(occ), res, roi, scene, _lib.ptr(pts), pts.shape[0],
                                         _lib.ptr(cams), cams.shape[0], float(render_step_size), float(cut_off),
                                         _lib.ptr(out), _lib.stream_ptr()), "drb_surface_mask")
+        _lib.check_device_flag("drb_surface_mask")
     return out.bool()
 
 
@@ -52,6 +53,8 @@ def compute_visibility_score(xyz_list: List[torch.Tensor], radiance_field, occup
     ``density_field``, the binary surface-field score for ``surface_field``."""
     if score_type not in ("density_field", "surface_field"):
         raise ValueError("score_type must be 'density_field' or 'surface_field'")
+    from .ngp import check_march_options
+    check_march_options(meta_data, cut_off)
     scores = []
     for xyz in xyz_list:
         num_layers, num_points = xyz.shape[0], xyz.shape[1]

@@ -717,6 +717,11 @@ extern "C" int drb_conv3d_tile_shape(int g, int d, int h, int w, int box[4], int
   return 0;
 }
 
+extern "C" int drb_error_flag_clear(void) {
+  igemm_clear_err_flag();
+  return 0;
+}
+
 extern "C" int drb_igemm_error_flag(int* host_value) {
   if (!host_value) return DRB_EINVAL;
   *host_value = 0;

@@ -21,7 +21,6 @@
 
 namespace drb {
 
-int igemm_num_sms();
 
 static constexpr int kLevels = 16;
 static constexpr int kHashSize = 1 << 19;
@@ -232,12 +231,8 @@ extern "C" int drb_ngp_density(const drb_ngp_params* pp, const float* x, int n, 
   if (n == 0) return 0;
   const NgpDev p = make_dev(pp);
   const size_t smem = field_smem_bytes(p.lv);
-  static bool attr = false;
-  if (!attr) {
-    DRB_CUDA_OK(cudaFuncSetAttribute(ngp_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    attr = true;
-  }
+  // set on every call: the attribute is per device and a process may drive several GPUs
+  DRB_CUDA_OK(cudaFuncSetAttribute(ngp_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = cdiv(n, 512);
   if (grid > 148) grid = 148;
   ngp_density_kernel<<<grid, 512, smem, stream>>>(p, x, n, density, feat);
@@ -459,11 +454,7 @@ extern "C" int drb_ngp_rgb_mean(const drb_ngp_params* pp, const float* feat, int
   dt.n = ndirs;
   for (int k = 0; k < ndirs; ++k)
     for (int d = 0; d < 3; ++d) dt.d[k][d] = host_dirs[k * 3 + d];
-  static bool attr = false;
-  if (!attr) {
-    DRB_CUDA_OK(cudaFuncSetAttribute(ngp_rgb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RgbSmem)));
-    attr = true;
-  }
+  DRB_CUDA_OK(cudaFuncSetAttribute(ngp_rgb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RgbSmem)));
   const int warps = kRgbThreads / 32;
   int grid = cdiv(cdiv(n, 32), warps);
   if (grid > igemm_num_sms()) grid = igemm_num_sms();
@@ -481,6 +472,9 @@ struct MarchArgs {
   int res;
   float step, cut_off;
   int max_skips;      // empty-space events a lane may take per outer iteration
+  long long watchdog_clocks;   // give up (and raise the device error flag) after this many SM clocks
+  uint32_t watchdog_mask;      // rounds between clock reads - 1
+  int* err;                    // per-device error flag (code 31 = marcher watchdog)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1038,8 +1032,12 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
   const long long t_start = clock64();
 
   for (uint32_t round = 0;; ++round) {
-    // watchdog: a scheduling bug must not hang the GPU box (~30 s at 2 GHz, then give up)
-    if ((round & 0xfffu) == 0xfffu && clock64() - t_start > 60000000000LL) break;
+    // watchdog: a scheduling bug must not hang the GPU box (~30 s at 2 GHz, then give up) - and a truncated
+    // march must not pass for a result: the flag makes the host call fail (drb_march_status)
+    if ((round & a.watchdog_mask) == a.watchdog_mask && clock64() - t_start > a.watchdog_clocks) {
+      if (lane == 0 && a.err) atomicExch(a.err, 31);
+      break;
+    }
     ++st_rounds;
     // ---------------- refill: lanes without a ray take a resumable one, else start new rays ------
     {
@@ -1300,16 +1298,16 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
 // The stream-ordered allocator gives memory back to the OS at every synchronisation unless a release
 // threshold is set; re-acquiring it costs milliseconds with a long tail.  Keep the pool.
 static void keep_async_pool() {
-  static bool done = false;
-  if (done) return;
+  static bool done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || done[dev]) return;
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     unsigned long long thr = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
-  done = true;
+  done[dev] = true;
 }
 
 struct MortonArgs { float roi_min[3], roi_inv[3]; };
@@ -1366,6 +1364,11 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
     static int skips = 0;
     if (!skips) { const char* env = getenv("DRB_MARCH_SKIPS"); skips = env ? atoi(env) : 16; if (skips < 1) skips = 16; }
     a.max_skips = skips;
+    // DRB_MARCH_WATCHDOG_CLOCKS: test hook (a tiny limit forces the watchdog path)
+    const char* wd = getenv("DRB_MARCH_WATCHDOG_CLOCKS");
+    a.watchdog_clocks = wd ? atoll(wd) : 60000000000LL;
+    a.watchdog_mask = wd ? 0x0u : 0xfffu;
+    a.err = igemm_err_flag();
   }
   DRB_REQUIRE(levels_ok(p.lv), "drb_surface_mask: compile-time level table disagrees with host_levels()");
   DRB_REQUIRE(((uintptr_t)pp->hash_table & 15) == 0, "drb_surface_mask: hash table must be 16-byte aligned");
@@ -1373,11 +1376,7 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
               "drb_surface_mask: at most %d points and %d cameras per call", (1 << kPiBits) - 1, kMaxCams);
   const size_t smem = march_smem_bytes(ncams);
   DRB_REQUIRE(smem <= 232448, "drb_surface_mask: %d cameras do not fit the shared-memory plan", ncams);
-  static size_t attr = 0;
-  if (attr < smem) {
-    DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   MarchAux aux;
   aux.coarse_shift = 0;
   while (((res + (1 << aux.coarse_shift) - 1) >> aux.coarse_shift) > kCoarseMaxDim) ++aux.coarse_shift;

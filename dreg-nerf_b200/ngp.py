@@ -10,6 +10,7 @@ table], ``color_mlp.params`` = [C1 64x32 | C2 64x64 | C3 16x64], ``direction_enc
 """
 import ctypes as C
 import math
+import struct
 
 import torch
 from torch import nn
@@ -18,6 +19,33 @@ from . import _lib
 
 N_W1, N_W2 = 64 * 32, 16 * 64
 N_C1, N_C2, N_C3 = 64 * 32, 64 * 64, 16 * 64
+
+
+def hash_table_entries():
+    """Entries ([2] floats each) of the 16-level table (levels concatenated): levels whose res^3 (rounded up to
+    8) fits 2^19 are dense, the others hashed (tiny-cuda-nn grid encoding; same arithmetic as
+    drb_ngp_table_entries, against which it is checked on first device use).  Pure Python so that building a
+    field - e.g. for the CPU reference arm of bench.py - does not load the CUDA library."""
+    total = 0
+    for level in range(16):
+        scale = struct.unpack("f", struct.pack("f", 2.0 ** (level * math.log2(1.4472692012786865)) * 16 - 1.0))[0]
+        res = int(math.ceil(scale)) + 1
+        total += min((res ** 3 + 7) // 8 * 8, 1 << 19)
+    return total
+
+
+def check_march_options(meta_data, cut_off):
+    """The marcher uses nerfacc's fixed step (cone_angle == 0) and never drops samples by alpha
+    (alpha_thre == 0): both are what eval_ngp_nerf.py:79-92 passes for bounded scenes.  A checkpoint trained
+    with other settings would get different sample positions - refuse instead of producing a wrong mask
+    (sample_grid.py:294-295, confidence_loss.py:137-138 forward both to ray_marching)."""
+    cone = meta_data.get("cone_angle", 0.0) if hasattr(meta_data, "get") else 0.0
+    thre = meta_data.get("alpha_thre", 0.0) if hasattr(meta_data, "get") else 0.0
+    if cone not in (None, 0, 0.0):
+        raise NotImplementedError("cone_angle=%r: libdregb200's marcher implements the fixed-step march only" % (cone,))
+    if thre not in (None, 0, 0.0) and float(thre) > float(cut_off):
+        raise NotImplementedError("alpha_thre=%r above the cut-off %r would drop decisive samples; not implemented"
+                                  % (thre, cut_off))
 
 
 class _FlatParams(nn.Module):
@@ -42,7 +70,7 @@ class NGPradianceField(nn.Module):
             aabb = torch.tensor(aabb, dtype=torch.float32)
         self.register_buffer("aabb", aabb.float())
         self.num_dim, self.geo_feat_dim, self.unbounded, self.use_viewdirs = 3, 15, False, True
-        self.table_entries = int(_lib.load().drb_ngp_table_entries())
+        self.table_entries = hash_table_entries()
         self.mlp_base = _FlatParams(N_W1 + N_W2 + 2 * self.table_entries)
         self.direction_encoding = _FlatParams(0)
         self.color_mlp = _FlatParams(N_C1 + N_C2 + N_C3)
@@ -71,6 +99,8 @@ class NGPradianceField(nn.Module):
         p, c = self.mlp_base.params, self.color_mlp.params
         if not p.is_cuda:
             raise _lib.DrbError("libdregb200 has no CPU path: move the field to a CUDA device")
+        if self.table_entries != int(_lib.load().drb_ngp_table_entries()):
+            raise _lib.DrbError("hash-table layout of the Python mirror and libdregb200 differ")
         base, cb = p.data_ptr(), c.data_ptr()
         s = _lib.NgpParams(hash_table=base + 4 * (N_W1 + N_W2), w1=base, w2=base + 4 * N_W1,
                            c1=cb, c2=cb + 4 * N_C1, c3=cb + 4 * (N_C1 + N_C2))
@@ -180,6 +210,7 @@ class SampleGrid(nn.Module):
         (their surface_mask entries stay False): identical voxel_grid / voxel_mask, ~3x less marching.
         """
         lib = _lib.load()
+        check_march_options(meta_data, cut_off)
         device = torch.device(device)
         binary = self._binary.to(device)
         indices = torch.nonzero(binary.flatten())[:, 0].contiguous()
@@ -215,6 +246,7 @@ class SampleGrid(nn.Module):
             _lib.check(lib.drb_extract_block(C.byref(ps), C.byref(desc), _lib.ptr(points), _lib.ptr(rgb),
                                              _lib.ptr(alpha), _lib.ptr(dmask), _lib.ptr(smask),
                                              _lib.ptr(grid), _lib.stream_ptr()), "drb_extract_block")
+            _lib.check_device_flag("drb_extract_block")      # the caller indexes with the masks next: no extra stall
         out = (points, rgb, alpha, indices, dmask.bool(), smask.bool())
         return out + (grid,) if return_grid else out
 

@@ -42,6 +42,9 @@ int drb_abi_version(void);
 const char* drb_last_error(void);
 /* Value of the device-side pipeline watchdog flag (0 = healthy).  Synchronous. */
 int drb_igemm_error_flag(int* host_value);
+/* The flag of the current device is sticky; codes: 1-4 / 11-14 tcgen05 pipeline watchdogs (igemm / wgrad), 21 mask
+ * index out of range, 31 surface-field marcher watchdog (result truncated).  Clears it. */
+int drb_error_flag_clear(void);
 
 /* ------------------------------------------------------------------------------------------
  * R2 / R6 / R7: nn.Conv3d (conerf/model/resnet3d.py:81-86,120, feature_pyramid_net.py:24,33)

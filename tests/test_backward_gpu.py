@@ -325,8 +325,19 @@ def test_fused_adamw_matches_torch(pkg, cuda):
 # ------------------------------------------------------------------------------------------------
 # the whole backward pass
 # ------------------------------------------------------------------------------------------------
-def _grad_case(pkg, cuda, res, training, precision="fp32"):
+def _oracle_grads(pkg, sd, data, names, training, dtype):
     from oracle import regtr
+    from oracle.make_goldens import training_loss
+    leaf = {k: (v.to(dtype).clone().requires_grad_(True) if k in names else (v.to(dtype) if v.is_floating_point() else v))
+            for k, v in sd.items()}
+    d = {k: (v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in data.items()}
+    out = regtr.forward(leaf, d, training=training)
+    loss = training_loss(out)
+    loss.backward()
+    return float(loss.detach()), {k: leaf[k].grad for k in names}, (out["src_kp"][0].shape[0], out["tgt_kp"][0].shape[0])
+
+
+def _grad_case(pkg, cuda, res, training, precision="fp32", want64=False):
     from oracle.make_goldens import training_loss
     torch.manual_seed(0)
     model = pkg.NeRFRegTr(precision=precision)
@@ -339,51 +350,77 @@ def _grad_case(pkg, cuda, res, training, precision="fp32"):
     loss.backward()
     torch.cuda.synchronize()
     grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
-    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k in grads else v) for k, v in sd.items()}
-    out_or = regtr.forward(leaf, data, training=training)
-    loss_or = training_loss(out_or)
-    loss_or.backward()
-    return model, float(loss), float(loss_or), grads, {k: leaf[k].grad for k in grads}
+    loss32, ref32, tok32 = _oracle_grads(pkg, sd, data, set(grads), training, torch.float32)
+    ref64 = None
+    if want64:
+        loss64, ref64, tok64 = _oracle_grads(pkg, sd, data, set(grads), training, torch.float64)
+        assert tok64 == tok32, "the fp64 study must see the same tokens"
+    return model, float(loss), loss32, grads, ref32, ref64
 
 
-def _report(grads, ref):
-    worst = []
+def _errs(grads, ref):
+    """Per-tensor max |diff| / max |ref|.  A tensor whose reference gradient is pure rounding noise (k_proj.bias:
+    adding a constant to every key's logit does not change a soft-max, its true gradient is 0) is compared against
+    the scale of the largest gradient instead."""
+    out = {}
+    top = max(float(v.abs().max()) for v in ref.values())
     for k in grads:
         assert ref[k] is not None, k
-        worst.append((_rel(grads[k], ref[k]), k))
-    worst.sort(reverse=True)
-    print("worst parameter gradients:")
+        if float(ref[k].abs().max()) < 1e-6 * top:
+            out[k] = float((grads[k].double() - ref[k].double()).abs().max()) / (1e-3 * top)
+        else:
+            out[k] = _rel(grads[k], ref[k])
+    return out
+
+
+def _report(errs, title="worst parameter gradients", extra=None):
+    worst = sorted(((e, k) for k, e in errs.items()), reverse=True)
+    print(title + ":")
     for e, k in worst[:12]:
-        print("   %.3e  %s" % (e, k))
+        print("   %.3e  %s%s" % (e, k, ("   (fp32 oracle vs fp64: %.3e)" % extra[k]) if extra else ""))
     return worst
 
 
 def test_backward_32_eval_matches_reference_fixture(pkg, cuda):
     """All 293 parameter gradients at 32^3 (running-statistics BatchNorm) against autograd through the oracle,
     and the reference-pinned digests of tests/golden/grad_32_eval.pt."""
-    model, loss, loss_or, grads, ref = _grad_case(pkg, cuda, 32, training=False)
+    model, loss, loss_or, grads, ref, _ = _grad_case(pkg, cuda, 32, training=False)
     fix = torch.load(os.path.join(GOLDEN, "grad_32_eval.pt"))
-    assert abs(loss_or - float(fix["loss"])) < 1e-6
+    assert abs(loss_or - float(fix["loss"])) < 1e-5 * abs(float(fix["loss"]))      # fp32 sums differ by an ulp or two across hosts
     assert abs(loss - float(fix["loss"])) < 1e-3 * abs(float(fix["loss"]))
     assert set(grads) == set(fix["digests"]), set(fix["digests"]) ^ set(grads)
     assert len(grads) == 293
-    worst = _report(grads, ref)
+    worst = _report(_errs(grads, ref))
     assert worst[0][0] < TOL, worst[0]
+    top = max(float(d[1]) / max(grads[k].numel(), 1) for k, d in fix["digests"].items())
     for k, d in fix["digests"].items():       # sum, sum |.|, sum of squares of the reference's gradient
         g = grads[k].double()
         got = torch.stack([g.sum(), g.abs().sum(), (g * g).sum()])
-        assert abs(got[1] - d[1]) <= 2e-3 * abs(d[1]) + 1e-12, (k, got, d)
-        assert abs(got[2] - d[2]) <= 4e-3 * abs(d[2]) + 1e-18, (k, got, d)
+        floor = 1e-6 * top * g.numel()        # tensors whose gradient is rounding noise (k_proj.bias)
+        assert abs(got[1] - d[1]) <= 2e-3 * abs(d[1]) + floor, (k, got, d)
+        assert abs(got[2] - d[2]) <= 4e-3 * abs(d[2]) + floor * floor, (k, got, d)
     for k, smp in fix["samples"].items():
         assert _rel(grads[k].reshape(-1)[:64], smp) < TOL, k
 
 
 def test_backward_64_train_bn(pkg, cuda):
-    """Batch-statistics BatchNorm backward (the training configuration) at 64^3."""
-    model, loss, loss_or, grads, ref = _grad_case(pkg, cuda, 64, training=True)
+    """Batch-statistics BatchNorm backward (the training configuration) at 64^3.
+
+    At 64^3 the deepest stage normalises over 2^3 = 8 voxels per grid: the gradient through those statistics is
+    ill conditioned and autograd through the fp32 reference modules itself is only accurate to ~1e-1 there
+    (measured against the same graph in fp64: layer4.1.conv3.weight 1.4e-1, layer4.1.bn3.bias 8e-2).  The
+    yard-stick is therefore the fp64 evaluation; a tensor passes at 1e-3, or at 3x the fp32 reference's own
+    error against fp64 where that is larger."""
+    model, loss, loss_or, grads, ref32, ref64 = _grad_case(pkg, cuda, 64, training=True, want64=True)
     assert abs(loss - loss_or) < 1e-3 * abs(loss_or)
-    worst = _report(grads, ref)
-    assert worst[0][0] < TOL, worst[0]
+    noise = _errs(ref32, ref64)
+    errs = _errs(grads, ref64)
+    _report(_errs(grads, ref32), "against the fp32 oracle (informational)")
+    worst = _report(errs, "against the fp64 oracle", noise)
+    bad = [(e, k, noise[k]) for e, k in worst if e > max(TOL, 3.0 * noise[k])]
+    n_tight = sum(1 for e, k in worst if e < TOL)
+    print("%d of %d tensors within 1e-3 of fp64; %d beyond max(1e-3, 3 x fp32-reference noise)" % (n_tight, len(worst), len(bad)))
+    assert not bad, bad[:5]
 
 
 def test_training_steps_run(pkg, cuda):
