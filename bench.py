@@ -73,12 +73,16 @@ def _state(pkg, model):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_extract_seconds(pkg, cams, ray_sample=20000):
+def cpu_extract_seconds(pkg, cams, ray_sample=20000, like_fraction=0.125):
     """CPU time of ONE block's extract (oracle port: the reference's own extract is CUDA-only, tcnn +
     nerfacc, so no reference CPU implementation exists).  Density / colour over all candidate cells is
-    timed in full (torch CPU ops); the surface-field ray march runs in the C / OpenMP restatement
-    (oracle/extract_c.c, all host threads) on a bounded sample of points - every camera's ray to each of
-    them, as sample_grid.py:245-318 marches them - and is scaled by the ray count."""
+    timed in full (torch CPU ops).  The surface-field ray march runs in the C / OpenMP restatement
+    (oracle/extract_c.c, all host threads) twice, each on a bounded sample scaled by its sample fraction:
+      like_for_like - the rays OUR arm marches: only cells whose density passes the threshold, cameras in order
+                      until one sees the point (identical masks; `like_fraction` of the candidate cells);
+      as_reference  - every (camera, point) ray to the end, as sample_grid.py:245-318 marches them
+                      (`ray_sample` rays).
+    Returns (seconds per block with the like-for-like march, info dict with both)."""
     import torch
     from oracle import extract, extract_c, ngp
     from oracle.make_goldens import make_field
@@ -94,17 +98,36 @@ def cpu_extract_seconds(pkg, cams, ray_sample=20000):
     dens, feat = ngp.query_density(pts, ref["aabb"], ref["table"], ref["w1"], ref["w2"])
     ngp.query_rgb_mean(ngp.fixed_viewing_directions(), feat, ref["c1"], ref["c2"], ref["c3"])
     t_field = time.perf_counter() - t0
+    cam_o = poses[:, :3, 3].contiguous()
+    extract_c.load()
+    # (1) like for like
+    n_like = max(1, int(idx.numel() * like_fraction))
+    pick = torch.randperm(idx.numel(), generator=gen)[:n_like]
+    dense = (dens[pick] > 0.7)
+    t0 = time.perf_counter()
+    _, _, n_s_like = extract_c.surface_mask(pts[pick], cam_o, occ, RES, roi, roi, meta["render_step_size"], 0.5, ref,
+                                            active=dense, all_rays=False)
+    t_like_meas = time.perf_counter() - t0
+    t_like = t_like_meas * (idx.numel() / n_like)
+    # (2) as the reference marches
     total_rays = idx.numel() * cams
     n_pts = max(1, min(idx.numel(), ray_sample // max(cams, 1)))
-    pick = torch.randperm(idx.numel(), generator=gen)[:n_pts]
-    extract_c.load()
+    pick2 = torch.randperm(idx.numel(), generator=gen)[:n_pts]
     t0 = time.perf_counter()
-    _, _, n_samples = extract_c.surface_mask(pts[pick], poses[:, :3, 3].contiguous(), occ, RES, roi, roi,
-                                             meta["render_step_size"], 0.5, ref, all_rays=True)
-    t_rays = (time.perf_counter() - t0) * (total_rays / (n_pts * cams))
-    return t_field + t_rays, {"field_s": t_field, "rays_s_extrapolated": t_rays, "rays_total": int(total_rays),
-                              "rays_sampled": int(n_pts * cams), "density_samples_in_sample": int(n_samples),
-                              "marcher": "oracle/extract_c.c (C, OpenMP, %d threads)" % (os.cpu_count() or 1)}
+    _, _, n_samples = extract_c.surface_mask(pts[pick2], cam_o, occ, RES, roi, roi, meta["render_step_size"], 0.5, ref,
+                                             all_rays=True)
+    t_all_meas = time.perf_counter() - t0
+    t_rays = t_all_meas * (total_rays / (n_pts * cams))
+    return t_field + t_like, {
+        "field_s": t_field,
+        "like_for_like": {"measured_s": t_like_meas, "cells_sampled": int(n_like), "cells_total": int(idx.numel()),
+                          "dense_in_sample": int(dense.sum()), "density_samples_in_sample": int(n_s_like),
+                          "block_s_extrapolated": t_like, "what": "dense cells only, cameras until one sees the point (the rays our arm marches)"},
+        "as_reference": {"measured_s": t_all_meas, "rays_sampled": int(n_pts * cams), "rays_total": int(total_rays),
+                         "density_samples_in_sample": int(n_samples), "block_s_extrapolated": t_rays,
+                         "what": "every (camera, point) ray marched to its end (sample_grid.py:245-318)"},
+        "measured_s_total": t_field + t_like_meas + t_all_meas,
+        "marcher": "oracle/extract_c.c (C, OpenMP, %d threads)" % (os.cpu_count() or 1)}
 
 
 def run_reference(args):
@@ -124,6 +147,20 @@ def run_reference(args):
     sd = _state(pkg, model)
     del model
     data = pkg.synthetic.make_pair(res=RES, pair_id=0)
+    if args.stage == "train":
+        model = pkg.NeRFRegTr()
+        model.load_state_dict(sd)
+        model.correspondence_decoder.q_norm.requires_grad_(False)
+        cb = cpu_train_baseline(pkg, model, steps=max(1, min(args.steps, 3)))
+        line = {"impl": "reference", "metric": "nerf_pairs_per_sec_128cube", "value": cb["value"], "unit": "pairs/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "128^3 training step (fwd + loss + bwd + clip + AdamW), one pair per step (bounded sample of the batch)",
+                           "stage": "train", "resolution": RES},
+                "cpu_baseline": cb, "gpu_launches": 0,
+                "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
     full = args.stage == "full"
     sample = "1 pair, 128^3, full NeRFRegTr.forward (oracle port of the reference, fp32, torch CPU ops)"
 
@@ -139,7 +176,7 @@ def run_reference(args):
 
     extract_s, extract_info = (0.0, None)
     if full:
-        one_block, extract_info = cpu_extract_seconds(pkg, args.cams, ray_sample=400000)
+        one_block, extract_info = cpu_extract_seconds(pkg, args.cams, ray_sample=200000, like_fraction=0.125)
         extract_s = 2.0 * one_block
     t0 = time.perf_counter()
     full_step()
@@ -161,8 +198,13 @@ def run_reference(args):
         for _ in range(args.steps):
             times.append(2.0 * fpn_once() + tail + extract_s)
     if full:
-        sample += ("; + extract of 2 blocks by the oracle port (%.1f s, ray march extrapolated from %d of %d rays)"
-                   % (extract_s, extract_info["rays_sampled"], extract_info["rays_total"]))
+        lf, ar = extract_info["like_for_like"], extract_info["as_reference"]
+        sample += ("; + extract of 2 blocks by the oracle port: field queries in full (%.1f s per block), ray march MEASURED on "
+                   "%d of %d candidate cells (%.1f s) and EXTRAPOLATED by the cell count to %.1f s per block, marching the "
+                   "rays our arm marches; marching every ray as the reference does would take %.0f s per block "
+                   "(extrapolated from %d of %d rays)"
+                   % (extract_info["field_s"], lf["cells_sampled"], lf["cells_total"], lf["measured_s"],
+                      lf["block_s_extrapolated"], ar["block_s_extrapolated"], ar["rays_sampled"], ar["rays_total"]))
     total = sum(times)
     value = len(times) / total
     line = {
@@ -177,6 +219,8 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    with open("/proc/self/maps") as fh:       # the reference arm must not touch the product library
+        line["native_so_loaded"] = "libdregb200" in fh.read()
     print(json.dumps(line), flush=True)
 
 
@@ -200,9 +244,17 @@ def run_ours(args):
     model = pkg.NeRFRegTr(precision=args.precision)
     model.load_state_dict(_state(pkg, model))
     model = model.to(dev).train(True)       # batch-statistics BatchNorm, as eval_nerf_regtr.py runs it
-    # rank r owns pairs r, r + world, ... (independent units, no data-path collective)
+    # rank r owns pairs r, r + world, ... of one list of distinct pairs (independent units, no data-path
+    # collective); the per-pair SE(3) of every rank meet in one all-gather per step (sharding.gather_poses)
+    from importlib import import_module
+    sharding = import_module("dreg-nerf_b200.sharding")
+    my_ids = sharding.shard_pairs(N_RESIDENT_PAIRS * world, rank, world)
     full = args.stage == "full"
-    gathered = [torch.empty((1, 3, 4), device=dev) for _ in range(world)] if world > 1 else None
+
+    def gather_pose(pose):
+        if world > 1:
+            return sharding.gather_poses(pose.reshape(1, 3, 4).contiguous(), world)
+        return pose
     stage_ms = {"extract": 0.0, "register": 0.0, "n": 0}
 
     def pin_grid_dict(p):
@@ -219,7 +271,7 @@ def run_ours(args):
         return q
 
     if not full:
-        host_pairs = [pkg.synthetic.make_pair(res=RES, pair_id=i) for i in range(N_RESIDENT_PAIRS)]
+        host_pairs = [pkg.synthetic.make_pair(res=RES, pair_id=i) for i in my_ids]
         dev_pairs = [pkg.synthetic.to_device(p, dev) for p in host_pairs]
         pinned = [pin_grid_dict(p) for p in host_pairs]
         h2d_bytes = sum(v.numel() * v.element_size() for k, v in pinned[0].items()
@@ -229,9 +281,7 @@ def run_ours(args):
         def step_resident(i):
             with torch.no_grad():
                 out = model(dict(dev_pairs[i % N_RESIDENT_PAIRS]))
-            pose = out["pose"][-1]
-            if world > 1:
-                dist.all_gather(gathered, pose.contiguous())      # per-pair SE(3), 48 B per rank
+            gather_pose(out["pose"][-1])      # per-pair SE(3), 48 B per rank
             return out
 
         # e2e: double-buffered H2D on a side stream (the copy of step i+1 overlaps the compute of step i);
@@ -271,9 +321,7 @@ def run_ours(args):
             data["tgt_mask"] = sl["tgt_mask"][:src["tgt_mask"].numel()]
             with torch.no_grad():
                 out = model(data)
-                pose = out["pose"][-1]
-                if world > 1:
-                    dist.all_gather(gathered, pose.contiguous())
+                pose = gather_pose(out["pose"][-1])
                 consumed[i % 2].record()
                 return pose.cpu()
     else:
@@ -285,7 +333,7 @@ def run_ours(args):
         sgrid = pkg.SampleGrid(list(pkg.synthetic.AABB), RES)
         host_fields, dev_fields = [], []
         for i in range(N_RESIDENT_PAIRS):
-            pid = i          # every rank runs the same synthetic pairs: per-GPU work is fixed (weak scaling)
+            pid = my_ids[i]  # distinct synthetic blocks per rank, same sizes: per-GPU work is fixed (weak scaling)
             pair = [pkg.synthetic.make_ngp_field(seed=500 + 2 * pid + side) for side in (0, 1)]
             host_fields.append([(f.mlp_base.params.detach().clone().pin_memory(),
                                  f.color_mlp.params.detach().clone().pin_memory()) for f in pair])
@@ -310,10 +358,7 @@ def run_ours(args):
             out = model(data)
             if timed_stages:
                 ev[2].record()
-            pose = out["pose"][-1]
-            if world > 1:
-                dist.all_gather(gathered, pose.contiguous())
-            return pose
+            return gather_pose(out["pose"][-1])
 
         def step_resident(i, timed_stages=False):
             with torch.no_grad():
@@ -445,8 +490,9 @@ def run_ours(args):
                        "resolution": RES, "pairs_per_step_per_gpu": 1, "masked_voxels": masked,
                        "tokens": [ns, nt], "bn_mode": "batch statistics",
                        "l2": "working set per step (2 x 58.7 MB grids, 0.6 GB weight planes, >3 GB activations) exceeds the 126 MB L2",
-                       "parallelism": "pairs sharded over %d GPU(s) (every rank times the same %d synthetic pairs: fixed "
-                                      "per-GPU work), one NCCL all-gather of the per-pair SE(3) per step" % (world, N_RESIDENT_PAIRS)},
+                       "parallelism": "a list of %d distinct synthetic pairs sharded over %d GPU(s) (sharding.shard_pairs, %d per rank, "
+                                      "fixed per-GPU work), one NCCL all-gather of the per-pair SE(3) per step"
+                                      % (N_RESIDENT_PAIRS * world, world, N_RESIDENT_PAIRS)},
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": 48, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -505,6 +551,307 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+def _setup_dist():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU: there is no CPU fallback for our arm"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    return world, rank, local_rank, dev
+
+
+def _pin_pair(p):
+    """Pinned host copy of one pair in the [X,Y,Z,7] storage order of voxel_grid.pt (the view the loader makes)."""
+    import torch
+    q = {}
+    for k, v in p.items():
+        if torch.is_tensor(v):
+            if v.dim() == 5:
+                store = v.permute(0, 3, 4, 2, 1).contiguous().pin_memory()
+                q[k] = store.permute(0, 4, 3, 1, 2)
+            else:
+                q[k] = v.contiguous().pin_memory()
+        else:
+            q[k] = v
+    return q
+
+
+def _h2d_pair(pinned, dev):
+    import torch
+    return {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in pinned.items()}
+
+
+def _pair_bytes(p):
+    import torch
+    return sum(v.numel() * v.element_size() for k, v in p.items() if torch.is_tensor(v))
+
+
+def run_train(args):
+    """BASELINE.json configs[2]: one step = `--batch` pairs at 128^3 through forward + loss + backward (gradients
+    accumulate over the pairs: the network is B = 1 by construction, nerf_regtr.py:144-147) + one fused
+    clip_grad_norm_(0.1) + AdamW update (train_nerf_regtr.py:171-239).  bf16 GEMM operands by default."""
+    import torch
+    import torch.distributed as dist
+    import dreg_nerf_b200 as pkg
+    world, rank, local_rank, dev = _setup_dist()
+    torch.manual_seed(0)
+    precision = args.precision or "bf16"
+    model = pkg.NeRFRegTr(precision=precision)
+    model.load_state_dict(_state(pkg, model))
+    model = model.to(dev).train(True)
+    model.correspondence_decoder.q_norm.requires_grad_(False)      # unused by the forward (no gradient in the reference either)
+    crit = pkg.RegistrationLoss().to(dev)
+    params = [p for p in model.parameters() if p.requires_grad] + list(crit.parameters())
+    opt = pkg.FusedAdamW(params, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1)
+    B = args.batch
+    n_res = min(B, 8)
+    ids = [rank * n_res + i for i in range(n_res)]             # distinct pairs per rank
+    host = [pkg.synthetic.make_pair(res=RES, pair_id=i) for i in ids]
+    pinned = [_pin_pair(p) for p in host]
+    resident = [pkg.synthetic.to_device(p, dev) for p in host]
+    h2d = sum(_pair_bytes(p) for p in pinned) / n_res * B
+    loss_buf = torch.zeros((), device=dev)
+
+    def one_pair(data):
+        out = model(data)
+        loss, _ = crit(out, data["pose"])
+        (loss / B).backward()
+        return loss.detach()
+
+    def grads_allreduce():
+        # data-parallel training (SURVEY 8f-4): gradients averaged over ranks, one flat bucket per dtype
+        if world > 1:
+            gs = [p.grad for p in params if p.grad is not None]
+            flat = torch.cat([g.reshape(-1) for g in gs])
+            dist.all_reduce(flat)
+            flat /= world
+            o = 0
+            for g in gs:
+                g.copy_(flat[o:o + g.numel()].view_as(g))
+                o += g.numel()
+
+    def step_resident(i):
+        opt.zero_grad(set_to_none=True)
+        tot = torch.zeros((), device=dev)
+        for b in range(B):
+            tot += one_pair(dict(resident[(i * B + b) % n_res]))
+        grads_allreduce()
+        opt.step()
+        return tot
+
+    def step_e2e(i):
+        opt.zero_grad(set_to_none=True)
+        tot = torch.zeros((), device=dev)
+        for b in range(B):
+            tot += one_pair(_h2d_pair(pinned[(i * B + b) % n_res], dev))
+        grads_allreduce()
+        opt.step()
+        return float(tot.cpu())                       # D2H of the step's loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        model.set_profile(profile)
+        if profile:
+            model.read_profile()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = model.launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        prof = model.read_profile() if profile else None
+        model.set_profile(False)
+        return float(t.item()), model.launch_count() - l0, prof
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, prof = timed(step_resident, args.steps, profile=True)
+    clocks = sampler.summary() if sampler else None
+    step_e2e(0)
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    if rank == 0:
+        peaks = _peaks()
+        pairs = world * B * args.steps
+        ig_ms, ig_flops, ig_n = prof
+        achieved = ig_flops / (ig_ms / 1e3) / 1e12 if ig_ms > 0 else 0.0
+        mma = 3 if precision == "fp32" else 1
+        peak = peaks["bf16_tflops_sustained"]
+        line = {
+            "metric": "nerf_pairs_per_sec_128cube", "value": pairs / (ms / 1e3), "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "batch %d pairs per GPU, 128^3, %s training step (fwd + loss + bwd + clip + AdamW) on %dxB200"
+                                   % (B, "bf16" if precision != "fp32" else "fp32-grade", world),
+                       "stage": "train", "resolution": RES, "pairs_per_step_per_gpu": B,
+                       "distinct_pairs_resident_per_gpu": n_res, "bn_mode": "batch statistics",
+                       "loss": "RegistrationLoss: InfoNCE (0.1) + robust-L1 correspondence both directions (1.0), synthetic GT pose",
+                       "optimizer": "FusedAdamW lr 1e-4 wd 1e-4, clip_grad_norm 0.1 (train_nerf_regtr.py:96-102,232-235)",
+                       "l2": "per-pair working set (2 x 58.7 MB grids, >4 GB of saved activations) exceeds the 126 MB L2",
+                       "parallelism": "data parallel over %d GPU(s): distinct pairs per rank, one flat gradient all-reduce per step" % world},
+            "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "igemm_kernel + wgrad_kernel (tcgen05 conv / linear forward, data gradient, weight gradient), all launches of the timed steps",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": peaks["source"] + ", bf16 sustained", "traffic": None, "launches": int(ig_n),
+                         "kernel_ms_per_step": ig_ms / args.steps, "kernel_share_of_step": ig_ms / ms,
+                         "mma_flops_factor": mma, "tensor_pipe_frac_est": mma * achieved / peak},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_train_baseline(pkg, model)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_train_baseline(pkg, model, steps=1):
+    """One pair through the oracle port's forward + autograd backward + torch AdamW on the host cores."""
+    import torch
+    from oracle import regtr
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    names = [k for k, p in model.named_parameters() if p.requires_grad]
+    leaf = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
+    crit = pkg.RegistrationLoss()
+    opt = torch.optim.AdamW([leaf[k] for k in names] + list(crit.parameters()), lr=1e-4, weight_decay=1e-4)
+    data = pkg.synthetic.make_pair(res=RES, pair_id=0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        opt.zero_grad()
+        loss, _ = crit(regtr.forward(leaf, data, training=True), data["pose"])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in leaf.values() if p.requires_grad], 0.1)
+        opt.step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": 1.0 / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": "%d pair(s), 128^3: oracle/regtr.py forward + torch autograd backward + clip + torch AdamW, fp32, %d threads (%.1f s per pair)"
+                      % (steps, cores, dt)}
+
+
+def run_batch(args):
+    """BASELINE.json configs[3]: a list of DISTINCT pairs sharded over the GPUs (sharding.shard_pairs: rank r takes
+    pairs r, r + N, ...), bf16 inference, ONE all-gather of the per-pair SE(3) per batch (sharding.gather_poses).
+    --pairs-per-gpu P: weak scaling (P x N pairs); --total-pairs T: strong scaling (T pairs whatever N)."""
+    import torch
+    import torch.distributed as dist
+    import dreg_nerf_b200 as pkg
+    from importlib import import_module
+    sharding = import_module("dreg-nerf_b200.sharding")
+    world, rank, local_rank, dev = _setup_dist()
+    torch.manual_seed(0)
+    precision = args.precision or "bf16"
+    model = pkg.NeRFRegTr(precision=precision)
+    model.load_state_dict(_state(pkg, model))
+    model = model.to(dev).train(True)      # batch-statistics BatchNorm, as eval_nerf_regtr.py runs it
+    strong = args.total_pairs > 0
+    n_pairs = args.total_pairs if strong else args.pairs_per_gpu * world
+    mine = sharding.shard_pairs(n_pairs, rank, world)
+    n_res = min(len(mine), 32)             # resident distinct pairs per rank (cycled beyond that)
+    host = [pkg.synthetic.make_pair(res=RES, pair_id=pid) for pid in mine[:n_res]]
+    pinned = [_pin_pair(p) for p in host]
+    resident = [pkg.synthetic.to_device(p, dev) for p in host]
+    h2d = sum(_pair_bytes(p) for p in pinned) / max(n_res, 1) * len(mine)
+
+    def batch(fetch):
+        local = torch.empty((len(mine), 3, 4), device=dev)
+        with torch.no_grad():
+            for j in range(len(mine)):
+                local[j] = model(fetch(j))["pose"][-1, 0]
+        return sharding.gather_poses(local, n_pairs)           # [n_pairs, 3, 4] on every rank
+
+    def step_resident(_):
+        return batch(lambda j: dict(resident[j % n_res]))
+
+    def step_e2e(_):
+        return batch(lambda j: _h2d_pair(pinned[j % n_res], dev)).cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        model.set_profile(profile)
+        if profile:
+            model.read_profile()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = model.launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        prof = model.read_profile() if profile else None
+        model.set_profile(False)
+        return float(t.item()), model.launch_count() - l0, prof
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, prof = timed(step_resident, args.steps, profile=True)
+    clocks = sampler.summary() if sampler else None
+    step_e2e(0)
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    if rank == 0:
+        peaks = _peaks()
+        total = n_pairs * args.steps
+        ig_ms, ig_flops, ig_n = prof
+        achieved = ig_flops / (ig_ms / 1e3) / 1e12 if ig_ms > 0 else 0.0
+        mma = 3 if precision == "fp32" else 1
+        peak = peaks["bf16_tflops_sustained"]
+        line = {
+            "metric": "nerf_pairs_per_sec_128cube", "value": total / (ms / 1e3), "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "batch %d pairs sharded across %dxB200, 128^3, %s, register forward, one all-gather of SE(3) per batch"
+                                   % (n_pairs, world, "bf16" if precision != "fp32" else "fp32-grade"),
+                       "stage": "batch", "resolution": RES, "pairs_per_step": n_pairs, "pairs_per_step_per_gpu": len(mine),
+                       "distinct_pairs_resident_per_gpu": n_res, "bn_mode": "batch statistics",
+                       "l2": "per-pair working set (2 x 58.7 MB grids, >3 GB activations) exceeds the 126 MB L2",
+                       "parallelism": "sharding.shard_pairs (round robin), no data-path collective, one NCCL all-gather of [%d,3,4] per batch"
+                                      % ((n_pairs + world - 1) // world)},
+            "e2e": {"value": total / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": n_pairs * 48, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv3d/linear), all launches of the timed steps",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": peaks["source"] + ", bf16 sustained", "traffic": None, "launches": int(ig_n),
+                         "kernel_ms_per_step": ig_ms / args.steps, "kernel_share_of_step": ig_ms / ms,
+                         "mma_flops_factor": mma, "tensor_pipe_frac_est": mma * achieved / peak},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(pkg, model, stage, cams):
     """The oracle (port of the reference, bit-identical to it for the register half) timed on the host
     cores: one pair (+ the bounded extract sample for the full path)."""
@@ -520,10 +867,14 @@ def cpu_baseline(pkg, model, stage, cams):
     dt = time.perf_counter() - t0
     sample = "1 pair, 128^3, NeRFRegTr.forward, fp32 torch CPU ops, %d threads, single cold run (%.1f s)" % (cores, dt)
     if stage == "full":
-        one_block, info = cpu_extract_seconds(pkg, cams, ray_sample=200000)
+        one_block, info = cpu_extract_seconds(pkg, cams, ray_sample=100000, like_fraction=0.125)
         dt += 2.0 * one_block
-        sample += ("; + extract of 2 blocks by the oracle port (%.1f s; ray march extrapolated from %d of %d rays)"
-                   % (2.0 * one_block, info["rays_sampled"], info["rays_total"]))
+        lf, ar = info["like_for_like"], info["as_reference"]
+        sample += ("; + extract of 2 blocks by the oracle port (%.1f s): field queries in full, ray march measured on %d of %d "
+                   "candidate cells (%.1f s) and extrapolated by the cell count, marching the rays our arm marches (every "
+                   "ray as the reference marches them: %.0f s per block, extrapolated from %d of %d rays)"
+                   % (2.0 * one_block, lf["cells_sampled"], lf["cells_total"], lf["measured_s"],
+                      ar["block_s_extrapolated"], ar["rays_sampled"], ar["rays_total"]))
     return {"value": 1.0 / dt, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
 
 
@@ -533,15 +884,25 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16"],
+                    help="default: fp32-grade for full / register (configs[1]), bf16 for train / batch (configs[2], [3])")
+    ap.add_argument("--batch", type=int, default=32, help="train: pairs per step per GPU")
+    ap.add_argument("--pairs-per-gpu", type=int, default=32, help="batch: weak scaling, pairs per GPU per step")
+    ap.add_argument("--total-pairs", type=int, default=0, help="batch: strong scaling, total pairs per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--stage", default="full", choices=["full", "register"],
-                    help="full = extract (2 NeRF blocks -> voxel grids) + register; register = NeRFRegTr.forward only")
+    ap.add_argument("--stage", default="full", choices=["full", "register", "train", "batch"],
+                    help="full = extract (2 NeRF blocks -> voxel grids) + register (configs[1], the default); register = "
+                         "NeRFRegTr.forward only; train = configs[2] (fwd + bwd + AdamW); batch = configs[3] (sharded list of pairs)")
     ap.add_argument("--cams", type=int, default=50)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.stage == "train":
+        run_train(args)
+    elif args.stage == "batch":
+        run_batch(args)
     else:
+        args.precision = args.precision or "fp32"
         run_ours(args)
 
 

@@ -168,7 +168,8 @@ SIGNATURES = {
     "drb_hierarchical_downsample_tape": (c_int, [c_void_p, c_int, c_int, c_int, c_int, C.c_double, c_int, c_void_p,
                                                  c_size_t, c_void_p, C.POINTER(c_int), C.POINTER(c_int), c_void_p, c_ll,
                                                  C.POINTER(c_int), C.POINTER(c_int), c_void_p]),
-    "drb_fpn_dilated_tiles": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "drb_fpn_dilated_tiles": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
     "drb_adamw_create": (c_int, [c_int, C.POINTER(c_void_p), C.POINTER(c_ll), C.POINTER(c_void_p)]),
     "drb_adamw_destroy": (None, [c_void_p]),
     "drb_adamw_step": (c_int, [c_void_p, C.POINTER(c_void_p), c_float, c_float, c_float, c_float, c_float, c_float,

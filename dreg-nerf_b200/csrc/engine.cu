@@ -182,8 +182,8 @@ static int build(drb_engine* e) {
     e->tiles_in = e->alloc<int>(nt);
     e->tiles_in2 = e->alloc<int>(nt);
     e->tile_counts = e->alloc<int>(3);
-    e->tile_totals = e->alloc<unsigned long long>(2);
-    cudaMemset(e->tile_totals, 0, 2 * sizeof(unsigned long long));
+    e->tile_totals = e->alloc<unsigned long long>(3);
+    cudaMemset(e->tile_totals, 0, 3 * sizeof(unsigned long long));
     // rows of tiles that are skipped keep whatever they held: start from zeros, not from garbage
     if (e->lat[0].f) cudaMemset(e->lat[0].f, 0, sizeof(float) * e->lat[0].numel());
     if (e->p[0].f) cudaMemset(e->p[0].f, 0, sizeof(float) * e->p[0].numel());
@@ -225,6 +225,11 @@ static int build(drb_engine* e) {
 
 // --------------------------------------------------------------------------------------------
 
+int engine_list_id(const drb_engine* e, const int* tile_list) {
+  if (tile_list == nullptr) return -1;
+  return tile_list == e->tiles_out ? 0 : (tile_list == e->tiles_in ? 1 : 2);
+}
+
 int engine_run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const plane_t* x_lo, int g, int d,
                      int h, int wd, int cin, int k, const float* bias, const float* residual,
                      int relu, float scale, float* out, plane_t* out_hi, plane_t* out_lo, long long ld,
@@ -254,7 +259,7 @@ int engine_run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   r.flops = 2.0 * (double)g * d * h * wd * (double)cd.cout * (double)cin * k * k * k;
-  r.list_id = tile_list == nullptr ? -1 : (tile_list == e->tiles_out ? 0 : 1);
+  r.list_id = engine_list_id(e, tile_list);
   r.flops_per_tile = 2.0 * 128.0 * (double)cd.cout * (double)cin * k * k * k;   // executed work of one listed tile
   cudaEventRecord(r.a, s);
   const int rc = drb_conv3d_igemm(&cd, s);
@@ -607,26 +612,26 @@ extern "C" int drb_engine_set_profile(drb_engine* e, int on) {
 extern "C" int drb_engine_profile_read(drb_engine* e, double* igemm_ms, double* igemm_flops, long long* n) {
   DRB_REQUIRE(e && igemm_ms && igemm_flops && n, "drb_engine_profile_read: null argument");
   double ms = 0.0, fl = 0.0;
-  // output-sparse launches: executed FLOPs = (sum of their tile-list lengths) x FLOPs of one tile
-  unsigned long long totals[2] = {0, 0};
-  double per_tile[2] = {0.0, 0.0};
+  // output-sparse launches: executed FLOPs = FLOPs of one tile x the mean length of the launch's tile list
+  unsigned long long totals[3] = {0, 0, 0};
   DRB_CUDA_OK(cudaDeviceSynchronize());
   if (e->tile_totals) {
     DRB_CUDA_OK(cudaMemcpy(totals, e->tile_totals, sizeof(totals), cudaMemcpyDeviceToHost));
     DRB_CUDA_OK(cudaMemset(e->tile_totals, 0, sizeof(totals)));
   }
+  const double forwards = e->prof_forwards > 0 ? (double)e->prof_forwards : 1.0;
   for (auto& r : e->prof) {
     DRB_CUDA_OK(cudaEventSynchronize(r.b));
     float t = 0.f;
     DRB_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
     ms += t;
-    if (r.list_id >= 0) per_tile[r.list_id] = r.flops_per_tile; else fl += r.flops;
+    if (r.list_id >= 0) fl += r.flops_per_tile * ((double)totals[r.list_id] / forwards); else fl += r.flops;
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
-  fl += (double)totals[0] * per_tile[0] + (double)totals[1] * per_tile[1];
   *igemm_ms = ms; *igemm_flops = fl; *n = (long long)e->prof.size();
   e->prof.clear();
+  e->prof_forwards = 0;
   return 0;
 }
 
@@ -700,6 +705,7 @@ extern "C" int drb_engine_encode(drb_engine* e, const drb_pair_io* io, int* host
     DRB_REQUIRE(e->committed, "drb_engine_encode: parameters not committed after grad mode was switched on");
   }
   e->graph_valid = false;
+  if (e->profile) e->prof_forwards += 1;
   if (e->sparse_fpn) {
     const long long* masks[2] = {io->src_mask, io->tgt_mask};
     const int ks[2] = {io->n_src_mask, io->n_tgt_mask};
@@ -708,7 +714,8 @@ extern "C" int drb_engine_encode(drb_engine* e, const drb_pair_io* io, int* host
                                e->tile_counts, e->profile ? e->tile_totals : nullptr, s));
     if (e->grad_mode) {   // the backward pass of pyramid_transformation_1 reaches one voxel further
       e->launches += 1;
-      DRB_TRY(drb_fpn_dilated_tiles(e->need, kG, p1.d, p1.h, p1.w, 2, e->tiles_in2, e->tile_counts + 2, s));
+      DRB_TRY(drb_fpn_dilated_tiles(e->need, kG, p1.d, p1.h, p1.w, 2, e->tiles_in2, e->tile_counts + 2,
+                                    e->profile ? e->tile_totals + 2 : nullptr, s));
     }
   }
   DRB_TRY(run_fpn(e, io, s));

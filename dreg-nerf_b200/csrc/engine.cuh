@@ -107,6 +107,7 @@ struct drb_engine {
   bool profile = false;
   struct ProfRec { cudaEvent_t a, b; double flops; int list_id; double flops_per_tile; };
   std::vector<ProfRec> prof;
+  long long prof_forwards = 0;      // encode calls since the last profile read (tile-list averages)
   std::string fail;
   int max_tokens = 3000;
 
@@ -138,7 +139,7 @@ struct drb_engine {
   bool sparse_fpn = true;
   uint8_t* need = nullptr;
   int *tiles_out = nullptr, *tiles_in = nullptr, *tiles_in2 = nullptr, *tile_counts = nullptr;   // counts: int[3]
-  unsigned long long* tile_totals = nullptr;   // running sums of the list lengths (profiling)
+  unsigned long long* tile_totals = nullptr;   // running sums of the 3 list lengths (profiling)
   // point stage
   float* rows = nullptr;            // [2*max_mask][260]
   float* rows_ds = nullptr;
@@ -208,6 +209,7 @@ static inline float* GRAD(drb_engine* e, int idx) { return idx >= 0 ? e->params[
 static inline plane_t* off(plane_t* p, long long n) { return p ? p + n : nullptr; }
 
 // engine.cu
+int engine_list_id(const drb_engine* e, const int* tile_list);
 int engine_run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const plane_t* x_lo, int g, int d, int h,
                      int wd, int cin, int k, const float* bias, const float* residual, int relu, float scale,
                      float* out, plane_t* out_hi, plane_t* out_lo, long long ld, cudaStream_t s,

@@ -112,7 +112,18 @@ static int wgrad(drb_engine* e, const ConvW& w, const GradPlanes& dy, const plan
   wd_.c_real = c_real; wd_.taps_real = taps_real;
   wd_.tile_list = tile_list; wd_.tile_count = tile_count;
   e->launches += 1;
-  return drb_conv3d_wgrad(&wd_, s);
+  if (!e->profile) return drb_conv3d_wgrad(&wd_, s);
+  drb_engine::ProfRec r;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  r.flops = 2.0 * (double)g * d * h * wd * (double)cout * (double)cin * k * k * k;
+  r.list_id = engine_list_id(e, tile_list);
+  r.flops_per_tile = 2.0 * 128.0 * (double)cout * (double)cin * k * k * k;
+  cudaEventRecord(r.a, s);
+  const int rc = drb_conv3d_wgrad(&wd_, s);
+  cudaEventRecord(r.b, s);
+  e->prof.push_back(r);
+  return rc;
 }
 
 // Backward of one convolution given its output gradient dy (fp32 [g][od*oh*ow][cout]):

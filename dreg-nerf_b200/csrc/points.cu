@@ -173,7 +173,7 @@ extern "C" int drb_fpn_need_tiles(const long long* const* masks_host, const int*
 // Extra tile list for the backward pass: tiles within `dilate` voxels of a needed voxel (need as left by
 // drb_fpn_need_tiles).  count: device int, zeroed by the call.
 extern "C" int drb_fpn_dilated_tiles(const uint8_t* need, int g, int dc, int hc, int wc, int dilate, int* list,
-                                     int* count, cudaStream_t stream) {
+                                     int* count, unsigned long long* total, cudaStream_t stream) {
   DRB_REQUIRE(need && list && count && g > 0 && dilate >= 0, "drb_fpn_dilated_tiles: bad arguments");
   DRB_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(int), stream));
   int box[4], tiles[4];
@@ -181,7 +181,7 @@ extern "C" int drb_fpn_dilated_tiles(const uint8_t* need, int g, int dc, int hc,
   if (rc) return rc;
   const int nt = tiles[0] * tiles[1] * tiles[2] * tiles[3];
   tile_list_kernel<<<nt, 128, 0, stream>>>(need, g, dc, hc, wc, box[0], box[1], box[2], box[3], tiles[0], tiles[1],
-                                           tiles[2], tiles[3], dilate, list, count, nullptr);
+                                           tiles[2], tiles[3], dilate, list, count, total);
   DRB_LAUNCH_OK();
   return 0;
 }

@@ -170,7 +170,7 @@ int drb_fpn_need_tiles(const long long* const* masks_host, const int* ks_host, i
 /* Tiles within `dilate` voxels of a voxel marked by drb_fpn_need_tiles (backward pass: the data gradient of
  * a 3^3 convolution spreads one voxel per layer).  count: device int, zeroed by the call. */
 int drb_fpn_dilated_tiles(const uint8_t* need, int g, int dc, int hc, int wc, int dilate, int* list, int* count,
-                          drb_stream_t stream);
+                          unsigned long long* total /* optional running total */, drb_stream_t stream);
 
 /* R4: hierarchical voxel-average down-sampling (conerf/register/grid_downsample.py:6-94).
  * rows [n_src + n_tgt][ld] = [x y z 0 | 256 features]; cells of size dl0 * 2^round; rows of one

@@ -137,6 +137,37 @@ def gradient_case():
           % (float(loss), len(grads), worst))
 
 
+def losses_case():
+    """InfoNCELoss fixture from the REFERENCE's own module (conerf/loss/feature_loss.py is importable as is):
+    inputs, loss value and gradients w.r.t. the features and W.  CorrespondenceLoss cannot be imported
+    (robust_loss_pytorch is absent): its fixture is evaluated with the published closed form of Barron's loss at
+    the call site's alpha = 1, scale = 0.5 in float64 - parity with the wheel itself is unpinned."""
+    import_reference()
+    from conerf.loss.feature_loss import InfoNCELoss
+    from conerf.register.se3 import se3_transform_list, se3_inv
+    g = torch.Generator().manual_seed(21)
+    ref = InfoNCELoss(256, 0.2, 0.4)
+    with torch.no_grad():
+        ref.W.copy_(torch.randn(256, 256, generator=g) * 0.1)
+    sf = torch.randn(300, 256, generator=g).requires_grad_(True)
+    tf = torch.randn(280, 256, generator=g).requires_grad_(True)
+    sx, tx = torch.rand(300, 3, generator=g), torch.rand(280, 3, generator=g)
+    loss = ref([sf], [tf], [sx], [tx])
+    gs, gt, gw = torch.autograd.grad(loss, [sf, tf, ref.W])
+    pose = torch.eye(4)[:3][None].clone()
+    pose[0, :, 3] = torch.tensor([0.1, -0.2, 0.3])
+    kp, pred = torch.rand(50, 3, generator=g), torch.rand(50, 3, generator=g)
+    w = torch.rand(6, 50, 1, generator=g)
+    gt_pts = se3_transform_list(pose, [kp])[0].double()
+    err = (torch.sqrt(((pred.double() - gt_pts) / 0.5) ** 2 + 1.0) - 1.0).abs().sum(-1)
+    corr = (w.double() * err).sum() / w.double().sum().clamp_min(1e-6)
+    fix = {"W": ref.W.detach().clone(), "sf": sf.detach(), "tf": tf.detach(), "sx": sx, "tx": tx,
+           "infonce": loss.detach(), "g_sf": gs, "g_tf": gt, "g_W": gw,
+           "pose": pose, "kp": kp, "pred": pred, "w": w, "corr": corr.float(), "pose_inv": se3_inv(pose)}
+    torch.save(fix, os.path.join(GOLDEN, "losses.pt"))
+    print("wrote losses: infonce %.6f corr %.6f" % (float(loss), float(corr)))
+
+
 def extract_case():
     """Extract fixture: a 32^3 block of a seeded random-weight field, evaluated by the (slow, pure
     Python) oracle here so that the GPU box only has to load the result."""
@@ -214,6 +245,9 @@ if __name__ == "__main__":
     if "--gradient-only" in sys.argv:
         gradient_case()
         sys.exit(0)
+    if "--losses-only" in sys.argv:
+        losses_case()
+        sys.exit(0)
     if "--visibility-only" in sys.argv:
         visibility_case()
         sys.exit(0)
@@ -222,3 +256,4 @@ if __name__ == "__main__":
     extract_case()
     visibility_case()
     gradient_case()
+    losses_case()

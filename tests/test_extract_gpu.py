@@ -228,3 +228,36 @@ def test_extract_block_128_against_c_oracle(pkg, cuda, seed):
           "mismatches elsewhere %d (C oracle: %.1f M density samples)"
           % (k, int(act.sum()), int(m_ref.sum()), int((s_band & act).sum()), int(mism.sum()), n_samples / 1e6))
     assert int(mism.sum()) == 0 and int(m_ref.sum()) > 1000
+
+
+def test_marcher_watchdog_raises_instead_of_truncating(pkg, cuda, monkeypatch):
+    """A march cut short by the device-side watchdog must fail the call: force it with a tiny limit."""
+    from importlib import import_module
+    lib_mod = import_module("dreg-nerf_b200._lib")
+    f, _ = _field(pkg, cuda, seed=11, table_std=8.0)
+    res = 64
+    occ, cams = _scene(res)
+    g = torch.Generator().manual_seed(2)
+    pts = (torch.rand(20000, 3, generator=g) * 2.6 - 1.3).to(cuda)
+    roi = [-1.5] * 3 + [1.5] * 3
+    step = 3.0 * math.sqrt(3) / 1024
+    want = pkg.surface_field_mask(f, occ.to(cuda), pts, cams, roi, roi, step)
+    monkeypatch.setenv("DRB_MARCH_WATCHDOG_CLOCKS", "1")
+    with pytest.raises(lib_mod.DrbError, match="watchdog"):
+        pkg.surface_field_mask(f, occ.to(cuda), pts, cams, roi, roi, step)
+    monkeypatch.delenv("DRB_MARCH_WATCHDOG_CLOCKS")
+    again = pkg.surface_field_mask(f, occ.to(cuda), pts, cams, roi, roi, step)     # the flag was cleared
+    assert torch.equal(want, again)
+
+
+def test_cone_angle_is_refused(pkg, cuda):
+    f, _ = _field(pkg, cuda, seed=11, table_std=8.0)
+    occ, cams = _scene(32)
+    sg = pkg.SampleGrid([-1.5] * 3 + [1.5] * 3, 32)
+    sg.set_binary_fields(occ)
+    poses = torch.eye(4).repeat(cams.shape[0], 1, 1)
+    poses[:, :3, 3] = cams
+    meta = {"aabb": [-1.5] * 3 + [1.5] * 3, "render_step_size": 0.01, "cone_angle": 0.004, "alpha_thre": 0.0,
+            "camera_poses": poses}
+    with pytest.raises(NotImplementedError, match="cone_angle"):
+        sg.query_radiance_and_density_from_camera(f, occ, meta, cuda)

@@ -144,3 +144,23 @@ def test_forward_128_train_bn(pkg, cuda):
     assert out["pose"].shape == (6, 1, 3, 4)
     print("tokens", model.last_token_counts, "masked voxels", data["src_mask"].numel(), data["tgt_mask"].numel())
     _check(out, ref)
+
+
+def test_stale_mask_is_rejected(pkg, cuda):
+    """A mask built for another resolution must raise, not corrupt memory."""
+    from importlib import import_module
+    lib_mod = import_module("dreg-nerf_b200._lib")
+    torch.manual_seed(0)
+    model = pkg.NeRFRegTr().to(cuda).eval()
+    good = pkg.synthetic.to_device(pkg.synthetic.make_pair(res=32, pair_id=0), cuda)
+    bad = dict(good)
+    bad["src_mask"] = good["src_mask"].clone()
+    bad["src_mask"][5] = 32 ** 3 + 17
+    with torch.no_grad():
+        with pytest.raises(lib_mod.DrbError, match="mask index"):
+            model(bad)
+        out = model(dict(good))                     # the engine is still usable
+    assert torch.isfinite(out["pose"]).all()
+    bad["src_mask"][5] = -3
+    with torch.no_grad(), pytest.raises(lib_mod.DrbError, match="mask index"):
+        model(bad)

@@ -161,3 +161,28 @@ def test_field_checkpoint_round_trip(tmp_path, pkg):
     torch.save(bad, path)
     with pytest.raises(ValueError):
         pkg.blockio.load_field(path)
+
+
+def test_training_losses_match_reference_fixture(pkg):
+    """InfoNCELoss against the reference's own module (fixture: oracle/make_goldens.py losses_case), value and
+    gradients bit for bit on the CPU; CorrespondenceLoss against the closed form of the robust loss at the call
+    site's alpha = 1, scale = 0.5."""
+    import os
+    import torch
+    fix = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "losses.pt"))
+    nce = pkg.InfoNCELoss(256, 0.2, 0.4)
+    assert list(nce.state_dict().keys()) == ["W"]                     # the reference checkpoint's key
+    nce.load_state_dict({"W": fix["W"]})
+    sf, tf = fix["sf"].clone().requires_grad_(True), fix["tf"].clone().requires_grad_(True)
+    loss = nce([sf], [tf], [fix["sx"]], [fix["tx"]])
+    gs, gt, gw = torch.autograd.grad(loss, [sf, tf, nce.W])
+    assert torch.allclose(loss, fix["infonce"], rtol=1e-6)
+    for got, want in ((gs, fix["g_sf"]), (gt, fix["g_tf"]), (gw, fix["g_W"])):
+        assert (got - want).abs().max() <= 1e-6 * want.abs().max()
+    corr = pkg.CorrespondenceLoss()([fix["kp"]], [fix["pred"]], fix["pose"], overlap_weights=[fix["w"]])
+    assert abs(float(corr) - float(fix["corr"])) < 1e-5 * abs(float(fix["corr"]))
+    assert torch.allclose(pkg.losses.se3_inv(fix["pose"]), fix["pose_inv"])
+    # the reference's broadcast quirk: [num_layers, N, 1] weights against the [N] error -> sum_j err_j
+    ones = pkg.CorrespondenceLoss()([fix["kp"]], [fix["pred"]], fix["pose"], overlap_weights=[torch.ones(6, 50, 1)])
+    direct = pkg.losses.robust_charbonnier(fix["pred"] - pkg.losses.se3_transform_list(fix["pose"], [fix["kp"]])[0])
+    assert abs(float(ones) - float(direct.abs().sum())) < 1e-4
