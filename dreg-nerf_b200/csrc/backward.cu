@@ -78,6 +78,23 @@ __global__ void grad_split_kernel(const float* __restrict__ x, long long rows, i
   }
 }
 
+// contiguous fast path: 4 values per thread
+__global__ void grad_split4_kernel(const float* __restrict__ x, long long n4, const unsigned int* __restrict__ slot_bits,
+                                   float* __restrict__ inv_scale_out, plane_t* __restrict__ hi, plane_t* __restrict__ lo) {
+  const bool pair = lo != nullptr;
+  const float scale = (pair && slot_bits) ? pow2_scale_for(*slot_bits) : 1.f;
+  if (inv_scale_out && blockIdx.x == 0 && threadIdx.x == 0) *inv_scale_out = 1.f / scale;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = *(const float4*)(x + i * 4);
+    plane_t h0, l0, h1, l1, h2, l2, h3, l3;
+    split16(v.x * scale, pair, h0, l0); split16(v.y * scale, pair, h1, l1);
+    split16(v.z * scale, pair, h2, l2); split16(v.w * scale, pair, h3, l3);
+    *(uint2*)(hi + i * 4) = make_uint2(pack16x2(h0, h1), pack16x2(h2, h3));
+    if (pair) *(uint2*)(lo + i * 4) = make_uint2(pack16x2(l0, l1), pack16x2(l2, l3));
+  }
+}
+
 extern "C" int drb_grad_split(const float* x, long long rows, int cols, long long ld_in, long long ld_out,
                               void* hi, void* lo, float* slot, cudaStream_t stream) {
   DRB_REQUIRE(x && hi && slot && rows >= 0 && cols > 0 && ld_in >= cols && ld_out >= cols,
@@ -90,6 +107,12 @@ extern "C" int drb_grad_split(const float* x, long long rows, int cols, long lon
     const long long span = (rows - 1) * ld_in + cols;
     grad_absmax_kernel<<<grid_for(span / 4 + 1, 256, 148 * 8), 256, 0, stream>>>(x, span, bits);
     DRB_LAUNCH_OK();
+  }
+  if (ld_in == cols && ld_out == cols && (rows * cols) % 4 == 0) {
+    grad_split4_kernel<<<grid_for(rows * cols / 4, 256, 148 * 16), 256, 0, stream>>>(
+        x, rows * cols / 4, lo ? bits : nullptr, slot + 1, (plane_t*)hi, (plane_t*)lo);
+    DRB_LAUNCH_OK();
+    return 0;
   }
   grad_split_kernel<<<grid_for(rows * ld_out, 256, 148 * 32), 256, 0, stream>>>(
       x, rows, cols, ld_in, ld_out, lo ? bits : nullptr, slot + 1, (plane_t*)hi, (plane_t*)lo);
@@ -131,26 +154,43 @@ extern "C" int drb_relu_mask_plane(float* dy, const void* hi, long long n, cudaS
   return 0;
 }
 
-// out[c] += sum over rows of x[r][c]  (bias gradients).  Block = 64 channels x 4 row lanes.
-__global__ void colsum_kernel(const float* __restrict__ x, long long rows, int c, long long ld,
-                              int rows_per_block, float* __restrict__ out) {
-  const int c0 = blockIdx.y * 64;
-  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
-  const int ch = c0 + cl;
+// out[c] += sum over rows of x[r][c]  (bias gradients).  Block = 16 channel groups (float4) x 16 row lanes.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long rows, int c, long long ld,
+                                                      int rows_per_block, float* __restrict__ out) {
+  const int cg = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int ch = blockIdx.y * 64 + cg * 4;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
-  double s = 0.0;
-  if (ch < c)
-    for (long long r = r0 + rl; r < r1; r += 4) s += (double)x[r * ld + ch];
-  __shared__ double sh[4][64];
-  sh[rl][cl] = s;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ch + 3 < c) {
+#pragma unroll 4
+    for (long long r = r0 + rl; r < r1; r += 16) {
+      const float4 v = *(const float4*)(x + r * ld + ch);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+  } else {
+    for (int j = 0; j < 4; ++j)
+      if (ch + j < c)
+        for (long long r = r0 + rl; r < r1; r += 16) s[j] += x[r * ld + ch + j];
+  }
+  __shared__ float sh[16][64];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sh[rl][cg * 4 + j] = s[j];
   __syncthreads();
-  if (rl == 0 && ch < c) atomicAdd(out + ch, (float)(sh[0][cl] + sh[1][cl] + sh[2][cl] + sh[3][cl]));
+  if (threadIdx.x < 64) {
+    const int cc = blockIdx.y * 64 + threadIdx.x;
+    if (cc < c) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t += (double)sh[k][threadIdx.x];
+      atomicAdd(out + cc, (float)t);
+    }
+  }
 }
 extern "C" int drb_colsum_add(const float* x, long long rows, int c, long long ld, float* out,
                               cudaStream_t stream) {
-  DRB_REQUIRE(x && out && c > 0 && ld >= c, "drb_colsum_add: bad arguments");
+  DRB_REQUIRE(x && out && c > 0 && ld >= c && ld % 4 == 0, "drb_colsum_add: bad arguments");
   if (rows == 0) return 0;
   int rpb = 256;
   while ((rows + rpb - 1) / rpb > 2048) rpb *= 2;
@@ -162,112 +202,143 @@ extern "C" int drb_colsum_add(const float* x, long long rows, int c, long long l
 
 // ------------------------------------------------------------------------------------------
 // BatchNorm3d backward.  raw = the convolution output the forward normalised, [g][m][c].
-//   pass 1 (reduce): optional ReLU mask applied to dy IN PLACE (post > 0 when the forward kept the
-//           activation in fp32, else sign of fma(raw, scale, shift) - the forward's own expression),
-//           then S1 = sum dy, S2 = sum dy * xhat per (g, c) in double.
+//   pass 1 (reduce): S1 = sum dy, S2 = sum dy * xhat per (g, c) over the ReLU-masked dy (mask: post > 0 when the
+//           forward kept the activation in fp32, else sign of fma(raw, scale, shift) - the forward's own
+//           expression); read only.
 //   pass 2 (apply):  batch statistics:  dx = gamma rstd (dy - S1/m - xhat S2/m)
 //                    running statistics: dx = gamma rstd dy
 //           dgamma += sum_g S2, dbeta += sum_g S1.
 // ------------------------------------------------------------------------------------------
-__global__ void bn_bwd_reduce_kernel(float* __restrict__ dy, const float* __restrict__ raw,
-                                     const float* __restrict__ post, const float* __restrict__ scale,
-                                     const float* __restrict__ shift, const float* __restrict__ mean,
-                                     const float* __restrict__ rstd, int relu, long long m, int c,
-                                     int rows_per_block, double* __restrict__ sums) {
+// Block = 16 channel groups (float4 = 4 channels each: 64 channels) x 16 row lanes.  The reduce pass only reads
+// (the mask is recomputed by the apply pass): per-thread fp32 partials over <= 64 rows, fp64 across the block.
+__device__ __forceinline__ float4 bn_mask4(float4 d, float4 x, const float* __restrict__ post4, float4 sc, float4 sf,
+                                           int relu) {
+  if (!relu) return d;
+  if (post4) {
+    const float4 p = *(const float4*)post4;
+    d.x = p.x > 0.f ? d.x : 0.f; d.y = p.y > 0.f ? d.y : 0.f; d.z = p.z > 0.f ? d.z : 0.f; d.w = p.w > 0.f ? d.w : 0.f;
+  } else {
+    d.x = fmaf(x.x, sc.x, sf.x) > 0.f ? d.x : 0.f; d.y = fmaf(x.y, sc.y, sf.y) > 0.f ? d.y : 0.f;
+    d.z = fmaf(x.z, sc.z, sf.z) > 0.f ? d.z : 0.f; d.w = fmaf(x.w, sc.w, sf.w) > 0.f ? d.w : 0.f;
+  }
+  return d;
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ raw, const float* __restrict__ post,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, int relu, long long m, int c,
+                     int rows_per_block, double* __restrict__ sums) {
   const int g = blockIdx.z;
-  const int c0 = blockIdx.y * 64;
-  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
-  const int ch = c0 + cl;
+  const int cg = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int ch = blockIdx.y * 64 + cg * 4;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > m) r1 = m;
-  double s1 = 0.0, s2 = 0.0;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   if (ch < c) {
     const long long gc = (long long)g * c + ch;
-    const float mu = mean[gc], rs = rstd[gc];
-    const float sc = scale ? scale[gc] : 0.f, sf = shift ? shift[gc] : 0.f;
+    const float4 mu = *(const float4*)(mean + gc), rs = *(const float4*)(rstd + gc);
+    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sf = sc;
+    if (scale) { sc = *(const float4*)(scale + gc); sf = *(const float4*)(shift + gc); }
     const long long base = ((long long)g * m) * c + ch;
-    for (long long r = r0 + rl; r < r1; r += 4) {
+#pragma unroll 4
+    for (long long r = r0 + rl; r < r1; r += 16) {
       const long long i = base + r * c;
-      float d = dy[i];
-      const float x = raw[i];
-      if (relu) {
-        const bool on = post ? (post[i] > 0.f) : (fmaf(x, sc, sf) > 0.f);
-        if (!on) { d = 0.f; dy[i] = 0.f; }
-      }
-      s1 += (double)d;
-      s2 += (double)d * (double)((x - mu) * rs);
+      const float4 x = *(const float4*)(raw + i);
+      const float4 d = bn_mask4(*(const float4*)(dy + i), x, post ? post + i : nullptr, sc, sf, relu);
+      s1[0] += d.x; s1[1] += d.y; s1[2] += d.z; s1[3] += d.w;
+      s2[0] = fmaf(d.x, (x.x - mu.x) * rs.x, s2[0]); s2[1] = fmaf(d.y, (x.y - mu.y) * rs.y, s2[1]);
+      s2[2] = fmaf(d.z, (x.z - mu.z) * rs.z, s2[2]); s2[3] = fmaf(d.w, (x.w - mu.w) * rs.w, s2[3]);
     }
   }
-  __shared__ double sh[2][4][64];
-  sh[0][rl][cl] = s1;
-  sh[1][rl][cl] = s2;
+  __shared__ float sh[2][16][64];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sh[0][rl][cg * 4 + j] = s1[j]; sh[1][rl][cg * 4 + j] = s2[j]; }
   __syncthreads();
-  if (rl == 0 && ch < c) {
-    s1 = sh[0][0][cl] + sh[0][1][cl] + sh[0][2][cl] + sh[0][3][cl];
-    s2 = sh[1][0][cl] + sh[1][1][cl] + sh[1][2][cl] + sh[1][3][cl];
-    atomicAdd(&sums[((long long)g * c + ch) * 2 + 0], s1);
-    atomicAdd(&sums[((long long)g * c + ch) * 2 + 1], s2);
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, cl = threadIdx.x & 63;
+    const int cc = blockIdx.y * 64 + cl;
+    if (cc < c) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t += (double)sh[which][k][cl];
+      atomicAdd(&sums[((long long)g * c + cc) * 2 + which], t);
+    }
   }
 }
 
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ raw,
-                                    const double* __restrict__ sums, const float* __restrict__ gamma,
-                                    const float* __restrict__ mean, const float* __restrict__ rstd,
-                                    int training, int g_total, long long m, int c, int rows_per_block,
-                                    float* __restrict__ dx, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta) {
+// dx = A dy_masked + B raw + C; optionally writes the masked dy back (the residual branch's gradient).
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* dy, const float* __restrict__ raw, const float* __restrict__ post,
+                    const float* __restrict__ scale, const float* __restrict__ shift, const double* __restrict__ sums,
+                    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    int relu, int training, int g_total, long long m, int c, int rows_per_block, float* dy_masked_out,
+                    float* dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int g = blockIdx.z;
-  const int c0 = blockIdx.y * 64;
-  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
-  const int ch = c0 + cl;
+  const int cg = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int ch = blockIdx.y * 64 + cg * 4;
   if (ch >= c) return;
   const long long gc = (long long)g * c + ch;
-  const float ga = gamma ? gamma[ch] : 1.f;
-  const float mu = mean[gc], rs = rstd[gc];
-  const double S1 = sums[gc * 2], S2 = sums[gc * 2 + 1];
-  // dx = A dy + B raw + C
-  const float A = ga * rs;
-  float B = 0.f, C = 0.f;
-  if (training) {
-    const double inv_m = 1.0 / (double)m;
-    B = (float)(-(double)ga * (double)rs * (double)rs * S2 * inv_m);
-    C = (float)(-(double)ga * (double)rs * S1 * inv_m + (double)ga * (double)rs * (double)rs * (double)mu * S2 * inv_m);
-  }
-  if (blockIdx.x == 0 && g == 0 && rl == 0) {
-    double t1 = 0.0, t2 = 0.0;
-    for (int gi = 0; gi < g_total; ++gi) {
-      t1 += sums[((long long)gi * c + ch) * 2];
-      t2 += sums[((long long)gi * c + ch) * 2 + 1];
+  float A[4], B[4], C[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float ga = gamma ? gamma[ch + j] : 1.f;
+    const float mu = mean[gc + j], rs = rstd[gc + j];
+    const double S1 = sums[(gc + j) * 2], S2 = sums[(gc + j) * 2 + 1];
+    A[j] = ga * rs; B[j] = 0.f; C[j] = 0.f;
+    if (training) {
+      const double inv_m = 1.0 / (double)m;
+      B[j] = (float)(-(double)ga * (double)rs * (double)rs * S2 * inv_m);
+      C[j] = (float)(-(double)ga * (double)rs * S1 * inv_m + (double)ga * (double)rs * (double)rs * (double)mu * S2 * inv_m);
     }
-    if (dbeta) dbeta[ch] += (float)t1;
-    if (dgamma) dgamma[ch] += (float)t2;
+    if (blockIdx.x == 0 && g == 0 && rl == 0) {
+      double t1 = 0.0, t2 = 0.0;
+      for (int gi = 0; gi < g_total; ++gi) {
+        t1 += sums[((long long)gi * c + ch + j) * 2];
+        t2 += sums[((long long)gi * c + ch + j) * 2 + 1];
+      }
+      if (dbeta) dbeta[ch + j] += (float)t1;
+      if (dgamma) dgamma[ch + j] += (float)t2;
+    }
   }
+  float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sf = sc;
+  if (scale) { sc = *(const float4*)(scale + gc); sf = *(const float4*)(shift + gc); }
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > m) r1 = m;
   const long long base = ((long long)g * m) * c + ch;
-  for (long long r = r0 + rl; r < r1; r += 4) {
+#pragma unroll 4
+  for (long long r = r0 + rl; r < r1; r += 16) {
     const long long i = base + r * c;
-    dx[i] = fmaf(A, dy[i], fmaf(B, raw[i], C));
+    const float4 x = *(const float4*)(raw + i);
+    const float4 d = bn_mask4(*(const float4*)(dy + i), x, post ? post + i : nullptr, sc, sf, relu);
+    if (dy_masked_out) *(float4*)(dy_masked_out + i) = d;
+    float4 o;
+    o.x = fmaf(A[0], d.x, fmaf(B[0], x.x, C[0])); o.y = fmaf(A[1], d.y, fmaf(B[1], x.y, C[1]));
+    o.z = fmaf(A[2], d.z, fmaf(B[2], x.z, C[2])); o.w = fmaf(A[3], d.w, fmaf(B[3], x.w, C[3]));
+    *(float4*)(dx + i) = o;
   }
 }
 
-// dy is masked in place when relu != 0; dx may alias dy.  sums: [g][c][2] doubles of scratch.
+// dy is masked in place when relu != 0 and dx != dy (the masked gradient is what a residual branch receives);
+// dx may alias dy.  sums: [g][c][2] doubles of scratch.  c must be a multiple of 4.
 extern "C" int drb_bn_backward(float* dy, const float* raw, const float* post, const float* scale,
                                const float* shift, const float* mean, const float* rstd, const float* gamma,
                                int relu, int training, int g, long long m, int c, double* sums, float* dx,
                                float* dgamma, float* dbeta, cudaStream_t stream) {
-  DRB_REQUIRE(dy && raw && mean && rstd && sums && dx && g > 0 && m > 0 && c > 0, "drb_bn_backward: bad arguments");
+  DRB_REQUIRE(dy && raw && mean && rstd && sums && dx && g > 0 && m > 0 && c > 0 && c % 4 == 0,
+              "drb_bn_backward: bad arguments");
   DRB_REQUIRE(!relu || post || (scale && shift), "drb_bn_backward: ReLU mask needs post or scale/shift");
   DRB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)g * c, stream));
   int rpb = 256;
-  while ((m + rpb - 1) / rpb > 4096) rpb *= 2;
+  while ((m + rpb - 1) / rpb > 2048) rpb *= 2;
   dim3 grid((unsigned)((m + rpb - 1) / rpb), (unsigned)((c + 63) / 64), (unsigned)g);
   bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(dy, raw, post, scale, shift, mean, rstd, relu, m, c, rpb, sums);
   DRB_LAUNCH_OK();
-  bn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(dy, raw, sums, gamma, mean, rstd, training, g, m, c, rpb, dx,
-                                                dgamma, dbeta);
+  float* masked_out = (relu && dx != dy) ? dy : nullptr;
+  bn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(dy, raw, post, scale, shift, sums, gamma, mean, rstd, relu, training, g,
+                                                m, c, rpb, masked_out, dx, dgamma, dbeta);
   DRB_LAUNCH_OK();
   return 0;
 }

@@ -12,6 +12,7 @@
 // L2 (the whole 48 MB table is L2 resident on B200) with 64-bit gathers; MLP weights live in
 // shared memory and are read as warp-uniform broadcasts.
 #include "common.cuh"
+#include "march_math.h"
 
 #include <cub/cub.cuh>
 #include <math.h>
@@ -929,6 +930,7 @@ struct MarchAux {
   const uint32_t* coarse;   // global copy of the coarse bitmap
   int coarse_shift, coarse_dim, coarse_words;
   float roi_rcp[3];         // RN(1 / roi extent)
+  float res_rcp;            // RN(1 / res)
 };
 
 // correctly rounded a / b given y = RN(1 / b) (no overflow / underflow in this range)
@@ -1001,8 +1003,6 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
   const int n_act = active_count ? *active_count : n;
   const unsigned long long total = (unsigned long long)n_act * (unsigned long long)ncams;
   const int kMaxSkips = a.max_skips;
-  const bool pow2_res = (a.res & (a.res - 1)) == 0;
-  const float inv_res = 1.f / (float)a.res;
   const float roi_ext[3] = {a.roi_max[0] - a.roi_min[0], a.roi_max[1] - a.roi_min[1], a.roi_max[2] - a.roi_min[2]};
 
   RayState ray;
@@ -1091,31 +1091,15 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
       if (!have && rank < take) {
         const uint32_t pc = l_cand[n_cand - take + rank];
         const int pi = (int)(pc & ((1u << kPiBits) - 1u)), ci = (int)(pc >> kPiBits);
-        float len = 0.f;
+        float pt[3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          ray.o[d] = s_cams[ci * 3 + d];
-          ray.dir[d] = points[pi * 3 + d] - ray.o[d];
-          len += ray.dir[d] * ray.dir[d];
-        }
-        len = sqrtf(len);
-        if (len > 0.f) {
-#pragma unroll
-          for (int d = 0; d < 3; ++d) { ray.dir[d] = ray.dir[d] / len; ray.inv[d] = 1.f / ray.dir[d]; }
-          // ray / scene AABB intersection -> t_min (nerfacc ray_aabb_intersect); t_max = |p - o|
-          float tn = -1e30f, tf = 1e30f;
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            float ta = (a.scene_min[d] - ray.o[d]) * ray.inv[d], tb = (a.scene_max[d] - ray.o[d]) * ray.inv[d];
-            if (ta > tb) { const float tmp = ta; ta = tb; tb = tmp; }
-            tn = fmaxf(tn, ta); tf = fminf(tf, tb);
-          }
-          if (!(tn > tf)) {                             // else the ray misses the box
-            ray.len = len; ray.pi = pi; ray.ci = ci;
-            ray.t0 = fmaxf(tn, 0.f); ray.t1 = ray.t0 + a.step; ray.tm = 0.5f * (ray.t0 + ray.t1);
-            ray.T = 1.f; ray.best = 0.f;
-            started = true;
-          }
+        for (int d = 0; d < 3; ++d) { ray.o[d] = s_cams[ci * 3 + d]; pt[d] = points[pi * 3 + d]; }
+        // unit direction, scene-box clip (nerfacc ray_aabb_intersect), t_max = |p - o|, first interval: march_math.h
+        if (drb_ray_begin(ray.o, pt, a.scene_min, a.scene_max, a.step, ray.dir, ray.inv, &ray.len, &ray.t0, &ray.t1,
+                          &ray.tm)) {
+          ray.pi = pi; ray.ci = ci;
+          ray.T = 1.f; ray.best = 0.f;
+          started = true;
         }
       }
       n_cand -= take;
@@ -1131,20 +1115,10 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
     // occupancy of the cell that contains o + tm * dir; u = (x - roi_min) / extent (IEEE division, as
     // nerfacc's roi_to_unit) is handed back for the distance-to-next-voxel rule
     auto occupied_at = [&](float tm, float (&u)[3]) -> bool {
-      bool in_roi = true;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float x = fmaf(tm, ray.dir[d], ray.o[d]);
-        u[d] = div_rn_rcp(x - a.roi_min[d], roi_ext[d], aux.roi_rcp[d]);
-        in_roi = in_roi && (u[d] >= 0.f) && (u[d] < 1.f);
-      }
-      if (!in_roi) return false;
+      float x[3];
       int idx[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const int i = (int)(u[d] * (float)a.res);
-        idx[d] = i < 0 ? 0 : (i > a.res - 1 ? a.res - 1 : i);
-      }
+      drb_sample_pos(tm, ray.dir, ray.o, x);
+      if (!drb_voxel_of(x, a.roi_min, roi_ext, aux.roi_rcp, a.res, u, idx)) return false;
       const int cb = ((idx[0] >> aux.coarse_shift) * aux.coarse_dim + (idx[1] >> aux.coarse_shift)) *
                          aux.coarse_dim + (idx[2] >> aux.coarse_shift);
       if (!((s_coarse[cb >> 5] >> (cb & 31)) & 1u)) return false;
@@ -1159,19 +1133,7 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
         float u[3];
         if (occupied_at(ray.tm, u)) { pending = true; break; }
         --budget;
-        // res is a power of two in practice, where "/ res" is an exact scaling
-        float dist = 1e30f;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const float ur = u[d] * (float)a.res;
-          const float sgn = ray.dir[d] > 0.f ? 1.f : (ray.dir[d] < 0.f ? -1.f : 0.f);
-          float td = (floorf(ur + 0.5f + 0.5f * sgn) - ur) * ray.inv[d];
-          td = pow2_res ? td * inv_res : __fdiv_rn(td, (float)a.res);
-          dist = fminf(dist, td * roi_ext[d]);
-        }
-        const float tt = ray.tm + fmaxf(dist, 0.f);
-        do { ray.tm += a.step; } while (ray.tm < tt);
-        ray.t0 = ray.tm - 0.5f * a.step; ray.t1 = ray.tm + 0.5f * a.step;
+        drb_skip_empty(u, ray.dir, ray.inv, a.res, aux.res_rcp, roi_ext, a.step, &ray.t0, &ray.t1, &ray.tm);
         ++st_skips;
       }
       if (pending && kSpec > 1) {
@@ -1181,11 +1143,9 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
         // terminates first.  They are evaluated in the same batch: consecutive samples of one ray are
         // 1 step apart and share table sectors (the density phase is bound by distinct sectors per
         // load instruction), at the price of a few wasted samples when a ray terminates early.
-        float t1s = ray.t1;
+        float t0s = ray.t0, t1s = ray.t1, tms = ray.tm;
         for (int j = 1; j < kSpec; ++j) {
-          const float t0s = t1s;
-          t1s = t0s + a.step;
-          const float tms = 0.5f * (t0s + t1s);
+          drb_chain_next(a.step, &t0s, &t1s, &tms);
           float u[3];
           if (!(tms < ray.len) || !occupied_at(tms, u)) break;
           ++nspec;
@@ -1225,11 +1185,11 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
         const int ci = (int)(__float_as_uint(slots[9 * kSlots + s]) >> kPiBits);
         // sample bj of the chain: the stored (t0, t1, tm) for bj = 0, then t0 = t1, t1 = t0 + step
         float t0 = slots[4 * kSlots + s], t1 = slots[5 * kSlots + s], tm = slots[6 * kSlots + s];
-        for (int jj = 0; jj < bj; ++jj) { t0 = t1; t1 = t0 + a.step; tm = 0.5f * (t0 + t1); }
+        for (int jj = 0; jj < bj; ++jj) drb_chain_next(a.step, &t0, &t1, &tm);
         dt = t1 - t0;
+        const float sdir[3] = {slots[0 * kSlots + s], slots[1 * kSlots + s], slots[2 * kSlots + s]};
         float x[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) x[d] = fmaf(tm, slots[d * kSlots + s], s_cams[ci * 3 + d]);
+        drb_sample_pos(tm, sdir, &s_cams[ci * 3], x);
         float xt[3];
         inside = normalise(p, x, xt);
         if (inside) { xn[0] = xt[0]; xn[1] = xt[1]; xn[2] = xt[2]; }
@@ -1237,7 +1197,7 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
       }
       const float raw = warp_density_raw(p, s_lvl, mlp, xn, lane);
       const float sigma = (valid && inside) ? expf(raw - 1.f) : 0.f;
-      const float alpha_mine = 1.f - expf(-sigma * dt);
+      const float alpha_mine = drb_alpha(sigma, dt);
       float alphas[kSpec];
 #pragma unroll
       for (int jj = 0; jj < kSpec; ++jj) alphas[jj] = __shfl_sync(0xffffffffu, alpha_mine, (lane & ~(kSpec - 1)) + jj);
@@ -1251,19 +1211,13 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
 #pragma unroll
         for (int jj = 0; jj < kSpec; ++jj) {
           if (jj < ns && !done) {
-            const float alpha = alphas[jj];
-            if (T < 1e-4f) {                         // samples past early_stop_eps are dropped (:209)
+            const int verdict = drb_accumulate(alphas[jj], a.cut_off, &T, &best);    // march_math.h
+            if (verdict == 1) surface[pi] = 1;
+            if (verdict != 0) {
               done = true;
-            } else {
-              best = fmaxf(best, alpha * T);
-              if (best >= a.cut_off) {
-                surface[pi] = 1;
-                done = true;
-              } else {
-                T *= 1.f - alpha;
-                // exact early out: every later sample contributes alpha * T' <= T' <= T < cut_off
-                if (T < a.cut_off || surface[pi]) done = true;
-              }
+            } else if (T < a.cut_off || surface[pi]) {
+              // exact early out: every later sample contributes alpha * T' <= T' <= T < cut_off
+              done = true;
             }
             if (!done) { t0 = t1; t1 = t0 + a.step; }
           }
@@ -1376,7 +1330,7 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
               "drb_surface_mask: at most %d points and %d cameras per call", (1 << kPiBits) - 1, kMaxCams);
   const size_t smem = march_smem_bytes(ncams);
   DRB_REQUIRE(smem <= 232448, "drb_surface_mask: %d cameras do not fit the shared-memory plan", ncams);
-  DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  DRB_CUDA_OK(cudaFuncSetAttribute(surface_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MarchAux aux;
   aux.coarse_shift = 0;
   while (((res + (1 << aux.coarse_shift) - 1) >> aux.coarse_shift) > kCoarseMaxDim) ++aux.coarse_shift;
@@ -1391,6 +1345,7 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
     DRB_REQUIRE((bits & 0x7fffffu) != 0x7fffffu, "drb_surface_mask: unsupported ROI extent");
     aux.roi_rcp[d] = (float)(1.0 / (double)ext);
   }
+  aux.res_rcp = (float)(1.0 / (double)res);
   // scratch: ray counter, active count, the active points in Morton order (rays of neighbouring points
   // run together in one warp), coarse occupancy bitmap, CUB temporaries
   keep_async_pool();

@@ -13,6 +13,8 @@
  */
 #include <math.h>
 #include <stdint.h>
+
+#include "march_math.h"   /* dreg-nerf_b200/csrc: the per-ray arithmetic shared with the CUDA kernel */
 #include <stdlib.h>
 #include <string.h>
 
@@ -106,61 +108,28 @@ void orc_density(const float* table, const float* w1, const float* w2, const flo
   for (int i = 0; i < n; ++i) out[i] = density_at(&f, x + 3 * (size_t)i);
 }
 
-static int occupied(const uint8_t* occ, int res, const float roi[6], const float x[3], float u[3]) {
-  int in = 1;
-  for (int d = 0; d < 3; ++d) {
-    u[d] = (x[d] - roi[d]) / (roi[3 + d] - roi[d]);
-    in = in && (u[d] >= 0.f) && (u[d] < 1.f);
-  }
-  if (!in) return 0;
-  int idx[3];
-  for (int d = 0; d < 3; ++d) {
-    int i = (int)(u[d] * (float)res);
-    idx[d] = i < 0 ? 0 : (i > res - 1 ? res - 1 : i);
-  }
-  return occ[((size_t)idx[0] * res + idx[1]) * res + idx[2]] != 0;
-}
-
-/* One ray camera -> point: returns the largest alpha * T reached (early exit at cut_off), counts samples. */
+/* One ray camera -> point: returns the largest alpha * T reached (early exit at cut_off), counts samples.
+ * Every arithmetic step is a function of dreg-nerf_b200/csrc/march_math.h, the header the CUDA kernel compiles
+ * too: positions, skips and the transmittance recurrence are bit-identical by construction. */
 static float march(const field_t* f, const uint8_t* occ, int res, const float roi[6], const float scene[6],
                    const float o[3], const float p[3], float step, float cut_off, long long* samples) {
-  float dir[3], inv[3], len = 0.f;
-  for (int d = 0; d < 3; ++d) { dir[d] = p[d] - o[d]; len += dir[d] * dir[d]; }
-  len = sqrtf(len);
-  if (!(len > 0.f)) return 0.f;
-  for (int d = 0; d < 3; ++d) { dir[d] = dir[d] / len; inv[d] = 1.f / dir[d]; }
-  float tn = -1e30f, tf = 1e30f;
-  for (int d = 0; d < 3; ++d) {
-    float ta = (scene[d] - o[d]) * inv[d], tb = (scene[3 + d] - o[d]) * inv[d];
-    if (ta > tb) { const float t = ta; ta = tb; tb = t; }
-    tn = fmaxf(tn, ta); tf = fminf(tf, tb);
-  }
-  if (tn > tf) return 0.f;
-  float t0 = fmaxf(tn, 0.f), t1 = t0 + step, tm = 0.5f * (t0 + t1);
+  float dir[3], inv[3], len, t0, t1, tm;
+  const float roi_ext[3] = {roi[3] - roi[0], roi[4] - roi[1], roi[5] - roi[2]};
+  const float roi_rcp[3] = {0.f, 0.f, 0.f};     /* unused on the host: drb_div divides */
+  if (!drb_ray_begin(o, p, scene, scene + 3, step, dir, inv, &len, &t0, &t1, &tm)) return 0.f;
   float T = 1.f, best = 0.f;
   while (tm < len) {
     float x[3], u[3];
-    for (int d = 0; d < 3; ++d) x[d] = fmaf(tm, dir[d], o[d]);
-    if (occupied(occ, res, roi, x, u)) {
+    int idx[3];
+    drb_sample_pos(tm, dir, o, x);
+    if (drb_voxel_of(x, roi, roi_ext, roi_rcp, res, u, idx) && occ[((size_t)idx[0] * res + idx[1]) * res + idx[2]] != 0) {
       const float sigma = density_at(f, x);
-      const float alpha = 1.f - expf(-sigma * (t1 - t0));
+      const float alpha = drb_alpha(sigma, t1 - t0);
       ++*samples;
-      if (T < 1e-4f) break;                       /* early_stop_eps, nerfacc_utils.py:209 */
-      best = fmaxf(best, alpha * T);
-      if (best >= cut_off) break;
-      T *= 1.f - alpha;
-      t0 = t1; t1 = t0 + step; tm = 0.5f * (t0 + t1);
+      if (drb_accumulate(alpha, cut_off, &T, &best)) break;
+      drb_chain_next(step, &t0, &t1, &tm);
     } else {
-      float dist = 1e30f;
-      for (int d = 0; d < 3; ++d) {
-        const float ur = u[d] * (float)res;
-        const float sgn = dir[d] > 0.f ? 1.f : (dir[d] < 0.f ? -1.f : 0.f);
-        const float td = (floorf(ur + 0.5f + 0.5f * sgn) - ur) * inv[d] / (float)res * (roi[3 + d] - roi[d]);
-        dist = fminf(dist, td);
-      }
-      const float tt = tm + fmaxf(dist, 0.f);
-      do { tm += step; } while (tm < tt);
-      t0 = tm - 0.5f * step; t1 = tm + 0.5f * step;
+      drb_skip_empty(u, dir, inv, res, 0.f, roi_ext, step, &t0, &t1, &tm);
     }
   }
   return best;
