@@ -625,17 +625,12 @@ def run_train(args):
         (loss / B).backward()
         return loss.detach()
 
+    from importlib import import_module
+    sharding = import_module("dreg-nerf_b200.sharding")
+
     def grads_allreduce():
-        # data-parallel training: gradients averaged over ranks, one flat bucket per dtype
-        if world > 1:
-            gs = [p.grad for p in params if p.grad is not None]
-            flat = torch.cat([g.reshape(-1) for g in gs])
-            dist.all_reduce(flat)
-            flat /= world
-            o = 0
-            for g in gs:
-                g.copy_(flat[o:o + g.numel()].view_as(g))
-                o += g.numel()
+        # data-parallel training: gradients averaged over ranks, one flat all-reduce per step
+        sharding.allreduce_gradients(params, world)
 
     def step_resident(i):
         opt.zero_grad(set_to_none=True)

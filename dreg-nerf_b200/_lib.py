@@ -115,6 +115,12 @@ SIGNATURES = {
                                  c_void_p]),
     "drb_mha_core": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float,
                              c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "drb_mha_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "drb_mha_tc_pack": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                c_size_t, c_void_p]),
+    "drb_mha_tc_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_int, c_void_p]),
+    "drb_engine_set_tc_attention": (c_int, [c_void_p, c_int]),
     "drb_softmax_weighted_xyz": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "drb_overlap_sigmoid": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "drb_procrustes": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int,

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdregb200.so")
-SOURCES = ["igemm.cu", "wgrad.cu", "elementwise.cu", "backward.cu", "points.cu", "transformer.cu",
+SOURCES = ["igemm.cu", "wgrad.cu", "elementwise.cu", "backward.cu", "points.cu", "transformer.cu", "attention.cu",
            "procrustes.cu", "ngp.cu", "engine.cu", "engine_bwd.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]

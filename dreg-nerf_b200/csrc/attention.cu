@@ -1,0 +1,364 @@
+// Multi-head attention core (head dim 32) as a FlashAttention-style tcgen05 kernel: replaces the bmm -> softmax ->
+// bmm of nn.MultiheadAttention inside TransformerCrossEncoderLayer.forward_pre
+// (conerf/register/transformer.py:225-299) for self- and cross-attention.
+//
+//   pack   : q / k / v fp32 rows [n][ld] -> 16-bit planes per head: Q' = q * scale * log2(e) and K as
+//            [head][token][64] (head dim zero-padded to one 128-byte swizzle row), V transposed as
+//            [head][32][token] (keys contiguous: K-major B operand of P V)
+//   kernel : one CTA per (head, 128-query tile).  warp 0 = TMA producer (Q once, K / V^T tiles of 128 keys, two
+//            stages), warp 1 = tcgen05.mma issuer, warps 2-5 = soft-max: each thread owns one query row,
+//            reads its 128 logits from TMEM (tcgen05.ld), keeps the online max / sum, writes P as a swizzled
+//            K-major A operand into shared memory, and after P V^T (accumulated per tile in TMEM) folds the
+//            tile's 32 output columns into its registers with the running rescale.
+//            S = Q' K^T: 128 x 128 x 64;  O_tile = P V: 128 x 32 x 128.  S and P never touch HBM.
+// Precision follows the GEMM planes: bf16, or fp16 hi/lo pairs with three MMAs per product (fp32-grade).
+#include "common.cuh"
+
+namespace drb {
+
+static constexpr int kAttThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 soft-max
+static constexpr int kAttQ = 128;            // queries per CTA == TMEM lanes
+static constexpr int kAttK = 128;            // keys per tile
+static constexpr uint32_t kQBytes = kAttQ * 64 * 2;          // 16 KB per plane
+static constexpr uint32_t kKBytes = kAttK * 64 * 2;          // 16 KB per plane
+static constexpr uint32_t kVBytes = 32 * kAttK * 2;          //  8 KB per plane (two [32][64] sub-tiles)
+static constexpr uint32_t kPBytes = kAttQ * kAttK * 2;       // 32 KB per plane (two [128][64] sub-tiles)
+
+struct AttArgs {
+  int nq, nk;               // valid queries / keys of this call
+  int q_row0, k_row0;       // first row of the query / key segment inside the packed planes
+  int heads, planes;
+  float* out;               // fp32 [.][ld_out] or null (row = q_row0-relative index + out_row0)
+  plane_t* out_hi;
+  plane_t* out_lo;
+  int ld_out, out_row0;
+  int* err;
+};
+
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kAttThreads, 1)
+att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmQ1,
+               const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmK1,
+               const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1, const AttArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * kAttQ;
+  const int P = a.planes;
+  // shared-memory plan: Q | 2 x (K, V^T) stages | P | barriers
+  const uint32_t stage_bytes = (uint32_t)P * (kKBytes + kVBytes);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + (size_t)P * kQBytes;
+  uint8_t* sP = sKV + 2 * (size_t)stage_bytes;
+  uint64_t* bars = (uint64_t*)(sP + (size_t)P * kPBytes);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t q_full = bar0, kv_full0 = bar0 + 8, kv_empty0 = bar0 + 24, s_full = bar0 + 40, s_free = bar0 + 48,
+                 p_full = bar0 + 56, pv_full = bar0 + 64;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 10);
+  const int ntiles = (a.nk + kAttK - 1) / kAttK;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(kv_full0 + 8 * s, 1); mbar_init(kv_empty0 + 8 * s, 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_full, 128);
+    mbar_init(pv_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ0); tma_prefetch_desc(&tmK0); tma_prefetch_desc(&tmV0);
+    if (P == 2) { tma_prefetch_desc(&tmQ1); tma_prefetch_desc(&tmK1); tma_prefetch_desc(&tmV1); }
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_pv = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, (uint32_t)P * kQBytes);
+      tma_load_3d(smem_u32(sQ), &tmQ0, q_full, 0, a.q_row0 + q0, head);
+      if (P == 2) tma_load_3d(smem_u32(sQ) + kQBytes, &tmQ1, q_full, 0, a.q_row0 + q0, head);
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        mbar_wait(kv_empty0 + 8 * s, (((uint32_t)t >> 1) & 1u) ^ 1u, a.err, 41);
+        const uint32_t fb = kv_full0 + 8 * s;
+        mbar_expect_tx(fb, stage_bytes);
+        const uint32_t sk = smem_u32(sKV + (size_t)s * stage_bytes);
+        const uint32_t sv = sk + (uint32_t)P * kKBytes;
+        const int key0 = a.k_row0 + t * kAttK;
+        for (int p = 0; p < P; ++p) {
+          tma_load_3d(sk + p * kKBytes, p ? &tmK1 : &tmK0, fb, 0, key0, head);
+          tma_load_3d(sv + p * kVBytes, p ? &tmV1 : &tmV0, fb, key0, 0, head);
+          tma_load_3d(sv + p * kVBytes + kVBytes / 2, p ? &tmV1 : &tmV0, fb, key0 + 64, 0, head);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_16(kAttQ, kAttK, P == 1);
+      const uint32_t idesc_pv = umma_idesc_16(kAttQ, 32, P == 1);
+      auto issue_s = [&](int t) {
+        const int s = t & 1;
+        mbar_wait(kv_full0 + 8 * s, ((uint32_t)t >> 1) & 1u, a.err, 42);
+        if (t > 0) mbar_wait(s_free, ((uint32_t)(t - 1)) & 1u, a.err, 43);    // soft-max has read S of tile t - 1
+        tc_fence_after();
+        const uint32_t sk = smem_u32(sKV + (size_t)s * stage_bytes);
+        const uint64_t dq0 = umma_desc_sw128(smem_u32(sQ)), dk0 = umma_desc_sw128(sk);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t koff = (uint64_t)(k * 2);
+          umma_f16(tmem_s, dq0 + koff, dk0 + koff, idesc_s, k ? 1u : 0u);
+          if (P == 2) {
+            const uint64_t dq1 = umma_desc_sw128(smem_u32(sQ) + kQBytes), dk1 = umma_desc_sw128(sk + kKBytes);
+            umma_f16(tmem_s, dq0 + koff, dk1 + koff, idesc_s, 1u);
+            umma_f16(tmem_s, dq1 + koff, dk0 + koff, idesc_s, 1u);
+          }
+        }
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0, a.err, 44);
+      issue_s(0);
+      for (int t = 0; t < ntiles; ++t) {
+        if (t + 1 < ntiles) issue_s(t + 1);
+        const int s = t & 1;
+        mbar_wait(p_full, (uint32_t)t & 1u, a.err, 45);
+        tc_fence_after();
+        const uint32_t sv = smem_u32(sKV + (size_t)s * stage_bytes) + (uint32_t)P * kKBytes;
+        const uint32_t sp = smem_u32(sP);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t sub = (uint32_t)(k >> 2);
+          const uint64_t koff = (uint64_t)((k & 3) * 2);
+          const uint64_t dp0 = umma_desc_sw128(sp + sub * (kPBytes / 2)) + koff;
+          const uint64_t dv0 = umma_desc_sw128(sv + sub * (kVBytes / 2)) + koff;
+          umma_f16(tmem_pv, dp0, dv0, idesc_pv, k ? 1u : 0u);
+          if (P == 2) {
+            const uint64_t dp1 = umma_desc_sw128(sp + kPBytes + sub * (kPBytes / 2)) + koff;
+            const uint64_t dv1 = umma_desc_sw128(sv + kVBytes + sub * (kVBytes / 2)) + koff;
+            umma_f16(tmem_pv, dp0, dv1, idesc_pv, 1u);
+            umma_f16(tmem_pv, dp1, dv0, idesc_pv, 1u);
+          }
+        }
+        umma_commit(pv_full);
+        umma_commit(kv_empty0 + 8 * s);
+      }
+    }
+  } else {
+    // ------------------------------- soft-max / accumulate: one query row per thread -------------
+    const int qd = warp & 3;                         // TMEM lane quarter this warp may access
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = ((uint32_t)(qd * 32)) << 16;
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const bool pair = P == 2;
+    for (int t = 0; t < ntiles; ++t) {
+      mbar_wait(s_full, (uint32_t)t & 1u, a.err, 46);
+      tc_fence_after();
+      float sv_[128];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)(b * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sv_[b * 32 + j] = __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      mbar_arrive(s_free);
+      const int valid = min(kAttK, a.nk - t * kAttK);       // keys of this tile that exist
+      float mx = m_run;
+#pragma unroll
+      for (int j = 0; j < 128; ++j)
+        if (j < valid) mx = fmaxf(mx, sv_[j]);
+      const float corr = exp2f(m_run - mx);                 // first tile: exp2(-inf) = 0
+      m_run = mx;
+      float lsum = 0.f;
+      // P in the swizzled K-major layout the tensor core reads: sub-tile (64 keys) / row / 16-byte chunk ^ (row & 7)
+      uint8_t* prow = sP + (size_t)row * 128;
+#pragma unroll
+      for (int c8 = 0; c8 < 16; ++c8) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j0 = c8 * 8 + 2 * u;
+          const float p0 = j0 < valid ? exp2f(sv_[j0] - mx) : 0.f;
+          const float p1 = j0 + 1 < valid ? exp2f(sv_[j0 + 1] - mx) : 0.f;
+          lsum += p0 + p1;
+          plane_t h0, l0, h1, l1;
+          split16(p0, pair, h0, l0);
+          split16(p1, pair, h1, l1);
+          hw[u] = pack16x2(h0, h1);
+          lw[u] = pack16x2(l0, l1);
+        }
+        const int sub = c8 >> 3, chunk = (c8 & 7) ^ (row & 7);
+        uint8_t* dst = prow + (size_t)sub * (kPBytes / 2) + chunk * 16;
+        *(uint4*)dst = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        if (pair) *(uint4*)(dst + kPBytes) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+      l_run = l_run * corr + lsum;
+      fence_proxy_async();                                  // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(p_full);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[j] *= corr;
+      mbar_wait(pv_full, (uint32_t)t & 1u, a.err, 47);
+      tc_fence_after();
+      {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_pv + lane_addr, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] += __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+    }
+    const int qi = q0 + row;
+    if (qi < a.nq) {
+      const float inv = 1.f / l_run;
+      const long long off = (long long)(a.out_row0 + qi) * a.ld_out + head * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float r0 = o[j] * inv, r1 = o[j + 1] * inv, r2 = o[j + 2] * inv, r3 = o[j + 3] * inv;
+        if (a.out) *(float4*)(a.out + off + j) = make_float4(r0, r1, r2, r3);
+        if (a.out_hi) {
+          plane_t h0, l0, h1, l1, h2, l2, h3, l3;
+          const bool pr = a.out_lo != nullptr;
+          split16(r0, pr, h0, l0); split16(r1, pr, h1, l1); split16(r2, pr, h2, l2); split16(r3, pr, h3, l3);
+          *(uint2*)(a.out_hi + off + j) = make_uint2(pack16x2(h0, h1), pack16x2(h2, h3));
+          if (pr) *(uint2*)(a.out_lo + off + j) = make_uint2(pack16x2(l0, l1), pack16x2(l2, l3));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// q / k / v: fp32 rows [n][ld] (columns head * 32 + d).  Qp, Kp: [heads][n_pad][64]; Vt: [heads][32][n_pad].
+__global__ void att_pack_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                const float* __restrict__ v, int ldv, int n, int n_pad, int heads, float q_scale,
+                                plane_t* __restrict__ qp_hi, plane_t* __restrict__ qp_lo, plane_t* __restrict__ kp_hi,
+                                plane_t* __restrict__ kp_lo, plane_t* __restrict__ vt_hi, plane_t* __restrict__ vt_lo) {
+  const bool pair = qp_lo != nullptr;
+  const long long total = (long long)heads * n_pad * 64;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int d = (int)(i & 63);
+    const long long r = i >> 6;
+    const int tok = (int)(r % n_pad), h = (int)(r / n_pad);
+    float qv = 0.f, kv = 0.f;
+    if (d < 32 && tok < n) {
+      qv = q[(long long)tok * ldq + h * 32 + d] * q_scale;
+      kv = k[(long long)tok * ldk + h * 32 + d];
+    }
+    plane_t a, b;
+    split16(qv, pair, a, b);
+    qp_hi[i] = a;
+    if (pair) qp_lo[i] = b;
+    split16(kv, pair, a, b);
+    kp_hi[i] = a;
+    if (pair) kp_lo[i] = b;
+  }
+  // V transposed: thread per (head, token, d) with token fastest for coalesced writes
+  const long long totv = (long long)heads * 32 * n_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totv; i += stride) {
+    const int tok = (int)(i % n_pad);
+    const long long r = i / n_pad;
+    const int d = (int)(r & 31), h = (int)(r >> 5);
+    const float vv = tok < n ? v[(long long)tok * ldv + h * 32 + d] : 0.f;
+    plane_t a, b;
+    split16(vv, pair, a, b);
+    vt_hi[i] = a;
+    if (pair) vt_lo[i] = b;
+  }
+}
+
+static size_t att_plane_elems(int n_pad, int heads) { return (size_t)heads * n_pad * 64; }
+
+extern "C" size_t drb_mha_tc_workspace_bytes(int n, int heads, int planes) {
+  const int n_pad = ((n + 127) / 128) * 128 + 128;
+  // Qp + Kp ([heads][n_pad][64]) + Vt ([heads][32][n_pad]) per plane
+  return (size_t)planes * (2 * att_plane_elems(n_pad, heads) + (size_t)heads * 32 * n_pad) * sizeof(plane_t) + 1024;
+}
+
+extern "C" int drb_mha_tc_pack(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int n,
+                               int heads, int planes, float scale, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream) {
+  DRB_REQUIRE(q && k && v && workspace && n > 0 && heads > 0 && (planes == 1 || planes == 2), "drb_mha_tc_pack: bad arguments");
+  DRB_REQUIRE(workspace_bytes >= drb_mha_tc_workspace_bytes(n, heads, planes), "drb_mha_tc_pack: workspace too small");
+  DRB_REQUIRE(((uintptr_t)workspace & 1023) == 0, "drb_mha_tc_pack: workspace must be 1024-byte aligned");
+  const int n_pad = ((n + 127) / 128) * 128 + 128;
+  const size_t pe = att_plane_elems(n_pad, heads), ve = (size_t)heads * 32 * n_pad;
+  plane_t* base = (plane_t*)workspace;
+  plane_t* qp_hi = base; plane_t* kp_hi = qp_hi + pe; plane_t* vt_hi = kp_hi + pe;
+  plane_t *qp_lo = nullptr, *kp_lo = nullptr, *vt_lo = nullptr;
+  if (planes == 2) { qp_lo = vt_hi + ve; kp_lo = qp_lo + pe; vt_lo = kp_lo + pe; }
+  const long long total = (long long)heads * n_pad * 64;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  att_pack_kernel<<<grid, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, n, n_pad, heads, scale * 1.4426950408889634f, qp_hi,
+                                            qp_lo, kp_hi, kp_lo, vt_hi, vt_lo);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+// Attention of the queries [q_row0, q_row0 + nq) against the keys / values [k_row0, k_row0 + nk) of ONE packed
+// workspace (n rows packed by drb_mha_tc_pack); output rows out_row0 + i.
+extern "C" int drb_mha_tc_forward(const void* workspace, int n, int heads, int planes, int q_row0, int nq, int k_row0,
+                                  int nk, float* out, void* out_hi, void* out_lo, int ld_out, int out_row0,
+                                  cudaStream_t stream) {
+  DRB_REQUIRE(workspace && n > 0 && heads > 0 && (planes == 1 || planes == 2), "drb_mha_tc_forward: bad arguments");
+  DRB_REQUIRE(nq >= 0 && nk > 0 && q_row0 >= 0 && k_row0 >= 0 && q_row0 + nq <= n && k_row0 + nk <= n,
+              "drb_mha_tc_forward: segment outside the packed rows");
+  DRB_REQUIRE((out || out_hi) && ld_out % 8 == 0, "drb_mha_tc_forward: bad output");
+  if (nq == 0) return 0;
+  const int n_pad = ((n + 127) / 128) * 128 + 128;
+  const size_t pe = att_plane_elems(n_pad, heads), ve = (size_t)heads * 32 * n_pad;
+  const plane_t* base = (const plane_t*)workspace;
+  const plane_t* qp[2] = {base, nullptr};
+  const plane_t* kp[2] = {base + pe, nullptr};
+  const plane_t* vt[2] = {base + 2 * pe, nullptr};
+  if (planes == 2) { qp[1] = vt[0] + ve; kp[1] = qp[1] + pe; vt[1] = kp[1] + pe; }
+  CUtensorMap mQ[2], mK[2], mV[2];
+  memset(mQ, 0, sizeof(mQ)); memset(mK, 0, sizeof(mK)); memset(mV, 0, sizeof(mV));
+  const uint64_t rdims[3] = {64, (uint64_t)n_pad, (uint64_t)heads};
+  const uint64_t rstr[2] = {64 * 2, (uint64_t)n_pad * 64 * 2};
+  const uint32_t rbox[3] = {64, 128, 1};
+  const uint64_t vdims[3] = {(uint64_t)n_pad, 32, (uint64_t)heads};
+  const uint64_t vstr[2] = {(uint64_t)n_pad * 2, (uint64_t)n_pad * 32 * 2};
+  const uint32_t vbox[3] = {64, 32, 1};
+  int rc;
+  for (int p = 0; p < planes; ++p) {
+    const bool bf = planes == 1;
+    if ((rc = igemm_make_map(&mQ[p], qp[p], 3, rdims, rstr, rbox, bf))) return rc;
+    if ((rc = igemm_make_map(&mK[p], kp[p], 3, rdims, rstr, rbox, bf))) return rc;
+    if ((rc = igemm_make_map(&mV[p], vt[p], 3, vdims, vstr, vbox, bf))) return rc;
+  }
+  if (planes == 1) { mQ[1] = mQ[0]; mK[1] = mK[0]; mV[1] = mV[0]; }
+  AttArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nq = nq; a.nk = nk; a.q_row0 = q_row0; a.k_row0 = k_row0; a.heads = heads; a.planes = planes;
+  a.out = out; a.out_hi = (plane_t*)out_hi; a.out_lo = (plane_t*)out_lo; a.ld_out = ld_out; a.out_row0 = out_row0;
+  a.err = igemm_err_flag();
+  const size_t smem = 1024 + (size_t)planes * (kQBytes + 2 * (kKBytes + kVBytes) + kPBytes) + 128;
+  DRB_CUDA_OK(cudaFuncSetAttribute(att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)cdiv(nq, kAttQ), (unsigned)heads);
+  att_fwd_kernel<<<grid, kAttThreads, smem, stream>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], a);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace drb

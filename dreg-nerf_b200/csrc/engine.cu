@@ -441,6 +441,8 @@ int engine_ensure_tokens(drb_engine* e, int m) {
   e->dec_hi = AP(kLayers * cap * kD); e->dec_lo = AL(kLayers * cap * kD);
   e->qp_hi = AP(kLayers * cap * kD); e->qp_lo = AL(kLayers * cap * kD);
   e->kp_hi = AP(kLayers * cap * kD); e->kp_lo = AL(kLayers * cap * kD);
+  e->att_ws_bytes = drb_mha_tc_workspace_bytes((int)cap, 8, e->cfg.planes);
+  e->att_ws = A((long long)e->att_ws_bytes);
   e->tok_grad = e->grad_mode;
   if (e->grad_mode) {
     // the training graph: per-layer copies of everything the backward pass re-reads, plus its scratch
@@ -684,6 +686,11 @@ extern "C" int drb_engine_bind_grad(drb_engine* e, int i, float* device_ptr) {
   e->params[i].grad = device_ptr;
   return 0;
 }
+extern "C" int drb_engine_set_tc_attention(drb_engine* e, int on) {
+  DRB_REQUIRE(e, "drb_engine_set_tc_attention: null engine");
+  e->tc_attention = on != 0;
+  return 0;
+}
 extern "C" int drb_engine_set_max_tokens(drb_engine* e, int max_total) {
   DRB_REQUIRE(e && max_total > 0, "drb_engine_set_max_tokens: bad arguments");
   e->max_tokens = max_total;
@@ -781,6 +788,24 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
                     int relu, float scale, float* out, plane_t* ohi, plane_t* olo) {
     return run_igemm(e, w, in_hi, in_lo, 1, 1, 1, rows, cin, 1, P(e, w.p_b), res, relu, scale, out, ohi, olo, 0, s);
   };
+  // multi-head attention of the query segment [q0, q0 + nq) against the key segment [k0, k0 + nk) of one in_proj
+  // output; `packed` says whether this qkv has already been packed for the tensor-core kernel
+  auto attend = [&](const float* qkv, bool& packed, int q0, int nq, int k0, int nk, plane_t* ohi, plane_t* olo) -> int {
+    if (e->tc_attention) {
+      if (!packed) {
+        e->launches += 1;
+        DRB_TRY(drb_mha_tc_pack(qkv, 768, qkv + 256, 768, qkv + 512, 768, m, 8, e->cfg.planes, att_scale, e->att_ws,
+                                e->att_ws_bytes, s));
+        packed = true;
+      }
+      e->launches += 1;
+      return drb_mha_tc_forward(e->att_ws, m, 8, e->cfg.planes, q0, nq, k0, nk, nullptr, ohi, olo, 256, q0, s);
+    }
+    e->launches += 1;
+    return drb_mha_core(qkv + (long long)q0 * 768, 768, qkv + (long long)k0 * 768 + 256, 768,
+                        qkv + (long long)k0 * 768 + 512, 768, nq, nk, 8, att_scale, nullptr, off(ohi, (long long)q0 * 256),
+                        off(olo, (long long)q0 * 256), 256, s);
+  };
   for (int l = 0; l < kLayers; ++l) {
     TLayer& t = e->tl[l];
     TSave& v = e->ts[l];
@@ -790,24 +815,21 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
     e->launches += 1;
     DRB_TRY(drb_layernorm256(x0, m, P(e, t.n1w), P(e, t.n1b), e->pos, nullptr, v.xn1_hi, v.xn1_lo, s));
     DRB_TRY(linear(t.self_attn.in_proj, v.xn1_hi, v.xn1_lo, m, 256, nullptr, 0, 1.f, v.qkv_s, nullptr, nullptr));
-    e->launches += 2;
-    DRB_TRY(drb_mha_core(v.qkv_s, 768, v.qkv_s + 256, 768, v.qkv_s + 512, 768, ns, ns, 8, att_scale, nullptr,
-                         v.att_s_hi, v.att_s_lo, 256, s));
-    DRB_TRY(drb_mha_core(v.qkv_s + (long long)ns * 768, 768, v.qkv_s + (long long)ns * 768 + 256, 768,
-                         v.qkv_s + (long long)ns * 768 + 512, 768, nt, nt, 8, att_scale, nullptr,
-                         v.att_s_hi + (long long)ns * 256, off(v.att_s_lo, (long long)ns * 256), 256, s));
+    {
+      bool packed = false;
+      DRB_TRY(attend(v.qkv_s, packed, 0, ns, 0, ns, v.att_s_hi, v.att_s_lo));
+      DRB_TRY(attend(v.qkv_s, packed, ns, nt, ns, nt, v.att_s_hi, v.att_s_lo));
+    }
     DRB_TRY(linear(t.self_attn.out_proj, v.att_s_hi, v.att_s_lo, m, 256, x0, 0, 1.f, v.x1, nullptr, nullptr));
     // cross attention, both directions from the same pre-update normalised features
     e->launches += 1;
     DRB_TRY(drb_layernorm256(v.x1, m, P(e, t.n2w), P(e, t.n2b), e->pos, nullptr, v.xn2_hi, v.xn2_lo, s));
     DRB_TRY(linear(t.cross_attn.in_proj, v.xn2_hi, v.xn2_lo, m, 256, nullptr, 0, 1.f, v.qkv_c, nullptr, nullptr));
-    e->launches += 2;
-    DRB_TRY(drb_mha_core(v.qkv_c, 768, v.qkv_c + (long long)ns * 768 + 256, 768,
-                         v.qkv_c + (long long)ns * 768 + 512, 768, ns, nt, 8, att_scale, nullptr, v.att_c_hi,
-                         v.att_c_lo, 256, s));
-    DRB_TRY(drb_mha_core(v.qkv_c + (long long)ns * 768, 768, v.qkv_c + 256, 768, v.qkv_c + 512, 768, nt, ns, 8,
-                         att_scale, nullptr, v.att_c_hi + (long long)ns * 256, off(v.att_c_lo, (long long)ns * 256),
-                         256, s));
+    {
+      bool packed = false;
+      DRB_TRY(attend(v.qkv_c, packed, 0, ns, ns, nt, v.att_c_hi, v.att_c_lo));
+      DRB_TRY(attend(v.qkv_c, packed, ns, nt, 0, ns, v.att_c_hi, v.att_c_lo));
+    }
     DRB_TRY(linear(t.cross_attn.out_proj, v.att_c_hi, v.att_c_lo, m, 256, v.x1, 0, 1.f, v.x2, nullptr, nullptr));
     // feed forward
     e->launches += 1;

@@ -156,6 +156,8 @@ struct drb_engine {
   drb::plane_t *ffn_hi = nullptr, *ffn_lo = nullptr, *dec_hi = nullptr, *dec_lo = nullptr;
   drb::plane_t *qp_hi = nullptr, *qp_lo = nullptr, *kp_hi = nullptr, *kp_lo = nullptr;
   std::vector<void*> tok_allocs;
+  bool tc_attention = false;        // attention through the tcgen05 kernel (attention.cu)
+  void* att_ws = nullptr; size_t att_ws_bytes = 0;
 
   // ---- training graph ----
   bool grad_mode = false;

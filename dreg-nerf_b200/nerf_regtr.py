@@ -9,6 +9,7 @@ reference's layout; all arithmetic happens in the C-ABI engine.  There is no PyT
 """
 import copy
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -16,6 +17,8 @@ from torch import nn
 from . import _lib
 
 _PRECISION_PLANES = {"fp32": 2, "bf16x3": 2, "bf16": 1}
+# attention through the tcgen05 FlashAttention-style kernel (csrc/attention.cu) instead of the mma.sync one
+TC_ATTENTION_DEFAULT = os.environ.get("DRB_TC_ATTENTION", "0") != "0"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -274,6 +277,7 @@ class NeRFRegTr(nn.Module):
             _lib.check(lib.drb_engine_set_training(handle, 1 if self.training else 0))
             _lib.check(lib.drb_engine_set_sparse_fpn(handle, 1 if self.sparse_fpn else 0))
             _lib.check(lib.drb_engine_set_max_tokens(handle, int(getattr(self, "max_tokens", 3000))))
+            _lib.check(lib.drb_engine_set_tc_attention(handle, 1 if getattr(self, "tc_attention", TC_ATTENTION_DEFAULT) else 0))
             io = self._pair_io(src, tgt, src_mask, tgt_mask)
             ns, nt = C.c_int(0), C.c_int(0)
             stream = _lib.stream_ptr()

@@ -505,3 +505,25 @@ def downsample_backward(dout, tape, rounds, c):
                                                 stream_ptr()), "drb_segment_mean_backward")
         cur = din
     return cur
+
+
+def mha_tc(qkv, segments, heads=8, planes=2, scale=None, want_planes=False):
+    """tcgen05 attention over one in_proj output qkv [n, 768]: ``segments`` = list of (q_row0, nq, k_row0, nk);
+    -> fp32 [n, 256] with the rows of every query segment filled (and optionally the 16-bit planes)."""
+    n = qkv.shape[0]
+    scale = scale if scale is not None else 32 ** -0.5
+    lib = _lib.load()
+    nbytes = lib.drb_mha_tc_workspace_bytes(n, heads, planes)
+    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=qkv.device)
+    base = (ws.data_ptr() + 1023) // 1024 * 1024
+    out = torch.zeros((n, 256), dtype=torch.float32, device=qkv.device)
+    o_hi = torch.zeros((n, 256), dtype=_plane_dtype(planes == 2), device=qkv.device) if want_planes else None
+    o_lo = torch.zeros((n, 256), dtype=torch.float16, device=qkv.device) if (want_planes and planes == 2) else None
+    with _dev(qkv):
+        check(lib.drb_mha_tc_pack(ptr(qkv), qkv.stride(0), C.c_void_p(qkv.data_ptr() + 4 * 256), qkv.stride(0),
+                                  C.c_void_p(qkv.data_ptr() + 4 * 512), qkv.stride(0), n, heads, planes, scale,
+                                  C.c_void_p(base), nbytes, stream_ptr()), "drb_mha_tc_pack")
+        for q0, nq, k0, nk in segments:
+            check(lib.drb_mha_tc_forward(C.c_void_p(base), n, heads, planes, q0, nq, k0, nk, ptr(out), ptr(o_hi), ptr(o_lo),
+                                         256, q0, stream_ptr()), "drb_mha_tc_forward")
+    return (out, (o_hi, o_lo)) if want_planes else out

@@ -81,7 +81,7 @@ def make_pair(res=32, pair_id=0, overlap_keep=0.8):
         "tgt_xyz_rgba": tgt_grid.permute(3, 2, 0, 1).unsqueeze(0),
         "src_mask": src_mask, "tgt_mask": tgt_mask,
         "src_nerf_path": "", "tgt_nerf_path": "",
-        "pose": T[:3].float().unsqueeze(0),
+        "pose": T.float().unsqueeze(0),          # [1, 4, 4] as NeRFRegDataset builds it (dataset.py:242)
         "scene": "synthetic_%d" % pair_id, "dataset": "synthetic", "index": pair_id,
     }
 

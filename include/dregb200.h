@@ -204,6 +204,17 @@ int drb_layernorm256(const float* x, int n, const float* gamma, const float* bet
 int drb_mha_core(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int nq,
                  int nk, int heads, float scale, float* out, void* out_hi, void* out_lo, int ld_out,
                  drb_stream_t stream);
+/* The same attention core on the 5th-gen tensor cores (tcgen05 + TMEM + TMA, FlashAttention style: logits and
+ * probabilities never leave the SM).  drb_mha_tc_pack converts the fp32 q / k / v rows of ONE in_proj output
+ * ([n][ld], head h at columns 32 h ..) into per-head 16-bit planes inside `workspace` (1024-byte aligned,
+ * drb_mha_tc_workspace_bytes); drb_mha_tc_forward then attends the queries [q_row0, q_row0 + nq) to the keys /
+ * values [k_row0, k_row0 + nk) of that workspace - self-attention of src and tgt and both cross directions are
+ * four calls over two packs.  Output row out_row0 + i, columns 32 h .. of out / out_hi / out_lo (pitch ld_out). */
+size_t drb_mha_tc_workspace_bytes(int n, int heads, int planes);
+int drb_mha_tc_pack(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int n, int heads,
+                    int planes, float scale, void* workspace, size_t workspace_bytes, drb_stream_t stream);
+int drb_mha_tc_forward(const void* workspace, int n, int heads, int planes, int q_row0, int nq, int k_row0, int nk,
+                       float* out, void* out_hi, void* out_lo, int ld_out, int out_row0, drb_stream_t stream);
 /* CorrespondenceDecoder.simple_attention tail (nerf_regtr.py:292-306): row softmax of s [nq][ld]
  * over nk keys, weighted sum of xyz [nk][ld_xyz] -> out [nq][3]. */
 int drb_softmax_weighted_xyz(const float* s, int ld, int nq, int nk, const float* xyz, int ld_xyz,
@@ -461,6 +472,8 @@ typedef struct drb_pair_grad {            /* gradients of the drb_pair_out tenso
 /* io / out: the arguments of the forward (same tensors, still alive). */
 int drb_engine_backward(drb_engine* e, const drb_pair_io* io, const drb_pair_out* out,
                         const drb_pair_grad* grad, drb_stream_t stream);
+/* 1: attention through drb_mha_tc_* (tcgen05), 0: the mma.sync kernel drb_mha_core. */
+int drb_engine_set_tc_attention(drb_engine* e, int on);
 /* Caps the down-sampler's stopping rule (grid_downsample.py:70,91; default 3000 tokens). */
 int drb_engine_set_max_tokens(drb_engine* e, int max_total);
 

@@ -179,14 +179,21 @@ def surface_mask_vectorized(points, cam_origins, occ, res, roi_aabb, scene_aabb,
 
 
 def extract_block(field, indices, jitter, occ, res, roi_aabb, scene_aabb, cam_origins, step,
-                  density_thre=0.7, cut_off=0.5, with_surface=True):
+                  density_thre=0.7, cut_off=0.5, with_surface=True, use_c_marcher=False):
     """eval_ngp_nerf.py:337-412 -> dict(points, rgb, alpha, density, density_mask, surface_mask, grid, mask)."""
     pts = sample_points(indices, jitter, res, roi_aabb)
     density, feat = ngp.query_density(pts, field["aabb"], field["table"], field["w1"], field["w2"])
     rgb = ngp.query_rgb_mean(ngp.fixed_viewing_directions(), feat, field["c1"], field["c2"], field["c3"])
     alpha = torch.clip(1 - torch.exp(-1e-2 * density), 0, 1)
     dmask = density > density_thre
-    if with_surface:
+    best = None
+    if with_surface and use_c_marcher:
+        # the C restatement: single precision + fused multiply-adds through dreg-nerf_b200/csrc/march_math.h, the
+        # arithmetic the CUDA kernel compiles too (this scalar Python marcher keeps doubles)
+        from oracle import extract_c
+        smask, best, _ = extract_c.surface_mask(pts, cam_origins, occ, res, roi_aabb, scene_aabb, step, cut_off, field,
+                                                all_rays=True)
+    elif with_surface:
         dens_fn = lambda x: ngp.query_density(x, field["aabb"], field["table"], field["w1"], field["w2"])[0]
         smask = surface_mask(pts, cam_origins, occ, res, roi_aabb, scene_aabb, step, cut_off, dens_fn)
     else:
@@ -197,4 +204,4 @@ def extract_block(field, indices, jitter, occ, res, roi_aabb, scene_aabb, cam_or
     grid[indices[keep], 3:6] = rgb[keep]
     grid[indices[keep], 6] = alpha[keep]
     return {"points": pts, "rgb": rgb, "alpha": alpha, "density": density, "density_mask": dmask,
-            "surface_mask": smask, "grid": grid.reshape(res, res, res, 7), "mask": indices[keep]}
+            "surface_mask": smask, "surface_best": best, "grid": grid.reshape(res, res, res, 7), "mask": indices[keep]}

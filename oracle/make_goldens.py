@@ -182,10 +182,14 @@ def extract_case():
     sub = idx[torch.randperm(idx.numel(), generator=gen)[:n_pts]].sort().values
     jitter = torch.rand(sub.numel(), 3, generator=gen)
     roi = [-1.5, -1.5, -1.5, 1.5, 1.5, 1.5]
-    o = extract.extract_block(field, sub, jitter, occ, res, roi, roi, cams, step)
+    o = extract.extract_block(field, sub, jitter, occ, res, roi, roi, cams, step, use_c_marcher=True)
+    o_py = extract.extract_block(field, sub, jitter, occ, res, roi, roi, cams, step)      # scalar Python marcher (doubles)
+    print("extract_32: C marcher vs scalar Python marcher: %d differing surface decisions"
+          % int((o["surface_mask"] != o_py["surface_mask"]).sum()))
     fix = {"res": res, "seed": 3, "table_std": table_std, "step": step, "n_cam": n_cam, "sub": sub, "jitter": jitter,
            "points": o["points"], "rgb": o["rgb"], "alpha": o["alpha"], "density": o["density"],
-           "density_mask": o["density_mask"], "surface_mask": o["surface_mask"], "mask": o["mask"],
+           "density_mask": o["density_mask"], "surface_mask": o["surface_mask"], "surface_best": o["surface_best"],
+           "mask": o["mask"], "marcher": "oracle/extract_c.c (fp32, march_math.h)",
            "rows": o["grid"].reshape(-1, 7)[sub]}
     fix = {k: (v.clone().contiguous() if torch.is_tensor(v) else v) for k, v in fix.items()}
     torch.save(fix, os.path.join(GOLDEN, "extract_32.pt"))
@@ -212,9 +216,13 @@ def visibility_case():
     pts = (cell + torch.rand(360, 3, generator=g)) / res * 3.0 - 1.5
     pts = torch.cat([pts, torch.rand(40, 3, generator=g) * 3.6 - 1.8])
     dens_fn = lambda x: ngp.query_density(x, ref["aabb"], ref["table"], ref["w1"], ref["w2"])[0]
-    want, best = extract.surface_mask(pts, cams, occ, res, roi, roi, step, 0.5, dens_fn, return_best=True)
+    from oracle import extract_c
+    want, best, _ = extract_c.surface_mask(pts, cams, occ, res, roi, roi, step, 0.5, ref, all_rays=True)
+    want_py, best_py = extract.surface_mask(pts, cams, occ, res, roi, roi, step, 0.5, dens_fn, return_best=True)
+    print("visibility_32: C marcher vs scalar Python marcher: %d differing decisions, max |best| difference %.2e"
+          % (int((want != want_py).sum()), float((best - best_py.float()).abs().max())))
     fix = {"res": res, "n_cam": n_cam, "seed": seed, "table_std": table_std, "step": step, "points": pts,
-           "visible": want, "best": best.float(), "density": dens_fn(pts)}
+           "visible": want, "best": best.float(), "density": dens_fn(pts), "marcher": "oracle/extract_c.c (fp32, march_math.h)"}
     torch.save(fix, os.path.join(GOLDEN, "visibility_32.pt"))
     print("wrote visibility_32: %d of %d visible, %d within 1e-3 of the cut-off"
           % (int(want.sum()), pts.shape[0], int(((best - 0.5).abs() < 1e-3).sum())))

@@ -54,3 +54,28 @@ def test_shard_partition_properties():
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
     with pytest.raises(ValueError):
         sharding.shard_pairs(4, 2, 2)
+
+
+def _grad_worker(rank, world, port, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from importlib import import_module
+    sharding = import_module("dreg-nerf_b200.sharding")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2))]
+    params[0].grad = torch.full((5, 3), float(rank + 1))
+    params[1].grad = torch.arange(7.0) * (rank + 1)
+    sharding.allreduce_gradients(params)                 # params[2] has no gradient: skipped
+    torch.save([p.grad for p in params], os.path.join(out_dir, "g%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_averages_over_ranks(tmp_path):
+    world = 2
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        g = torch.load(os.path.join(str(tmp_path), "g%d.pt" % r))
+        assert torch.equal(g[0], torch.full((5, 3), 1.5)) and torch.equal(g[1], torch.arange(7.0) * 1.5) and g[2] is None

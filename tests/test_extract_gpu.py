@@ -7,6 +7,12 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+# Width of the bands around the two thresholds inside which a decision may legitimately differ from the oracle
+# (and is COUNTED, not ignored): round 1 used 1e-3 / 1e-4; with the ray arithmetic shared through
+# csrc/march_math.h only the density network's rounding is left.
+S_BAND = 1e-5      # |max alpha T - cut_off|
+D_BAND = 2e-5      # |density - 0.7|
+
 
 def _field(pkg, cuda, seed=0, table_std=1.0):
     from oracle.make_goldens import make_field
@@ -74,11 +80,18 @@ def test_extract_block_small(pkg, cuda):
     assert (pts.cpu() - fix["points"]).abs().max() < 1e-6
     assert (rgb.cpu() - fix["rgb"]).abs().max() < 2e-5
     assert (alpha.cpu()[:, 0] - fix["alpha"]).abs().max() < 1e-6
-    border = (fix["density"] - 0.7).abs() < 1e-4
+    border = (fix["density"] - 0.7).abs() < D_BAND
     assert torch.equal(dmask.cpu()[~border], fix["density_mask"][~border]), "density mask must match off the threshold"
-    mism = int((smask.cpu() != fix["surface_mask"]).sum())
-    print("density>0.7: %d / %d (border %d); surface: %d, mismatches %d"
-          % (int(fix["density_mask"].sum()), sub.numel(), int(border.sum()), int(fix["surface_mask"].sum()), mism))
+    # the fixture's marcher is the C oracle: the per-ray arithmetic is the header the kernel compiles too
+    # (csrc/march_math.h), so decisions can only differ where alpha * T is within the density network's rounding
+    # (tensor-core 3xTF32 first layer vs sequential fp32) of the cut-off
+    mism_all = smask.cpu() != fix["surface_mask"]
+    s_band = (fix["surface_best"] - 0.5).abs() < S_BAND
+    mism = int((mism_all & ~s_band).sum())
+    print("density>0.7: %d / %d (border %d); surface: %d; within %.0e of the cut-off: %d (mismatching there: %d); "
+          "mismatches elsewhere %d" % (int(fix["density_mask"].sum()), sub.numel(), int(border.sum()),
+                                        int(fix["surface_mask"].sum()), S_BAND, int(s_band.sum()),
+                                        int((mism_all & s_band).sum()), mism))
     assert mism == 0, "surface-field mask differs from the oracle"
     keep = (dmask & smask).cpu()
     assert torch.equal(sub[keep], fix["mask"])                       # voxel_mask.pt content
@@ -178,16 +191,17 @@ def test_compute_visibility_score(pkg, cuda):
     poses[:, :3, 3] = cams
     meta = {"aabb": roi, "render_step_size": step, "camera_poses": poses.to(cuda)}
     n = pts.shape[0]
-    # points whose best surface-field value lies within 1e-3 of the cut-off: the decision hangs on the
-    # last bits of the density (fp32 summation order, 3xTF32); set aside like the 0.7 density band
-    band = (fix["best"] - 0.5).abs() < 1e-3
+    # points whose best surface-field value lies within S_BAND of the cut-off: the decision hangs on the
+    # last bits of the density (fp32 summation order, 3xTF32); counted separately
+    band = (fix["best"] - 0.5).abs() < S_BAND
     xyz = pts.reshape(2, n // 2, 3).to(cuda)                      # [num_layers, N, 3]
     got = pkg.compute_visibility_score([xyz], f, occ, meta)[0]
     assert got.shape == (2, n // 2, 1) and got.dtype == torch.float32
     got_b = got.cpu().reshape(-1).bool()
     mism = (got_b != fix["visible"]) & ~band
-    print("visibility: %d of %d points visible, %d within 1e-3 of the cut-off, mismatches elsewhere %d"
-          % (int(fix["visible"].sum()), n, int(band.sum()), int(mism.sum())))
+    print("visibility: %d of %d points visible, %d within %.0e of the cut-off (mismatching there: %d), mismatches "
+          "elsewhere %d" % (int(fix["visible"].sum()), n, int(band.sum()), S_BAND,
+                            int(((got_b != fix["visible"]) & band).sum()), int(mism.sum())))
     assert int(mism.sum()) == 0 and 0 < int(fix["visible"].sum()) < n and int(band.sum()) < 8
     dens = pkg.compute_visibility_score([xyz], f, occ, meta, score_type="density_field")[0]
     want_alpha = torch.clip(1 - torch.exp(-1e-2 * fix["density"]), 0, 1)
@@ -198,8 +212,9 @@ def test_compute_visibility_score(pkg, cuda):
 def test_extract_block_128_against_c_oracle(pkg, cuda, seed):
     """BASELINE.json configs[1] size: a full 128^3 block (169 512 candidate cells, 50 cameras) against the C
     restatement of the reference algorithm (oracle/extract_c.c: no cross-ray early outs, fp32 like nerfacc).
-    Density mask equal off a 1e-4 band around 0.7, surface mask equal off a 1e-3 band around the cut-off;
-    this also checks that the kernel's exact early outs (T < cut_off, point already seen) are exact."""
+    Density mask equal off a D_BAND band around 0.7, surface mask equal off an S_BAND band around the cut-off
+    (mismatches inside the bands are counted and printed); this also checks that the kernel's exact early outs
+    (T < cut_off, point already seen) are exact."""
     from oracle import extract, extract_c
     from oracle.make_goldens import make_field
     res = 128
@@ -217,16 +232,24 @@ def test_extract_block_128_against_c_oracle(pkg, cuda, seed):
     pts_ref = extract.sample_points(idx.cpu(), jitter, res, roi)
     assert (pts.cpu() - pts_ref).abs().max() < 1e-6
     d_ref = extract_c.query_density(pts_ref, ref["aabb"], ref["table"], ref["w1"], ref["w2"])
-    d_band = (d_ref - 0.7).abs() < 1e-4
-    assert torch.equal(dmask.cpu()[~d_band], (d_ref > 0.7)[~d_band])
-    act = dmask.cpu()
+    d_band = (d_ref - 0.7).abs() < D_BAND
+    d_mism = dmask.cpu() != (d_ref > 0.7)
+    print("density mask: %d cells within %.0e of 0.7 (mismatching there: %d), mismatches elsewhere %d; farthest "
+          "mismatch |d - 0.7| = %.2e" % (int(d_band.sum()), D_BAND, int((d_mism & d_band).sum()),
+                                        int((d_mism & ~d_band).sum()),
+                                        float((d_ref - 0.7).abs()[d_mism].max()) if bool(d_mism.any()) else 0.0))
+    assert int((d_mism & ~d_band).sum()) == 0
+    # the marcher runs where OUR density test passed; compare only cells on whose density both sides agree
+    act = dmask.cpu() & ~d_mism
     m_ref, best, n_samples = extract_c.surface_mask(pts_ref, poses[:, :3, 3].contiguous(), occ, res, roi, roi,
                                                     meta["render_step_size"], 0.5, ref, active=act)
-    s_band = (best - 0.5).abs() < 1e-3
-    mism = (smask.cpu() != m_ref) & ~s_band & act
-    print("128^3 block: %d candidate cells, %d dense, %d on the surface; %d within 1e-3 of the cut-off; "
-          "mismatches elsewhere %d (C oracle: %.1f M density samples)"
-          % (k, int(act.sum()), int(m_ref.sum()), int((s_band & act).sum()), int(mism.sum()), n_samples / 1e6))
+    s_band = (best - 0.5).abs() < S_BAND
+    s_mism = (smask.cpu() != m_ref) & act
+    mism = s_mism & ~s_band
+    print("128^3 block: %d candidate cells, %d dense, %d on the surface; %d within %.0e of the cut-off (mismatching "
+          "there: %d); mismatches elsewhere %d, farthest |best - 0.5| = %.2e (C oracle: %.1f M density samples)"
+          % (k, int(act.sum()), int(m_ref.sum()), int((s_band & act).sum()), S_BAND, int((s_mism & s_band).sum()),
+             int(mism.sum()), float((best - 0.5).abs()[s_mism].max()) if bool(s_mism.any()) else 0.0, n_samples / 1e6))
     assert int(mism.sum()) == 0 and int(m_ref.sum()) > 1000
 
 

@@ -186,3 +186,72 @@ def test_training_losses_match_reference_fixture(pkg):
     ones = pkg.CorrespondenceLoss()([fix["kp"]], [fix["pred"]], fix["pose"], overlap_weights=[torch.ones(6, 50, 1)])
     direct = pkg.losses.robust_charbonnier(fix["pred"] - pkg.losses.se3_transform_list(fix["pose"], [fix["kp"]])[0])
     assert abs(float(ones) - float(direct.abs().sum())) < 1e-4
+
+
+def test_device_side_augmentations_keep_the_pair_consistent(pkg):
+    """dataset.py:277-331 restated for resident tensors: after jitter + rigid perturbation + swap the ground-truth
+    pose still maps the source points of overlapping voxels onto the target frame exactly as before (the
+    augmentations only move points rigidly and update `pose` accordingly); the jitter touches masked voxels only."""
+    import torch
+    gen = torch.Generator().manual_seed(3)
+    base = pkg.synthetic.make_pair(res=16, pair_id=1)
+    clone = lambda d: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in d.items()}
+
+    def masked_xyz(d, side):
+        g = d[side + "_xyz_rgba"]
+        return g[:, :3].permute(0, 3, 4, 2, 1).reshape(1, -1, 3)[0, d[side + "_mask"]]
+
+    # jitter: only masked voxels move, by ~scale
+    d = clone(base)
+    d["src_xyz_rgba"] = pkg.augment.points_jitter(d["src_xyz_rgba"], d["src_mask"], 0.005, gen)
+    diff = (d["src_xyz_rgba"] - base["src_xyz_rgba"]).abs()
+    assert float(diff[:, 3:].max()) == 0.0
+    moved = diff[:, :3].permute(0, 3, 4, 2, 1).reshape(-1, 3).sum(1) > 0
+    assert set(torch.nonzero(moved)[:, 0].tolist()) <= set(base["src_mask"].tolist())
+    assert 0.001 < float(diff.max()) < 0.05
+    # rigid perturbation of either side: pose_new(src_new) == the same target-frame points as before
+    for perturb_source in (True, False):
+        d = pkg.augment.rigid_perturb(clone(base), 0.1, gen, perturb_source=perturb_source)
+        P0, P1 = base["pose"][0], d["pose"][0]
+        src0, src1 = masked_xyz(base, "src"), masked_xyz(d, "src")
+        tgt0, tgt1 = masked_xyz(base, "tgt"), masked_xyz(d, "tgt")
+        if perturb_source:
+            a = src0 @ P0[:3, :3].T + P0[:3, 3]
+            b = src1 @ P1[:3, :3].T + P1[:3, 3]
+            assert torch.equal(tgt0, tgt1) and not torch.equal(src0, src1)
+        else:      # the target moved by M: pose_new = M pose, so pose_new(src) = M (pose(src))
+            M = P1 @ torch.linalg.inv(P0)
+            a = (src0 @ P0[:3, :3].T + P0[:3, 3]) @ M[:3, :3].T + M[:3, 3]
+            b = src1 @ P1[:3, :3].T + P1[:3, 3]
+            assert torch.equal(src0, src1) and (tgt1 - (tgt0 @ M[:3, :3].T + M[:3, 3])).abs().max() < 1e-5
+        assert (a - b).abs().max() < 1e-5
+        rot = P1[:3, :3]
+        assert (rot @ rot.T - torch.eye(3)).abs().max() < 1e-5
+    # swap
+    d = pkg.augment.random_swap(clone(base), swap=True)
+    assert torch.equal(d["src_mask"], base["tgt_mask"]) and torch.equal(d["tgt_xyz_rgba"], base["src_xyz_rgba"])
+    assert (d["pose"][0] @ base["pose"][0] - torch.eye(4)).abs().max() < 1e-5
+    s = pkg.augment.sample_se3_small(0.1, gen)
+    assert s.shape == (4, 4) and abs(float(torch.det(s[:3, :3])) - 1.0) < 1e-5
+
+
+def test_occupancy_grid_fill_semantics(pkg):
+    """nerfacc 0.3.5 OccupancyGrid.every_n_step restated (train_ngp_nerf.py:293): warm-up touches every cell, the
+    EMA keeps the running maximum, the binary grid thresholds at min(mean, occ_thre)."""
+    import torch
+    og = pkg.OccupancyGrid([-1.5] * 3 + [1.5] * 3, 16).train()
+    ball = lambda x: (x.norm(dim=1) < 1.0).float() * 0.5
+    og.every_n_step(0, ball)
+    n0 = int(og.binary.sum())
+    assert og.binary.shape == (16, 16, 16) and 300 < n0 < 900          # ~ the cells of a radius-1 ball in a 3^3 box
+    og.every_n_step(3, lambda x: torch.ones(x.shape[0]))                # not a multiple of n = 16: no update
+    assert int(og.binary.sum()) == n0
+    before = og.occs.clone()
+    og.every_n_step(16, lambda x: torch.zeros(x.shape[0]))              # decay only
+    assert torch.allclose(og.occs, before * 0.95)
+    og.every_n_step(512, ball, generator=torch.Generator().manual_seed(0))   # past warm-up: a subset of the cells
+    assert int(og.binary.sum()) > 0
+    og.eval()
+    import pytest
+    with pytest.raises(RuntimeError):
+        og.every_n_step(0, ball)
