@@ -759,11 +759,15 @@ def run_batch(args):
     model = pkg.NeRFRegTr(precision=precision)
     model.load_state_dict(_state(pkg, model))
     model = model.to(dev).train(True)      # batch-statistics BatchNorm, as eval_nerf_regtr.py runs it
+    res = args.res
+    if args.max_tokens:
+        model.set_max_tokens(args.max_tokens)     # configs[4]: ~8k tokens per cloud instead of the reference's 1500
+    model.tc_attention = args.attention == "tc"
     strong = args.total_pairs > 0
     n_pairs = args.total_pairs if strong else args.pairs_per_gpu * world
     mine = sharding.shard_pairs(n_pairs, rank, world)
     n_res = min(len(mine), 32)             # resident distinct pairs per rank (cycled beyond that)
-    host = [pkg.synthetic.make_pair(res=RES, pair_id=pid) for pid in mine[:n_res]]
+    host = [pkg.synthetic.make_pair(res=res, pair_id=pid) for pid in mine[:n_res]]
     pinned = [_pin_pair(p) for p in host]
     resident = [pkg.synthetic.to_device(p, dev) for p in host]
     h2d = sum(_pair_bytes(p) for p in pinned) / max(n_res, 1) * len(mine)
@@ -822,13 +826,14 @@ def run_batch(args):
         mma = 3 if precision == "fp32" else 1
         peak = peaks["bf16_tflops_sustained"]
         line = {
-            "metric": "nerf_pairs_per_sec_128cube", "value": total / (ms / 1e3), "unit": "pairs/s", "n_gpus": world,
+            "metric": "nerf_pairs_per_sec_%dcube" % res, "value": total / (ms / 1e3), "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": "batch %d pairs sharded across %dxB200, 128^3, %s, register forward, one all-gather of SE(3) per batch"
-                                   % (n_pairs, world, "bf16" if precision != "fp32" else "fp32-grade"),
-                       "stage": "batch", "resolution": RES, "pairs_per_step": n_pairs, "pairs_per_step_per_gpu": len(mine),
+            "config": {"workload": "batch %d pairs sharded across %dxB200, %d^3, %s, register forward, one all-gather of SE(3) per batch"
+                                   % (n_pairs, world, res, "bf16" if precision != "fp32" else "fp32-grade"),
+                       "stage": "batch", "resolution": res, "tokens": list(model.last_token_counts),
+                       "max_tokens": int(model.max_tokens), "attention": "tcgen05 (attention.cu)" if model.tc_attention else "mma.sync (transformer.cu)", "pairs_per_step": n_pairs, "pairs_per_step_per_gpu": len(mine),
                        "distinct_pairs_resident_per_gpu": n_res, "bn_mode": "batch statistics",
                        "l2": "per-pair working set (2 x 58.7 MB grids, >3 GB activations) exceeds the 126 MB L2",
                        "parallelism": "sharding.shard_pairs (round robin), no data-path collective, one NCCL all-gather of [%d,3,4] per batch"
@@ -884,6 +889,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="train: pairs per step per GPU")
     ap.add_argument("--pairs-per-gpu", type=int, default=32, help="batch: weak scaling, pairs per GPU per step")
     ap.add_argument("--total-pairs", type=int, default=0, help="batch: strong scaling, total pairs per step")
+    ap.add_argument("--res", type=int, default=RES, help="batch: grid resolution (256 for configs[4])")
+    ap.add_argument("--max-tokens", type=int, default=0, help="batch: cap of the down-sampler (tokens of the pair); 0 = the reference's 3000")
+    ap.add_argument("--attention", default="mma", choices=["tc", "mma"], help="tc = tcgen05 FlashAttention-style kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage", default="full", choices=["full", "register", "train", "batch"],
                     help="full = extract (2 NeRF blocks -> voxel grids) + register (configs[1], the default); register = "

@@ -83,6 +83,7 @@ SIGNATURES = {
     "drb_last_error": (C.c_char_p, []),
     "drb_igemm_error_flag": (c_int, [C.POINTER(c_int)]),
     "drb_error_flag_clear": (c_int, []),
+    "drb_error_flag_detail": (c_int, [C.POINTER(c_int * 16)]),
     "drb_conv3d_igemm": (c_int, [C.POINTER(Conv3dDesc), c_void_p]),
     "drb_conv3d_tile_shape": (c_int, [c_int, c_int, c_int, c_int, C.POINTER(c_int * 4), C.POINTER(c_int * 4)]),
     "drb_split_planes": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),

@@ -124,7 +124,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (((++spins) & 0x3ff) == 0 && clock64() - t0 > 8000000000LL) {
-      if (err) atomicExch(err, code);
+      if (err) {                                  // mapped pinned host memory: survives the trap
+        *(volatile int*)err = code;
+        ((volatile int*)err)[1 + (code & 7) + ((code >= 40) ? 8 : 0) - ((code >= 40) ? 1 : 0)] = code;   // per-site detail
+      }
       __threadfence_system();
       asm volatile("trap;");
     }

@@ -483,7 +483,8 @@ int igemm_make_map(CUtensorMap* map, const void* base, int rank, const uint64_t*
 static constexpr int kMaxDevices = 64;
 struct DeviceState {
   int num_sms = 0;
-  int* err_flag = nullptr;
+  int* err_flag = nullptr;        // device view of the flag
+  int* err_flag_host = nullptr;   // the flag lives in mapped pinned host memory: still readable after a device trap
   bool attr_set = false;
 };
 static DeviceState g_dev[kMaxDevices];
@@ -508,14 +509,19 @@ int igemm_num_sms() {
 
 void igemm_clear_err_flag() {
   DeviceState& st = device_state();
-  if (st.err_flag) cudaMemset(st.err_flag, 0, sizeof(int));
+  if (st.err_flag_host) memset(st.err_flag_host, 0, 16 * sizeof(int));
 }
 
 int* igemm_err_flag() {
   DeviceState& st = device_state();
   if (!st.err_flag) {
-    if (cudaMalloc(&st.err_flag, sizeof(int)) != cudaSuccess) { st.err_flag = nullptr; return nullptr; }
-    cudaMemset(st.err_flag, 0, sizeof(int));
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, 16 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    memset(h, 0, 16 * sizeof(int));       // [0] the flag, [1..15] per-site detail of the pipeline watchdogs
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaFreeHost(h); return nullptr; }
+    st.err_flag_host = (int*)h;
+    st.err_flag = (int*)d;
   }
   return st.err_flag;
 }
@@ -717,6 +723,16 @@ extern "C" int drb_conv3d_tile_shape(int g, int d, int h, int w, int box[4], int
   return 0;
 }
 
+extern "C" int drb_error_flag_detail(int* host16) {
+  if (!host16) return DRB_EINVAL;
+  memset(host16, 0, 16 * sizeof(int));
+  int* flag = device_state().err_flag_host;
+  if (!flag) return 0;
+  (void)cudaDeviceSynchronize();
+  for (int i = 0; i < 16; ++i) host16[i] = ((volatile int*)flag)[i];
+  return 0;
+}
+
 extern "C" int drb_error_flag_clear(void) {
   igemm_clear_err_flag();
   return 0;
@@ -725,9 +741,12 @@ extern "C" int drb_error_flag_clear(void) {
 extern "C" int drb_igemm_error_flag(int* host_value) {
   if (!host_value) return DRB_EINVAL;
   *host_value = 0;
-  int* flag = device_state().err_flag;
+  int* flag = device_state().err_flag_host;
   if (!flag) return 0;
-  DRB_CUDA_OK(cudaMemcpy(host_value, flag, sizeof(int), cudaMemcpyDeviceToHost));
+  // wait for the work in flight; after a device-side trap this returns an error, but the flag (pinned host
+  // memory, written with a system-scope fence before the trap) still tells which watchdog fired
+  (void)cudaDeviceSynchronize();
+  *host_value = *(volatile int*)flag;
   return 0;
 }
 

@@ -1035,7 +1035,7 @@ surface_mask_kernel(const NgpDev p, const MarchArgs a, const MarchAux aux, const
     // watchdog: a scheduling bug must not hang the GPU box (~30 s at 2 GHz, then give up) - and a truncated
     // march must not pass for a result: the flag makes the host call fail (drb_march_status)
     if ((round & a.watchdog_mask) == a.watchdog_mask && clock64() - t_start > a.watchdog_clocks) {
-      if (lane == 0 && a.err) atomicExch(a.err, 31);
+      if (lane == 0 && a.err) *(volatile int*)a.err = 31;
       break;
     }
     ++st_rounds;

@@ -22,7 +22,7 @@ __global__ void trilinear_gather_kernel(const float* __restrict__ p1, int dc, in
   if (warp >= k) return;
   const long long idx = mask[warp];
   if (idx < 0 || idx >= (long long)X * Y * Z) {      // stale mask of another resolution: flag, do not touch memory
-    if (lane == 0 && err) atomicExch(err, 21);
+    if (lane == 0 && err) *(volatile int*)err = 21;
     return;
   }
   const int z = (int)(idx % Z);
@@ -92,7 +92,7 @@ __global__ void mark_need_kernel(const long long* __restrict__ mask, int k, int 
   if (i >= k) return;
   const long long idx = mask[i];
   if (idx < 0 || idx >= (long long)X * Y * Z) {
-    if (err) atomicExch(err, 21);
+    if (err) *(volatile int*)err = 21;
     return;
   }
   const int z = (int)(idx % Z);

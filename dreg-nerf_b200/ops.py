@@ -96,6 +96,12 @@ def conv3d_igemm(x_planes, w_planes, k, planes=2, bias=None, residual=None, relu
     return out, (o_hi, o_lo)
 
 
+def error_flag_detail():
+    v = (C.c_int * 16)()
+    check(_lib.load().drb_error_flag_detail(C.byref(v)), "drb_error_flag_detail")
+    return list(v)
+
+
 def igemm_error_flag():
     v = C.c_int(0)
     check(_lib.load().drb_igemm_error_flag(C.byref(v)), "drb_igemm_error_flag")

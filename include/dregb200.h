@@ -45,6 +45,8 @@ int drb_igemm_error_flag(int* host_value);
 /* The flag of the current device is sticky; codes: 1-4 / 11-14 tcgen05 pipeline watchdogs (igemm / wgrad), 21 mask
  * index out of range, 31 surface-field marcher watchdog (result truncated).  Clears it. */
 int drb_error_flag_clear(void);
+/* Debug: the flag and 15 per-site detail words (which watchdog sites fired).  Synchronises. */
+int drb_error_flag_detail(int* host16);
 
 /* ------------------------------------------------------------------------------------------
  * R2 / R6 / R7: nn.Conv3d (conerf/model/resnet3d.py:81-86,120, feature_pyramid_net.py:24,33)
