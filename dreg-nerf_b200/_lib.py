@@ -22,7 +22,7 @@ class Conv3dDesc(C.Structure):
                 ("bias", c_void_p), ("residual", c_void_p),
                 ("out", c_void_p), ("out_hi", c_void_p), ("out_lo", c_void_p),
                 ("ld_out", c_ll), ("bn_accum", c_void_p), ("tile_list", c_void_p), ("tile_count", c_void_p),
-                ("acc_scale_dev", c_void_p * 2)]
+                ("acc_scale_dev", c_void_p * 2), ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_size_t)]
 
 
 class WgradDesc(C.Structure):
@@ -117,10 +117,10 @@ SIGNATURES = {
     "drb_mha_core": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float,
                              c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "drb_mha_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "drb_mha_tc_pack": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
-                                c_size_t, c_void_p]),
-    "drb_mha_tc_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                                   c_void_p, c_int, c_int, c_void_p]),
+    "drb_mha_tc_pack": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                c_void_p, c_size_t, c_void_p]),
+    "drb_mha_tc_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_void_p]),
     "drb_engine_set_tc_attention": (c_int, [c_void_p, c_int]),
     "drb_softmax_weighted_xyz": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "drb_overlap_sigmoid": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -248,19 +248,28 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
 }
 
 // q / k / v: fp32 rows [n][ld] (columns head * 32 + d).  Qp, Kp: [heads][n_pad][64]; Vt: [heads][32][n_pad].
+// The rows form two segments (source cloud [0, split), target cloud [split, n)); the second one starts at the
+// 128-aligned packed row split_pad: TMA needs the innermost start of a box 16-byte aligned, and tokens are the
+// innermost axis of V^T.
 __global__ void att_pack_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
-                                const float* __restrict__ v, int ldv, int n, int n_pad, int heads, float q_scale,
-                                plane_t* __restrict__ qp_hi, plane_t* __restrict__ qp_lo, plane_t* __restrict__ kp_hi,
-                                plane_t* __restrict__ kp_lo, plane_t* __restrict__ vt_hi, plane_t* __restrict__ vt_lo) {
+                                const float* __restrict__ v, int ldv, int n, int split, int split_pad, int n_pad,
+                                int heads, float q_scale, plane_t* __restrict__ qp_hi, plane_t* __restrict__ qp_lo,
+                                plane_t* __restrict__ kp_hi, plane_t* __restrict__ kp_lo, plane_t* __restrict__ vt_hi,
+                                plane_t* __restrict__ vt_lo) {
   const bool pair = qp_lo != nullptr;
   const long long total = (long long)heads * n_pad * 64;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  auto source_row = [&](int ptok) -> int {      // packed row -> input row, -1 for padding
+    if (ptok < split) return ptok;
+    const int r = ptok - split_pad + split;
+    return (ptok >= split_pad && r < n) ? r : -1;
+  };
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int d = (int)(i & 63);
     const long long r = i >> 6;
-    const int tok = (int)(r % n_pad), h = (int)(r / n_pad);
+    const int tok = source_row((int)(r % n_pad)), h = (int)(r / n_pad);
     float qv = 0.f, kv = 0.f;
-    if (d < 32 && tok < n) {
+    if (d < 32 && tok >= 0) {
       qv = q[(long long)tok * ldq + h * 32 + d] * q_scale;
       kv = k[(long long)tok * ldk + h * 32 + d];
     }
@@ -272,13 +281,13 @@ __global__ void att_pack_kernel(const float* __restrict__ q, int ldq, const floa
     kp_hi[i] = a;
     if (pair) kp_lo[i] = b;
   }
-  // V transposed: thread per (head, token, d) with token fastest for coalesced writes
+  // V transposed: thread per (head, d, token) with token fastest for coalesced writes
   const long long totv = (long long)heads * 32 * n_pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totv; i += stride) {
-    const int tok = (int)(i % n_pad);
+    const int tok = source_row((int)(i % n_pad));
     const long long r = i / n_pad;
     const int d = (int)(r & 31), h = (int)(r >> 5);
-    const float vv = tok < n ? v[(long long)tok * ldv + h * 32 + d] : 0.f;
+    const float vv = tok >= 0 ? v[(long long)tok * ldv + h * 32 + d] : 0.f;
     plane_t a, b;
     split16(vv, pair, a, b);
     vt_hi[i] = a;
@@ -286,21 +295,24 @@ __global__ void att_pack_kernel(const float* __restrict__ q, int ldq, const floa
   }
 }
 
+static inline int att_pad128(int n) { return ((n + 127) / 128) * 128; }
+static inline int att_n_pad(int n) { return att_pad128(n) + 256; }      // two padded segments + one spare tile
 static size_t att_plane_elems(int n_pad, int heads) { return (size_t)heads * n_pad * 64; }
 
 extern "C" size_t drb_mha_tc_workspace_bytes(int n, int heads, int planes) {
-  const int n_pad = ((n + 127) / 128) * 128 + 128;
+  const int n_pad = att_n_pad(n);
   // Qp + Kp ([heads][n_pad][64]) + Vt ([heads][32][n_pad]) per plane
   return (size_t)planes * (2 * att_plane_elems(n_pad, heads) + (size_t)heads * 32 * n_pad) * sizeof(plane_t) + 1024;
 }
 
 extern "C" int drb_mha_tc_pack(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int n,
-                               int heads, int planes, float scale, void* workspace, size_t workspace_bytes,
+                               int split, int heads, int planes, float scale, void* workspace, size_t workspace_bytes,
                                cudaStream_t stream) {
   DRB_REQUIRE(q && k && v && workspace && n > 0 && heads > 0 && (planes == 1 || planes == 2), "drb_mha_tc_pack: bad arguments");
+  DRB_REQUIRE(split >= 0 && split <= n, "drb_mha_tc_pack: split outside [0, n]");
   DRB_REQUIRE(workspace_bytes >= drb_mha_tc_workspace_bytes(n, heads, planes), "drb_mha_tc_pack: workspace too small");
   DRB_REQUIRE(((uintptr_t)workspace & 1023) == 0, "drb_mha_tc_pack: workspace must be 1024-byte aligned");
-  const int n_pad = ((n + 127) / 128) * 128 + 128;
+  const int n_pad = att_n_pad(n);
   const size_t pe = att_plane_elems(n_pad, heads), ve = (size_t)heads * 32 * n_pad;
   plane_t* base = (plane_t*)workspace;
   plane_t* qp_hi = base; plane_t* kp_hi = qp_hi + pe; plane_t* vt_hi = kp_hi + pe;
@@ -309,23 +321,25 @@ extern "C" int drb_mha_tc_pack(const float* q, int ldq, const float* k, int ldk,
   const long long total = (long long)heads * n_pad * 64;
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  att_pack_kernel<<<grid, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, n, n_pad, heads, scale * 1.4426950408889634f, qp_hi,
-                                            qp_lo, kp_hi, kp_lo, vt_hi, vt_lo);
+  att_pack_kernel<<<grid, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, n, split, att_pad128(split), n_pad, heads,
+                                            scale * 1.4426950408889634f, qp_hi, qp_lo, kp_hi, kp_lo, vt_hi, vt_lo);
   DRB_LAUNCH_OK();
   return 0;
 }
 
-// Attention of the queries [q_row0, q_row0 + nq) against the keys / values [k_row0, k_row0 + nk) of ONE packed
-// workspace (n rows packed by drb_mha_tc_pack); output rows out_row0 + i.
-extern "C" int drb_mha_tc_forward(const void* workspace, int n, int heads, int planes, int q_row0, int nq, int k_row0,
-                                  int nk, float* out, void* out_hi, void* out_lo, int ld_out, int out_row0,
-                                  cudaStream_t stream) {
+// Attention of the queries of segment q_seg (0: rows [0, split), 1: rows [split, n)) against the keys / values of
+// segment k_seg of ONE packed workspace; output rows are the queries' input row indices.
+extern "C" int drb_mha_tc_forward(const void* workspace, int n, int split, int heads, int planes, int q_seg, int k_seg,
+                                  float* out, void* out_hi, void* out_lo, int ld_out, cudaStream_t stream) {
   DRB_REQUIRE(workspace && n > 0 && heads > 0 && (planes == 1 || planes == 2), "drb_mha_tc_forward: bad arguments");
-  DRB_REQUIRE(nq >= 0 && nk > 0 && q_row0 >= 0 && k_row0 >= 0 && q_row0 + nq <= n && k_row0 + nk <= n,
-              "drb_mha_tc_forward: segment outside the packed rows");
+  DRB_REQUIRE(split >= 0 && split <= n && (q_seg == 0 || q_seg == 1) && (k_seg == 0 || k_seg == 1),
+              "drb_mha_tc_forward: bad segment");
   DRB_REQUIRE((out || out_hi) && ld_out % 8 == 0, "drb_mha_tc_forward: bad output");
+  const int nq = q_seg ? n - split : split, nk = k_seg ? n - split : split;
+  DRB_REQUIRE(nk > 0, "drb_mha_tc_forward: empty key segment");
   if (nq == 0) return 0;
-  const int n_pad = ((n + 127) / 128) * 128 + 128;
+  const int split_pad = att_pad128(split);
+  const int n_pad = att_n_pad(n);
   const size_t pe = att_plane_elems(n_pad, heads), ve = (size_t)heads * 32 * n_pad;
   const plane_t* base = (const plane_t*)workspace;
   const plane_t* qp[2] = {base, nullptr};
@@ -350,8 +364,11 @@ extern "C" int drb_mha_tc_forward(const void* workspace, int n, int heads, int p
   if (planes == 1) { mQ[1] = mQ[0]; mK[1] = mK[0]; mV[1] = mV[0]; }
   AttArgs a;
   memset(&a, 0, sizeof(a));
-  a.nq = nq; a.nk = nk; a.q_row0 = q_row0; a.k_row0 = k_row0; a.heads = heads; a.planes = planes;
-  a.out = out; a.out_hi = (plane_t*)out_hi; a.out_lo = (plane_t*)out_lo; a.ld_out = ld_out; a.out_row0 = out_row0;
+  a.nq = nq; a.nk = nk;
+  a.q_row0 = q_seg ? split_pad : 0; a.k_row0 = k_seg ? split_pad : 0;
+  a.heads = heads; a.planes = planes;
+  a.out = out; a.out_hi = (plane_t*)out_hi; a.out_lo = (plane_t*)out_lo; a.ld_out = ld_out;
+  a.out_row0 = q_seg ? split : 0;
   a.err = igemm_err_flag();
   const size_t smem = 1024 + (size_t)planes * (kQBytes + 2 * (kKBytes + kVBytes) + kPBytes) + 128;
   DRB_CUDA_OK(cudaFuncSetAttribute(att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -163,6 +163,8 @@ static int build(drb_engine* e) {
   e->raw = e->alloc<float>(raw_max);
   e->raw2 = e->alloc<float>(raw_max);
   e->bn_accum = e->alloc<double>((long long)kG * 2048 * 2);
+  e->splitk_ws_bytes = (size_t)24 << 20;     // <= 148 (tile, slice) pairs of 128 x 256 fp32
+  e->splitk_ws = e->alloc<uint8_t>((long long)e->splitk_ws_bytes);
   // FPN: lat[i] / p[i] live at the resolution of c(i+1); c1 for i = 0
   const Act* feats[5] = {&e->c1, &e->c[0], &e->c[1], &e->c[2], &e->c[3]};
   for (int i = 0; i < 5; ++i) {
@@ -253,6 +255,8 @@ int engine_run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
   // the weight pre-scale lives on the device (drb_engine_commit_params never synchronises)
   cd.acc_scale_dev[0] = scale_dev0;
   cd.acc_scale_dev[1] = scale_dev1;
+  cd.splitk_ws = e->splitk_ws;
+  cd.splitk_ws_bytes = e->splitk_ws_bytes;
   e->launches += 1;
   if (!e->profile) return drb_conv3d_igemm(&cd, s);
   drb_engine::ProfRec r;
@@ -790,17 +794,18 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
   };
   // multi-head attention of the query segment [q0, q0 + nq) against the key segment [k0, k0 + nk) of one in_proj
   // output; `packed` says whether this qkv has already been packed for the tensor-core kernel
-  auto attend = [&](const float* qkv, bool& packed, int q0, int nq, int k0, int nk, plane_t* ohi, plane_t* olo) -> int {
+  auto attend = [&](const float* qkv, bool& packed, int q_seg, int k_seg, plane_t* ohi, plane_t* olo) -> int {
     if (e->tc_attention) {
       if (!packed) {
         e->launches += 1;
-        DRB_TRY(drb_mha_tc_pack(qkv, 768, qkv + 256, 768, qkv + 512, 768, m, 8, e->cfg.planes, att_scale, e->att_ws,
+        DRB_TRY(drb_mha_tc_pack(qkv, 768, qkv + 256, 768, qkv + 512, 768, m, ns, 8, e->cfg.planes, att_scale, e->att_ws,
                                 e->att_ws_bytes, s));
         packed = true;
       }
       e->launches += 1;
-      return drb_mha_tc_forward(e->att_ws, m, 8, e->cfg.planes, q0, nq, k0, nk, nullptr, ohi, olo, 256, q0, s);
+      return drb_mha_tc_forward(e->att_ws, m, ns, 8, e->cfg.planes, q_seg, k_seg, nullptr, ohi, olo, 256, s);
     }
+    const int q0 = q_seg ? ns : 0, nq = q_seg ? nt : ns, k0 = k_seg ? ns : 0, nk = k_seg ? nt : ns;
     e->launches += 1;
     return drb_mha_core(qkv + (long long)q0 * 768, 768, qkv + (long long)k0 * 768 + 256, 768,
                         qkv + (long long)k0 * 768 + 512, 768, nq, nk, 8, att_scale, nullptr, off(ohi, (long long)q0 * 256),
@@ -817,8 +822,8 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
     DRB_TRY(linear(t.self_attn.in_proj, v.xn1_hi, v.xn1_lo, m, 256, nullptr, 0, 1.f, v.qkv_s, nullptr, nullptr));
     {
       bool packed = false;
-      DRB_TRY(attend(v.qkv_s, packed, 0, ns, 0, ns, v.att_s_hi, v.att_s_lo));
-      DRB_TRY(attend(v.qkv_s, packed, ns, nt, ns, nt, v.att_s_hi, v.att_s_lo));
+      DRB_TRY(attend(v.qkv_s, packed, 0, 0, v.att_s_hi, v.att_s_lo));
+      DRB_TRY(attend(v.qkv_s, packed, 1, 1, v.att_s_hi, v.att_s_lo));
     }
     DRB_TRY(linear(t.self_attn.out_proj, v.att_s_hi, v.att_s_lo, m, 256, x0, 0, 1.f, v.x1, nullptr, nullptr));
     // cross attention, both directions from the same pre-update normalised features
@@ -827,8 +832,8 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
     DRB_TRY(linear(t.cross_attn.in_proj, v.xn2_hi, v.xn2_lo, m, 256, nullptr, 0, 1.f, v.qkv_c, nullptr, nullptr));
     {
       bool packed = false;
-      DRB_TRY(attend(v.qkv_c, packed, 0, ns, ns, nt, v.att_c_hi, v.att_c_lo));
-      DRB_TRY(attend(v.qkv_c, packed, ns, nt, 0, ns, v.att_c_hi, v.att_c_lo));
+      DRB_TRY(attend(v.qkv_c, packed, 0, 1, v.att_c_hi, v.att_c_lo));
+      DRB_TRY(attend(v.qkv_c, packed, 1, 0, v.att_c_hi, v.att_c_lo));
     }
     DRB_TRY(linear(t.cross_attn.out_proj, v.att_c_hi, v.att_c_lo, m, 256, v.x1, 0, 1.f, v.x2, nullptr, nullptr));
     // feed forward

@@ -132,6 +132,7 @@ struct drb_engine {
   long long raw_elems = 0;
   float* raw2 = nullptr;            // second scratch (downsample branch)
   double* bn_accum = nullptr;
+  void* splitk_ws = nullptr; size_t splitk_ws_bytes = 0;   // split-K slices of the deep, few-tile GEMMs
   drb::Act c1, x0, c[4];            // c[0..3] = c2..c5
   std::vector<drb::Act> tmp;        // per-block temporaries
   drb::Act lat[5], sum[4], p[5];    // p[0] = p1 ... p[4] = p5

@@ -38,7 +38,10 @@ struct IgemmArgs {
   int stages;
   int chunk;             // k-iterations accumulated in TMEM before the fp32 register add
   int cs;                // cluster size along M (1, 2 or 4): the weight tile is TMA-multicast
-  int splits;            // split-K factor (> 1: partial sums are red.add'ed into a pre-zeroed `out`)
+  int splits;            // split-K factor (> 1: every K slice stores its partial tile into `splitk_ws`, a second
+                         // kernel adds the slices in a fixed order: run-to-run bit-stable, no atomics)
+  float* splitk_ws;      // [splits][M][ld] fp32
+  long long m_total;     // M = G*D*H*W
   int kper;              // k-iterations per split (multiple of chunk)
   double* bn_accum;      // optional [G][Cout][2]: per-channel sum / sum of squares of the output (fused BN stats)
   const int* tile_list;  // optional: compacted list of M-tile indices to compute (output-sparse conv)
@@ -65,14 +68,15 @@ __device__ __forceinline__ void epilogue_store32(const IgemmArgs& a, float (&f)[
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] *= acc_scale;
   if (a.splits > 1) {
-    // split-K: partial sums of the K slices meet in a pre-zeroed fp32 output (bias joins slice 0)
+    // split-K: this K slice's partial tile goes to its own plane of the workspace (plain stores)
+    float* dst = a.splitk_ws + (long long)split * a.m_total * a.ld + off;
+    if (full) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (n + j < a.Cout) {
-        float v = f[j];
-        if (a.bias && split == 0) v += __ldg(a.bias + n + j);
-        atomicAdd(a.out + off + j, v);
-      }
+      for (int j = 0; j < 32; j += 4) *(float4*)(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < a.Cout) dst[j] = f[j];
     }
     return;
   }
@@ -434,6 +438,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   }
 }
 
+// out[m][n] = bias[n] + sum over the K slices, slices added in index order (deterministic).
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long m_total, int cout, long long ld,
+                                     const float* __restrict__ bias, float* __restrict__ out) {
+  const long long total = m_total * ld;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int n = (int)(i % ld);
+    if (n >= cout) continue;
+    float acc = bias ? bias[n] : 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * total + i];
+    out[i] = acc;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -586,7 +604,8 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   a.splits = 1;
   a.kper = kiters_h;
   const bool plain = d->out && !d->out_hi && !d->residual && !d->relu && (d->out_scale == 0.f || d->out_scale == 1.f);
-  if (plain && tiles_h * 2 <= nsm && kiters_h >= 4 * a.chunk) {
+  a.m_total = (long long)a.G * a.D * a.H * a.W;
+  if (plain && d->splitk_ws && tiles_h * 2 <= nsm && kiters_h >= 4 * a.chunk) {
     int want = (int)(nsm / tiles_h);
     int maxs = kiters_h / (2 * a.chunk);
     int sp = want < maxs ? want : maxs;
@@ -595,8 +614,14 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
       kper = ((kper + a.chunk - 1) / a.chunk) * a.chunk;
       a.kper = kper;
       a.splits = (kiters_h + kper - 1) / kper;
+      // the slices meet in the caller's workspace; too small a workspace simply means no split
+      if ((size_t)a.splits * (size_t)a.m_total * (size_t)ld * sizeof(float) > d->splitk_ws_bytes) {
+        a.splits = 1;
+        a.kper = kiters_h;
+      }
     }
   }
+  a.splitk_ws = (float*)d->splitk_ws;
   a.tile_list = d->tile_list;
   a.tile_count = d->tile_count;
   // BatchNorm statistics of the output: fused into the epilogue when a tile never straddles two grids
@@ -687,8 +712,6 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   }
   const int tiles_m = cdiv(a.W, a.bw) * cdiv(a.H, a.bh) * cdiv(a.D, a.bd) * cdiv(a.G, a.bg);
   const int tiles = cdiv(tiles_m, a.cs) * cdiv(a.Cout, a.BN) * a.splits;     // work items (one per cluster)
-  if (a.splits > 1)
-    DRB_CUDA_OK(cudaMemsetAsync(a.out, 0, sizeof(float) * (size_t)a.G * a.D * a.H * a.W * (size_t)a.ld, stream));
   const int max_clusters = igemm_num_sms() / a.cs;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   cudaLaunchConfig_t cfg;
@@ -709,6 +732,13 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
     DRB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel<true>, mA[0], mA[1], mB[0], mB[1], a));
   else
     DRB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel<false>, mA[0], mA[1], mB[0], mB[1], a));
+  if (a.splits > 1) {
+    const long long total = a.m_total * a.ld;
+    int rgrid = (int)((total + 255) / 256);
+    if (rgrid > 148 * 8) rgrid = 148 * 8;
+    splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(a.splitk_ws, a.splits, a.m_total, a.Cout, a.ld, a.bias, a.out);
+    DRB_LAUNCH_OK();
+  }
   if (bn_separate)
     return drb_bn_stats(a.out, a.G, (long long)a.D * a.H * a.W, a.Cout, d->bn_accum, stream);
   return 0;

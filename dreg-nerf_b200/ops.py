@@ -91,6 +91,8 @@ def conv3d_igemm(x_planes, w_planes, k, planes=2, bias=None, residual=None, relu
                            out_hi=o_hi.data_ptr() if o_hi is not None else None,
                            out_lo=o_lo.data_ptr() if o_lo is not None else None, ld_out=ld,
                            bn_accum=bn_accum.data_ptr() if bn_accum is not None else None)
+    ws = torch.empty(24 << 20, dtype=torch.uint8, device=dev)      # split-K slices (deterministic reduction)
+    desc.splitk_ws, desc.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     with _dev(x_hi):
         check(_lib.load().drb_conv3d_igemm(C.byref(desc), stream_ptr()), "drb_conv3d_igemm")
     return out, (o_hi, o_lo)
@@ -513,9 +515,10 @@ def downsample_backward(dout, tape, rounds, c):
     return cur
 
 
-def mha_tc(qkv, segments, heads=8, planes=2, scale=None, want_planes=False):
-    """tcgen05 attention over one in_proj output qkv [n, 768]: ``segments`` = list of (q_row0, nq, k_row0, nk);
-    -> fp32 [n, 256] with the rows of every query segment filled (and optionally the 16-bit planes)."""
+def mha_tc(qkv, split, pairs, heads=8, planes=2, scale=None, want_planes=False):
+    """tcgen05 attention over one in_proj output qkv [n, 768] whose rows are two segments [0, split) and
+    [split, n); ``pairs`` = list of (q_seg, k_seg); -> fp32 [n, 256] with the rows of every query segment filled
+    (and optionally the 16-bit planes)."""
     n = qkv.shape[0]
     scale = scale if scale is not None else 32 ** -0.5
     lib = _lib.load()
@@ -527,9 +530,9 @@ def mha_tc(qkv, segments, heads=8, planes=2, scale=None, want_planes=False):
     o_lo = torch.zeros((n, 256), dtype=torch.float16, device=qkv.device) if (want_planes and planes == 2) else None
     with _dev(qkv):
         check(lib.drb_mha_tc_pack(ptr(qkv), qkv.stride(0), C.c_void_p(qkv.data_ptr() + 4 * 256), qkv.stride(0),
-                                  C.c_void_p(qkv.data_ptr() + 4 * 512), qkv.stride(0), n, heads, planes, scale,
+                                  C.c_void_p(qkv.data_ptr() + 4 * 512), qkv.stride(0), n, split, heads, planes, scale,
                                   C.c_void_p(base), nbytes, stream_ptr()), "drb_mha_tc_pack")
-        for q0, nq, k0, nk in segments:
-            check(lib.drb_mha_tc_forward(C.c_void_p(base), n, heads, planes, q0, nq, k0, nk, ptr(out), ptr(o_hi), ptr(o_lo),
-                                         256, q0, stream_ptr()), "drb_mha_tc_forward")
+        for q_seg, k_seg in pairs:
+            check(lib.drb_mha_tc_forward(C.c_void_p(base), n, split, heads, planes, q_seg, k_seg, ptr(out), ptr(o_hi),
+                                         ptr(o_lo), 256, stream_ptr()), "drb_mha_tc_forward")
     return (out, (o_hi, o_lo)) if want_planes else out

@@ -84,6 +84,11 @@ typedef struct drb_conv3d_desc {
   /* Optional device scalars multiplied into acc_scale inside the kernel (pre-scales that only exist on the
    * device: packed weights, gradient planes of drb_grad_split); NULL = 1.                               */
   const float* acc_scale_dev[2];
+  /* Optional split-K workspace (device).  Few output tiles but a long reduction (deep backbone layers) are split
+   * over K: every slice stores its partial tile here and a second kernel adds the slices in index order, so the
+   * result is run-to-run bit-stable (no atomics).  NULL / too small: the reduction is not split.            */
+  void* splitk_ws;
+  size_t splitk_ws_bytes;
 } drb_conv3d_desc;
 /* Geometry of the 128-row output tiles drb_conv3d_igemm uses for a [g][d][h][w] volume: box extents
  * (bg, bd, bh, bw) and tile counts (tg, td, th, tw); tile index = ((ig*td + id)*th + ih)*tw + iw. */
@@ -209,14 +214,15 @@ int drb_mha_core(const float* q, int ldq, const float* k, int ldk, const float* 
 /* The same attention core on the 5th-gen tensor cores (tcgen05 + TMEM + TMA, FlashAttention style: logits and
  * probabilities never leave the SM).  drb_mha_tc_pack converts the fp32 q / k / v rows of ONE in_proj output
  * ([n][ld], head h at columns 32 h ..) into per-head 16-bit planes inside `workspace` (1024-byte aligned,
- * drb_mha_tc_workspace_bytes); drb_mha_tc_forward then attends the queries [q_row0, q_row0 + nq) to the keys /
- * values [k_row0, k_row0 + nk) of that workspace - self-attention of src and tgt and both cross directions are
- * four calls over two packs.  Output row out_row0 + i, columns 32 h .. of out / out_hi / out_lo (pitch ld_out). */
+ * drb_mha_tc_workspace_bytes); the rows form two segments - the source cloud [0, split) and the target cloud
+ * [split, n) (split = n: one segment).  drb_mha_tc_forward attends the queries of segment q_seg to the keys /
+ * values of segment k_seg: self-attention of both clouds and both cross directions are four calls over two packs.
+ * Output rows are the queries' input row indices, columns 32 h .. of out / out_hi / out_lo (pitch ld_out). */
 size_t drb_mha_tc_workspace_bytes(int n, int heads, int planes);
-int drb_mha_tc_pack(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int n, int heads,
-                    int planes, float scale, void* workspace, size_t workspace_bytes, drb_stream_t stream);
-int drb_mha_tc_forward(const void* workspace, int n, int heads, int planes, int q_row0, int nq, int k_row0, int nk,
-                       float* out, void* out_hi, void* out_lo, int ld_out, int out_row0, drb_stream_t stream);
+int drb_mha_tc_pack(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int n, int split,
+                    int heads, int planes, float scale, void* workspace, size_t workspace_bytes, drb_stream_t stream);
+int drb_mha_tc_forward(const void* workspace, int n, int split, int heads, int planes, int q_seg, int k_seg,
+                       float* out, void* out_hi, void* out_lo, int ld_out, drb_stream_t stream);
 /* CorrespondenceDecoder.simple_attention tail (nerf_regtr.py:292-306): row softmax of s [nq][ld]
  * over nk keys, weighted sum of xyz [nk][ld_xyz] -> out [nq][3]. */
 int drb_softmax_weighted_xyz(const float* s, int ld, int nq, int nk, const float* xyz, int ld_xyz,
