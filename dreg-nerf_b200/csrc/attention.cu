@@ -24,14 +24,18 @@ static constexpr uint32_t kKBytes = kAttK * 64 * 2;          // 16 KB per plane
 static constexpr uint32_t kVBytes = 32 * kAttK * 2;          //  8 KB per plane (two [32][64] sub-tiles)
 static constexpr uint32_t kPBytes = kAttQ * kAttK * 2;       // 32 KB per plane (two [128][64] sub-tiles)
 
-struct AttArgs {
-  int nq, nk;               // valid queries / keys of this call
+struct AttProblem {
+  int nq, nk;               // valid queries / keys
   int q_row0, k_row0;       // first row of the query / key segment inside the packed planes
+  int out_row0;             // output row of query 0
+};
+struct AttArgs {
+  AttProblem pr[2];         // blockIdx.z selects the problem (both directions of one attention in one launch)
   int heads, planes;
-  float* out;               // fp32 [.][ld_out] or null (row = q_row0-relative index + out_row0)
+  float* out;               // fp32 [.][ld_out] or null
   plane_t* out_hi;
   plane_t* out_lo;
-  int ld_out, out_row0;
+  int ld_out;
   int* err;
 };
 
@@ -42,13 +46,16 @@ __device__ __forceinline__ void fence_proxy_async() {
 __global__ void __launch_bounds__(kAttThreads, 1)
 att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmQ1,
                const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmK1,
-               const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1, const AttArgs a) {
+               const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1, const AttArgs args) {
+  const AttProblem a = args.pr[blockIdx.z];
+  if ((int)blockIdx.x * kAttQ >= a.nq) return;       // this direction has fewer query tiles (whole CTA leaves)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y;
   const int q0 = blockIdx.x * kAttQ;
-  const int P = a.planes;
+  const int P = args.planes;
+  int* const err = args.err;
   // shared-memory plan: Q | 2 x (K, V^T) stages | P | barriers
   const uint32_t stage_bytes = (uint32_t)P * (kKBytes + kVBytes);
   uint8_t* sQ = smem;
@@ -88,7 +95,7 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
       if (P == 2) tma_load_3d(smem_u32(sQ) + kQBytes, &tmQ1, q_full, 0, a.q_row0 + q0, head);
       for (int t = 0; t < ntiles; ++t) {
         const int s = t & 1;
-        mbar_wait(kv_empty0 + 8 * s, (((uint32_t)t >> 1) & 1u) ^ 1u, a.err, 41);
+        mbar_wait(kv_empty0 + 8 * s, (((uint32_t)t >> 1) & 1u) ^ 1u, err, 41);
         const uint32_t fb = kv_full0 + 8 * s;
         mbar_expect_tx(fb, stage_bytes);
         const uint32_t sk = smem_u32(sKV + (size_t)s * stage_bytes);
@@ -107,8 +114,8 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
       const uint32_t idesc_pv = umma_idesc_16(kAttQ, 32, P == 1);
       auto issue_s = [&](int t) {
         const int s = t & 1;
-        mbar_wait(kv_full0 + 8 * s, ((uint32_t)t >> 1) & 1u, a.err, 42);
-        if (t > 0) mbar_wait(s_free, ((uint32_t)(t - 1)) & 1u, a.err, 43);    // soft-max has read S of tile t - 1
+        mbar_wait(kv_full0 + 8 * s, ((uint32_t)t >> 1) & 1u, err, 42);
+        if (t > 0) mbar_wait(s_free, ((uint32_t)(t - 1)) & 1u, err, 43);    // soft-max has read S of tile t - 1
         tc_fence_after();
         const uint32_t sk = smem_u32(sKV + (size_t)s * stage_bytes);
         const uint64_t dq0 = umma_desc_sw128(smem_u32(sQ)), dk0 = umma_desc_sw128(sk);
@@ -124,12 +131,12 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
         }
         umma_commit(s_full);
       };
-      mbar_wait(q_full, 0, a.err, 44);
+      mbar_wait(q_full, 0, err, 44);
       issue_s(0);
       for (int t = 0; t < ntiles; ++t) {
         if (t + 1 < ntiles) issue_s(t + 1);
         const int s = t & 1;
-        mbar_wait(p_full, (uint32_t)t & 1u, a.err, 45);
+        mbar_wait(p_full, (uint32_t)t & 1u, err, 45);
         tc_fence_after();
         const uint32_t sv = smem_u32(sKV + (size_t)s * stage_bytes) + (uint32_t)P * kKBytes;
         const uint32_t sp = smem_u32(sP);
@@ -162,7 +169,7 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
     float m_run = -INFINITY, l_run = 0.f;
     const bool pair = P == 2;
     for (int t = 0; t < ntiles; ++t) {
-      mbar_wait(s_full, (uint32_t)t & 1u, a.err, 46);
+      mbar_wait(s_full, (uint32_t)t & 1u, err, 46);
       tc_fence_after();
       float sv_[128];
 #pragma unroll
@@ -210,7 +217,7 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
       mbar_arrive(p_full);
 #pragma unroll
       for (int j = 0; j < 32; ++j) o[j] *= corr;
-      mbar_wait(pv_full, (uint32_t)t & 1u, a.err, 47);
+      mbar_wait(pv_full, (uint32_t)t & 1u, err, 47);
       tc_fence_after();
       {
         uint32_t v[32];
@@ -224,17 +231,17 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
     const int qi = q0 + row;
     if (qi < a.nq) {
       const float inv = 1.f / l_run;
-      const long long off = (long long)(a.out_row0 + qi) * a.ld_out + head * 32;
+      const long long off = (long long)(a.out_row0 + qi) * args.ld_out + head * 32;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float r0 = o[j] * inv, r1 = o[j + 1] * inv, r2 = o[j + 2] * inv, r3 = o[j + 3] * inv;
-        if (a.out) *(float4*)(a.out + off + j) = make_float4(r0, r1, r2, r3);
-        if (a.out_hi) {
+        if (args.out) *(float4*)(args.out + off + j) = make_float4(r0, r1, r2, r3);
+        if (args.out_hi) {
           plane_t h0, l0, h1, l1, h2, l2, h3, l3;
-          const bool pr = a.out_lo != nullptr;
+          const bool pr = args.out_lo != nullptr;
           split16(r0, pr, h0, l0); split16(r1, pr, h1, l1); split16(r2, pr, h2, l2); split16(r3, pr, h3, l3);
-          *(uint2*)(a.out_hi + off + j) = make_uint2(pack16x2(h0, h1), pack16x2(h2, h3));
-          if (pr) *(uint2*)(a.out_lo + off + j) = make_uint2(pack16x2(l0, l1), pack16x2(l2, l3));
+          *(uint2*)(args.out_hi + off + j) = make_uint2(pack16x2(h0, h1), pack16x2(h2, h3));
+          if (pr) *(uint2*)(args.out_lo + off + j) = make_uint2(pack16x2(l0, l1), pack16x2(l2, l3));
         }
       }
     }
@@ -327,19 +334,34 @@ extern "C" int drb_mha_tc_pack(const float* q, int ldq, const float* k, int ldk,
   return 0;
 }
 
-// Attention of the queries of segment q_seg (0: rows [0, split), 1: rows [split, n)) against the keys / values of
-// segment k_seg of ONE packed workspace; output rows are the queries' input row indices.
-extern "C" int drb_mha_tc_forward(const void* workspace, int n, int split, int heads, int planes, int q_seg, int k_seg,
+// Attention of the queries of segment q_seg (0: rows [0, split), 1: rows [split, n), -1: both segments in one
+// launch) against the keys / values of ONE packed workspace: cross == 0: the queries' own segment (self-attention),
+// cross != 0: the other segment.  Output rows are the queries' input row indices.
+extern "C" int drb_mha_tc_forward(const void* workspace, int n, int split, int heads, int planes, int q_seg, int cross,
                                   float* out, void* out_hi, void* out_lo, int ld_out, cudaStream_t stream) {
   DRB_REQUIRE(workspace && n > 0 && heads > 0 && (planes == 1 || planes == 2), "drb_mha_tc_forward: bad arguments");
-  DRB_REQUIRE(split >= 0 && split <= n && (q_seg == 0 || q_seg == 1) && (k_seg == 0 || k_seg == 1),
-              "drb_mha_tc_forward: bad segment");
+  DRB_REQUIRE(split >= 0 && split <= n && q_seg >= -1 && q_seg <= 1, "drb_mha_tc_forward: bad segment");
   DRB_REQUIRE((out || out_hi) && ld_out % 8 == 0, "drb_mha_tc_forward: bad output");
-  const int nq = q_seg ? n - split : split, nk = k_seg ? n - split : split;
-  DRB_REQUIRE(nk > 0, "drb_mha_tc_forward: empty key segment");
-  if (nq == 0) return 0;
   const int split_pad = att_pad128(split);
   const int n_pad = att_n_pad(n);
+  AttArgs a;
+  memset(&a, 0, sizeof(a));
+  int nprob = 0, max_q = 0;
+  for (int seg = 0; seg < 2; ++seg) {
+    if (q_seg >= 0 && q_seg != seg) continue;
+    const int kseg = cross ? 1 - seg : seg;
+    AttProblem& p = a.pr[nprob];
+    p.nq = seg ? n - split : split;
+    p.nk = kseg ? n - split : split;
+    p.q_row0 = seg ? split_pad : 0;
+    p.k_row0 = kseg ? split_pad : 0;
+    p.out_row0 = seg ? split : 0;
+    if (p.nq == 0) continue;
+    DRB_REQUIRE(p.nk > 0, "drb_mha_tc_forward: empty key segment");
+    if (p.nq > max_q) max_q = p.nq;
+    ++nprob;
+  }
+  if (nprob == 0) return 0;
   const size_t pe = att_plane_elems(n_pad, heads), ve = (size_t)heads * 32 * n_pad;
   const plane_t* base = (const plane_t*)workspace;
   const plane_t* qp[2] = {base, nullptr};
@@ -362,17 +384,12 @@ extern "C" int drb_mha_tc_forward(const void* workspace, int n, int split, int h
     if ((rc = igemm_make_map(&mV[p], vt[p], 3, vdims, vstr, vbox, bf))) return rc;
   }
   if (planes == 1) { mQ[1] = mQ[0]; mK[1] = mK[0]; mV[1] = mV[0]; }
-  AttArgs a;
-  memset(&a, 0, sizeof(a));
-  a.nq = nq; a.nk = nk;
-  a.q_row0 = q_seg ? split_pad : 0; a.k_row0 = k_seg ? split_pad : 0;
   a.heads = heads; a.planes = planes;
   a.out = out; a.out_hi = (plane_t*)out_hi; a.out_lo = (plane_t*)out_lo; a.ld_out = ld_out;
-  a.out_row0 = q_seg ? split : 0;
   a.err = igemm_err_flag();
   const size_t smem = 1024 + (size_t)planes * (kQBytes + 2 * (kKBytes + kVBytes) + kPBytes) + 128;
   DRB_CUDA_OK(cudaFuncSetAttribute(att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)cdiv(nq, kAttQ), (unsigned)heads);
+  dim3 grid((unsigned)cdiv(max_q, kAttQ), (unsigned)heads, (unsigned)nprob);
   att_fwd_kernel<<<grid, kAttThreads, smem, stream>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], a);
   DRB_LAUNCH_OK();
   return 0;

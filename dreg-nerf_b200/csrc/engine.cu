@@ -794,22 +794,23 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
   };
   // multi-head attention of the query segment [q0, q0 + nq) against the key segment [k0, k0 + nk) of one in_proj
   // output; `packed` says whether this qkv has already been packed for the tensor-core kernel
-  auto attend = [&](const float* qkv, bool& packed, int q_seg, int k_seg, plane_t* ohi, plane_t* olo) -> int {
+  // multi-head attention of both clouds over one in_proj output: self (cross == 0) or against the other cloud
+  auto attend = [&](const float* qkv, int cross, plane_t* ohi, plane_t* olo) -> int {
     if (e->tc_attention) {
-      if (!packed) {
-        e->launches += 1;
-        DRB_TRY(drb_mha_tc_pack(qkv, 768, qkv + 256, 768, qkv + 512, 768, m, ns, 8, e->cfg.planes, att_scale, e->att_ws,
-                                e->att_ws_bytes, s));
-        packed = true;
-      }
-      e->launches += 1;
-      return drb_mha_tc_forward(e->att_ws, m, ns, 8, e->cfg.planes, q_seg, k_seg, nullptr, ohi, olo, 256, s);
+      e->launches += 2;
+      DRB_TRY(drb_mha_tc_pack(qkv, 768, qkv + 256, 768, qkv + 512, 768, m, ns, 8, e->cfg.planes, att_scale, e->att_ws,
+                              e->att_ws_bytes, s));
+      return drb_mha_tc_forward(e->att_ws, m, ns, 8, e->cfg.planes, -1, cross, nullptr, ohi, olo, 256, s);
     }
-    const int q0 = q_seg ? ns : 0, nq = q_seg ? nt : ns, k0 = k_seg ? ns : 0, nk = k_seg ? nt : ns;
-    e->launches += 1;
-    return drb_mha_core(qkv + (long long)q0 * 768, 768, qkv + (long long)k0 * 768 + 256, 768,
-                        qkv + (long long)k0 * 768 + 512, 768, nq, nk, 8, att_scale, nullptr, off(ohi, (long long)q0 * 256),
-                        off(olo, (long long)q0 * 256), 256, s);
+    for (int q_seg = 0; q_seg < 2; ++q_seg) {
+      const int k_seg = cross ? 1 - q_seg : q_seg;
+      const int q0 = q_seg ? ns : 0, nq = q_seg ? nt : ns, k0 = k_seg ? ns : 0, nk = k_seg ? nt : ns;
+      e->launches += 1;
+      DRB_TRY(drb_mha_core(qkv + (long long)q0 * 768, 768, qkv + (long long)k0 * 768 + 256, 768,
+                           qkv + (long long)k0 * 768 + 512, 768, nq, nk, 8, att_scale, nullptr,
+                           off(ohi, (long long)q0 * 256), off(olo, (long long)q0 * 256), 256, s));
+    }
+    return 0;
   };
   for (int l = 0; l < kLayers; ++l) {
     TLayer& t = e->tl[l];
@@ -820,21 +821,13 @@ extern "C" int drb_engine_decode(drb_engine* e, const drb_pair_out* o, cudaStrea
     e->launches += 1;
     DRB_TRY(drb_layernorm256(x0, m, P(e, t.n1w), P(e, t.n1b), e->pos, nullptr, v.xn1_hi, v.xn1_lo, s));
     DRB_TRY(linear(t.self_attn.in_proj, v.xn1_hi, v.xn1_lo, m, 256, nullptr, 0, 1.f, v.qkv_s, nullptr, nullptr));
-    {
-      bool packed = false;
-      DRB_TRY(attend(v.qkv_s, packed, 0, 0, v.att_s_hi, v.att_s_lo));
-      DRB_TRY(attend(v.qkv_s, packed, 1, 1, v.att_s_hi, v.att_s_lo));
-    }
+    DRB_TRY(attend(v.qkv_s, 0, v.att_s_hi, v.att_s_lo));
     DRB_TRY(linear(t.self_attn.out_proj, v.att_s_hi, v.att_s_lo, m, 256, x0, 0, 1.f, v.x1, nullptr, nullptr));
     // cross attention, both directions from the same pre-update normalised features
     e->launches += 1;
     DRB_TRY(drb_layernorm256(v.x1, m, P(e, t.n2w), P(e, t.n2b), e->pos, nullptr, v.xn2_hi, v.xn2_lo, s));
     DRB_TRY(linear(t.cross_attn.in_proj, v.xn2_hi, v.xn2_lo, m, 256, nullptr, 0, 1.f, v.qkv_c, nullptr, nullptr));
-    {
-      bool packed = false;
-      DRB_TRY(attend(v.qkv_c, packed, 0, 1, v.att_c_hi, v.att_c_lo));
-      DRB_TRY(attend(v.qkv_c, packed, 1, 0, v.att_c_hi, v.att_c_lo));
-    }
+    DRB_TRY(attend(v.qkv_c, 1, v.att_c_hi, v.att_c_lo));
     DRB_TRY(linear(t.cross_attn.out_proj, v.att_c_hi, v.att_c_lo, m, 256, v.x1, 0, 1.f, v.x2, nullptr, nullptr));
     // feed forward
     e->launches += 1;

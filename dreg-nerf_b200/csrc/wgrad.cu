@@ -305,7 +305,6 @@ extern "C" int drb_conv3d_wgrad(const drb_wgrad_desc* d, cudaStream_t stream) {
   else { a.sdim = 3; a.bw = a.fbw / 2; }
   a.planes = d->planes;
   a.chunk = d->planes == 2 ? 2 : 4;
-  a.BN = d->cin >= 256 ? 256 : (d->cin >= 128 ? 128 : 64);
   const int taps = a.kd * a.kh * a.kw;
   a.c_real = d->c_real > 0 ? d->c_real : d->cin;
   a.taps_real = d->taps_real > 0 ? d->taps_real : taps;
@@ -324,10 +323,19 @@ extern "C" int drb_conv3d_wgrad(const drb_wgrad_desc* d, cudaStream_t stream) {
   const int nsm = igemm_num_sms();
   const long long ftiles = (long long)cdiv(a.W, a.fbw) * cdiv(a.H, a.fbh) * cdiv(a.D, a.fbd) * cdiv(a.G, a.fbg);
   const long long nboxes = 2 * ftiles;
-  const long long base_items = (long long)taps * cdiv(a.Cout, kWM) * cdiv(a.Cin, a.BN);
-  long long splits = (2LL * nsm + base_items - 1) / base_items;
-  long long max_splits = nboxes / (2 * a.chunk);
+  // Work decomposition: (tap, 128 co, BN ci) tiles x K splits.  Small problems (a few hundred tokens, deep
+  // backbone levels) are latency bound: prefer narrower ci tiles and finer K splits until every SM has an item;
+  // large ones (level-1 FPN: thousands of boxes) take the widest tile and ~2 items per SM.
+  long long max_splits = nboxes / a.chunk;
   if (max_splits < 1) max_splits = 1;
+  long long base_items = 0;
+  for (int bn = 256; bn >= 64; bn >>= 1) {
+    if (bn > d->cin && bn != 64) continue;
+    a.BN = bn;
+    base_items = (long long)taps * cdiv(a.Cout, kWM) * cdiv(a.Cin, bn);
+    if (base_items * max_splits >= nsm) break;
+  }
+  long long splits = (2LL * nsm + base_items - 1) / base_items;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   a.splits = (int)splits;

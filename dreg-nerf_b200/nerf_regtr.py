@@ -18,7 +18,7 @@ from . import _lib
 
 _PRECISION_PLANES = {"fp32": 2, "bf16x3": 2, "bf16": 1}
 # attention through the tcgen05 FlashAttention-style kernel (csrc/attention.cu) instead of the mma.sync one
-TC_ATTENTION_DEFAULT = os.environ.get("DRB_TC_ATTENTION", "0") != "0"
+TC_ATTENTION_DEFAULT = os.environ.get("DRB_TC_ATTENTION", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------

@@ -517,8 +517,8 @@ def downsample_backward(dout, tape, rounds, c):
 
 def mha_tc(qkv, split, pairs, heads=8, planes=2, scale=None, want_planes=False):
     """tcgen05 attention over one in_proj output qkv [n, 768] whose rows are two segments [0, split) and
-    [split, n); ``pairs`` = list of (q_seg, k_seg); -> fp32 [n, 256] with the rows of every query segment filled
-    (and optionally the 16-bit planes)."""
+    [split, n); ``pairs`` = list of (q_seg, cross) with q_seg in {0, 1, -1 = both} and cross = attend to the other
+    segment; -> fp32 [n, 256] with the rows of every query segment filled (and optionally the 16-bit planes)."""
     n = qkv.shape[0]
     scale = scale if scale is not None else 32 ** -0.5
     lib = _lib.load()
@@ -532,7 +532,7 @@ def mha_tc(qkv, split, pairs, heads=8, planes=2, scale=None, want_planes=False):
         check(lib.drb_mha_tc_pack(ptr(qkv), qkv.stride(0), C.c_void_p(qkv.data_ptr() + 4 * 256), qkv.stride(0),
                                   C.c_void_p(qkv.data_ptr() + 4 * 512), qkv.stride(0), n, split, heads, planes, scale,
                                   C.c_void_p(base), nbytes, stream_ptr()), "drb_mha_tc_pack")
-        for q_seg, k_seg in pairs:
-            check(lib.drb_mha_tc_forward(C.c_void_p(base), n, split, heads, planes, q_seg, k_seg, ptr(out), ptr(o_hi),
+        for q_seg, cross in pairs:
+            check(lib.drb_mha_tc_forward(C.c_void_p(base), n, split, heads, planes, q_seg, int(cross), ptr(out), ptr(o_hi),
                                          ptr(o_lo), 256, stream_ptr()), "drb_mha_tc_forward")
     return (out, (o_hi, o_lo)) if want_planes else out

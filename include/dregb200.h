@@ -215,13 +215,14 @@ int drb_mha_core(const float* q, int ldq, const float* k, int ldk, const float* 
  * probabilities never leave the SM).  drb_mha_tc_pack converts the fp32 q / k / v rows of ONE in_proj output
  * ([n][ld], head h at columns 32 h ..) into per-head 16-bit planes inside `workspace` (1024-byte aligned,
  * drb_mha_tc_workspace_bytes); the rows form two segments - the source cloud [0, split) and the target cloud
- * [split, n) (split = n: one segment).  drb_mha_tc_forward attends the queries of segment q_seg to the keys /
- * values of segment k_seg: self-attention of both clouds and both cross directions are four calls over two packs.
- * Output rows are the queries' input row indices, columns 32 h .. of out / out_hi / out_lo (pitch ld_out). */
+ * [split, n) (split = n: one segment).  drb_mha_tc_forward attends the queries of segment q_seg (-1: both
+ * segments in one launch) to the keys / values of their own segment (cross == 0, self-attention) or of the other
+ * one (cross != 0): a transformer layer is two packs and two launches.  Output rows are the queries' input row
+ * indices, columns 32 h .. of out / out_hi / out_lo (pitch ld_out). */
 size_t drb_mha_tc_workspace_bytes(int n, int heads, int planes);
 int drb_mha_tc_pack(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int n, int split,
                     int heads, int planes, float scale, void* workspace, size_t workspace_bytes, drb_stream_t stream);
-int drb_mha_tc_forward(const void* workspace, int n, int split, int heads, int planes, int q_seg, int k_seg,
+int drb_mha_tc_forward(const void* workspace, int n, int split, int heads, int planes, int q_seg, int cross,
                        float* out, void* out_hi, void* out_lo, int ld_out, drb_stream_t stream);
 /* CorrespondenceDecoder.simple_attention tail (nerf_regtr.py:292-306): row softmax of s [nq][ld]
  * over nk keys, weighted sum of xyz [nk][ld_xyz] -> out [nq][3]. */

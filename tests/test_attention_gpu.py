@@ -30,8 +30,8 @@ def test_mha_tc_matches_torch(pkg, cuda, planes, tol, ns, nt):
     want_self = torch.cat([_ref_attention(q[:ns], k[:ns], v[:ns]), _ref_attention(q[ns:], k[ns:], v[ns:])])
     want_cross = torch.cat([_ref_attention(q[:ns], k[ns:], v[ns:]), _ref_attention(q[ns:], k[:ns], v[:ns])])
     dq = qkv.to(cuda)
-    got_self, (hi, lo) = ops.mha_tc(dq, ns, [(0, 0), (1, 1)], planes=planes, want_planes=True)
-    got_cross = ops.mha_tc(dq, ns, [(0, 1), (1, 0)], planes=planes)
+    got_self, (hi, lo) = ops.mha_tc(dq, ns, [(-1, 0)], planes=planes, want_planes=True)     # both clouds, one launch
+    got_cross = ops.mha_tc(dq, ns, [(0, 1), (1, 1)], planes=planes)                          # one direction per launch
     flag = ops.igemm_error_flag()          # synchronises; readable even after a device-side watchdog trap
     assert flag == 0, "pipeline watchdog code %d, sites %s" % (flag, ops.error_flag_detail())
     e1 = ((got_self.cpu().double() - want_self).abs().max() / want_self.abs().max()).item()
@@ -50,7 +50,7 @@ def test_mha_tc_long_sequence(pkg, cuda):
     n = 8192
     qkv = torch.randn(2 * n, 768)
     want = _ref_attention(qkv[:n, :256], qkv[n:, 256:512], qkv[n:, 512:])
-    got = ops.mha_tc(qkv.to(cuda), n, [(0, 1)], planes=2)[:n]
+    got = ops.mha_tc(qkv.to(cuda), n, [(0, 1)], planes=2)[:n]           # source queries against the target cloud
     err = ((got.cpu().double() - want).abs().max() / want.abs().max()).item()
     print("tcgen05 attention 8192 x 8192: rel err %.2e" % err)
     assert err < 2e-5
