@@ -61,12 +61,18 @@ struct NgpDev {
   const float *w1, *w2, *c1, *c2, *c3;
   float amin[3], ainv[3];   // aabb min, 1 / extent
   LevelTable lv;
+  // marcher only: cell-major copy of the dense levels 1..4 - the 8 corners of a cell in one 64-byte record
+  // (2 sectors per sample and level instead of up to 8); cm_off[l] = first cell of level l
+  const float4* cm;
+  uint32_t cm_off[5];
 };
 
 static NgpDev make_dev(const drb_ngp_params* p) {
   NgpDev d;
   d.table = (const float2*)p->hash_table;
   d.w1 = p->w1; d.w2 = p->w2; d.c1 = p->c1; d.c2 = p->c2; d.c3 = p->c3;
+  d.cm = nullptr;
+  for (int i = 0; i < 5; ++i) d.cm_off[i] = 0;
   for (int i = 0; i < 3; ++i) {
     d.amin[i] = p->aabb[i];
     d.ainv[i] = p->aabb[3 + i] - p->aabb[i];
@@ -739,6 +745,59 @@ __device__ __forceinline__ void encode_dense(const NgpDev& p, int l, const float
   o1 = a1;
 }
 
+// Cell-major variant of encode_dense: the same 8 table entries (same index arithmetic, copied by
+// cellmajor_kernel), read as one 64-byte record -> identical features, 2 sectors instead of up to 8.
+__device__ __forceinline__ void encode_dense_cm(const NgpDev& p, int l, const float xn[3], float& o0, float& o1) {
+  const float scale = p.lv.scale[l];
+  const uint32_t res = p.lv.res[l];
+  float fr[3];
+  uint32_t g[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float pos = fmaf(xn[d], scale, 0.5f);
+    const float fl = floorf(pos);
+    fr[d] = pos - fl;
+    g[d] = (uint32_t)(int)fl;
+  }
+  const uint32_t cell = g[0] + g[1] * res + g[2] * res * res;
+  const float4* rec = p.cm + ((size_t)p.cm_off[l] + cell) * 4;
+  float2 v[8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 q = __ldg(rec + c);
+    v[2 * c] = make_float2(q.x, q.y);
+    v[2 * c + 1] = make_float2(q.z, q.w);
+  }
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float w = 1.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) w *= (c & (1 << d)) ? fr[d] : 1.f - fr[d];
+    a0 = fmaf(w, v[c].x, a0);
+    a1 = fmaf(w, v[c].y, a1);
+  }
+  o0 = a0;
+  o1 = a1;
+}
+
+// record[cell][c] = table entry of corner c (bit 0 = x, bit 1 = y, bit 2 = z) of cell (g0, g1, g2), with
+// encode_dense's conditional wrap.  One thread per (cell, corner).
+__global__ void cellmajor_kernel(const NgpDev p, float2* __restrict__ cm) {
+  const uint32_t total = p.cm_off[4] + p.lv.res[4] * p.lv.res[4] * p.lv.res[4];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total * 8u) return;
+  const uint32_t c = i & 7u, cell_g = i >> 3;
+  int l = 1;
+  while (l < 4 && cell_g >= p.cm_off[l + 1]) ++l;
+  const uint32_t cell = cell_g - p.cm_off[l];
+  const uint32_t res = p.lv.res[l], size = p.lv.size[l];
+  const uint32_t g0 = cell % res, g1 = (cell / res) % res, g2 = cell / (res * res);
+  uint32_t idx = g0 + (c & 1u) + (g1 + ((c >> 1) & 1u)) * res + (g2 + ((c >> 2) & 1u)) * res * res;
+  if (idx >= size) idx -= size;
+  cm[i] = p.table[p.lv.offset[l] + idx];
+}
+
 // One K-step of layer 1: the 32 x 8 tile (this warp's rows are complete) -> A fragments -> 48 MMAs.
 __device__ __forceinline__ void mlp_kstep(const WarpMlp& m, int ks, float (&acc)[2][8][4], int lane) {
   const int g = lane >> 2, t = lane & 3;
@@ -791,7 +850,7 @@ __device__ __forceinline__ float warp_density_raw(const NgpDev& p, const float2*
 #pragma unroll 1
   for (int l = 1; l < 5; ++l) {
     float f0, f1;
-    encode_dense(p, l, xn, f0, f1);
+    if (p.cm) encode_dense_cm(p, l, xn, f0, f1); else encode_dense(p, l, xn, f0, f1);
     *(float2*)(row + 2 * (l & 3)) = make_float2(f0, f1);
     if ((l & 3) == 3) mlp_kstep(m, l >> 2, acc, lane);
   }
@@ -1357,7 +1416,15 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
   const size_t off_kin = 256, off_kout = off_kin + arr, off_vin = off_kout + arr, off_vout = off_vin + arr;
   const size_t off_coarse = off_vout + arr;
   const size_t off_cub = off_coarse + (size_t)kCoarseWords * 4;
-  DRB_CUDA_OK(cudaMallocAsync(&scratch, off_cub + cub_bytes + 256, stream));
+  // cell-major records of the dense levels 1..4 (DRB_MARCH_CELLMAJOR=0 keeps the plain table layout)
+  static int use_cm = -1;
+  if (use_cm < 0) { const char* env = getenv("DRB_MARCH_CELLMAJOR"); use_cm = env ? atoi(env) : 1; }
+  NgpDev pm = p;
+  uint32_t cm_cells = 0;
+  for (int l = 1; l <= 4; ++l) { pm.cm_off[l] = cm_cells; cm_cells += p.lv.res[l] * p.lv.res[l] * p.lv.res[l]; }
+  const size_t off_cm = (off_cub + cub_bytes + 255) & ~(size_t)255;
+  const size_t cm_bytes = use_cm ? (size_t)cm_cells * 64 : 0;
+  DRB_CUDA_OK(cudaMallocAsync(&scratch, off_cm + cm_bytes + 256, stream));
   DRB_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, stream));
   unsigned long long* counter = (unsigned long long*)scratch;
   int* count = (int*)(scratch + 64);
@@ -1376,9 +1443,14 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
   coarse_occ_kernel<<<cdiv(aux.coarse_words * 32, 256), 256, 0, stream>>>(occ_binary, res, aux.coarse_shift,
                                                                          aux.coarse_dim, (uint32_t*)(scratch + off_coarse));
   DRB_LAUNCH_OK();
+  if (use_cm) {
+    cellmajor_kernel<<<cdiv((long long)cm_cells * 8, 256), 256, 0, stream>>>(pm, (float2*)(scratch + off_cm));
+    DRB_LAUNCH_OK();
+    pm.cm = (const float4*)(scratch + off_cm);
+  }
   const int grid = igemm_num_sms();
   const int* cnt = count;
-  surface_mask_kernel<<<grid, kMarchThreads, smem, stream>>>(p, a, aux, occ_binary, points, n, cam_origins, ncams,
+  surface_mask_kernel<<<grid, kMarchThreads, smem, stream>>>(pm, a, aux, occ_binary, points, n, cam_origins, ncams,
                                                              idx, cnt, counter, surface);
   DRB_LAUNCH_OK();
   DRB_CUDA_OK(cudaFreeAsync(scratch, stream));
