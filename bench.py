@@ -567,6 +567,21 @@ def _setup_dist():
     return world, rank, local_rank, dev
 
 
+def _timed_with_profile(timed, step, pipe, pipe1, steps):
+    """-> (ms of the timed region, launches, (kernel ms, flops, launches), note).  One stream: the tensor-core
+    GEMM launches are event-bracketed inside the timed region itself.  Several streams: kernels of different pairs
+    overlap, an event pair around one launch then also spans other pairs' kernels - the timed region runs without
+    the brackets and the per-launch durations come from a second pass over the same steps on ONE stream."""
+    if pipe.n == 1:
+        ms, launches, prof = timed(step, steps, profile=True)
+        return ms, launches, prof, {"ms": ms, "what": "CUDA events around every launch, inside the timed region"}
+    ms, launches, _ = timed(step, steps)
+    ms1, _, prof = timed(lambda i: step(i, pipe1), steps, profile=True)
+    return ms, launches, prof, {"ms": ms1, "what": "CUDA events around every launch in a second pass over the same steps on ONE "
+                                "stream (%.1f ms per step): in the timed region %d pairs are in flight and an event pair "
+                                "around one launch would span other pairs' kernels" % (ms1 / steps, pipe.n)}
+
+
 def _pin_pair(p):
     """Pinned host copy of one pair in the [X,Y,Z,7] storage order of voxel_grid.pt (the view the loader makes)."""
     import torch
@@ -632,20 +647,23 @@ def run_train(args):
         # data-parallel training: gradients averaged over ranks, one flat all-reduce per step
         sharding.allreduce_gradients(params, world)
 
-    def step_resident(i):
+    # the pairs of a step are independent until the optimiser: `--streams` of them in flight (pipeline.PairPipeline)
+    pipe = pkg.PairPipeline(dev, streams=args.streams)
+    pipe1 = pkg.PairPipeline(dev, streams=1)
+    model.reserve_mask_capacity(max(max(p["src_mask"].numel(), p["tgt_mask"].numel()) for p in host))
+
+    def step_resident(i, pipe=pipe):
         opt.zero_grad(set_to_none=True)
-        tot = torch.zeros((), device=dev)
-        for b in range(B):
-            tot += one_pair(dict(resident[(i * B + b) % n_res]))
+        losses = pipe.map(lambda b: one_pair(dict(resident[(i * B + b) % n_res])), range(B))
+        tot = torch.stack(losses).sum()
         grads_allreduce()
         opt.step()
         return tot
 
     def step_e2e(i):
         opt.zero_grad(set_to_none=True)
-        tot = torch.zeros((), device=dev)
-        for b in range(B):
-            tot += one_pair(_h2d_pair(pinned[(i * B + b) % n_res], dev))
+        losses = pipe.map(lambda b: one_pair(_h2d_pair(pinned[(i * B + b) % n_res], dev)), range(B))
+        tot = torch.stack(losses).sum()
         grads_allreduce()
         opt.step()
         return float(tot.cpu())                       # D2H of the step's loss
@@ -679,7 +697,7 @@ def run_train(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms, launches, prof = timed(step_resident, args.steps, profile=True)
+    ms, launches, prof, prof_note = _timed_with_profile(timed, step_resident, pipe, pipe1, args.steps)
     clocks = sampler.summary() if sampler else None
     step_e2e(0)
     ms_e2e, _, _ = timed(step_e2e, args.steps)
@@ -698,6 +716,7 @@ def run_train(args):
             "config": {"workload": "batch %d pairs per GPU, 128^3, %s training step (fwd + loss + bwd + clip + AdamW) on %dxB200"
                                    % (B, "bf16" if precision != "fp32" else "fp32-grade", world),
                        "stage": "train", "resolution": RES, "pairs_per_step_per_gpu": B,
+                       "streams": "%d pairs in flight per GPU, one CUDA stream + engine each (pipeline.PairPipeline)" % pipe.n,
                        "distinct_pairs_resident_per_gpu": n_res, "bn_mode": "batch statistics",
                        "loss": "RegistrationLoss: InfoNCE (0.1) + robust-L1 correspondence both directions (1.0), synthetic GT pose",
                        "optimizer": "FusedAdamW lr 1e-4 wd 1e-4, clip_grad_norm 0.1 (train_nerf_regtr.py:96-102,232-235)",
@@ -709,7 +728,8 @@ def run_train(args):
             "roofline": {"bound": "tensor", "kernel": "igemm_kernel + wgrad_kernel (tcgen05 conv / linear forward, data gradient, weight gradient), all launches of the timed steps",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": peaks["source"] + ", bf16 sustained", "traffic": None, "launches": int(ig_n),
-                         "kernel_ms_per_step": ig_ms / args.steps, "kernel_share_of_step": ig_ms / ms,
+                         "kernel_ms_per_step": ig_ms / args.steps, "kernel_share_of_step": ig_ms / prof_note["ms"],
+                         "timing": prof_note["what"],
                          "mma_flops_factor": mma, "tensor_pipe_frac_est": mma * achieved / peak},
         }
         if not args.no_cpu_baseline and world == 1:
@@ -772,15 +792,24 @@ def run_batch(args):
     resident = [pkg.synthetic.to_device(p, dev) for p in host]
     h2d = sum(_pair_bytes(p) for p in pinned) / max(n_res, 1) * len(mine)
 
-    def batch(fetch):
-        local = torch.empty((len(mine), 3, 4), device=dev)
+    pipe = pkg.PairPipeline(dev, streams=args.streams)     # `--streams` pairs in flight, one CUDA stream + engine each
+    model.reserve_mask_capacity(max(max(p["src_mask"].numel(), p["tgt_mask"].numel()) for p in host))
+    tokens = {}
+
+    def one(fetch, j):
+        pose = model(fetch(j))["pose"][-1, 0]
+        tokens[j] = model.last_token_counts
+        return pose
+
+    pipe1 = pkg.PairPipeline(dev, streams=1)
+
+    def batch(fetch, pipe=pipe):
         with torch.no_grad():
-            for j in range(len(mine)):
-                local[j] = model(fetch(j))["pose"][-1, 0]
+            local = torch.stack(pipe.map(lambda j: one(fetch, j), range(len(mine))))
         return sharding.gather_poses(local, n_pairs)           # [n_pairs, 3, 4] on every rank
 
-    def step_resident(_):
-        return batch(lambda j: dict(resident[j % n_res]))
+    def step_resident(_, pipe=pipe):
+        return batch(lambda j: dict(resident[j % n_res]), pipe)
 
     def step_e2e(_):
         return batch(lambda j: _h2d_pair(pinned[j % n_res], dev)).cpu()
@@ -814,7 +843,7 @@ def run_batch(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms, launches, prof = timed(step_resident, args.steps, profile=True)
+    ms, launches, prof, prof_note = _timed_with_profile(timed, step_resident, pipe, pipe1, args.steps)
     clocks = sampler.summary() if sampler else None
     step_e2e(0)
     ms_e2e, _, _ = timed(step_e2e, args.steps)
@@ -832,7 +861,8 @@ def run_batch(args):
             "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": "batch %d pairs sharded across %dxB200, %d^3, %s, register forward, one all-gather of SE(3) per batch"
                                    % (n_pairs, world, res, "bf16" if precision != "fp32" else "fp32-grade"),
-                       "stage": "batch", "resolution": res, "tokens": list(model.last_token_counts),
+                       "stage": "batch", "resolution": res, "tokens": list(tokens.get(0, model.last_token_counts)),
+                       "streams": "%d pairs in flight per GPU, one CUDA stream + engine each (pipeline.PairPipeline)" % pipe.n,
                        "max_tokens": int(model.max_tokens), "attention": "tcgen05 (attention.cu)" if model.tc_attention else "mma.sync (transformer.cu)", "pairs_per_step": n_pairs, "pairs_per_step_per_gpu": len(mine),
                        "distinct_pairs_resident_per_gpu": n_res, "bn_mode": "batch statistics",
                        "l2": "per-pair working set (2 x 58.7 MB grids, >3 GB activations) exceeds the 126 MB L2",
@@ -844,7 +874,8 @@ def run_batch(args):
             "roofline": {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv3d/linear), all launches of the timed steps",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": peaks["source"] + ", bf16 sustained", "traffic": None, "launches": int(ig_n),
-                         "kernel_ms_per_step": ig_ms / args.steps, "kernel_share_of_step": ig_ms / ms,
+                         "kernel_ms_per_step": ig_ms / args.steps, "kernel_share_of_step": ig_ms / prof_note["ms"],
+                         "timing": prof_note["what"],
                          "mma_flops_factor": mma, "tensor_pipe_frac_est": mma * achieved / peak},
         }
         print(json.dumps(line), flush=True)
@@ -892,6 +923,8 @@ def main():
     ap.add_argument("--res", type=int, default=RES, help="batch: grid resolution (256 for configs[4])")
     ap.add_argument("--max-tokens", type=int, default=0, help="batch: cap of the down-sampler (tokens of the pair); 0 = the reference's 3000")
     ap.add_argument("--attention", default="mma", choices=["tc", "mma"], help="tc = tcgen05 FlashAttention-style kernel")
+    ap.add_argument("--streams", type=int, default=4,
+                    help="train / batch: pairs in flight per GPU (pipeline.PairPipeline; 1 = the sequential loop)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage", default="full", choices=["full", "register", "train", "batch"],
                     help="full = extract (2 NeRF blocks -> voxel grids) + register (configs[1], the default); register = "

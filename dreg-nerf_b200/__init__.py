@@ -7,7 +7,8 @@ interfaces (``NeRFRegTr``, ``NGPradianceField`` / ``SampleGrid`` extract).
 from ._lib import DrbError, load as load_library  # noqa: F401
 from .nerf_regtr import NeRFRegTr  # noqa: F401
 from .ngp import NGPradianceField, SampleGrid, extract_block  # noqa: F401
-from . import augment, blockio, losses, synthetic  # noqa: F401
+from . import augment, blockio, losses, pipeline, synthetic  # noqa: F401
+from .pipeline import PairPipeline  # noqa: F401
 from .occupancy import OccupancyGrid  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 from .losses import CorrespondenceLoss, InfoNCELoss, RegistrationLoss  # noqa: F401

@@ -198,6 +198,7 @@ SIGNATURES = {
     "drb_engine_commit_params": (c_int, [c_void_p, c_void_p]),
     "drb_engine_set_training": (c_int, [c_void_p, c_int]),
     "drb_engine_set_sparse_fpn": (c_int, [c_void_p, c_int]),
+    "drb_engine_set_update_running": (c_int, [c_void_p, c_int]),
     "drb_engine_encode": (c_int, [c_void_p, C.POINTER(PairIO), C.POINTER(c_int), C.POINTER(c_int), c_void_p]),
     "drb_engine_decode": (c_int, [c_void_p, C.POINTER(PairOut), c_void_p]),
     "drb_engine_tap": (c_int, [c_void_p, C.c_char_p, c_int, c_void_p, c_ll, C.POINTER(c_ll), c_void_p]),

@@ -43,6 +43,7 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 int igemm_num_sms();                 // SM count of the current device
 int* igemm_err_flag();               // per-device pipeline watchdog flag (device int), lazily allocated
 void igemm_clear_err_flag();
+int igemm_peek_err_flag();            // the flag as the host sees it now (no synchronisation)
 void igemm_choose_box(int G, int D, int H, int W, int& bg, int& bd, int& bh, int& bw);
 int igemm_make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, bool is_bf16);

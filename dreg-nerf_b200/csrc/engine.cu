@@ -325,8 +325,11 @@ static int bn_apply(drb_engine* e, const BnP& b, const float* rawp, long long m,
                               1e-5f, b.mean, b.rstd, b.scale, b.shift, s));
   }
   e->launches += 1;
-  return drb_bn_apply(rawp, e->bn_accum, kG, m, b.c, P(e, b.p_w), P(e, b.p_b), P(e, b.p_rm), P(e, b.p_rv), training,
-                      0.1f, 1e-5f, residual, relu, out, out_hi, out_lo, s);
+  // a secondary engine of a stream pipeline (drb_engine_set_update_running(e, 0)) normalises with its own batch
+  // statistics but leaves the shared running buffers to the primary engine (the replicas of a DDP job do the same)
+  const bool upd = !training || e->update_running;
+  return drb_bn_apply(rawp, e->bn_accum, kG, m, b.c, P(e, b.p_w), P(e, b.p_b), upd ? P(e, b.p_rm) : nullptr,
+                      upd ? P(e, b.p_rv) : nullptr, training, 0.1f, 1e-5f, residual, relu, out, out_hi, out_lo, s);
 }
 
 // conv1 (5^3 s2, Cin 4 = rgba channels 3..6 of the [1,7,Z,X,Y] grid): im2col of both grids into the shared
@@ -424,6 +427,9 @@ int engine_ensure_tokens(drb_engine* e, int m) {
   for (void* p : e->tok_allocs) cudaFree(p);
   e->tok_allocs.clear();
   if (m < e->tok_cap) m = e->tok_cap;
+  // the down-sampler stops at max_tokens points for the pair: allocate for that bound once instead of growing
+  // pair by pair (cudaFree / cudaMalloc wait for the whole device - every stream of a pipeline would stall)
+  if (m < e->max_tokens && e->max_tokens <= 32768) m = e->max_tokens;
   const long long cap = ((m + 127) / 128) * 128 + 128;
   bool ok = true;
   auto A = [&](long long bytes) -> void* {
@@ -609,6 +615,12 @@ extern "C" int drb_engine_set_sparse_fpn(drb_engine* e, int on) {
   return 0;
 }
 
+extern "C" int drb_engine_set_update_running(drb_engine* e, int on) {
+  DRB_REQUIRE(e, "drb_engine_set_update_running: null engine");
+  e->update_running = on != 0;
+  return 0;
+}
+
 extern "C" int drb_engine_set_profile(drb_engine* e, int on) {
   DRB_REQUIRE(e, "drb_engine_set_profile: null engine");
   e->profile = on != 0;
@@ -761,9 +773,9 @@ extern "C" int drb_engine_encode(drb_engine* e, const drb_pair_io* io, int* host
                                         dl0, e->max_tokens, e->ds_ws, e->ds_ws_bytes, e->rows_ds, &e->n_src,
                                         &e->n_tgt, s));
   }
-  // the down-sampler synchronised: the mask range check of the gather kernels is readable for free
-  int flag = 0;
-  DRB_TRY(drb_igemm_error_flag(&flag));
+  // the down-sampler synchronised THIS stream: the mask range check of the gather kernels is readable for free
+  // (no device-wide wait: other streams may be registering other pairs, pipeline.py)
+  const int flag = igemm_peek_err_flag();
   if (flag == 21) {
     igemm_clear_err_flag();
     set_error("drb_engine_encode: a mask index is outside [0, X*Y*Z) (mask of another resolution?)");

@@ -530,6 +530,13 @@ void igemm_clear_err_flag() {
   if (st.err_flag_host) memset(st.err_flag_host, 0, 16 * sizeof(int));
 }
 
+// Current value of the flag without waiting for anything: it lives in mapped pinned host memory, so whatever a
+// kernel of an already synchronised stream wrote is visible.  (drb_igemm_error_flag waits for the whole device.)
+int igemm_peek_err_flag() {
+  int* flag = device_state().err_flag_host;
+  return flag ? *(volatile int*)flag : 0;
+}
+
 int* igemm_err_flag() {
   DeviceState& st = device_state();
   if (!st.err_flag) {

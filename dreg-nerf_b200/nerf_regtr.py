@@ -10,6 +10,7 @@ reference's layout; all arithmetic happens in the C-ABI engine.  There is no PyT
 import copy
 import ctypes as C
 import os
+import threading
 
 import torch
 from torch import nn
@@ -19,6 +20,21 @@ from . import _lib
 _PRECISION_PLANES = {"fp32": 2, "bf16x3": 2, "bf16": 1}
 # attention through the tcgen05 FlashAttention-style kernel (csrc/attention.cu) instead of the mma.sync one
 TC_ATTENTION_DEFAULT = os.environ.get("DRB_TC_ATTENTION", "1") != "0"
+
+
+# Engine slot of the calling thread.  An engine's workspaces belong to the work queued on ONE stream, so pairs that
+# are in flight on different CUDA streams (pipeline.PairPipeline: one worker thread + stream per slot) each need an
+# engine of their own; slot 0 is the ordinary single-stream use.
+_tls = threading.local()
+_ENGINE_LOCK = threading.Lock()     # engine creation (module level: the module stays deep-copyable / picklable)
+
+
+def engine_slot():
+    return getattr(_tls, "slot", 0)
+
+
+def set_engine_slot(slot):
+    _tls.slot = int(slot)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -177,10 +193,16 @@ class NeRFRegTr(nn.Module):
         object.__setattr__(self, "_tensor_cache", None)
 
     def _get_engine(self, res_xyz, device, max_mask):
-        key = (tuple(res_xyz), device.index, self.precision)
+        slot = engine_slot()
+        max_mask = max(int(max_mask), int(getattr(self, "min_mask_capacity", 0)))
+        key = (tuple(res_xyz), device.index, self.precision, slot)
         ent = self._engines.get(key)
         if ent is not None and ent["max_mask"] >= max_mask:
             return ent
+        with _ENGINE_LOCK:
+            return self._create_engine(key, ent, res_xyz, device, max_mask, slot)
+
+    def _create_engine(self, key, ent, res_xyz, device, max_mask, slot):
         lib = _lib.load()
         if ent is not None:
             lib.drb_engine_destroy(ent["handle"])
@@ -194,7 +216,9 @@ class NeRFRegTr(nn.Module):
         with torch.cuda.device(device):
             _lib.check(lib.drb_engine_create(C.byref(cfg), C.byref(handle)), "drb_engine_create")
         names = [lib.drb_engine_param_name(handle, i).decode() for i in range(lib.drb_engine_num_params(handle))]
-        ent = {"handle": handle, "names": names, "max_mask": cap, "sig": None, "device": device}
+        # slot > 0: a secondary engine of a stream pipeline leaves the shared BatchNorm running buffers to slot 0
+        _lib.check(lib.drb_engine_set_update_running(handle, 1 if slot == 0 else 0))
+        ent = {"handle": handle, "names": names, "max_mask": cap, "sig": None, "device": device, "slot": slot}
         idx = [i for i in range(len(names)) if lib.drb_engine_param_trainable(handle, i)]
         numels = [int(lib.drb_engine_param_numel(handle, i)) for i in idx]
         offs, total = [], 0
@@ -261,6 +285,12 @@ class NeRFRegTr(nn.Module):
             pass
 
     # -------------------------------------------------------------------------------------------
+    def reserve_mask_capacity(self, n_masked):
+        """Engines are (re)built when a pair brings more masked voxels than the engine was sized for (a few GB of
+        workspace and a repack of the weights).  A caller that knows its largest pair - a data loader, a stream
+        pipeline with one engine per slot - reserves it once and no engine is rebuilt mid-run."""
+        self.min_mask_capacity = max(int(n_masked), int(getattr(self, "min_mask_capacity", 0)))
+
     def set_max_tokens(self, max_total):
         """Stopping rule of the down-sampler (grid_downsample.py:70,91 hard-code 3000 points for the pair);
         BASELINE.json's 8k-token configuration raises it."""
@@ -313,7 +343,7 @@ class NeRFRegTr(nn.Module):
                     torch.empty((6, 1, 3, 4), **f32))
             out = self._pair_out(outs)
             _lib.check(lib.drb_engine_decode(handle, C.byref(out), stream), "drb_engine_decode")
-            if self.training:
+            if self.training and ent.get("slot", 0) == 0:
                 # nn.BatchNorm3d bookkeeping: two training-mode calls (src, tgt) per forward
                 if getattr(self, "_nbt", None) is None or self._nbt[0].device != device:
                     self._nbt = [b for n, b in self.named_buffers() if n.endswith("num_batches_tracked")]

@@ -440,6 +440,12 @@ int drb_engine_set_training(drb_engine* e, int training_bn);
 /* on (default): evaluate the level-1 FPN convolutions only on the output tiles the masked gather reads
  * (identical results at every voxel that is read); off: dense evaluation (debug taps of p1). */
 int drb_engine_set_sparse_fpn(drb_engine* e, int on);
+/* Several engines may share one set of bound parameters, one engine per CUDA stream (pipeline.py: pairs of a
+ * batch in flight on different streams).  on (default): training-mode BatchNorm updates the bound running_mean /
+ * running_var in place (nn.BatchNorm3d, momentum 0.1); off: this engine normalises with its batch statistics
+ * but leaves the shared running buffers alone - exactly one engine of the group updates them, as rank 0's
+ * buffers win among the replicas of a DistributedDataParallel job. */
+int drb_engine_set_update_running(drb_engine* e, int on);
 
 typedef struct drb_pair_io {
   const float* src_grid;   /* fp32 [1,7,Z,X,Y] view, element strides below                   */

@@ -255,3 +255,29 @@ def test_occupancy_grid_fill_semantics(pkg):
     import pytest
     with pytest.raises(RuntimeError):
         og.every_n_step(0, ball)
+
+
+def test_pair_pipeline_host_logic(pkg):
+    """pipeline.PairPipeline without a GPU: results in item order, one engine slot per worker thread, the first
+    exception reaches the caller and the pipeline stays usable."""
+    import threading
+    import time
+    from importlib import import_module
+    import torch
+    nr = import_module("dreg-nerf_b200.nerf_regtr")
+    seen = set()
+
+    def fn(i):
+        seen.add((threading.current_thread().name, nr.engine_slot(), torch.is_grad_enabled()))
+        time.sleep(0.005)
+        return i * i
+
+    with pkg.PairPipeline(torch.device("cpu"), streams=3) as pipe:
+        with torch.no_grad():
+            assert pipe.map(fn, range(10)) == [i * i for i in range(10)]
+        assert {s for _, s, _ in seen} == {0, 1, 2} and not any(g for _, _, g in seen)   # grad mode follows the caller
+        with pytest.raises(ZeroDivisionError):
+            pipe.map(lambda i: 1 / (i - 3), range(8))
+        assert pipe.map(fn, range(4)) == [0, 1, 4, 9]
+    assert nr.engine_slot() == 0                                  # the caller's thread keeps slot 0
+    assert pkg.PairPipeline(None, streams=1).map(fn, [2, 3]) == [4, 9]
