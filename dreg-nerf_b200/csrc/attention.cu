@@ -16,7 +16,7 @@
 
 namespace drb {
 
-static constexpr int kAttThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 soft-max
+static constexpr int kAttThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 soft-max (two threads per query row)
 static constexpr int kAttQ = 128;            // queries per CTA == TMEM lanes
 static constexpr int kAttK = 128;            // keys per tile
 static constexpr uint32_t kQBytes = kAttQ * 64 * 2;          // 16 KB per plane
@@ -42,7 +42,68 @@ struct AttArgs {
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// 2^x for x <= 0 on the MUFU (rel. error 2^-22; below -126 the result flushes to 0, which is what a soft-max wants)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
+// p = 2^(s - mx) of one thread's 64 logits -> 16-bit planes in shared memory (8 swizzled 16-byte chunks); returns the sum.
+template <int P, bool kFull>
+__device__ __forceinline__ float softmax_half_row(const float (&sv_)[64], float mx, int valid, uint32_t prow, int row) {
+  float lsum = 0.f;
+#pragma unroll
+  for (int c8 = 0; c8 < 8; ++c8) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j0 = c8 * 8 + 2 * u;
+      float p0 = ex2_fast(sv_[j0] - mx), p1 = ex2_fast(sv_[j0 + 1] - mx);
+      if (!kFull) { p0 = j0 < valid ? p0 : 0.f; p1 = j0 + 1 < valid ? p1 : 0.f; }
+      lsum += p0 + p1;
+      if (P == 1) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+        hw[u] = *(const uint32_t*)&h2;
+        lw[u] = 0u;
+      } else {
+        const __half2 h2 = __floats2half2_rn(p0, p1);
+        const float2 hf = __half22float2(h2);
+        const __half2 l2 = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+        hw[u] = *(const uint32_t*)&h2;
+        lw[u] = *(const uint32_t*)&l2;
+      }
+    }
+    const uint32_t dst = prow + (uint32_t)((c8 ^ (row & 7)) * 16);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]) : "memory");
+    if (P == 2)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kPBytes), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3]) : "memory");
+  }
+  return lsum;
+}
+
+// Schedule of one CTA (head, 128 queries), tiles of 128 keys:
+//   MMA warp : S(0); for t: S(t+1) as soon as every soft-max thread has read S(t); P V(t) when P(t) is in smem.
+//   soft-max : 8 warps, the two threads of a row (warps w and w + 4 share a TMEM lane quarter) take 64 keys each:
+//              read S from TMEM, exchange the row maximum through shared memory (named barrier of the warp pair),
+//              exp2 on the MUFU, write their half of P (swizzled K-major A operand), and fold the P V product of
+//              the PREVIOUS tile into their 16 output columns - P and the P V accumulator are double buffered
+//              (bf16; the fp16-pair planes only fit one P buffer), so the soft-max never waits for the tensor core.
+//   Roofline of this kernel is the MUFU (128 x 128 exp2 per tile = 1024 clk per SM at 16 / clk) - the two MMAs of a
+//   tile take ~390 clk - so the tensor pipe cannot exceed ~35 % here whatever the schedule (head dim 32).
+template <int P>
 __global__ void __launch_bounds__(kAttThreads, 1)
 att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmQ1,
                const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmK1,
@@ -54,27 +115,30 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y;
   const int q0 = blockIdx.x * kAttQ;
-  const int P = args.planes;
   int* const err = args.err;
-  // shared-memory plan: Q | 2 x (K, V^T) stages | P | barriers
-  const uint32_t stage_bytes = (uint32_t)P * (kKBytes + kVBytes);
+  constexpr int kPBufs = P == 1 ? 2 : 1;             // P buffers (the fp16-pair planes leave room for one)
+  constexpr int kDepth = kPBufs - 1;                 // tiles by which the P V read-back trails the soft-max
+  // shared-memory plan: Q | 2 x (K, V^T) stages | P buffers | barriers | row-maximum exchange
+  constexpr uint32_t stage_bytes = (uint32_t)P * (kKBytes + kVBytes);
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + (size_t)P * kQBytes;
   uint8_t* sP = sKV + 2 * (size_t)stage_bytes;
-  uint64_t* bars = (uint64_t*)(sP + (size_t)P * kPBytes);
+  uint64_t* bars = (uint64_t*)(sP + (size_t)kPBufs * P * kPBytes);
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t q_full = bar0, kv_full0 = bar0 + 8, kv_empty0 = bar0 + 24, s_full = bar0 + 40, s_free = bar0 + 48,
-                 p_full = bar0 + 56, pv_full = bar0 + 64;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 10);
+                 p_full0 = bar0 + 56, pv_full0 = bar0 + 72;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+  float* xch = (float*)(bars + 14);                  // [2 parities][2 halves][128 rows]
   const int ntiles = (a.nk + kAttK - 1) / kAttK;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(kv_full0 + 8 * s, 1); mbar_init(kv_empty0 + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(kv_full0 + 8 * s, 1); mbar_init(kv_empty0 + 8 * s, 1);
+      mbar_init(p_full0 + 8 * s, 256); mbar_init(pv_full0 + 8 * s, 1);
+    }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
-    mbar_init(pv_full, 1);
+    mbar_init(s_free, 256);
     mbar_fence_init();
   }
   if (warp == 0 && lane == 0) {
@@ -86,7 +150,7 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_pv = tmem_base + 128;
+  const uint32_t tmem_s = tmem_base, tmem_pv = tmem_base + 128;      // S: 128 columns; P V: 2 x 32 columns
 
   if (warp == 0) {
     if (lane == 0) {
@@ -101,6 +165,7 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
         const uint32_t sk = smem_u32(sKV + (size_t)s * stage_bytes);
         const uint32_t sv = sk + (uint32_t)P * kKBytes;
         const int key0 = a.k_row0 + t * kAttK;
+#pragma unroll
         for (int p = 0; p < P; ++p) {
           tma_load_3d(sk + p * kKBytes, p ? &tmK1 : &tmK0, fb, 0, key0, head);
           tma_load_3d(sv + p * kVBytes, p ? &tmV1 : &tmV0, fb, key0, 0, head);
@@ -136,104 +201,110 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
       for (int t = 0; t < ntiles; ++t) {
         if (t + 1 < ntiles) issue_s(t + 1);
         const int s = t & 1;
-        mbar_wait(p_full, (uint32_t)t & 1u, err, 45);
+        // P(t) is in shared memory; its arrival also tells that the P V accumulator of tile t - 2 has been read
+        mbar_wait(p_full0 + 8 * s, ((uint32_t)t >> 1) & 1u, err, 45);
         tc_fence_after();
         const uint32_t sv = smem_u32(sKV + (size_t)s * stage_bytes) + (uint32_t)P * kKBytes;
-        const uint32_t sp = smem_u32(sP);
+        const uint32_t sp = smem_u32(sP) + (uint32_t)(t % kPBufs) * (uint32_t)P * kPBytes;
+        const uint32_t tmem_o = tmem_pv + (uint32_t)s * 32u;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t sub = (uint32_t)(k >> 2);
           const uint64_t koff = (uint64_t)((k & 3) * 2);
           const uint64_t dp0 = umma_desc_sw128(sp + sub * (kPBytes / 2)) + koff;
           const uint64_t dv0 = umma_desc_sw128(sv + sub * (kVBytes / 2)) + koff;
-          umma_f16(tmem_pv, dp0, dv0, idesc_pv, k ? 1u : 0u);
+          umma_f16(tmem_o, dp0, dv0, idesc_pv, k ? 1u : 0u);
           if (P == 2) {
             const uint64_t dp1 = umma_desc_sw128(sp + kPBytes + sub * (kPBytes / 2)) + koff;
             const uint64_t dv1 = umma_desc_sw128(sv + kVBytes + sub * (kVBytes / 2)) + koff;
-            umma_f16(tmem_pv, dp0, dv1, idesc_pv, 1u);
-            umma_f16(tmem_pv, dp1, dv0, idesc_pv, 1u);
+            umma_f16(tmem_o, dp0, dv1, idesc_pv, 1u);
+            umma_f16(tmem_o, dp1, dv0, idesc_pv, 1u);
           }
         }
-        umma_commit(pv_full);
+        umma_commit(pv_full0 + 8 * s);
         umma_commit(kv_empty0 + 8 * s);
       }
     }
   } else {
-    // ------------------------------- soft-max / accumulate: one query row per thread -------------
+    // ------------------------------- soft-max / accumulate: two threads per query row ------------
     const int qd = warp & 3;                         // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                // keys [64 half, 64 half + 64) of a tile, output columns [16 half, +16)
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = ((uint32_t)(qd * 32)) << 16;
-    float o[32];
+    float o[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
-    const bool pair = P == 2;
+    for (int j = 0; j < 16; ++j) o[j] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, corr_prev = 0.f;
+    // o <- o * corr(tt) + (P V)(tt), this thread's 16 columns
+    auto fold_pv = [&](int tt, float c) {
+      mbar_wait(pv_full0 + 8 * (tt & 1), ((uint32_t)tt >> 1) & 1u, err, 47);
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_pv + lane_addr + (uint32_t)((tt & 1) * 32 + half * 16), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = fmaf(o[j], c, __uint_as_float(v[j]));
+      tc_fence_before();
+    };
     for (int t = 0; t < ntiles; ++t) {
       mbar_wait(s_full, (uint32_t)t & 1u, err, 46);
       tc_fence_after();
-      float sv_[128];
+      float sv_[64];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
+      for (int b = 0; b < 2; ++b) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)(b * 32), v);
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)(half * 64 + b * 32), v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) sv_[b * 32 + j] = __uint_as_float(v[j]);
       }
       tc_fence_before();
       mbar_arrive(s_free);
-      const int valid = min(kAttK, a.nk - t * kAttK);       // keys of this tile that exist
-      float mx = m_run;
+      const int valid = min(64, max(0, a.nk - t * kAttK - half * 64));      // of this thread's 64 keys
+      float mloc = -INFINITY;
+      if (valid == 64) {
 #pragma unroll
-      for (int j = 0; j < 128; ++j)
-        if (j < valid) mx = fmaxf(mx, sv_[j]);
-      const float corr = exp2f(m_run - mx);                 // first tile: exp2(-inf) = 0
+        for (int j = 0; j < 64; ++j) mloc = fmaxf(mloc, sv_[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j)
+          if (j < valid) mloc = fmaxf(mloc, sv_[j]);
+      }
+      float* xc = xch + (t & 1) * 256;
+      xc[half * 128 + row] = mloc;
+      named_bar_sync(1 + qd, 64);                           // the two warps of this lane quarter
+      const float mx = fmaxf(m_run, fmaxf(mloc, xc[(half ^ 1) * 128 + row]));
+      const float corr = ex2_fast(m_run - mx);              // first tile: 2^(-inf) = 0
       m_run = mx;
-      float lsum = 0.f;
-      // P in the swizzled K-major layout the tensor core reads: sub-tile (64 keys) / row / 16-byte chunk ^ (row & 7)
-      uint8_t* prow = sP + (size_t)row * 128;
-#pragma unroll
-      for (int c8 = 0; c8 < 16; ++c8) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j0 = c8 * 8 + 2 * u;
-          const float p0 = j0 < valid ? exp2f(sv_[j0] - mx) : 0.f;
-          const float p1 = j0 + 1 < valid ? exp2f(sv_[j0 + 1] - mx) : 0.f;
-          lsum += p0 + p1;
-          plane_t h0, l0, h1, l1;
-          split16(p0, pair, h0, l0);
-          split16(p1, pair, h1, l1);
-          hw[u] = pack16x2(h0, h1);
-          lw[u] = pack16x2(l0, l1);
-        }
-        const int sub = c8 >> 3, chunk = (c8 & 7) ^ (row & 7);
-        uint8_t* dst = prow + (size_t)sub * (kPBytes / 2) + chunk * 16;
-        *(uint4*)dst = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        if (pair) *(uint4*)(dst + kPBytes) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      }
-      l_run = l_run * corr + lsum;
+      // this thread's half of the row of P, in the swizzled K-major layout the tensor core reads:
+      // sub-tile (= half) / row / 16-byte chunk ^ (row & 7)
+      const uint32_t prow = smem_u32(sP) + (uint32_t)(t % kPBufs) * (uint32_t)P * kPBytes +
+                            (uint32_t)half * (kPBytes / 2) + (uint32_t)row * 128u;
+      float lsum;
+      if (valid == 64) lsum = softmax_half_row<P, true>(sv_, mx, 64, prow, row);
+      else lsum = softmax_half_row<P, false>(sv_, mx, valid, prow, row);
+      l_run = fmaf(l_run, corr, lsum);
       fence_proxy_async();                                  // generic-proxy writes -> visible to the tensor core
-      mbar_arrive(p_full);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) o[j] *= corr;
-      mbar_wait(pv_full, (uint32_t)t & 1u, err, 47);
-      tc_fence_after();
-      {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_pv + lane_addr, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] += __uint_as_float(v[j]);
+      mbar_arrive(p_full0 + 8 * (t & 1));
+      if (kDepth == 0) {
+        fold_pv(t, corr);
+      } else {
+        if (t > 0) fold_pv(t - 1, corr_prev);
+        corr_prev = corr;
       }
-      tc_fence_before();
     }
+    if (kDepth == 1) fold_pv(ntiles - 1, corr_prev);
+    // the row sum is the sum of the two halves
+    float* xc = xch + (ntiles & 1) * 256;
+    xc[half * 128 + row] = l_run;
+    named_bar_sync(1 + qd, 64);
+    const float l_tot = l_run + xc[(half ^ 1) * 128 + row];
     const int qi = q0 + row;
     if (qi < a.nq) {
-      const float inv = 1.f / l_run;
-      const long long off = (long long)(a.out_row0 + qi) * args.ld_out + head * 32;
+      const float inv = 1.f / l_tot;
+      const long long off = (long long)(a.out_row0 + qi) * args.ld_out + head * 32 + half * 16;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < 16; j += 4) {
         const float r0 = o[j] * inv, r1 = o[j + 1] * inv, r2 = o[j + 2] * inv, r3 = o[j + 3] * inv;
         if (args.out) *(float4*)(args.out + off + j) = make_float4(r0, r1, r2, r3);
         if (args.out_hi) {
@@ -387,10 +458,17 @@ extern "C" int drb_mha_tc_forward(const void* workspace, int n, int split, int h
   a.heads = heads; a.planes = planes;
   a.out = out; a.out_hi = (plane_t*)out_hi; a.out_lo = (plane_t*)out_lo; a.ld_out = ld_out;
   a.err = igemm_err_flag();
-  const size_t smem = 1024 + (size_t)planes * (kQBytes + 2 * (kKBytes + kVBytes) + kPBytes) + 128;
-  DRB_CUDA_OK(cudaFuncSetAttribute(att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int pbufs = planes == 1 ? 2 : 1;
+  const size_t smem = 1024 + (size_t)planes * (kQBytes + 2 * (kKBytes + kVBytes) + (size_t)pbufs * kPBytes) + 14 * 8 +
+                      2 * 2 * 128 * sizeof(float) + 16;
   dim3 grid((unsigned)cdiv(max_q, kAttQ), (unsigned)heads, (unsigned)nprob);
-  att_fwd_kernel<<<grid, kAttThreads, smem, stream>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], a);
+  if (planes == 1) {
+    DRB_CUDA_OK(cudaFuncSetAttribute(att_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    att_fwd_kernel<1><<<grid, kAttThreads, smem, stream>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], a);
+  } else {
+    DRB_CUDA_OK(cudaFuncSetAttribute(att_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    att_fwd_kernel<2><<<grid, kAttThreads, smem, stream>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], a);
+  }
   DRB_LAUNCH_OK();
   return 0;
 }
