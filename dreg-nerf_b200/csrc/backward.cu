@@ -878,6 +878,74 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
     }
   }
 }
+// The same product for a long reduction and few output tiles (attention backward: dV = P^T dO, dQ = dS K,
+// dK = dS^T Q with N = 32 and K = tokens; decoder backward with N = 256): the 64 x 64 kernel above then runs a
+// handful of blocks through a serial, latency-bound k loop (measured 32 us per launch at 500 tokens).  Here a block
+// owns a 16 x 32 tile and its 8 warps take interleaved 32-wide k chunks: the A sub-tile goes through a per-warp
+// shared-memory tile (broadcast reads), lane = output column, all B values of a chunk are fetched up front, and
+// the 8 partial tiles meet in shared memory in warp order (deterministic, no atomics).
+static constexpr int kKsM = 16, kKsPitch = 20;
+__global__ void __launch_bounds__(256) sgemm_ksplit_kernel(const SgemmArgs a) {
+  __shared__ __align__(16) float As[8][32][kKsPitch];     // [warp][k][m]
+  __shared__ float red[8][kKsM][32];
+  const int b = blockIdx.z;
+  const float* __restrict__ A = a.A + (long long)b * a.a_b;
+  const float* __restrict__ B = a.B + (long long)b * a.b_b;
+  float* C = a.C + (long long)b * a.c_b;
+  const int m0 = blockIdx.y * kKsM, n0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool a_kfast = (a.a_k == 1);
+  const bool n_ok = n0 + lane < a.N;
+  float acc[kKsM];
+#pragma unroll
+  for (int i = 0; i < kKsM; ++i) acc[i] = 0.f;
+  for (int k0 = warp * 32; k0 < a.K; k0 += 256) {
+    // B values of this chunk (lane = output column): one round of loads in flight
+    float bv[32];
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk)
+      bv[kk] = (n_ok && k0 + kk < a.K) ? B[(long long)(k0 + kk) * a.b_k + (long long)(n0 + lane) * a.b_n] : 0.f;
+    __syncwarp();                                        // the previous chunk's tile has been read
+    if (a_kfast) {                                       // rows of A are contiguous in k: lane = k
+#pragma unroll
+      for (int m = 0; m < kKsM; ++m)
+        As[warp][lane][m] = (m0 + m < a.M && k0 + lane < a.K) ? A[(long long)(m0 + m) * a.a_m + (k0 + lane)] : 0.f;
+    } else {                                             // columns contiguous in m (transposed operand): lane = m
+      for (int kk = 0; kk < 32; kk += 2) {
+        const int mm = lane & 15, kx = kk + (lane >> 4);
+        As[warp][kx][mm] = (m0 + mm < a.M && k0 + kx < a.K)
+                               ? A[(long long)(m0 + mm) * a.a_m + (long long)(k0 + kx) * a.a_k] : 0.f;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      const float4* ar = (const float4*)&As[warp][kk][0];
+#pragma unroll
+      for (int q = 0; q < kKsM / 4; ++q) {
+        const float4 v = ar[q];
+        acc[4 * q] = fmaf(v.x, bv[kk], acc[4 * q]);
+        acc[4 * q + 1] = fmaf(v.y, bv[kk], acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(v.z, bv[kk], acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(v.w, bv[kk], acc[4 * q + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kKsM; ++i) red[warp][i][lane] = acc[i];
+  __syncthreads();
+  for (int o = threadIdx.x; o < kKsM * 32; o += 256) {
+    const int m = o >> 5, n = o & 31;
+    if (m0 + m >= a.M || n0 + n >= a.N) continue;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w][m][n];
+    float* dst = C + (long long)(m0 + m) * a.c_m + (n0 + n);
+    const float v = a.alpha * sum;
+    *dst = a.accumulate ? *dst + v : v;
+  }
+}
+
 extern "C" int drb_sgemm_strided(const float* A, long long a_b, long long a_m, long long a_k, const float* B,
                                  long long b_b, long long b_k, long long b_n, float* Cm, long long c_b, long long c_m,
                                  int M, int N, int K, int batch, float alpha, int accumulate, cudaStream_t stream) {
@@ -888,6 +956,13 @@ extern "C" int drb_sgemm_strided(const float* A, long long a_b, long long a_m, l
   a.B = B; a.b_b = b_b; a.b_k = b_k; a.b_n = b_n;
   a.C = Cm; a.c_b = c_b; a.c_m = c_m;
   a.M = M; a.N = N; a.K = K; a.alpha = alpha; a.accumulate = accumulate;
+  const long long tiles64 = (long long)cdiv(N, 64) * cdiv(M, 64) * batch;
+  if (K >= 128 && tiles64 < 2 * 148) {                   // long reduction, few tiles: in-block split-K
+    dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(M, kKsM), (unsigned)batch);
+    sgemm_ksplit_kernel<<<grid, 256, 0, stream>>>(a);
+    DRB_LAUNCH_OK();
+    return 0;
+  }
   dim3 grid((unsigned)cdiv(N, 64), (unsigned)cdiv(M, 64), (unsigned)batch);
   sgemm_kernel<<<grid, 256, 0, stream>>>(a);
   DRB_LAUNCH_OK();

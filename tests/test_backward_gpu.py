@@ -257,6 +257,29 @@ def test_attention_backward(pkg, cuda):
     assert float(ds[:, nk:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("M,N,K,batch", [(333, 32, 257, 8), (500, 256, 487, 1), (70, 20, 1000, 3), (257, 300, 32, 8),
+                                          (64, 64, 64, 1)])
+@pytest.mark.parametrize("a_t,b_t", [(False, False), (True, False), (False, True), (True, True)])
+def test_sgemm_strided_both_kernels(pkg, cuda, M, N, K, batch, a_t, b_t):
+    """drb_sgemm_strided against fp64 torch: the 64 x 64 kernel and the in-block split-K kernel (long K, few tiles),
+    every operand layout, alpha / accumulate."""
+    ops = _ops()
+    torch.manual_seed(M + N + K)
+    A = torch.randn(batch, K, M) if a_t else torch.randn(batch, M, K)
+    B = torch.randn(batch, N, K) if b_t else torch.randn(batch, K, N)
+    C0 = torch.randn(batch, M, N)
+    Am = A.transpose(1, 2) if a_t else A
+    Bm = B.transpose(1, 2) if b_t else B
+    want = C0.double() + 0.5 * (Am.double() @ Bm.double())
+    a_str = (M * K, 1, M) if a_t else (M * K, K, 1)          # (batch, m, k) element strides
+    b_str = (N * K, 1, K) if b_t else (N * K, N, 1)          # (batch, k, n)
+    Cd = C0.to(cuda).contiguous()
+    ops.sgemm_strided(A.to(cuda).contiguous(), a_str, B.to(cuda).contiguous(), b_str, Cd, (M * N, N), M, N, K,
+                      batch=batch, alpha=0.5, accumulate=True)
+    err = _rel(Cd, want)
+    assert err < 2e-6, err
+
+
 def test_procrustes_backward(pkg, cuda):
     from oracle import regtr
     ops = _ops()
