@@ -278,6 +278,8 @@ class NeRFRegTr(nn.Module):
 
     def __del__(self):
         try:
+            if not self._engines:          # a module that never ran owns nothing (and must not map the library)
+                return
             lib = _lib.load()
             for ent in self._engines.values():
                 lib.drb_engine_destroy(ent["handle"])

@@ -281,3 +281,21 @@ def test_pair_pipeline_host_logic(pkg):
         assert pipe.map(fn, range(4)) == [0, 1, 4, 9]
     assert nr.engine_slot() == 0                                  # the caller's thread keeps slot 0
     assert pkg.PairPipeline(None, streams=1).map(fn, [2, 3]) == [4, 9]
+
+
+def test_reference_arm_does_not_map_the_product_library():
+    """bench.py --impl reference builds its inputs with the package's pure-Python pieces (module skeleton, seeded
+    state dict, synthetic pairs, NGP field mirror) - none of them may dlopen libdregb200.so."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, gc; sys.path.insert(0, %r)\n"
+        "import torch, dreg_nerf_b200 as pkg\n"
+        "from oracle.make_goldens import make_field\n"
+        "m = pkg.NeRFRegTr(); sd = pkg.synthetic.seeded_state_dict(m, seed=0, attn_gain=4.0); del m; gc.collect()\n"
+        "pkg.synthetic.make_pair(res=32, pair_id=0); make_field(pkg, 500, 8.0); pkg.synthetic.extract_scene(32, 4)\n"
+        "print('MAPPED' if 'libdregb200' in open('/proc/self/maps').read() else 'CLEAN')\n" % root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().endswith("CLEAN")
