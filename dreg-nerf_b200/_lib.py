@@ -54,7 +54,8 @@ class ExtractDesc(C.Structure):
                 ("occupied", c_void_p), ("n_occupied", c_int), ("jitter", c_void_p),
                 ("occ_binary", c_void_p), ("cam_origins", c_void_p), ("ncams", c_int),
                 ("render_step_size", c_float), ("density_thre", c_float), ("cut_off", c_float),
-                ("host_dirs", C.POINTER(c_float)), ("ndirs", c_int), ("surface_only_where_dense", c_int)]
+                ("host_dirs", C.POINTER(c_float)), ("ndirs", c_int), ("surface_only_where_dense", c_int),
+                ("rgb_only_where_masked", c_int)]
 
 
 class EngineConfig(C.Structure):
@@ -95,6 +96,10 @@ SIGNATURES = {
     "drb_im2col_stem": (c_int, [c_void_p, c_ll, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
     "drb_bn_stats": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p]),
+    "drb_bn_small_supported": (c_int, [c_ll, c_int]),
+    "drb_bn_small": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
+                             c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p]),
     "drb_bn_finalize": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "drb_scale_shift_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int,

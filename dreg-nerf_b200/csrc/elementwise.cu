@@ -504,6 +504,125 @@ extern "C" int drb_bn_apply(const float* x, const double* accum, int g, long lon
 }
 
 // ------------------------------------------------------------------------------------------
+// Small tensors (the deep ResNet stages: m = 512 ... 8 voxels per grid, 256 ... 2048 channels): statistics,
+// running-buffer update, normalisation (+ residual, ReLU, plane split) and the backward's mean / rstd / scale /
+// shift in ONE launch.  The three launches of the general path (memset + bn_stats + bn_apply, + bn_save in grad
+// mode) cost ~30 us per BatchNorm there, all of it latency (46 of the 53 BatchNorms of a forward).
+// A block owns 32 channels of all g grids: 8 channel quads x 32 row lanes, fp64 sums as in bn_stats_kernel,
+// grids in order (the running buffers see g successive forward calls, like bn_apply_kernel).
+// ------------------------------------------------------------------------------------------
+static constexpr int kBnSmallMaxRows = 1024;
+__global__ void __launch_bounds__(256) bn_small_kernel(const float* __restrict__ x, int g, int m, int c,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float* running_mean, float* running_var, int training,
+                                                       float momentum, float eps, const float* __restrict__ residual,
+                                                       int relu, float* __restrict__ out, plane_t* __restrict__ out_hi,
+                                                       plane_t* __restrict__ out_lo, float* __restrict__ save_mean,
+                                                       float* __restrict__ save_rstd, float* __restrict__ save_scale,
+                                                       float* __restrict__ save_shift) {
+  __shared__ double s_sum[32][33], s_sq[32][33];       // [row lane][channel]
+  __shared__ float s_scale[32], s_shift[32];
+  const int c0 = blockIdx.x * 32;
+  const int q = threadIdx.x & 7, rl = threadIdx.x >> 3;            // channel quad, row lane
+  const int ch4 = c0 + 4 * q;
+  const bool ch_ok = ch4 < c;                                      // c % 4 == 0: a quad is in or out as a whole
+  for (int gi = 0; gi < g; ++gi) {
+    const float* xg = x + (long long)gi * m * c;
+    if (training) {
+      double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
+      if (ch_ok) {
+        for (int r = rl; r < m; r += 32) {
+          const float4 v = *(const float4*)(xg + (long long)r * c + ch4);
+          s[0] += (double)v.x; ss[0] += (double)v.x * (double)v.x;
+          s[1] += (double)v.y; ss[1] += (double)v.y * (double)v.y;
+          s[2] += (double)v.z; ss[2] += (double)v.z * (double)v.z;
+          s[3] += (double)v.w; ss[3] += (double)v.w * (double)v.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s_sum[rl][4 * q + j] = s[j]; s_sq[rl][4 * q + j] = ss[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int ch = c0 + threadIdx.x;
+      if (ch < c) {
+        const float ga = gamma ? gamma[ch] : 1.f, be = beta ? beta[ch] : 0.f;
+        float mu, rs;
+        if (training) {
+          double a = 0.0, b = 0.0;
+          for (int r = 0; r < 32; ++r) { a += s_sum[r][threadIdx.x]; b += s_sq[r][threadIdx.x]; }
+          const double mean = a / (double)m;
+          double var = b / (double)m - mean * mean;
+          if (var < 0.0) var = 0.0;
+          rs = (float)(1.0 / sqrt(var + (double)eps));
+          mu = (float)mean;
+          if (running_mean && running_var) {
+            const double unbiased = m > 1 ? var * ((double)m / (double)(m - 1)) : var;
+            running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
+            running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+          }
+        } else {
+          rs = 1.f / sqrtf(running_var[ch] + eps);
+          mu = running_mean[ch];
+        }
+        const float sc = ga * rs, sf = be - mu * sc;
+        s_scale[threadIdx.x] = sc; s_shift[threadIdx.x] = sf;
+        if (save_mean) {
+          const long long i = (long long)gi * c + ch;
+          save_mean[i] = mu; save_rstd[i] = rs; save_scale[i] = sc; save_shift[i] = sf;
+        }
+      }
+    }
+    __syncthreads();
+    if (ch_ok) {
+      const float4 sc = *(const float4*)&s_scale[4 * q], sf = *(const float4*)&s_shift[4 * q];
+      const bool pair = out_lo != nullptr;
+      for (int r = rl; r < m; r += 32) {
+        const long long i = ((long long)gi * m + r) * c + ch4;
+        float4 v = *(const float4*)(x + i);
+        v.x = fmaf(v.x, sc.x, sf.x); v.y = fmaf(v.y, sc.y, sf.y);
+        v.z = fmaf(v.z, sc.z, sf.z); v.w = fmaf(v.w, sc.w, sf.w);
+        if (residual) {
+          const float4 rr = *(const float4*)(residual + i);
+          v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+        }
+        if (relu) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        if (out) *(float4*)(out + i) = v;
+        if (out_hi) {
+          plane_t h0, l0, h1, l1, h2, l2, h3, l3;
+          split16(v.x, pair, h0, l0); split16(v.y, pair, h1, l1);
+          split16(v.z, pair, h2, l2); split16(v.w, pair, h3, l3);
+          *(uint2*)(out_hi + i) = make_uint2(pack16x2(h0, h1), pack16x2(h2, h3));
+          if (pair) *(uint2*)(out_lo + i) = make_uint2(pack16x2(l0, l1), pack16x2(l2, l3));
+        }
+      }
+    }
+    __syncthreads();          // s_scale / s_sum are reused by the next grid
+  }
+}
+
+extern "C" int drb_bn_small_supported(long long m, int c) { return m > 0 && m <= kBnSmallMaxRows && c > 0 && c % 4 == 0; }
+
+extern "C" int drb_bn_small(const float* x, int g, long long m, int c, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, int training, float momentum, float eps,
+                            const float* residual, int relu, float* out, void* out_hi, void* out_lo, float* save_mean,
+                            float* save_rstd, float* save_scale, float* save_shift, cudaStream_t stream) {
+  DRB_REQUIRE(x && g > 0 && (out || out_hi), "drb_bn_small: bad arguments");
+  DRB_REQUIRE(drb_bn_small_supported(m, c), "drb_bn_small: m = %lld rows per grid / c = %d not supported (m <= %d, c %% 4 == 0)",
+              m, c, kBnSmallMaxRows);
+  DRB_REQUIRE(training || (running_mean && running_var), "drb_bn_small: missing statistics");
+  DRB_REQUIRE((save_mean == nullptr) == (save_rstd == nullptr) && (save_mean == nullptr) == (save_scale == nullptr) &&
+                  (save_mean == nullptr) == (save_shift == nullptr), "drb_bn_small: save buffers come as a set");
+  bn_small_kernel<<<(c + 31) / 32, 256, 0, stream>>>(x, g, (int)m, c, gamma, beta, running_mean, running_var, training,
+                                                     momentum, eps, residual, relu, out, (plane_t*)out_hi,
+                                                     (plane_t*)out_lo, save_mean, save_rstd, save_scale, save_shift);
+  DRB_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 __global__ void maxpool_kernel(const float* __restrict__ x, int g, int d, int h, int w, int c,
                                int od, int oh, int ow, float* __restrict__ out,
                                plane_t* __restrict__ out_hi, plane_t* __restrict__ out_lo) {

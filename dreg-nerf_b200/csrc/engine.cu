@@ -315,6 +315,15 @@ static int conv_any(drb_engine* e, const ConvW& w, const Act& in, int od, int oh
 static int bn_apply(drb_engine* e, const BnP& b, const float* rawp, long long m, const float* residual,
                     int relu, float* out, plane_t* out_hi, plane_t* out_lo, cudaStream_t s) {
   const int training = e->cfg.training_bn;
+  if (e->bn_small && drb_bn_small_supported(m, b.c)) {
+    // deep stages: statistics + running update + apply (+ the backward's saved statistics) in one launch
+    const bool upd_s = !training || e->update_running;
+    e->launches += 1;
+    return drb_bn_small(rawp, kG, m, b.c, P(e, b.p_w), P(e, b.p_b), upd_s ? P(e, b.p_rm) : nullptr,
+                        upd_s ? P(e, b.p_rv) : nullptr, training, 0.1f, 1e-5f, residual, relu, out, out_hi, out_lo,
+                        e->grad_mode ? b.mean : nullptr, e->grad_mode ? b.rstd : nullptr,
+                        e->grad_mode ? b.scale : nullptr, e->grad_mode ? b.shift : nullptr, s);
+  }
   if (training) {
     e->launches += 2;
     DRB_TRY(drb_bn_stats(rawp, kG, m, b.c, e->bn_accum, s));
@@ -572,6 +581,7 @@ extern "C" int drb_engine_create(const drb_engine_config* cfg, drb_engine** out)
   DRB_REQUIRE(cfg->max_mask > 0, "drb_engine_create: max_mask must be positive");
   drb_engine* e = new drb_engine();
   e->cfg = *cfg;
+  if (const char* env = getenv("DRB_BN_SMALL")) e->bn_small = atoi(env) != 0;
   int rc = build(e);
   if (rc) {
     set_error("drb_engine_create: %s", e->fail.c_str());

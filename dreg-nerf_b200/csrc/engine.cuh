@@ -138,6 +138,7 @@ struct drb_engine {
   drb::Act lat[5], sum[4], p[5];    // p[0] = p1 ... p[4] = p5
   // output-sparse evaluation of the two level-1 FPN convolutions
   bool sparse_fpn = true;
+  bool bn_small = true;         // one-launch BatchNorm for the deep stages (DRB_BN_SMALL=0: the general path)
   bool update_running = true;   // training-mode BatchNorm writes running_mean / running_var (primary engine only)
   uint8_t* need = nullptr;
   int *tiles_out = nullptr, *tiles_in = nullptr, *tiles_in2 = nullptr, *tile_counts = nullptr;   // counts: int[3]

@@ -306,8 +306,10 @@ __device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ahi)[4], co
 }
 
 __global__ void __launch_bounds__(kRgbThreads, 1)
-ngp_rgb_kernel(const NgpDev p, const float* __restrict__ feat, int n, const DirTable dirs,
-               float* __restrict__ rgb) {
+ngp_rgb_kernel(const NgpDev p, const float* __restrict__ feat, int n_all, const DirTable dirs,
+               float* __restrict__ rgb, const int* __restrict__ idx, const int* __restrict__ idx_count) {
+  // optional row list: evaluate only the points idx[0 .. *idx_count) (rows are independent: same bits per row)
+  const int n = idx_count ? *idx_count : n_all;
   extern __shared__ __align__(16) uint8_t rgb_smem_raw[];
   RgbSmem& sm = *(RgbSmem*)rgb_smem_raw;
   // ---- staging: B fragments with the permuted K order, per-direction SH contributions ----
@@ -365,7 +367,8 @@ ngp_rgb_kernel(const NgpDev p, const float* __restrict__ feat, int n, const DirT
         for (int i = 0; i < 4; ++i) {
           // fragment (row g + 8*(i&1), column t + 4*(i>>1)) <-> feature 8*ks + 2t + (i>>1)
           const int r = row0 + 16 * mt + g + 8 * (i & 1), q = 8 * ks + 2 * t + (i >> 1);
-          const float v = (r < n && q < 15) ? feat[(long long)r * 15 + q] : 0.f;
+          float v = 0.f;
+          if (r < n && q < 15) v = feat[(long long)(idx ? idx[r] : r) * 15 + q];
           const float hi = tf32_trunc(v);
           ahi[mt][i] = f2u(hi);
           alo[mt][i] = f2u(tf32_trunc(v - hi));
@@ -446,13 +449,21 @@ ngp_rgb_kernel(const NgpDev p, const float* __restrict__ feat, int n, const DirT
     const int r = row0 + g + 8 * t;
     if (r < n) {
       const float inv = 1.f / (float)dirs.n;
-      rgb[(long long)r * 3] = sum[0] * inv; rgb[(long long)r * 3 + 1] = sum[1] * inv; rgb[(long long)r * 3 + 2] = sum[2] * inv;
+      const long long o3 = (long long)(idx ? idx[r] : r) * 3;
+      rgb[o3] = sum[0] * inv; rgb[o3 + 1] = sum[1] * inv; rgb[o3 + 2] = sum[2] * inv;
     }
   }
 }
 
+// idx / idx_count (device, optional): evaluate only the listed points (drb_extract_block: the cells that passed both masks)
+static int rgb_mean_impl(const drb_ngp_params* pp, const float* feat, int n, const float* host_dirs, int ndirs,
+                         float* rgb, const int* idx, const int* idx_count, cudaStream_t stream);
 extern "C" int drb_ngp_rgb_mean(const drb_ngp_params* pp, const float* feat, int n, const float* host_dirs,
                                 int ndirs, float* rgb, cudaStream_t stream) {
+  return rgb_mean_impl(pp, feat, n, host_dirs, ndirs, rgb, nullptr, nullptr, stream);
+}
+static int rgb_mean_impl(const drb_ngp_params* pp, const float* feat, int n, const float* host_dirs, int ndirs,
+                         float* rgb, const int* idx, const int* idx_count, cudaStream_t stream) {
   DRB_REQUIRE(pp && pp->c1 && pp->c2 && pp->c3 && feat && host_dirs && rgb, "drb_ngp_rgb_mean: null argument");
   DRB_REQUIRE(ndirs > 0 && ndirs <= kMaxDirs, "drb_ngp_rgb_mean: 1..%d directions", kMaxDirs);
   if (n == 0) return 0;
@@ -465,7 +476,7 @@ extern "C" int drb_ngp_rgb_mean(const drb_ngp_params* pp, const float* feat, int
   const int warps = kRgbThreads / 32;
   int grid = cdiv(cdiv(n, 32), warps);
   if (grid > igemm_num_sms()) grid = igemm_num_sms();
-  ngp_rgb_kernel<<<grid, kRgbThreads, sizeof(RgbSmem), stream>>>(p, feat, n, dt, rgb);
+  ngp_rgb_kernel<<<grid, kRgbThreads, sizeof(RgbSmem), stream>>>(p, feat, n, dt, rgb, idx, idx_count);
   DRB_LAUNCH_OK();
   return 0;
 }
@@ -1516,6 +1527,20 @@ __global__ void finish_extract_kernel(const long long* __restrict__ occupied, in
 // Profile mode: every drb_extract_block of this thread appends an event pair; drb_extract_read_profile
 // synchronises on them once, returns the summed kernel time and the launch count, and clears the list
 // (this is how bench.py times the kernel INSIDE its timed steps without a sync per call).
+// idx[0 .. *count) = points with both masks set (any order); warp-aggregated atomics
+__global__ void compact_masked_kernel(const uint8_t* __restrict__ dmask, const uint8_t* __restrict__ smask, int n,
+                                      int* __restrict__ idx, int* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool keep = i < n && dmask[i] != 0 && smask[i] != 0;
+  const uint32_t m = __ballot_sync(0xffffffffu, keep);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (keep) idx[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+
 static thread_local cudaEvent_t g_surf_ev[2] = {nullptr, nullptr};
 static thread_local bool g_surf_valid = false;
 static thread_local bool g_surf_profile = false;
@@ -1575,7 +1600,8 @@ extern "C" int drb_extract_block(const drb_ngp_params* pp, const drb_extract_des
     density_mask_kernel<<<cdiv(n, 256), 256, 0, stream>>>(density, n, e->density_thre, alpha, density_mask);
     if (cudaGetLastError() != cudaSuccess) rc = DRB_ECUDA;
   }
-  if (!rc) rc = drb_ngp_rgb_mean(pp, feat, n, e->host_dirs, e->ndirs, rgb, stream);
+  const bool rgb_late = e->rgb_only_where_masked != 0;     // colour only for the cells both masks keep
+  if (!rc && !rgb_late) rc = drb_ngp_rgb_mean(pp, feat, n, e->host_dirs, e->ndirs, rgb, stream);
   if (!rc) {
     if (!g_surf_ev[0]) { cudaEventCreate(&g_surf_ev[0]); cudaEventCreate(&g_surf_ev[1]); }
     cudaEvent_t pe[2] = {nullptr, nullptr};
@@ -1587,6 +1613,19 @@ extern "C" int drb_extract_block(const drb_ngp_params* pp, const drb_extract_des
     cudaEventRecord(g_surf_ev[1], stream);
     if (g_surf_profile) { cudaEventRecord(pe[1], stream); g_surf_list->push_back(pe[0]); g_surf_list->push_back(pe[1]); }
     g_surf_valid = true;
+  }
+  if (!rc && rgb_late) {
+    int* idx = nullptr;
+    if (cudaMallocAsync(&idx, sizeof(int) * ((size_t)n + 1), stream) != cudaSuccess) rc = DRB_ENOMEM;
+    if (!rc) {
+      int* count = idx + n;
+      cudaMemsetAsync(count, 0, sizeof(int), stream);
+      cudaMemsetAsync(rgb, 0, sizeof(float) * 3 * (size_t)n, stream);
+      compact_masked_kernel<<<cdiv(n, 256), 256, 0, stream>>>(density_mask, surface_mask, n, idx, count);
+      if (cudaGetLastError() != cudaSuccess) rc = DRB_ECUDA;
+      if (!rc) rc = rgb_mean_impl(pp, feat, n, e->host_dirs, e->ndirs, rgb, idx, count, stream);
+      cudaFreeAsync(idx, stream);
+    }
   }
   if (!rc) {
     finish_extract_kernel<<<cdiv(n, 256), 256, 0, stream>>>(e->occupied, n, points, rgb, surface_mask, alpha,

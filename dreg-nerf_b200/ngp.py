@@ -201,13 +201,16 @@ class SampleGrid(nn.Module):
     @torch.no_grad()
     def query_radiance_and_density_from_camera(self, radiance_field, occupancy_grid, meta_data, device,
                                                density_thre=0.7, cut_off: float = 0.5, jitter=None,
-                                               return_grid: bool = False, surface_only_where_dense: bool = False):
+                                               return_grid: bool = False, surface_only_where_dense: bool = False,
+                                               rgb_only_where_masked: bool = False):
         """sample_grid.py:208-343 -> (points, color, alpha, indices, density_mask, surface_mask).
 
         ``jitter`` (U[0,1) [K,3]) may be supplied for reproducibility; by default it is drawn with
         torch.rand on the grid's device exactly where the reference calls torch.rand_like.
         ``surface_only_where_dense`` skips the ray march of cells whose density fails the threshold
         (their surface_mask entries stay False): identical voxel_grid / voxel_mask, ~3x less marching.
+        ``rgb_only_where_masked`` evaluates the colour head only for cells that pass both masks (their rows are
+        the only ones voxel_grid keeps); the colour of every other cell is returned as 0.
         """
         lib = _lib.load()
         check_march_options(meta_data, cut_off)
@@ -229,7 +232,8 @@ class SampleGrid(nn.Module):
                                 render_step_size=float(meta_data["render_step_size"]),
                                 density_thre=float(density_thre), cut_off=float(cut_off),
                                 host_dirs=host_dirs, ndirs=dirs.shape[0],
-                                surface_only_where_dense=int(surface_only_where_dense))
+                                surface_only_where_dense=int(surface_only_where_dense),
+                                rgb_only_where_masked=int(rgb_only_where_masked))
         roi = self._roi_aabb.detach().cpu().tolist()
         scene = [float(v) for v in torch.as_tensor(meta_data["aabb"]).reshape(-1).tolist()]
         for i in range(6):
@@ -258,5 +262,5 @@ def extract_block(radiance_field, sample_grid, occupancy_binary, meta_data, devi
     sample_grid.set_binary_fields(occupancy_binary)
     pts, rgb, alpha, indices, dmask, smask, grid = sample_grid.query_radiance_and_density_from_camera(
         radiance_field, occupancy_binary, meta_data, device, jitter=jitter, return_grid=True,
-        surface_only_where_dense=True)
+        surface_only_where_dense=True, rgb_only_where_masked=True)
     return grid, indices[dmask & smask]

@@ -178,6 +178,23 @@ def batchnorm_fused(x, gamma, beta, running_mean, running_var, training, residua
     return out, (o_hi, o_lo)
 
 
+def batchnorm_small(x, gamma, beta, running_mean, running_var, training, residual=None, relu=False,
+                    momentum=0.1, eps=1e-5, want_planes=False, want_stats=False):
+    """Same contract as ``batchnorm`` through the one-launch kernel of the deep stages (m <= 1024 rows per grid);
+    ``want_stats`` also returns (mean, rstd, scale, shift) [g, c] as drb_bn_save_stats produces them."""
+    g, m, c = x.shape
+    lib = _lib.load()
+    out = torch.empty_like(x)
+    o_hi = torch.empty_like(x, dtype=torch.float16) if want_planes else None
+    o_lo = torch.empty_like(x, dtype=torch.float16) if want_planes else None
+    st = [torch.empty((g, c), dtype=torch.float32, device=x.device) for _ in range(4)] if want_stats else [None] * 4
+    with _dev(x):
+        check(lib.drb_bn_small(ptr(x), g, m, c, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                               int(training), momentum, eps, ptr(residual), int(relu), ptr(out), ptr(o_hi), ptr(o_lo),
+                               ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]), stream_ptr()), "drb_bn_small")
+    return (out, (o_hi, o_lo), tuple(st)) if want_stats else (out, (o_hi, o_lo))
+
+
 def maxpool3d(x):
     g, d, h, w, c = x.shape
     od, oh, ow = (d - 1) // 2 + 1, (h - 1) // 2 + 1, (w - 1) // 2 + 1

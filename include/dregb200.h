@@ -148,6 +148,16 @@ int drb_bn_apply(const float* x, const double* accum, int g, long long m, int c,
                  float eps, const float* residual, int relu, float* out, void* out_hi, void* out_lo,
                  drb_stream_t stream);
 
+/* The same BatchNorm (nn.BatchNorm3d of resnet3d.py:88-100 in both modes) for SMALL tensors - the deep ResNet
+ * stages, m <= 1024 rows per grid - in one launch: fp64 statistics, running-buffer update, normalise (+ residual,
+ * ReLU, plane split) and, when the save buffers are given ([g][c] each; all four or none), the mean / rstd /
+ * scale / shift the backward pass needs (drb_bn_save_stats).  drb_bn_small_supported tells whether (m, c) qualifies. */
+int drb_bn_small_supported(long long m, int c);
+int drb_bn_small(const float* x, int g, long long m, int c, const float* gamma, const float* beta,
+                 float* running_mean, float* running_var, int training, float momentum, float eps,
+                 const float* residual, int relu, float* out, void* out_hi, void* out_lo, float* save_mean,
+                 float* save_rstd, float* save_scale, float* save_shift, drb_stream_t stream);
+
 /* nn.MaxPool3d(3, 2, 1) (resnet3d.py:123) on fp32 [g][d][h][w][c]. */
 int drb_maxpool3d(const float* x, int g, int d, int h, int w, int c, float* out, void* out_hi,
                   void* out_lo, drb_stream_t stream);
@@ -289,6 +299,8 @@ typedef struct drb_extract_desc {
   int surface_only_where_dense;  /* 1: march rays only for cells with density > density_thre; their
                                   * surface_mask entries stay 0.  Exact for voxel_grid / voxel_mask
                                   * (eval_ngp_nerf.py:383 keeps surface & density only).             */
+  int rgb_only_where_masked;     /* 1: evaluate the colour head only for cells that pass both masks (after the
+                                  * march); rgb rows of the other cells are 0.  Exact for voxel_grid.       */
 } drb_extract_desc;
 /* Writes points [n][3], rgb [n][3], alpha [n], density_mask [n], surface_mask [n] and scatters
  * rows of cells with both masks set into voxel_grid [R^3][7] (pre-zeroed by the call). */

@@ -106,6 +106,13 @@ def test_extract_block_small(pkg, cuda):
                                                      surface_only_where_dense=True)
     assert torch.equal(out2[6].cpu(), grid.cpu())
     assert torch.equal((out2[4] & out2[5]).cpu(), keep)
+    # ... and with the colour head evaluated only on the cells both masks keep (what extract_block runs):
+    # the same grid bit for bit, colour rows of the other cells zero
+    out3 = sg.query_radiance_and_density_from_camera(f, occ, meta, cuda, jitter=jitter, return_grid=True,
+                                                     surface_only_where_dense=True, rgb_only_where_masked=True)
+    assert torch.equal(out3[6].cpu(), grid.cpu())
+    assert torch.equal(out3[1].cpu()[keep], out2[1].cpu()[keep])
+    assert (out3[1].cpu()[~keep] == 0).all()
 
 
 def test_extract_then_register_128(pkg, cuda):

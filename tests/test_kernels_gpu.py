@@ -185,6 +185,39 @@ def test_batchnorm(cuda, training, fused):
     assert _rel(rm_d, rm_ref) < 1e-5 and _rel(rv_d, rv_ref) < 1e-5
 
 
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("g,m,c", [(2, 512, 256), (2, 64, 2048), (2, 8, 512), (3, 1000, 36)])
+def test_batchnorm_small_matches_general_path(cuda, training, g, m, c):
+    """The one-launch BatchNorm of the deep stages against torch and against the general three-launch path,
+    including the statistics the backward pass keeps."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(g * m + c)
+    x = torch.randn(g, m, c, generator=gen) * 3 + 1.5
+    gamma, beta = torch.rand(c, generator=gen) + 0.5, torch.randn(c, generator=gen)
+    rm, rv = torch.randn(c, generator=gen) * 0.1, torch.rand(c, generator=gen) + 0.5
+    res = torch.randn(g, m, c, generator=gen)
+    dev = lambda t: t.clone().to(cuda)
+    rm_a, rv_a, rm_b, rv_b = dev(rm), dev(rv), dev(rm), dev(rv)
+    out, (hi, lo), st = ops.batchnorm_small(dev(x), dev(gamma), dev(beta), rm_a, rv_a, training, residual=dev(res),
+                                            relu=True, want_planes=True, want_stats=True)
+    ref_out, (rhi, rlo) = ops.batchnorm_fused(dev(x), dev(gamma), dev(beta), rm_b, rv_b, training, residual=dev(res),
+                                              relu=True, want_planes=True)
+    want = ops.bn_forward_stats(dev(x), dev(gamma), dev(beta), dev(rm), dev(rv), training)
+    torch.cuda.synchronize()
+    assert _rel(out, ref_out) < 2e-6 and _rel(rm_a, rm_b) < 1e-6 and _rel(rv_a, rv_b) < 1e-6
+    assert _rel(hi.float() + lo.float(), rhi.float() + rlo.float()) < 4e-6
+    for a, b in zip(st, want):
+        assert _rel(a, b) < 2e-6
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    refs = []
+    for gi in range(g):
+        xi = x[gi].t().reshape(1, c, m, 1, 1)
+        yi = F.batch_norm(xi, rm_ref, rv_ref, gamma, beta, training, 0.1, 1e-5)
+        refs.append(torch.relu(yi.reshape(c, m).t() + res[gi]))
+    assert _rel(out, torch.stack(refs)) < 1e-5
+    assert _rel(rm_a, rm_ref) < 1e-5 and _rel(rv_a, rv_ref) < 1e-5
+
+
 def test_maxpool_upsample(cuda):
     ops = _ops()
     gen = torch.Generator().manual_seed(9)
