@@ -265,6 +265,7 @@ int engine_run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
   r.flops = 2.0 * (double)g * d * h * wd * (double)cd.cout * (double)cin * k * k * k;
   r.list_id = engine_list_id(e, tile_list);
   r.flops_per_tile = 2.0 * 128.0 * (double)cd.cout * (double)cin * k * k * k;   // executed work of one listed tile
+  r.m = g * d * h * wd; r.cin = cin; r.cout = cd.cout; r.k = k;
   cudaEventRecord(r.a, s);
   const int rc = drb_conv3d_igemm(&cd, s);
   cudaEventRecord(r.b, s);
@@ -648,12 +649,17 @@ extern "C" int drb_engine_profile_read(drb_engine* e, double* igemm_ms, double* 
     DRB_CUDA_OK(cudaMemset(e->tile_totals, 0, sizeof(totals)));
   }
   const double forwards = e->prof_forwards > 0 ? (double)e->prof_forwards : 1.0;
+  const bool dump = getenv("DRB_PROFILE_DUMP") != nullptr;
   for (auto& r : e->prof) {
     DRB_CUDA_OK(cudaEventSynchronize(r.b));
     float t = 0.f;
     DRB_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
     ms += t;
-    if (r.list_id >= 0) fl += r.flops_per_tile * ((double)totals[r.list_id] / forwards); else fl += r.flops;
+    const double f_exec = r.list_id >= 0 ? r.flops_per_tile * ((double)totals[r.list_id] / forwards) : r.flops;
+    fl += f_exec;
+    if (dump)     // DRB_PROFILE_DUMP=1: one line per launch (development aid: which GEMM shapes run below the average)
+      fprintf(stderr, "igemm M=%d Cin=%d Cout=%d k=%d%s: %.1f us, %.1f TFLOP/s executed\n", r.m, r.cin, r.cout, r.k,
+              r.list_id >= 0 ? " (tile list)" : "", t * 1e3, t > 0.f ? f_exec / (t * 1e-3) / 1e12 : 0.0);
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }

@@ -105,7 +105,7 @@ struct drb_engine {
   long long launches = 0;
   bool committed = false;
   bool profile = false;
-  struct ProfRec { cudaEvent_t a, b; double flops; int list_id; double flops_per_tile; };
+  struct ProfRec { cudaEvent_t a, b; double flops; int list_id; double flops_per_tile; int m, cin, cout, k; };
   std::vector<ProfRec> prof;
   long long prof_forwards = 0;      // encode calls since the last profile read (tile-list averages)
   std::string fail;

@@ -119,6 +119,7 @@ static int wgrad(drb_engine* e, const ConvW& w, const GradPlanes& dy, const plan
   r.flops = 2.0 * (double)g * d * h * wd * (double)cout * (double)cin * k * k * k;
   r.list_id = engine_list_id(e, tile_list);
   r.flops_per_tile = 2.0 * 128.0 * (double)cout * (double)cin * k * k * k;
+  r.m = -(g * d * h * wd); r.cin = cin; r.cout = cout; r.k = k;      // negative M marks a weight-gradient launch in the dump
   cudaEventRecord(r.a, s);
   const int rc = drb_conv3d_wgrad(&wd_, s);
   cudaEventRecord(r.b, s);
