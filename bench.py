@@ -24,6 +24,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 RES = 128
+DEFAULT_FULL_STREAMS = 4        # pairs in flight of the full stage (1 = one pair at a time, as round 1 ran it)
 N_RESIDENT_PAIRS = 3        # distinct synthetic pairs cycled through the timed steps
 FPN_FLOPS_PER_GRID_128 = 1384.0e9   # BASELINE.md section 2 (measured, 2*MAC)
 
@@ -346,8 +347,9 @@ def run_ours(args):
                      + poses_pinned.numel() * 4)
         masked = [0, 0]
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        model.reserve_mask_capacity(int(occ.sum()))      # no engine is rebuilt mid-run when a block keeps more cells
 
-        def extract_and_register(fields, occ_d, meta_d, timed_stages):
+        def extract_and_register(fields, occ_d, meta_d, timed_stages, gather=True):
             grids = []
             if timed_stages:
                 ev[0].record()
@@ -361,7 +363,30 @@ def run_ours(args):
             out = model(data)
             if timed_stages:
                 ev[2].record()
-            return gather_pose(out["pose"][-1])
+            return gather_pose(out["pose"][-1]) if gather else out["pose"][-1]
+
+        # several pairs in flight (--streams > 1, pipeline.PairPipeline): the same work per pair on a worker's own
+        # stream / engine; the per-pair all-gather stays on the caller's thread (one communicator, one thread)
+        from importlib import import_module as _imp
+        _slot = _imp("dreg-nerf_b200.nerf_regtr").engine_slot
+        multi_bufs = [dict(fields=[pkg.synthetic.make_ngp_field(seed=950 + side_).to(dev) for side_ in (0, 1)],
+                           occ=torch.empty_like(occ.to(torch.uint8), device=dev), poses=torch.empty_like(poses, device=dev))
+                      for _ in range(args.streams if args.streams > 1 else 0)]
+
+        def pair_resident(i):
+            with torch.no_grad():
+                return extract_and_register(dev_fields[i % N_RESIDENT_PAIRS], occ_dev, meta, False, gather=False)
+
+        def pair_e2e(i):
+            sb = multi_bufs[_slot()]
+            with torch.no_grad():
+                for f, (hp, hc) in zip(sb["fields"], host_fields[i % N_RESIDENT_PAIRS]):
+                    f.mlp_base.params.data.copy_(hp, non_blocking=True)
+                    f.color_mlp.params.data.copy_(hc, non_blocking=True)
+                sb["occ"].copy_(occ_pinned, non_blocking=True)
+                sb["poses"].copy_(poses_pinned, non_blocking=True)
+                meta_d = dict(meta_host, camera_poses=sb["poses"])
+                return extract_and_register(sb["fields"], sb["occ"].bool(), meta_d, False, gather=False)
 
         def step_resident(i, timed_stages=False):
             with torch.no_grad():
@@ -451,16 +476,52 @@ def run_ours(args):
         return float(t.item()), model.launch_count() - l0, prof
 
     torch.manual_seed(1000 + rank)      # per-rank sampling jitter from here on (make_ngp_field reseeds while it builds)
+    multi = full and args.streams > 1
+    pipe = pkg.PairPipeline(dev, streams=args.streams) if multi else None
+
+    def timed_multi(pair_fn, steps, to_host):
+        # `steps` pairs, args.streams of them in flight; the per-pair SE(3) all-gather (and the D2H read of the end-to-end
+        # path) follow on the caller's stream in pair order
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = model.launch_count()
+        e0.record()
+        for pose in pipe.map(pair_fn, range(steps)):
+            pose = gather_pose(pose)
+            if to_host:
+                pose.cpu()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), model.launch_count() - l0
+
     for i in range(max(args.warmup, 3)):
         step_resident(i)
+    if multi:
+        timed_multi(pair_resident, max(args.warmup, 3) * args.streams, False)      # every slot's engine warm
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms, launches, prof = timed(step_resident, args.steps, profile=True)
+    profile_note = "CUDA events around the kernel, inside the timed region"
+    if multi:
+        ms, launches = timed_multi(pair_resident, args.steps, False)
+        ms_1, _, prof = timed(step_resident, args.steps, profile=True)
+        profile_note = ("CUDA events around the kernel in a second pass over the same steps on ONE stream (%.2f ms per step): in "
+                        "the timed region %d pairs are in flight and the brackets would span other pairs' kernels"
+                        % (ms_1 / args.steps, args.streams))
+    else:
+        ms, launches, prof = timed(step_resident, args.steps, profile=True)
+        ms_1 = ms
     clocks = sampler.summary() if sampler else None
-    for i in range(2):
-        step_e2e(i)
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    if multi:
+        timed_multi(pair_e2e, 2 * args.streams, True)
+        ms_e2e, _ = timed_multi(pair_e2e, args.steps, True)
+    else:
+        for i in range(2):
+            step_e2e(i)
+        ms_e2e, _, _ = timed(step_e2e, args.steps)
     if full:
         for i in range(min(args.steps, 3)):          # untimed extra steps: per-stage split
             step_resident(i, timed_stages=True)
@@ -507,9 +568,12 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": peaks["source"] + ", bf16 sustained",
                          "traffic": None, "launches": int(ig_n), "kernel_ms_per_step": ig_ms / args.steps,
-                         "kernel_share_of_step": ig_ms / ms,
+                         "kernel_share_of_step": ig_ms / ms_1, "timing": profile_note,
                          "mma_flops_factor": mma_factor, "tensor_pipe_frac_est": mma_factor * achieved / peak},
         }
+        if multi:
+            line["config"]["streams"] = ("%d pairs in flight per GPU, one CUDA stream + engine each (pipeline.PairPipeline); "
+                                         "one pair at a time: %.2f ms per pair" % (args.streams, ms_1 / args.steps))
         if full:
             # In the full path the surface-field ray marcher is the dominant kernel.  DRAM is idle (the 48 MB
             # table is L2 resident); the kernel is bound by the rate at which an SM can miss 32-byte sectors
@@ -533,7 +597,7 @@ def run_ours(args):
                 "traffic_note": "dram read+write of one launch, ncu --set full (profiles/r01_v6_ncu_surface_seed501_keys.txt)",
                 "kernel_ms_per_launch": surf_ms, "launches": surf_prof["launches"],
                 "kernel_ms_per_step": surf_prof["ms"] / args.steps,
-                "kernel_share_of_step": surf_prof["ms"] / ms,
+                "kernel_share_of_step": surf_prof["ms"] / ms_1, "timing": profile_note,
                 "per_launch": {"rays": rays / n_l, "skip_events": skips / n_l, "density_samples": samples / n_l},
                 "issued_gather_bytes_per_launch": issued,
                 "issued_gather_gbs": issued / (surf_ms / 1e3) / 1e9 if surf_ms > 0 else 0.0,
@@ -929,14 +993,17 @@ def main():
     ap.add_argument("--res", type=int, default=RES, help="batch: grid resolution (256 for configs[4])")
     ap.add_argument("--max-tokens", type=int, default=0, help="batch: cap of the down-sampler (tokens of the pair); 0 = the reference's 3000")
     ap.add_argument("--attention", default="mma", choices=["tc", "mma"], help="tc = tcgen05 FlashAttention-style kernel")
-    ap.add_argument("--streams", type=int, default=4,
-                    help="train / batch: pairs in flight per GPU (pipeline.PairPipeline; 1 = the sequential loop)")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="pairs in flight per GPU (pipeline.PairPipeline; 1 = the sequential loop); default 4 for train / "
+                         "batch, 1 for full / register")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage", default="full", choices=["full", "register", "train", "batch"],
                     help="full = extract (2 NeRF blocks -> voxel grids) + register (configs[1], the default); register = "
                          "NeRFRegTr.forward only; train = configs[2] (fwd + bwd + AdamW); batch = configs[3] (sharded list of pairs)")
     ap.add_argument("--cams", type=int, default=50)
     args = ap.parse_args()
+    if args.streams <= 0:
+        args.streams = 4 if args.stage in ("train", "batch") else (DEFAULT_FULL_STREAMS if args.stage == "full" else 1)
     if args.impl == "reference":
         run_reference(args)
     elif args.stage == "train":

@@ -84,6 +84,7 @@ SIGNATURES = {
     "drb_last_error": (C.c_char_p, []),
     "drb_igemm_error_flag": (c_int, [C.POINTER(c_int)]),
     "drb_error_flag_clear": (c_int, []),
+    "drb_error_flag_peek": (c_int, [C.POINTER(c_int)]),
     "drb_error_flag_detail": (c_int, [C.POINTER(c_int * 16)]),
     "drb_conv3d_igemm": (c_int, [C.POINTER(Conv3dDesc), c_void_p]),
     "drb_conv3d_tile_shape": (c_int, [c_int, c_int, c_int, c_int, C.POINTER(c_int * 4), C.POINTER(c_int * 4)]),
@@ -249,6 +250,20 @@ def check_device_flag(what=""):
     lib = load()
     v = C.c_int(0)
     check(lib.drb_igemm_error_flag(C.byref(v)), "drb_igemm_error_flag")
+    if v.value != 0:
+        lib.drb_error_flag_clear()
+        raise DrbError("%s: device error flag %d (%s)" % (what or "libdregb200", v.value,
+                                                          _FLAG_TEXT.get(v.value, "tensor-core pipeline watchdog")))
+
+
+def check_stream_flag(what=""):
+    """Same check for the work queued on the CURRENT stream only: waits for that stream, then reads the flag without
+    a device-wide wait - pairs in flight on other streams (pipeline.PairPipeline) keep running."""
+    import torch
+    lib = load()
+    torch.cuda.current_stream().synchronize()
+    v = C.c_int(0)
+    check(lib.drb_error_flag_peek(C.byref(v)), "drb_error_flag_peek")
     if v.value != 0:
         lib.drb_error_flag_clear()
         raise DrbError("%s: device error flag %d (%s)" % (what or "libdregb200", v.value,

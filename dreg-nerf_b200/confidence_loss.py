@@ -38,7 +38,7 @@ def surface_field_mask(radiance_field, occupancy_binary, points, cam_origins, ro
         _lib.check(lib.drb_surface_mask(C.byref(ps), _lib.ptr(occ), res, roi, scene, _lib.ptr(pts), pts.shape[0],
                                         _lib.ptr(cams), cams.shape[0], float(render_step_size), float(cut_off),
                                         _lib.ptr(out), _lib.stream_ptr()), "drb_surface_mask")
-        _lib.check_device_flag("drb_surface_mask")
+        _lib.check_stream_flag("drb_surface_mask")
     return out.bool()
 
 

@@ -770,6 +770,12 @@ extern "C" int drb_error_flag_detail(int* host16) {
   return 0;
 }
 
+extern "C" int drb_error_flag_peek(int* host_value) {
+  if (!host_value) return DRB_EINVAL;
+  *host_value = igemm_peek_err_flag();
+  return 0;
+}
+
 extern "C" int drb_error_flag_clear(void) {
   igemm_clear_err_flag();
   return 0;

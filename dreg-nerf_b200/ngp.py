@@ -250,7 +250,7 @@ class SampleGrid(nn.Module):
             _lib.check(lib.drb_extract_block(C.byref(ps), C.byref(desc), _lib.ptr(points), _lib.ptr(rgb),
                                              _lib.ptr(alpha), _lib.ptr(dmask), _lib.ptr(smask),
                                              _lib.ptr(grid), _lib.stream_ptr()), "drb_extract_block")
-            _lib.check_device_flag("drb_extract_block")      # the caller indexes with the masks next: no extra stall
+            _lib.check_stream_flag("drb_extract_block")      # the caller indexes with the masks next: no extra stall
         out = (points, rgb, alpha, indices, dmask.bool(), smask.bool())
         return out + (grid,) if return_grid else out
 

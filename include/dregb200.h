@@ -45,6 +45,10 @@ int drb_igemm_error_flag(int* host_value);
 /* The flag of the current device is sticky; codes: 1-4 / 11-14 tcgen05 pipeline watchdogs (igemm / wgrad), 21 mask
  * index out of range, 31 surface-field marcher watchdog (result truncated).  Clears it. */
 int drb_error_flag_clear(void);
+/* The flag as the host sees it NOW, without waiting for the device (it lives in mapped pinned host memory): valid
+ * for work the caller has already synchronised with - e.g. after cudaStreamSynchronize of its own stream, while
+ * other streams keep running (drb_igemm_error_flag waits for the whole device). */
+int drb_error_flag_peek(int* host_value);
 /* Debug: the flag and 15 per-site detail words (which watchdog sites fired).  Synchronises. */
 int drb_error_flag_detail(int* host16);
 
