@@ -91,3 +91,39 @@ def test_pipeline_propagates_errors(pkg, cuda):
             pipe.map(lambda d: model(dict(d))["pose"], [good, bad, good, good])
         pose = pipe.map(lambda d: model(dict(d))["pose"], [good, good])       # the pipeline is still usable
     assert torch.equal(pose[0], pose[1])
+
+
+def test_pipeline_full_path_is_bit_identical_to_the_loop(pkg, cuda):
+    """extract (two NeRF blocks -> voxel grids) + register per pair, several pairs in flight: every kernel of the
+    path - marcher, field queries, CUB sorts, engine - on a worker's own stream gives the loop's bits."""
+    res, n_cam = 64, 8
+    model = _model(pkg, cuda)
+    occ, poses = pkg.synthetic.extract_scene(res, n_cam)
+    meta = dict(pkg.synthetic.extract_meta(poses), camera_poses=poses.to(cuda))
+    occ_d = occ.to(cuda)
+    sgrid = pkg.SampleGrid(list(pkg.synthetic.AABB), res)
+    k = int(occ.sum())
+    fields = [[pkg.synthetic.make_ngp_field(seed=700 + 2 * i + s).to(cuda) for s in (0, 1)] for i in range(5)]
+    gen = torch.Generator().manual_seed(5)
+    jitters = [[torch.rand(k, 3, generator=gen).to(cuda) for _ in (0, 1)] for _ in range(5)]
+
+    def one(i):
+        grids = [pkg.extract_block(f, sgrid, occ_d, meta, cuda, jitter=j) for f, j in zip(fields[i], jitters[i])]
+        if min(g[1].numel() for g in grids) < 16:
+            return grids[0][0], grids[1][0], grids[0][1], grids[1][1]
+        out = model({"src_xyz_rgba": grids[0][0].permute(3, 2, 0, 1).unsqueeze(0), "src_mask": grids[0][1],
+                     "tgt_xyz_rgba": grids[1][0].permute(3, 2, 0, 1).unsqueeze(0), "tgt_mask": grids[1][1]})
+        return grids[0][0], grids[1][0], grids[0][1], grids[1][1], out["pose"], out["src_feats"][0]
+
+    with torch.no_grad():
+        want = [one(i) for i in range(5)]
+        with pkg.PairPipeline(cuda, streams=3) as pipe:
+            got = pipe.map(one, range(5))
+        torch.cuda.synchronize()
+    kept = [int(w[2].numel()) for w in want]
+    print("masked cells per source block:", kept)
+    assert max(kept) > 0
+    for a, b in zip(want, got):
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
