@@ -6,7 +6,7 @@ interfaces (``NeRFRegTr``, ``NGPradianceField`` / ``SampleGrid`` extract).
 """
 from ._lib import DrbError, load as load_library  # noqa: F401
 from .nerf_regtr import NeRFRegTr  # noqa: F401
-from .ngp import NGPradianceField, SampleGrid, extract_block  # noqa: F401
+from .ngp import NGPradianceField, SampleGrid, extract_block, extract_workspace_bytes  # noqa: F401
 from . import augment, blockio, losses, pipeline, synthetic  # noqa: F401
 from .pipeline import PairPipeline  # noqa: F401
 from .occupancy import OccupancyGrid  # noqa: F401

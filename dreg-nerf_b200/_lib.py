@@ -141,6 +141,13 @@ SIGNATURES = {
                                  c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_void_p, c_void_p]),
     "drb_extract_block": (c_int, [C.POINTER(NgpParams), C.POINTER(ExtractDesc), c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "drb_surface_mask_workspace_bytes": (C.c_size_t, [c_int]),
+    "drb_surface_mask_ws": (c_int, [C.POINTER(NgpParams), c_void_p, c_int, C.POINTER(c_float), C.POINTER(c_float),
+                                    c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, C.c_size_t,
+                                    c_void_p]),
+    "drb_extract_workspace_bytes": (C.c_size_t, [c_int]),
+    "drb_extract_block_ws": (c_int, [C.POINTER(NgpParams), C.POINTER(ExtractDesc), c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, C.c_size_t, c_void_p]),
     "drb_extract_last_surface_ms": (c_int, [C.POINTER(c_float)]),
     "drb_march_stats": (c_int, [C.POINTER(C.c_ulonglong), c_int]),
     "drb_extract_set_profile": (c_int, [c_int]),

@@ -1368,15 +1368,58 @@ __global__ void morton_key_kernel(const MortonArgs m, const float* __restrict__ 
   if ((threadIdx.x & 31) == 0 && mask) atomicAdd(count, __popc(mask));
 }
 
+// Scratch of the extract entry points: carved from a caller workspace (the *_ws variants: no allocation inside the
+// call) or taken from the stream-ordered allocator and given back when the call returns.
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, used = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> owned;
+  Arena(void* ws, size_t bytes, cudaStream_t s) : base((uint8_t*)ws), cap(bytes), stream(s) {
+    const uintptr_t mis = (uintptr_t)base & 255;
+    if (base && mis) { const size_t skip = 256 - mis; base += skip; cap = cap > skip ? cap - skip : 0; }
+  }
+  void* take(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (base) {
+      if (used + bytes > cap) return nullptr;
+      void* p = base + used;
+      used += bytes;
+      return p;
+    }
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, bytes, stream) != cudaSuccess) return nullptr;
+    owned.push_back(p);
+    return p;
+  }
+  ~Arena() { for (void* p : owned) cudaFreeAsync(p, stream); }
+};
+static size_t march_scratch_bytes(int n, bool cellmajor) {
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const int*)nullptr, (int*)nullptr, n > 0 ? n : 1, 0, 32, nullptr);
+  const size_t arr = ((size_t)(n > 0 ? n : 1) * 4 + 255) & ~(size_t)255;
+  const LevelTable lv = host_levels();
+  size_t cm_cells = 0;
+  for (int l = 1; l <= 4; ++l) cm_cells += (size_t)lv.res[l] * lv.res[l] * lv.res[l];
+  return 256 + 4 * arr + (size_t)kCoarseWords * 4 + cub_bytes + 256 + (cellmajor ? cm_cells * 64 : 0) + 1024;
+}
+
+// ev: optional {before, after, before2, after2} events recorded right around the marcher kernel itself (not the
+// Morton sort / coarse bitmap / cell-major copy that precede it) - roofline instrumentation
 static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary, int res,
                              const float* roi_aabb_host, const float* scene_aabb_host, const float* points,
                              int n, const float* cam_origins, int ncams, float step, float cut_off,
-                             const uint8_t* active, uint8_t* surface, cudaStream_t stream) {
+                             const uint8_t* active, uint8_t* surface, cudaStream_t stream,
+                             cudaEvent_t* ev = nullptr, Arena* arena_in = nullptr) {
   DRB_REQUIRE(pp && occ_binary && roi_aabb_host && scene_aabb_host && points && cam_origins && surface,
               "drb_surface_mask: null argument");
   DRB_REQUIRE(res > 0 && step > 0.f, "drb_surface_mask: bad grid / step");
   DRB_CUDA_OK(cudaMemsetAsync(surface, 0, (size_t)(n > 0 ? n : 0), stream));
-  if (n == 0 || ncams == 0) return 0;
+  if (n == 0 || ncams == 0) {
+    if (ev) for (int i = 0; i < 4; ++i) if (ev[i]) cudaEventRecord(ev[i], stream);     // nothing to march: zero-length bracket
+    return 0;
+  }
   const NgpDev p = make_dev(pp);
   MarchArgs a;
   for (int d = 0; d < 3; ++d) {
@@ -1435,7 +1478,11 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
   for (int l = 1; l <= 4; ++l) { pm.cm_off[l] = cm_cells; cm_cells += p.lv.res[l] * p.lv.res[l] * p.lv.res[l]; }
   const size_t off_cm = (off_cub + cub_bytes + 255) & ~(size_t)255;
   const size_t cm_bytes = use_cm ? (size_t)cm_cells * 64 : 0;
-  DRB_CUDA_OK(cudaMallocAsync(&scratch, off_cm + cm_bytes + 256, stream));
+  Arena local(nullptr, 0, stream);
+  Arena& arena = arena_in ? *arena_in : local;
+  scratch = (uint8_t*)arena.take(off_cm + cm_bytes + 256);
+  DRB_REQUIRE(scratch != nullptr, "drb_surface_mask: %s",
+              arena.base ? "workspace too small (see the *_workspace_bytes query)" : "out of device memory");
   DRB_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, stream));
   unsigned long long* counter = (unsigned long long*)scratch;
   int* count = (int*)(scratch + 64);
@@ -1461,11 +1508,24 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
   }
   const int grid = igemm_num_sms();
   const int* cnt = count;
+  if (ev) { if (ev[0]) cudaEventRecord(ev[0], stream); if (ev[2]) cudaEventRecord(ev[2], stream); }
   surface_mask_kernel<<<grid, kMarchThreads, smem, stream>>>(pm, a, aux, occ_binary, points, n, cam_origins, ncams,
                                                              idx, cnt, counter, surface);
+  if (ev) { if (ev[1]) cudaEventRecord(ev[1], stream); if (ev[3]) cudaEventRecord(ev[3], stream); }
   DRB_LAUNCH_OK();
-  DRB_CUDA_OK(cudaFreeAsync(scratch, stream));
   return 0;
+}
+
+extern "C" size_t drb_surface_mask_workspace_bytes(int n) { return march_scratch_bytes(n, true) + 512; }
+
+extern "C" int drb_surface_mask_ws(const drb_ngp_params* pp, const uint8_t* occ_binary, int res,
+                                   const float* roi_aabb_host, const float* scene_aabb_host, const float* points,
+                                   int n, const float* cam_origins, int ncams, float step, float cut_off,
+                                   uint8_t* surface, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  DRB_REQUIRE(workspace != nullptr, "drb_surface_mask_ws: null workspace");
+  Arena arena(workspace, workspace_bytes, stream);
+  return surface_mask_impl(pp, occ_binary, res, roi_aabb_host, scene_aabb_host, points, n, cam_origins, ncams,
+                           step, cut_off, nullptr, surface, stream, nullptr, &arena);
 }
 
 extern "C" int drb_surface_mask(const drb_ngp_params* pp, const uint8_t* occ_binary, int res,
@@ -1575,9 +1635,32 @@ extern "C" int drb_extract_read_profile(float* total_ms, int* launches) {
   return 0;
 }
 
+static int extract_block_impl(const drb_ngp_params* pp, const drb_extract_desc* e, float* points, float* rgb,
+                              float* alpha, uint8_t* density_mask, uint8_t* surface_mask, float* voxel_grid,
+                              Arena& arena, cudaStream_t stream);
 extern "C" int drb_extract_block(const drb_ngp_params* pp, const drb_extract_desc* e, float* points, float* rgb,
                                  float* alpha, uint8_t* density_mask, uint8_t* surface_mask, float* voxel_grid,
                                  cudaStream_t stream) {
+  keep_async_pool();
+  Arena arena(nullptr, 0, stream);
+  return extract_block_impl(pp, e, points, rgb, alpha, density_mask, surface_mask, voxel_grid, arena, stream);
+}
+extern "C" size_t drb_extract_workspace_bytes(int n_occupied) {
+  const size_t n = (size_t)(n_occupied > 0 ? n_occupied : 1);
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  return up(sizeof(float) * 15 * n) + up(sizeof(float) * n) + up(sizeof(int) * (n + 1)) +
+         march_scratch_bytes(n_occupied, true) + 1024;
+}
+extern "C" int drb_extract_block_ws(const drb_ngp_params* pp, const drb_extract_desc* e, float* points, float* rgb,
+                                    float* alpha, uint8_t* density_mask, uint8_t* surface_mask, float* voxel_grid,
+                                    void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  DRB_REQUIRE(workspace != nullptr, "drb_extract_block_ws: null workspace");
+  Arena arena(workspace, workspace_bytes, stream);
+  return extract_block_impl(pp, e, points, rgb, alpha, density_mask, surface_mask, voxel_grid, arena, stream);
+}
+static int extract_block_impl(const drb_ngp_params* pp, const drb_extract_desc* e, float* points, float* rgb,
+                              float* alpha, uint8_t* density_mask, uint8_t* surface_mask, float* voxel_grid,
+                              Arena& arena, cudaStream_t stream) {
   DRB_REQUIRE(pp && e && points && rgb && alpha && density_mask && surface_mask, "drb_extract_block: null argument");
   DRB_REQUIRE(e->occupied && e->jitter && e->occ_binary && e->cam_origins && e->host_dirs,
               "drb_extract_block: null descriptor field");
@@ -1590,11 +1673,10 @@ extern "C" int drb_extract_block(const drb_ngp_params* pp, const drb_extract_des
       e->roi_aabb[3] - e->roi_aabb[0], e->roi_aabb[4] - e->roi_aabb[1], e->roi_aabb[5] - e->roi_aabb[2], points);
   DRB_LAUNCH_OK();
   // density / features go through scratch carved from the outputs: feat needs its own buffer
-  float* feat = nullptr;
-  float* density = nullptr;
-  keep_async_pool();
-  DRB_CUDA_OK(cudaMallocAsync(&feat, sizeof(float) * 15 * (size_t)n, stream));
-  DRB_CUDA_OK(cudaMallocAsync(&density, sizeof(float) * (size_t)n, stream));
+  float* feat = (float*)arena.take(sizeof(float) * 15 * (size_t)n);
+  float* density = (float*)arena.take(sizeof(float) * (size_t)n);
+  DRB_REQUIRE(feat && density, "drb_extract_block: %s",
+              arena.base ? "workspace too small (drb_extract_workspace_bytes)" : "out of device memory");
   int rc = drb_ngp_density(pp, points, n, density, feat, stream);
   if (!rc) {
     density_mask_kernel<<<cdiv(n, 256), 256, 0, stream>>>(density, n, e->density_thre, alpha, density_mask);
@@ -1605,18 +1687,17 @@ extern "C" int drb_extract_block(const drb_ngp_params* pp, const drb_extract_des
   if (!rc) {
     if (!g_surf_ev[0]) { cudaEventCreate(&g_surf_ev[0]); cudaEventCreate(&g_surf_ev[1]); }
     cudaEvent_t pe[2] = {nullptr, nullptr};
-    if (g_surf_profile) { cudaEventCreate(&pe[0]); cudaEventCreate(&pe[1]); cudaEventRecord(pe[0], stream); }
-    cudaEventRecord(g_surf_ev[0], stream);
+    if (g_surf_profile) { cudaEventCreate(&pe[0]); cudaEventCreate(&pe[1]); }
+    cudaEvent_t evs[4] = {g_surf_ev[0], g_surf_ev[1], pe[0], pe[1]};
     rc = surface_mask_impl(pp, e->occ_binary, e->res, e->roi_aabb, e->scene_aabb, points, n, e->cam_origins,
                            e->ncams, e->render_step_size, e->cut_off,
-                           e->surface_only_where_dense ? density_mask : nullptr, surface_mask, stream);
-    cudaEventRecord(g_surf_ev[1], stream);
-    if (g_surf_profile) { cudaEventRecord(pe[1], stream); g_surf_list->push_back(pe[0]); g_surf_list->push_back(pe[1]); }
+                           e->surface_only_where_dense ? density_mask : nullptr, surface_mask, stream, evs, &arena);
+    if (g_surf_profile) { g_surf_list->push_back(pe[0]); g_surf_list->push_back(pe[1]); }
     g_surf_valid = true;
   }
   if (!rc && rgb_late) {
-    int* idx = nullptr;
-    if (cudaMallocAsync(&idx, sizeof(int) * ((size_t)n + 1), stream) != cudaSuccess) rc = DRB_ENOMEM;
+    int* idx = (int*)arena.take(sizeof(int) * ((size_t)n + 1));
+    if (!idx) rc = DRB_ENOMEM;
     if (!rc) {
       int* count = idx + n;
       cudaMemsetAsync(count, 0, sizeof(int), stream);
@@ -1624,7 +1705,6 @@ extern "C" int drb_extract_block(const drb_ngp_params* pp, const drb_extract_des
       compact_masked_kernel<<<cdiv(n, 256), 256, 0, stream>>>(density_mask, surface_mask, n, idx, count);
       if (cudaGetLastError() != cudaSuccess) rc = DRB_ECUDA;
       if (!rc) rc = rgb_mean_impl(pp, feat, n, e->host_dirs, e->ndirs, rgb, idx, count, stream);
-      cudaFreeAsync(idx, stream);
     }
   }
   if (!rc) {
@@ -1632,9 +1712,7 @@ extern "C" int drb_extract_block(const drb_ngp_params* pp, const drb_extract_des
                                                            density_mask, voxel_grid);
     if (cudaGetLastError() != cudaSuccess) rc = DRB_ECUDA;
   }
-  cudaFreeAsync(feat, stream);
-  cudaFreeAsync(density, stream);
-  return rc;
+  return rc;       // stream-ordered scratch goes back with the arena
 }
 
 }  // namespace drb

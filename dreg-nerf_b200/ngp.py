@@ -202,7 +202,7 @@ class SampleGrid(nn.Module):
     def query_radiance_and_density_from_camera(self, radiance_field, occupancy_grid, meta_data, device,
                                                density_thre=0.7, cut_off: float = 0.5, jitter=None,
                                                return_grid: bool = False, surface_only_where_dense: bool = False,
-                                               rgb_only_where_masked: bool = False):
+                                               rgb_only_where_masked: bool = False, workspace=None):
         """sample_grid.py:208-343 -> (points, color, alpha, indices, density_mask, surface_mask).
 
         ``jitter`` (U[0,1) [K,3]) may be supplied for reproducibility; by default it is drawn with
@@ -211,6 +211,8 @@ class SampleGrid(nn.Module):
         (their surface_mask entries stay False): identical voxel_grid / voxel_mask, ~3x less marching.
         ``rgb_only_where_masked`` evaluates the colour head only for cells that pass both masks (their rows are
         the only ones voxel_grid keeps); the colour of every other cell is returned as 0.
+        ``workspace``: a uint8 CUDA tensor of at least ``extract_workspace_bytes(k)`` bytes - the call then allocates
+        nothing (drb_extract_block_ws); by default scratch comes from the stream-ordered allocator.
         """
         lib = _lib.load()
         check_march_options(meta_data, cut_off)
@@ -247,20 +249,31 @@ class SampleGrid(nn.Module):
         grid = torch.empty((self.res, self.res, self.res, 7), **f32) if return_grid else None
         ps = radiance_field._params_struct()
         with torch.cuda.device(device):
-            _lib.check(lib.drb_extract_block(C.byref(ps), C.byref(desc), _lib.ptr(points), _lib.ptr(rgb),
-                                             _lib.ptr(alpha), _lib.ptr(dmask), _lib.ptr(smask),
-                                             _lib.ptr(grid), _lib.stream_ptr()), "drb_extract_block")
+            if workspace is None:
+                _lib.check(lib.drb_extract_block(C.byref(ps), C.byref(desc), _lib.ptr(points), _lib.ptr(rgb),
+                                                 _lib.ptr(alpha), _lib.ptr(dmask), _lib.ptr(smask),
+                                                 _lib.ptr(grid), _lib.stream_ptr()), "drb_extract_block")
+            else:
+                _lib.check(lib.drb_extract_block_ws(C.byref(ps), C.byref(desc), _lib.ptr(points), _lib.ptr(rgb),
+                                                    _lib.ptr(alpha), _lib.ptr(dmask), _lib.ptr(smask), _lib.ptr(grid),
+                                                    _lib.ptr(workspace), workspace.numel() * workspace.element_size(),
+                                                    _lib.stream_ptr()), "drb_extract_block_ws")
             _lib.check_stream_flag("drb_extract_block")      # the caller indexes with the masks next: no extra stall
         out = (points, rgb, alpha, indices, dmask.bool(), smask.bool())
         return out + (grid,) if return_grid else out
 
 
+def extract_workspace_bytes(n_occupied):
+    """Bytes of scratch one extract of ``n_occupied`` candidate cells needs (drb_extract_workspace_bytes)."""
+    return int(_lib.load().drb_extract_workspace_bytes(int(n_occupied)))
+
+
 @torch.no_grad()
-def extract_block(radiance_field, sample_grid, occupancy_binary, meta_data, device, jitter=None):
+def extract_block(radiance_field, sample_grid, occupancy_binary, meta_data, device, jitter=None, workspace=None):
     """Evaluator.sample_points (eval_ngp_nerf.py:337-412) without the .ply side products:
     -> (voxel_grid float32 [R,R,R,7], voxel_mask int64 [K]) ready for torch.save."""
     sample_grid.set_binary_fields(occupancy_binary)
     pts, rgb, alpha, indices, dmask, smask, grid = sample_grid.query_radiance_and_density_from_camera(
         radiance_field, occupancy_binary, meta_data, device, jitter=jitter, return_grid=True,
-        surface_only_where_dense=True, rgb_only_where_masked=True)
+        surface_only_where_dense=True, rgb_only_where_masked=True, workspace=workspace)
     return grid, indices[dmask & smask]

@@ -283,6 +283,13 @@ int drb_surface_mask(const drb_ngp_params* p, const uint8_t* occ_binary, int res
                      const float* roi_aabb_host, const float* scene_aabb_host, const float* points,
                      int n, const float* cam_origins, int ncams, float step, float cut_off,
                      uint8_t* surface, drb_stream_t stream);
+/* The same call with its scratch (Morton sort buffers, coarse bitmap, cell-major records of the dense hash levels)
+ * in a caller workspace of at least drb_surface_mask_workspace_bytes(n) bytes: no allocation inside the call. */
+size_t drb_surface_mask_workspace_bytes(int n);
+int drb_surface_mask_ws(const drb_ngp_params* p, const uint8_t* occ_binary, int res,
+                        const float* roi_aabb_host, const float* scene_aabb_host, const float* points,
+                        int n, const float* cam_origins, int ncams, float step, float cut_off,
+                        uint8_t* surface, void* workspace, size_t workspace_bytes, drb_stream_t stream);
 /* SampleGrid sampling + Evaluator.sample_points scatter (sample_grid.py:223-243,
  * eval_ngp_nerf.py:383-412): fused extract of one NeRF block; see INTEGRATION.md. */
 typedef struct drb_extract_desc {
@@ -311,6 +318,14 @@ typedef struct drb_extract_desc {
 int drb_extract_block(const drb_ngp_params* p, const drb_extract_desc* e, float* points, float* rgb,
                       float* alpha, uint8_t* density_mask, uint8_t* surface_mask, float* voxel_grid,
                       drb_stream_t stream);
+
+/* drb_extract_block with all scratch (features, densities, index list, the marcher's buffers) in a caller
+ * workspace of at least drb_extract_workspace_bytes(n_occupied) bytes: no allocation inside the call
+ * (drb_extract_block itself uses the stream-ordered allocator). */
+size_t drb_extract_workspace_bytes(int n_occupied);
+int drb_extract_block_ws(const drb_ngp_params* p, const drb_extract_desc* e, float* points, float* rgb,
+                         float* alpha, uint8_t* density_mask, uint8_t* surface_mask, float* voxel_grid,
+                         void* workspace, size_t workspace_bytes, drb_stream_t stream);
 
 /* Device time (ms) of the surface-field kernel inside the calling thread's most recent
  * drb_extract_block (roofline instrumentation; waits for that kernel). */

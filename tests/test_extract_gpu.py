@@ -291,3 +291,26 @@ def test_cone_angle_is_refused(pkg, cuda):
             "camera_poses": poses}
     with pytest.raises(NotImplementedError, match="cone_angle"):
         sg.query_radiance_and_density_from_camera(f, occ, meta, cuda)
+
+
+def test_extract_block_with_caller_workspace(pkg, cuda):
+    """drb_extract_block_ws: all scratch in a caller workspace (no allocation inside the call) - the same files bit
+    for bit; a workspace that is too small is refused, not overrun."""
+    res = 64
+    f, _ = _field(pkg, cuda, seed=21, table_std=8.0)
+    occ, cams = _scene(res)
+    sg = pkg.SampleGrid([-1.5] * 3 + [1.5] * 3, res)
+    poses = torch.eye(4).repeat(cams.shape[0], 1, 1)
+    poses[:, :3, 3] = cams
+    meta = {"aabb": [-1.5] * 3 + [1.5] * 3, "render_step_size": 3.0 * math.sqrt(3) / 1024,
+            "cone_angle": 0.0, "alpha_thre": 0.0, "camera_poses": poses}
+    k = int(occ.sum())
+    jitter = torch.rand(k, 3, generator=torch.Generator().manual_seed(2))
+    grid_a, mask_a = pkg.extract_block(f, sg, occ.to(cuda), meta, cuda, jitter=jitter)
+    need = pkg.extract_workspace_bytes(k)
+    assert need > k * 15 * 4
+    ws = torch.empty(need + 100, dtype=torch.uint8, device=cuda)
+    grid_b, mask_b = pkg.extract_block(f, sg, occ.to(cuda), meta, cuda, jitter=jitter, workspace=ws[3:])   # misaligned on purpose
+    assert torch.equal(grid_a, grid_b) and torch.equal(mask_a, mask_b) and mask_a.numel() > 0
+    with pytest.raises(pkg.DrbError, match="workspace too small"):
+        pkg.extract_block(f, sg, occ.to(cuda), meta, cuda, jitter=jitter, workspace=ws[: need // 4])
