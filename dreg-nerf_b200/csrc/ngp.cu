@@ -1412,10 +1412,12 @@ static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary
                              int n, const float* cam_origins, int ncams, float step, float cut_off,
                              const uint8_t* active, uint8_t* surface, cudaStream_t stream,
                              cudaEvent_t* ev = nullptr, Arena* arena_in = nullptr) {
-  DRB_REQUIRE(pp && occ_binary && roi_aabb_host && scene_aabb_host && points && cam_origins && surface,
-              "drb_surface_mask: null argument");
+  // empty inputs are legal (no point, or no camera: nothing is seen) and come with null data pointers
+  DRB_REQUIRE(n >= 0 && ncams >= 0, "drb_surface_mask: negative count");
+  DRB_REQUIRE(pp && occ_binary && roi_aabb_host && scene_aabb_host && (n == 0 || (points && surface)) &&
+                  (ncams == 0 || cam_origins), "drb_surface_mask: null argument");
   DRB_REQUIRE(res > 0 && step > 0.f, "drb_surface_mask: bad grid / step");
-  DRB_CUDA_OK(cudaMemsetAsync(surface, 0, (size_t)(n > 0 ? n : 0), stream));
+  if (n > 0) DRB_CUDA_OK(cudaMemsetAsync(surface, 0, (size_t)n, stream));
   if (n == 0 || ncams == 0) {
     if (ev) for (int i = 0; i < 4; ++i) if (ev[i]) cudaEventRecord(ev[i], stream);     // nothing to march: zero-length bracket
     return 0;
@@ -1661,10 +1663,12 @@ extern "C" int drb_extract_block_ws(const drb_ngp_params* pp, const drb_extract_
 static int extract_block_impl(const drb_ngp_params* pp, const drb_extract_desc* e, float* points, float* rgb,
                               float* alpha, uint8_t* density_mask, uint8_t* surface_mask, float* voxel_grid,
                               Arena& arena, cudaStream_t stream) {
-  DRB_REQUIRE(pp && e && points && rgb && alpha && density_mask && surface_mask, "drb_extract_block: null argument");
-  DRB_REQUIRE(e->occupied && e->jitter && e->occ_binary && e->cam_origins && e->host_dirs,
-              "drb_extract_block: null descriptor field");
+  DRB_REQUIRE(pp && e, "drb_extract_block: null argument");
   const int n = e->n_occupied;
+  // a block without candidate cells is legal: zero grid, nothing else to write (the per-cell arrays may be null)
+  DRB_REQUIRE(n >= 0 && (n == 0 || (points && rgb && alpha && density_mask && surface_mask)), "drb_extract_block: null argument");
+  DRB_REQUIRE(n == 0 || (e->occupied && e->jitter && e->occ_binary && e->host_dirs && (e->ncams == 0 || e->cam_origins)),
+              "drb_extract_block: null descriptor field");
   if (voxel_grid)
     DRB_CUDA_OK(cudaMemsetAsync(voxel_grid, 0, sizeof(float) * 7 * (size_t)e->res * e->res * e->res, stream));
   if (n == 0) return 0;
