@@ -593,8 +593,8 @@ def run_ours(args):
                 "bound": "hbm", "kernel": "surface_mask_kernel (occupancy-grid ray marcher + fused hash-grid / tensor-core "
                                           "MLP density), the %d launches of the timed steps" % surf_prof["launches"],
                 "achieved": hb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hb / peaks["hbm_gbs"],
-                "peak_source": peaks["source"], "traffic": 46.1e6,
-                "traffic_note": "dram read+write of one launch, ncu --set full (profiles/r01_v6_ncu_surface_seed501_keys.txt)",
+                "peak_source": peaks["source"], "traffic": 50.1e6,
+                "traffic_note": "dram read+write of one launch, ncu --set full (profiles/r02_ncu_surface_seed501_keys.txt)",
                 "kernel_ms_per_launch": surf_ms, "launches": surf_prof["launches"],
                 "kernel_ms_per_step": surf_prof["ms"] / args.steps,
                 "kernel_share_of_step": surf_prof["ms"] / ms_1, "timing": profile_note,
@@ -605,13 +605,14 @@ def run_ours(args):
                 # The limit that binds: an SM's L1 retires one distinct 32-byte sector per load instruction per
                 # clock whatever the occupancy or ILP (scripts/ubench/gather*.cu on this pool's B200: 287 G
                 # sectors/s per chip, halved when the shared-memory carve-out leaves < ~64 KB of L1).  The kernel
-                # presents ~62 sectors per density sample to the L1 tag stage (ncu l1tex__t_sectors / samples on
-                # the heaviest synthetic block, profiles/r01_v6_ncu_surface_seed501_keys.txt; 15 levels x 8
-                # corners = 120 before pair loads and in-instruction sharing between coherent lanes).
-                "gather_roofline": {"l1_sectors_per_sample": 62,
-                                    "achieved_g_sectors_per_s": 62.0 * samples / (surf_prof["ms"] / 1e3) / 1e9 if surf_prof["ms"] > 0 else 0.0,
+                # presents ~59 sectors per density sample to the L1 tag stage (ncu lts__t_sectors / (1 - L1 hit rate) /
+                # samples on the heaviest synthetic block, profiles/r02_ncu_surface_seed501_keys.txt; round 1: 62;
+                # 15 levels x 8 corners = 120 before pair loads, cell-major dense levels and in-instruction
+                # sharing between coherent lanes).
+                "gather_roofline": {"l1_sectors_per_sample": 59,
+                                    "achieved_g_sectors_per_s": 59.0 * samples / (surf_prof["ms"] / 1e3) / 1e9 if surf_prof["ms"] > 0 else 0.0,
                                     "peak_g_sectors_per_s": 287.0, "peak_source": "measured, scripts/ubench/gather.cu (profiles/r01_ubench_gather.txt)",
-                                    "frac": 62.0 * samples / (surf_prof["ms"] / 1e3) / 287e9 if surf_prof["ms"] > 0 else 0.0},
+                                    "frac": 59.0 * samples / (surf_prof["ms"] / 1e3) / 287e9 if surf_prof["ms"] > 0 else 0.0},
                 "note": "algorithmic bytes = hash table + occupancy grid + points + masks + cameras, each read once per "
                         "launch; the kernel is L1-miss / L2-gather bound (DRAM idle), not bandwidth bound"}
         if not args.no_cpu_baseline and world == 1:
