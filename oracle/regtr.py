@@ -25,6 +25,38 @@ LAYERS = (3, 4, 6, 3)            # resnet50, resnet3d.py:197-205
 PLANES = (64, 128, 256, 512)
 
 
+# Optional operand rounding (TEST INFRASTRUCTURE for the bf16 parity gate): inside `with operand_rounding(fn):` every
+# tensor-core operand of the GPU path - inputs and weights of each convolution / linear layer, Q' K V P of the
+# attention core, q / k of the decoder - is passed through `fn` (e.g. round to bf16) before it is used, at exactly the
+# places where the engine writes its 16-bit planes.  Accumulation, bias, residuals, BatchNorm / LayerNorm / soft-max
+# statistics and the Procrustes solve stay fp32.  Outside the context (`_R is None`) nothing changes: the functions
+# below are the reference-pinned fp32 restatement.
+_R = None
+
+
+class operand_rounding:
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __enter__(self):
+        global _R
+        self.prev, _R = _R, self.fn
+        return self
+
+    def __exit__(self, *exc):
+        global _R
+        _R = self.prev
+        return False
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _r(t):
+    return t if _R is None else _R(t)
+
+
 def _bn(x, sd, prefix, training, running=None):
     """nn.BatchNorm3d: batch statistics when ``training`` (the eval script never
     calls .eval(), eval_nerf_regtr.py:212-218), running statistics otherwise."""
@@ -40,20 +72,20 @@ def _bn(x, sd, prefix, training, running=None):
 
 def _bottleneck(x, sd, p, stride, has_down, training, running):
     """resnet3d.py:76-113."""
-    out = F.relu(_bn(F.conv3d(x, sd[p + ".conv1.weight"]), sd, p + ".bn1", training, running))
-    out = F.conv3d(out, sd[p + ".conv2.weight"], stride=stride, padding=1)
+    out = F.relu(_bn(F.conv3d(_r(x), _r(sd[p + ".conv1.weight"])), sd, p + ".bn1", training, running))
+    out = F.conv3d(_r(out), _r(sd[p + ".conv2.weight"]), stride=stride, padding=1)
     out = F.relu(_bn(out, sd, p + ".bn2", training, running))
-    out = _bn(F.conv3d(out, sd[p + ".conv3.weight"]), sd, p + ".bn3", training, running)
+    out = _bn(F.conv3d(_r(out), _r(sd[p + ".conv3.weight"])), sd, p + ".bn3", training, running)
     res = x
     if has_down:
-        res = _bn(F.conv3d(x, sd[p + ".downsample.0.weight"], stride=stride),
+        res = _bn(F.conv3d(_r(x), _r(sd[p + ".downsample.0.weight"]), stride=stride),
                   sd, p + ".downsample.1", training, running)
     return F.relu(out + res)
 
 
 def resnet3d(x, sd, prefix="fpn3d.backbone_net", training=True, running=None, capture=None):
     """resnet3d.py:157-172 -> (c1..c5)."""
-    c1 = F.conv3d(x, sd[prefix + ".conv1.weight"], stride=2, padding=2)
+    c1 = F.conv3d(_r(x), _r(sd[prefix + ".conv1.weight"]), stride=2, padding=2)
     c1 = F.relu(_bn(c1, sd, prefix + ".bn1", training, running))
     feats = [c1]
     y = F.max_pool3d(c1, kernel_size=3, stride=2, padding=1)
@@ -75,13 +107,13 @@ def fpn3d(x, sd, training=True, running=None, capture=None):
     fp = "fpn3d.feature_pyramid."
 
     def lateral(i, c, pad):
-        return F.conv3d(c, sd[fp + "pyramid_transformation_%d.weight" % i],
+        return F.conv3d(_r(c), _r(sd[fp + "pyramid_transformation_%d.weight" % i]),
                         sd[fp + "pyramid_transformation_%d.bias" % i], padding=pad)
 
     def merge(i, top, lat):
         d, h, w = lat.shape[2:]
         up = F.interpolate(top, scale_factor=2)[:, :, :d, :h, :w]      # nearest, :58-61
-        return F.conv3d(up + lat, sd[fp + "upsample_transform_%d.weight" % i],
+        return F.conv3d(_r(up + lat), _r(sd[fp + "upsample_transform_%d.weight" % i]),
                         sd[fp + "upsample_transform_%d.bias" % i], padding=1)
 
     p5 = lateral(5, c5, 0)
@@ -111,16 +143,26 @@ def _mha(q_in, k_in, v_in, sd, p, nhead=8):
     """nn.MultiheadAttention forward (batch 1, no masks, dropout 0); q_in [Nq,D]."""
     d = q_in.shape[-1]
     w, b = sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"]
-    q = F.linear(q_in, w[:d], b[:d])
-    k = F.linear(k_in, w[d:2 * d], b[d:2 * d])
-    v = F.linear(v_in, w[2 * d:], b[2 * d:])
+    q = F.linear(_r(q_in), _r(w[:d]), b[:d])
+    k = F.linear(_r(k_in), _r(w[d:2 * d]), b[d:2 * d])
+    v = F.linear(_r(v_in), _r(w[2 * d:]), b[2 * d:])
     hd = d // nhead
-    qh = q.view(-1, nhead, hd).transpose(0, 1) * (1.0 / math.sqrt(hd))
-    kh = k.view(-1, nhead, hd).transpose(0, 1)
-    vh = v.view(-1, nhead, hd).transpose(0, 1)
-    att = torch.softmax(qh @ kh.transpose(1, 2), dim=-1)
-    o = (att @ vh).transpose(0, 1).reshape(-1, d)
-    return F.linear(o, sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"])
+    if _R is None:
+        qh = q.view(-1, nhead, hd).transpose(0, 1) * (1.0 / math.sqrt(hd))
+        kh = k.view(-1, nhead, hd).transpose(0, 1)
+        vh = v.view(-1, nhead, hd).transpose(0, 1)
+        att = torch.softmax(qh @ kh.transpose(1, 2), dim=-1)
+        o = (att @ vh).transpose(0, 1).reshape(-1, d)
+    else:
+        # the tensor-core attention kernel (csrc/attention.cu): Q' = q scale log2(e), K, V and P = 2^(S - max) are
+        # 16-bit operands, the row sum is taken over the unrounded P
+        qh = _r(q * (torch.tensor(1.0 / math.sqrt(hd), dtype=torch.float32) * 1.4426950408889634)).view(-1, nhead, hd).transpose(0, 1)
+        kh = _r(k).view(-1, nhead, hd).transpose(0, 1)
+        vh = _r(v).view(-1, nhead, hd).transpose(0, 1)
+        sc = qh @ kh.transpose(1, 2)
+        pr = torch.exp2(sc - sc.max(dim=-1, keepdim=True).values)
+        o = ((_r(pr) @ vh) / pr.sum(dim=-1, keepdim=True)).transpose(0, 1).reshape(-1, d)
+    return F.linear(_r(o), _r(sd[p + ".out_proj.weight"]), sd[p + ".out_proj.bias"])
 
 
 def _ln(x, sd, p):
@@ -142,11 +184,11 @@ def cross_encoder(src, tgt, src_pos, tgt_pos, sd, prefix="transformer_encoder", 
         t3 = _mha(t2, s2, s2, sd, p + ".cross_attn")
         src, tgt = src + s3, tgt + t3
         s2 = _ln(src, sd, p + ".norm3")
-        src = src + F.linear(F.relu(F.linear(s2, sd[p + ".linear1.weight"], sd[p + ".linear1.bias"])),
-                             sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
+        src = src + F.linear(_r(F.relu(F.linear(_r(s2), _r(sd[p + ".linear1.weight"]), sd[p + ".linear1.bias"]))),
+                             _r(sd[p + ".linear2.weight"]), sd[p + ".linear2.bias"])
         t2 = _ln(tgt, sd, p + ".norm3")
-        tgt = tgt + F.linear(F.relu(F.linear(t2, sd[p + ".linear1.weight"], sd[p + ".linear1.bias"])),
-                             sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
+        tgt = tgt + F.linear(_r(F.relu(F.linear(_r(t2), _r(sd[p + ".linear1.weight"]), sd[p + ".linear1.bias"]))),
+                             _r(sd[p + ".linear2.weight"]), sd[p + ".linear2.bias"])
         outs_s.append(_ln(src, sd, prefix + ".norm"))
         outs_t.append(_ln(tgt, sd, prefix + ".norm"))
     return torch.stack(outs_s), torch.stack(outs_t)
@@ -160,8 +202,8 @@ def correspondence_decoder(src_f, tgt_f, src_xyz, tgt_xyz, sd, pos_scale=1.0,
     t2 = tgt_f + pos_embed_sine(tgt_xyz, d, scale=pos_scale)
 
     def attend(qf, kf, val):
-        q = F.linear(qf, sd[prefix + ".q_proj.weight"], sd[prefix + ".q_proj.bias"]) / math.sqrt(d)
-        k = F.linear(kf, sd[prefix + ".k_proj.weight"], sd[prefix + ".k_proj.bias"])
+        q = _r(F.linear(_r(qf), _r(sd[prefix + ".q_proj.weight"]), sd[prefix + ".q_proj.bias"]) / math.sqrt(d))
+        k = _r(F.linear(_r(kf), _r(sd[prefix + ".k_proj.weight"]), sd[prefix + ".k_proj.bias"]))
         att = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
         return att @ val
 

@@ -112,6 +112,91 @@ def test_forward_bf16_mode_runs(pkg, cuda):
     assert _relerr(out["src_feats"][0], ref["src_feats"][0]) < 0.15
 
 
+# bf16 operands (BASELINE configs[2]-[4]): one bf16 product per MMA, fp32 accumulation, fp32 BatchNorm / LayerNorm /
+# soft-max / Procrustes.  A random-weight network is ill conditioned (53 BatchNorms over a few voxels, sharp soft-max
+# over near-random logits): bf16 rounding moves the fp32 result by up to 1e-1 on the features and tens of degrees on
+# the pose, and any two bf16 evaluations that differ in one rounding tie drift apart by the same amount.  Two gates:
+#   * stage by stage (test_bf16_stage_taps_64): against the oracle evaluated with every tensor-core operand rounded
+#     to bf16 at the places where the engine writes its planes (oracle.regtr.operand_rounding) the first stages must
+#     agree tightly - a wrong rounding point, scale or plane would show there - and the distance may only grow as
+#     ties accumulate;
+#   * end to end (test_forward_bf16_parity_gate): the GPU path may not be farther from the fp32 oracle than
+#     BF16_SLACK x the bf16-operand oracle itself is (it loses what bf16 arithmetic loses, no more).
+BF16_SLACK = 2.0
+BF16_FLOOR = 1e-2
+
+
+def _pose_errors(pose, ref):
+    """RRE (degrees) / RTE of the last decoder layer's pose against the oracle's (eval_nerf_regtr.py:46-65 metric)."""
+    a, b = pose[-1, 0].double().cpu(), ref[-1, 0].double()
+    cos = ((a[:, :3].T @ b[:, :3]).trace() - 1.0) / 2.0
+    rre = torch.rad2deg(torch.acos(cos.clamp(-1.0, 1.0))).item()
+    return rre, (a[:, 3] - b[:, 3]).norm().item()
+
+
+def _all_errs(out, ref):
+    errs = {"feats": max(_relerr(out["src_feats"][0], ref["src_feats"][0]), _relerr(out["tgt_feats"][0], ref["tgt_feats"][0])),
+            "kp_warped": max(_relerr(out["src_kp_warped"][0], ref["src_kp_warped"][0]),
+                             _relerr(out["tgt_kp_warped"][0], ref["tgt_kp_warped"][0])),
+            "overlap": max(_relerr(out["src_overlap"][0], ref["src_overlap"][0]),
+                           _relerr(out["tgt_overlap"][0], ref["tgt_overlap"][0])),
+            "pose": _relerr(out["pose"], ref["pose"])}
+    errs["rre_deg"], errs["rte"] = _pose_errors(out["pose"], ref["pose"])
+    return errs
+
+
+@pytest.mark.parametrize("res,training", [(32, False), (64, True), (128, True)])
+def test_forward_bf16_parity_gate(pkg, cuda, res, training):
+    """precision='bf16': key points bit exact (the token selection never sees a bf16 value); features, soft
+    correspondences and overlap no farther from the fp32 oracle than BF16_SLACK x the bf16-operand oracle is.  The
+    pose of a random-weight network is a Procrustes fit of near-random correspondences: reported, not gated."""
+    from oracle import regtr
+    model, sd, data, out, ref32, _ = _run(pkg, cuda, res, training=training, precision="bf16")
+    with torch.no_grad(), regtr.operand_rounding(regtr.bf16_round):
+        ref = regtr.forward(sd, data, training=training)
+    assert torch.equal(out["src_kp"][0].cpu(), ref32["src_kp"][0]) and torch.equal(out["tgt_kp"][0].cpu(), ref32["tgt_kp"][0])
+    ours, theirs, between = _all_errs(out, ref32), _all_errs(ref, ref32), _all_errs(out, ref)
+    tag = "%d^3 (%s BN)" % (res, "batch" if training else "running")
+    print("bf16 GPU vs fp32 oracle at %s:" % tag, {k: "%.2e" % v for k, v in ours.items()})
+    print("bf16-operand oracle vs fp32 oracle at %s (what bf16 costs):" % tag, {k: "%.2e" % v for k, v in theirs.items()})
+    print("bf16 GPU vs bf16-operand oracle at %s:" % tag, {k: "%.2e" % v for k, v in between.items()})
+    for k in ("feats", "kp_warped", "overlap"):
+        assert ours[k] < BF16_SLACK * theirs[k] + BF16_FLOOR, \
+            "%s: bf16 path %.3e from the fp32 oracle, bf16 arithmetic alone %.3e" % (k, ours[k], theirs[k])
+    assert all(torch.isfinite(t).all() for t in (out["pose"], out["src_feats"][0], out["src_kp_warped"][0]))
+
+
+def test_bf16_stage_taps_64(pkg, cuda):
+    """bf16 mode stage by stage against the bf16-operand oracle (dense FPN, batch-statistics BatchNorm)."""
+    from oracle import regtr
+    torch.manual_seed(0)
+    model = pkg.NeRFRegTr(precision="bf16")
+    sd = pkg.synthetic.seeded_state_dict(model, seed=0, attn_gain=4.0)
+    model.load_state_dict(sd)
+    model = model.to(cuda).train(True)
+    model.sparse_fpn = False
+    data = pkg.synthetic.make_pair(res=64, pair_id=1)
+    cap, cap32 = {}, {}
+    with torch.no_grad():
+        model(pkg.synthetic.to_device(data, cuda))
+        regtr.forward(sd, data, training=True, capture=cap32)
+        with regtr.operand_rounding(regtr.bf16_round):
+            regtr.forward(sd, data, training=True, capture=cap)
+    # bound against the bf16-operand oracle per stage: tight while no rounding tie has flipped, then growing
+    # measured on B200: c1 3e-7 (the stem computes exactly what bf16 arithmetic computes), c2 2e-3, c3 1.4e-2, c4 4e-2,
+    # c5 2.5e-1 (BatchNorm over 8 voxels), p5..p1 1.4e-1 ... 3.7e-2 - always 2-3x closer than bf16 is to fp32
+    bounds = {"c1": 1e-5, "c2": 1e-2, "c3": 5e-2, "c4": 1.5e-1, "c5": 6e-1, "p5": 4e-1, "p4": 3e-1, "p3": 1.5e-1,
+              "p2": 1.5e-1, "p1": 1.5e-1}
+    for name in ("c1", "c2", "c3", "c4", "c5", "p5", "p4", "p3", "p2", "p1"):
+        for which, side in ((0, "src"), (1, "tgt")):
+            ref = cap["%s_%s" % (side, name)][0].permute(1, 2, 3, 0).reshape(-1)
+            ref32 = cap32["%s_%s" % (side, name)][0].permute(1, 2, 3, 0).reshape(-1)
+            got = model.tap(name, which).cpu()
+            err, cost = _relerr(got, ref), _relerr(ref, ref32)
+            print("bf16 %s %s: vs bf16-operand oracle %.2e (bf16 itself costs %.2e vs fp32)" % (name, side, err, cost))
+            assert err < bounds[name], "%s/%s: %.3e" % (name, side, err)
+
+
 def test_256_cube_plumbing(pkg, cuda):
     """BASELINE.json configs[4] shape: a 256^3 block goes through extract and a 256^3 pair through
     NeRFRegTr.forward (index arithmetic beyond 2^24 cells, coarse occupancy bitmap with 8^3-voxel cells,
