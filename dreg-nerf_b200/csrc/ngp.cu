@@ -1395,6 +1395,7 @@ struct Arena {
   ~Arena() { for (void* p : owned) cudaFreeAsync(p, stream); }
 };
 static size_t march_scratch_bytes(int n, bool cellmajor) {
+  if (n > (1 << 22) - 1) n = (1 << 22) - 1;            // larger point sets are marched in chunks
   size_t cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                   (const int*)nullptr, (int*)nullptr, n > 0 ? n : 1, 0, 32, nullptr);
@@ -1407,11 +1408,38 @@ static size_t march_scratch_bytes(int n, bool cellmajor) {
 
 // ev: optional {before, after, before2, after2} events recorded right around the marcher kernel itself (not the
 // Morton sort / coarse bitmap / cell-major copy that precede it) - roofline instrumentation
+static int surface_mask_chunk(const drb_ngp_params* pp, const uint8_t* occ_binary, int res,
+                              const float* roi_aabb_host, const float* scene_aabb_host, const float* points,
+                              int n, const float* cam_origins, int ncams, float step, float cut_off,
+                              const uint8_t* active, uint8_t* surface, cudaStream_t stream,
+                              cudaEvent_t* ev, Arena* arena_in);
+// A ray word holds 22 bits of point index: larger point sets (a 256^3 block with more than a quarter of its cells
+// occupied) are marched in chunks of points - the chunks are independent, the scratch is reused (same stream).
 static int surface_mask_impl(const drb_ngp_params* pp, const uint8_t* occ_binary, int res,
                              const float* roi_aabb_host, const float* scene_aabb_host, const float* points,
                              int n, const float* cam_origins, int ncams, float step, float cut_off,
                              const uint8_t* active, uint8_t* surface, cudaStream_t stream,
                              cudaEvent_t* ev = nullptr, Arena* arena_in = nullptr) {
+  const int kMaxPoints = (1 << 22) - 1;
+  if (n <= kMaxPoints)
+    return surface_mask_chunk(pp, occ_binary, res, roi_aabb_host, scene_aabb_host, points, n, cam_origins, ncams, step,
+                              cut_off, active, surface, stream, ev, arena_in);
+  for (int c0 = 0; c0 < n; c0 += kMaxPoints) {
+    const int nn = n - c0 < kMaxPoints ? n - c0 : kMaxPoints;
+    const size_t mark = arena_in ? arena_in->used : 0;
+    const int rc = surface_mask_chunk(pp, occ_binary, res, roi_aabb_host, scene_aabb_host, points + 3 * (size_t)c0, nn,
+                                      cam_origins, ncams, step, cut_off, active ? active + c0 : nullptr, surface + c0,
+                                      stream, ev, arena_in);
+    if (arena_in && arena_in->base) arena_in->used = mark;       // caller workspace: the next chunk reuses it
+    if (rc) return rc;
+  }
+  return 0;
+}
+static int surface_mask_chunk(const drb_ngp_params* pp, const uint8_t* occ_binary, int res,
+                              const float* roi_aabb_host, const float* scene_aabb_host, const float* points,
+                              int n, const float* cam_origins, int ncams, float step, float cut_off,
+                              const uint8_t* active, uint8_t* surface, cudaStream_t stream,
+                              cudaEvent_t* ev, Arena* arena_in) {
   // empty inputs are legal (no point, or no camera: nothing is seen) and come with null data pointers
   DRB_REQUIRE(n >= 0 && ncams >= 0, "drb_surface_mask: negative count");
   DRB_REQUIRE(pp && occ_binary && roi_aabb_host && scene_aabb_host && (n == 0 || (points && surface)) &&

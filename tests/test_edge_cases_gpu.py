@@ -128,3 +128,27 @@ def test_ragged_pair_tiny_against_large_cloud(pkg, cuda):
     assert rel(out["src_feats"][0], ref["src_feats"][0]) < 1e-3
     assert rel(out["tgt_feats"][0], ref["tgt_feats"][0]) < 1e-3
     assert rel(out["pose"], ref["pose"]) < 1e-3
+
+
+def test_surface_mask_beyond_the_ray_word(pkg, cuda):
+    """More than 2^22 points in one call (a 256^3 block with over a quarter of its cells occupied): marched in
+    chunks of points, same answer as two separate calls."""
+    n = (1 << 22) + 12345
+    gen = torch.Generator().manual_seed(7)
+    pts = (torch.rand(n, 3, generator=gen) * 2.0 - 1.0).to(cuda)
+    res = 32
+    ax = (torch.arange(res, dtype=torch.float32) + 0.5) / res * 3.0 - 1.5
+    X, Y, Z = torch.meshgrid(ax, ax, ax, indexing="ij")
+    occ = ((X ** 2 + Y ** 2 + Z ** 2) < 0.6 ** 2).to(cuda)
+    f = pkg.synthetic.make_ngp_field(seed=501, table_std=8.0).to(cuda)
+    roi = [-1.5] * 3 + [1.5] * 3
+    cams = torch.tensor([[4.0, 0.0, 1.0], [-4.0, 0.5, 0.0]])
+    step = 3.0 * math.sqrt(3) / 1024
+    whole = pkg.surface_field_mask(f, occ, pts, cams, roi, roi, step)
+    half = n // 2
+    parts = torch.cat([pkg.surface_field_mask(f, occ, pts[:half], cams, roi, roi, step),
+                       pkg.surface_field_mask(f, occ, pts[half:], cams, roi, roi, step)])
+    assert whole.shape == (n,) and torch.equal(whole, parts)
+    frac = float(whole.float().mean())
+    print("points seen: %.3f of %d" % (frac, n))
+    assert 0.0 < frac < 1.0
