@@ -236,7 +236,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.drb_abi_version() != 2:
+    if lib.drb_abi_version() != 3:
         raise DrbError("libdregb200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -34,7 +34,7 @@ extern "C" {
 #define DRB_ENOMEM (-3)
 #define DRB_ESTATE (-4)
 
-#define DRB_ABI_VERSION 2
+#define DRB_ABI_VERSION 3
 
 typedef struct CUstream_st* drb_stream_t; /* == cudaStream_t */
 
