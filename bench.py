@@ -993,7 +993,7 @@ def main():
     ap.add_argument("--total-pairs", type=int, default=0, help="batch: strong scaling, total pairs per step")
     ap.add_argument("--res", type=int, default=RES, help="batch: grid resolution (256 for configs[4])")
     ap.add_argument("--max-tokens", type=int, default=0, help="batch: cap of the down-sampler (tokens of the pair); 0 = the reference's 3000")
-    ap.add_argument("--attention", default="mma", choices=["tc", "mma"], help="tc = tcgen05 FlashAttention-style kernel")
+    ap.add_argument("--attention", default="tc", choices=["tc", "mma"], help="tc = tcgen05 FlashAttention-style kernel")
     ap.add_argument("--streams", type=int, default=0,
                     help="pairs in flight per GPU (pipeline.PairPipeline; 1 = the sequential loop); default 4 for train / "
                          "batch, 1 for full / register")

@@ -64,7 +64,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 // p = 2^(s - mx) of one thread's 64 logits -> 16-bit planes in shared memory (8 swizzled 16-byte chunks); returns the sum.
 template <int P, bool kFull>
 __device__ __forceinline__ float softmax_half_row(const float (&sv_)[64], float mx, int valid, uint32_t prow, int row) {
-  float lsum = 0.f;
+  float ls[4] = {0.f, 0.f, 0.f, 0.f};                 // four partial sums: no 32-deep add chain
 #pragma unroll
   for (int c8 = 0; c8 < 8; ++c8) {
     uint32_t hw[4], lw[4];
@@ -73,7 +73,7 @@ __device__ __forceinline__ float softmax_half_row(const float (&sv_)[64], float 
       const int j0 = c8 * 8 + 2 * u;
       float p0 = ex2_fast(sv_[j0] - mx), p1 = ex2_fast(sv_[j0 + 1] - mx);
       if (!kFull) { p0 = j0 < valid ? p0 : 0.f; p1 = j0 + 1 < valid ? p1 : 0.f; }
-      lsum += p0 + p1;
+      ls[u] += p0 + p1;
       if (P == 1) {
         const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
         hw[u] = *(const uint32_t*)&h2;
@@ -91,7 +91,7 @@ __device__ __forceinline__ float softmax_half_row(const float (&sv_)[64], float 
     if (P == 2)
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kPBytes), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3]) : "memory");
   }
-  return lsum;
+  return (ls[0] + ls[1]) + (ls[2] + ls[3]);
 }
 
 // Schedule of one CTA (head, 128 queries), tiles of 128 keys:
@@ -250,21 +250,28 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
       mbar_wait(s_full, (uint32_t)t & 1u, err, 46);
       tc_fence_after();
       float sv_[64];
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)(half * 64 + b * 32), v);
+      {
+        uint32_t v0[32], v1[32];                         // both loads in flight, one wait
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)(half * 64), v0);
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)(half * 64 + 32), v1);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sv_[b * 32 + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) { sv_[j] = __uint_as_float(v0[j]); sv_[32 + j] = __uint_as_float(v1[j]); }
       }
       tc_fence_before();
       mbar_arrive(s_free);
       const int valid = min(64, max(0, a.nk - t * kAttK - half * 64));      // of this thread's 64 keys
       float mloc = -INFINITY;
       if (valid == 64) {
+        // four independent chains (a single running maximum is a 64-deep dependency chain for a thread that
+        // shares its scheduler with one other warp)
+        float m4[4] = {sv_[0], sv_[1], sv_[2], sv_[3]};
 #pragma unroll
-        for (int j = 0; j < 64; ++j) mloc = fmaxf(mloc, sv_[j]);
+        for (int j = 4; j < 64; j += 4) {
+          m4[0] = fmaxf(m4[0], sv_[j]); m4[1] = fmaxf(m4[1], sv_[j + 1]);
+          m4[2] = fmaxf(m4[2], sv_[j + 2]); m4[3] = fmaxf(m4[3], sv_[j + 3]);
+        }
+        mloc = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       } else {
 #pragma unroll
         for (int j = 0; j < 64; ++j)
