@@ -14,6 +14,8 @@
 // Precision follows the GEMM planes: bf16, or fp16 hi/lo pairs with three MMAs per product (fp32-grade).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace drb {
 
 static constexpr int kAttThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 soft-max (two threads per query row)
@@ -332,6 +334,216 @@ att_fwd_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// bf16, TWO query tiles per CTA (256 queries), ping-pong: the same 8 soft-max warps alternate between tile A and
+// tile B, so while they exponentiate one tile the tensor core runs S = Q'K^T of the next key tile and P V of the
+// previous one for the other - the MMA / barrier round trip that a single tile has to wait out (2900 clk per tile
+// against 1024 clk of MUFU work, ncu round 2) is covered by useful work, and K / V^T tiles are fetched once for 256
+// queries.  One P buffer and one P V accumulator per query tile suffice: P_X(t + 1) is written after the fold of
+// (P V)_X(t), which happens a whole other-tile soft-max after its MMA was issued.
+//   TMEM: S_A, S_B (2 x 128 columns) + (P V)_A, (P V)_B (2 x 32)        smem: Q 32 KB, K / V^T 2 x 24 KB, P 64 KB
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAttThreads, 1)
+att_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttArgs args) {
+  const AttProblem a = args.pr[blockIdx.z];
+  if ((int)blockIdx.x * 2 * kAttQ >= a.nq) return;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * 2 * kAttQ;
+  int* const err = args.err;
+  constexpr uint32_t stage_bytes = kKBytes + kVBytes;
+  uint8_t* sQ = smem;                                  // [2 tiles][128][64]
+  uint8_t* sKV = sQ + 2 * (size_t)kQBytes;
+  uint8_t* sP = sKV + 2 * (size_t)stage_bytes;         // [2 tiles][32 KB]
+  uint64_t* bars = (uint64_t*)(sP + 2 * (size_t)kPBytes);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t q_full = bar0, kv_full0 = bar0 + 8, kv_empty0 = bar0 + 24, s_full0 = bar0 + 40, s_free0 = bar0 + 56,
+                 p_full0 = bar0 + 72, pv_full0 = bar0 + 88;                  // [2] each, indexed by query tile
+  uint32_t* tmem_slot = (uint32_t*)(bars + 14);
+  float* xch = (float*)(bars + 16);                    // [2 tiles][2 parities][2 halves][128 rows]
+  const int ntiles = (a.nk + kAttK - 1) / kAttK;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(kv_full0 + 8 * s, 1); mbar_init(kv_empty0 + 8 * s, 1);
+      mbar_init(s_full0 + 8 * s, 1); mbar_init(s_free0 + 8 * s, 256);
+      mbar_init(p_full0 + 8 * s, 256); mbar_init(pv_full0 + 8 * s, 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_pv = tmem_base + 256;       // S_A, S_B: 2 x 128 columns; P V: 2 x 32
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * kQBytes);
+      tma_load_3d(smem_u32(sQ), &tmQ, q_full, 0, a.q_row0 + q0, head);
+      tma_load_3d(smem_u32(sQ) + kQBytes, &tmQ, q_full, 0, a.q_row0 + q0 + kAttQ, head);
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        mbar_wait(kv_empty0 + 8 * s, (((uint32_t)t >> 1) & 1u) ^ 1u, err, 41);
+        const uint32_t fb = kv_full0 + 8 * s;
+        mbar_expect_tx(fb, stage_bytes);
+        const uint32_t sk = smem_u32(sKV + (size_t)s * stage_bytes);
+        const uint32_t sv = sk + kKBytes;
+        const int key0 = a.k_row0 + t * kAttK;
+        tma_load_3d(sk, &tmK, fb, 0, key0, head);
+        tma_load_3d(sv, &tmV, fb, key0, 0, head);
+        tma_load_3d(sv + kVBytes / 2, &tmV, fb, key0 + 64, 0, head);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_16(kAttQ, kAttK, true);
+      const uint32_t idesc_pv = umma_idesc_16(kAttQ, 32, true);
+      auto issue_s = [&](int x, int t) {               // S_x(t) = Q'_x K(t)^T
+        const int s = t & 1;
+        if (x == 0) mbar_wait(kv_full0 + 8 * s, ((uint32_t)t >> 1) & 1u, err, 42);
+        if (t > 0) mbar_wait(s_free0 + 8 * x, ((uint32_t)(t - 1)) & 1u, err, 43);
+        tc_fence_after();
+        const uint64_t dq = umma_desc_sw128(smem_u32(sQ) + (uint32_t)x * kQBytes);
+        const uint64_t dk = umma_desc_sw128(smem_u32(sKV + (size_t)s * stage_bytes));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_s + (uint32_t)x * 128u, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
+        umma_commit(s_full0 + 8 * x);
+      };
+      auto issue_pv = [&](int x, int t) {              // (P V)_x(t)
+        const int s = t & 1;
+        mbar_wait(p_full0 + 8 * x, (uint32_t)t & 1u, err, 45);
+        tc_fence_after();
+        const uint32_t sv = smem_u32(sKV + (size_t)s * stage_bytes) + kKBytes;
+        const uint32_t sp = smem_u32(sP) + (uint32_t)x * kPBytes;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t sub = (uint32_t)(k >> 2);
+          const uint64_t koff = (uint64_t)((k & 3) * 2);
+          umma_f16(tmem_pv + (uint32_t)x * 32u, umma_desc_sw128(sp + sub * (kPBytes / 2)) + koff,
+                   umma_desc_sw128(sv + sub * (kVBytes / 2)) + koff, idesc_pv, k ? 1u : 0u);
+        }
+        umma_commit(pv_full0 + 8 * x);
+      };
+      mbar_wait(q_full, 0, err, 44);
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int t = 0; t < ntiles; ++t) {
+        issue_pv(0, t);
+        if (t + 1 < ntiles) issue_s(0, t + 1);
+        issue_pv(1, t);
+        umma_commit(kv_empty0 + 8 * (t & 1));          // K(t) / V(t) are free once everything issued so far retires
+        if (t + 1 < ntiles) issue_s(1, t + 1);
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = ((uint32_t)(qd * 32)) << 16;
+    float o[2][16];
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[x][j] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f}, corr_prev[2] = {0.f, 0.f};
+    auto fold_pv = [&](int x, int tt, float c) {        // o_x <- o_x corr(tt) + (P V)_x(tt)
+      mbar_wait(pv_full0 + 8 * x, (uint32_t)tt & 1u, err, 47);
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_pv + lane_addr + (uint32_t)(x * 32 + half * 16), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[x][j] = fmaf(o[x][j], c, __uint_as_float(v[j]));
+      tc_fence_before();
+    };
+    for (int t = 0; t < ntiles; ++t) {
+      const int valid = min(64, max(0, a.nk - t * kAttK - half * 64));
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        mbar_wait(s_full0 + 8 * x, (uint32_t)t & 1u, err, 46);
+        tc_fence_after();
+        float sv_[64];
+        {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)(x * 128 + half * 64), v0);
+          tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)(x * 128 + half * 64 + 32), v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { sv_[j] = __uint_as_float(v0[j]); sv_[32 + j] = __uint_as_float(v1[j]); }
+        }
+        tc_fence_before();
+        mbar_arrive(s_free0 + 8 * x);
+        float mloc = -INFINITY;
+        if (valid == 64) {
+          float m4[4] = {sv_[0], sv_[1], sv_[2], sv_[3]};
+#pragma unroll
+          for (int j = 4; j < 64; j += 4) {
+            m4[0] = fmaxf(m4[0], sv_[j]); m4[1] = fmaxf(m4[1], sv_[j + 1]);
+            m4[2] = fmaxf(m4[2], sv_[j + 2]); m4[3] = fmaxf(m4[3], sv_[j + 3]);
+          }
+          mloc = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (j < valid) mloc = fmaxf(mloc, sv_[j]);
+        }
+        float* xc = xch + (x * 2 + (t & 1)) * 256;
+        xc[half * 128 + row] = mloc;
+        named_bar_sync(1 + qd, 64);
+        const float mx = fmaxf(m_run[x], fmaxf(mloc, xc[(half ^ 1) * 128 + row]));
+        const float corr = ex2_fast(m_run[x] - mx);
+        m_run[x] = mx;
+        // (P V)_x(t - 1) was issued a whole other-tile soft-max ago: fold it, which also frees this tile's P buffer
+        if (t > 0) fold_pv(x, t - 1, corr_prev[x]);
+        corr_prev[x] = corr;
+        const uint32_t prow = smem_u32(sP) + (uint32_t)x * kPBytes + (uint32_t)half * (kPBytes / 2) + (uint32_t)row * 128u;
+        float lsum;
+        if (valid == 64) lsum = softmax_half_row<1, true>(sv_, mx, 64, prow, row);
+        else lsum = softmax_half_row<1, false>(sv_, mx, valid, prow, row);
+        l_run[x] = fmaf(l_run[x], corr, lsum);
+        fence_proxy_async();
+        mbar_arrive(p_full0 + 8 * x);
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      fold_pv(x, ntiles - 1, corr_prev[x]);
+      float* xc = xch + (x * 2 + (ntiles & 1)) * 256;
+      xc[half * 128 + row] = l_run[x];
+      named_bar_sync(1 + qd, 64);
+      const float l_tot = l_run[x] + xc[(half ^ 1) * 128 + row];
+      const int qi = q0 + x * kAttQ + row;
+      if (qi < a.nq) {
+        const float inv = 1.f / l_tot;
+        const long long off = (long long)(a.out_row0 + qi) * args.ld_out + head * 32 + half * 16;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float r0 = o[x][j] * inv, r1 = o[x][j + 1] * inv, r2 = o[x][j + 2] * inv, r3 = o[x][j + 3] * inv;
+          if (args.out) *(float4*)(args.out + off + j) = make_float4(r0, r1, r2, r3);
+          if (args.out_hi) {
+            const __nv_bfloat162 a2 = __floats2bfloat162_rn(r0, r1), b2 = __floats2bfloat162_rn(r2, r3);
+            *(uint2*)(args.out_hi + off + j) = make_uint2(*(const uint32_t*)&a2, *(const uint32_t*)&b2);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // q / k / v: fp32 rows [n][ld] (columns head * 32 + d).  Qp, Kp: [heads][n_pad][64]; Vt: [heads][32][n_pad].
 // The rows form two segments (source cloud [0, split), target cloud [split, n)); the second one starts at the
 // 128-aligned packed row split_pad: TMA needs the innermost start of a box 16-byte aligned, and tokens are the
@@ -469,6 +681,17 @@ extern "C" int drb_mha_tc_forward(const void* workspace, int n, int split, int h
   const size_t smem = 1024 + (size_t)planes * (kQBytes + 2 * (kKBytes + kVBytes) + (size_t)pbufs * kPBytes) + 14 * 8 +
                       2 * 2 * 128 * sizeof(float) + 16;
   dim3 grid((unsigned)cdiv(max_q, kAttQ), (unsigned)heads, (unsigned)nprob);
+  static int two_tiles = -1;     // DRB_ATT_TWO_TILES=0: the one-tile kernel for bf16 too
+  if (two_tiles < 0) { const char* env = getenv("DRB_ATT_TWO_TILES"); two_tiles = env ? atoi(env) : 1; }
+  if (planes == 1 && two_tiles && max_q > kAttQ && a.out_lo == nullptr) {
+    const size_t smem2 = 1024 + 2 * (size_t)kQBytes + 2 * (size_t)(kKBytes + kVBytes) + 2 * (size_t)kPBytes + 16 * 8 +
+                         2 * 2 * 2 * 128 * sizeof(float) + 16;
+    DRB_CUDA_OK(cudaFuncSetAttribute(att_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    dim3 grid2((unsigned)cdiv(max_q, 2 * kAttQ), (unsigned)heads, (unsigned)nprob);
+    att_fwd2_kernel<<<grid2, kAttThreads, smem2, stream>>>(mQ[0], mK[0], mV[0], a);
+    DRB_LAUNCH_OK();
+    return 0;
+  }
   if (planes == 1) {
     DRB_CUDA_OK(cudaFuncSetAttribute(att_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     att_fwd_kernel<1><<<grid, kAttThreads, smem, stream>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], a);
