@@ -22,7 +22,8 @@ class Conv3dDesc(C.Structure):
                 ("bias", c_void_p), ("residual", c_void_p),
                 ("out", c_void_p), ("out_hi", c_void_p), ("out_lo", c_void_p),
                 ("ld_out", c_ll), ("bn_accum", c_void_p), ("tile_list", c_void_p), ("tile_count", c_void_p),
-                ("acc_scale_dev", c_void_p * 2), ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_size_t)]
+                ("acc_scale_dev", c_void_p * 2), ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_size_t),
+                ("res_d", c_int), ("res_h", c_int), ("res_w", c_int)]
 
 
 class WgradDesc(C.Structure):

@@ -237,7 +237,7 @@ int engine_run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
                      int relu, float scale, float* out, plane_t* out_hi, plane_t* out_lo, long long ld,
                      cudaStream_t s, const plane_t* w_hi, const plane_t* w_lo, int cout_override,
                      const int* tile_list, const int* tile_count, const float* scale_dev0,
-                     const float* scale_dev1) {
+                     const float* scale_dev1, const int* res_dims) {
   drb_conv3d_desc cd;
   memset(&cd, 0, sizeof(cd));
   cd.g = g; cd.d = d; cd.h = h; cd.w = wd;
@@ -257,6 +257,7 @@ int engine_run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
   cd.acc_scale_dev[1] = scale_dev1;
   cd.splitk_ws = e->splitk_ws;
   cd.splitk_ws_bytes = e->splitk_ws_bytes;
+  if (res_dims) { cd.res_d = res_dims[0]; cd.res_h = res_dims[1]; cd.res_w = res_dims[2]; }
   e->launches += 1;
   if (!e->profile) return drb_conv3d_igemm(&cd, s);
   drb_engine::ProfRec r;
@@ -278,10 +279,11 @@ static int run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
                      int h, int wd, int cin, int k, const float* bias, const float* residual,
                      int relu, float scale, float* out, plane_t* out_hi, plane_t* out_lo, long long ld,
                      cudaStream_t s, const plane_t* w_hi = nullptr, const plane_t* w_lo = nullptr,
-                     int cout_override = 0, const int* tile_list = nullptr, const int* tile_count = nullptr) {
+                     int cout_override = 0, const int* tile_list = nullptr, const int* tile_count = nullptr,
+                     const int* res_dims = nullptr) {
   const float* wscale = (w_hi == nullptr && e->cfg.planes == 2 && w.slot) ? w.slot + 1 : nullptr;
   return engine_run_igemm(e, w, x_hi, x_lo, g, d, h, wd, cin, k, bias, residual, relu, scale, out, out_hi, out_lo, ld,
-                          s, w_hi, w_lo, cout_override, tile_list, tile_count, wscale, nullptr);
+                          s, w_hi, w_lo, cout_override, tile_list, tile_count, wscale, nullptr, res_dims);
 }
 
 
@@ -408,13 +410,24 @@ static int run_fpn(drb_engine* e, const drb_pair_io* io, cudaStream_t s) {
   for (int i = 3; i >= 0; --i) {
     const Act& f = *feats[i];
     const bool sparse = (i == 0) && e->sparse_fpn;
-    DRB_TRY(run_igemm(e, e->pyr[i], f.hi, f.lo, kG, f.d, f.h, f.w, f.c, e->pyr[i].k, P(e, e->pyr[i].p_b),
-                      nullptr, 0, 1.f, e->lat[i].f, nullptr, nullptr, 0, s, nullptr, nullptr, 0,
-                      sparse ? e->tiles_in : nullptr, sparse ? e->tile_counts + 1 : nullptr));
     const Act& top = e->p[i + 1];
-    e->launches += 1;
-    DRB_TRY(drb_upsample2_add(top.f, top.d, top.h, top.w, e->lat[i].f, kG, f.d, f.h, f.w, 256, nullptr,
-                              e->sum[i].hi, e->sum[i].lo, s));
+    // The two large levels: the top-down merge up(top) + lateral (feature_pyramid_net.py:58-61) happens in the lateral
+    // convolution's epilogue (the residual is the coarser level, read with nearest x2 up-sampling) and goes straight
+    // to the planes the smoothing convolution reads - no fp32 lateral tensor, no separate pass (0.54 GB written +
+    // 0.54 GB read back at level 1).  The small levels keep the split-K lateral + separate merge.
+    if (e->fuse_topdown && i <= 1) {
+      const int rd[3] = {top.d, top.h, top.w};
+      DRB_TRY(run_igemm(e, e->pyr[i], f.hi, f.lo, kG, f.d, f.h, f.w, f.c, e->pyr[i].k, P(e, e->pyr[i].p_b),
+                        top.f, 0, 1.f, nullptr, e->sum[i].hi, e->sum[i].lo, 0, s, nullptr, nullptr, 0,
+                        sparse ? e->tiles_in : nullptr, sparse ? e->tile_counts + 1 : nullptr, rd));
+    } else {
+      DRB_TRY(run_igemm(e, e->pyr[i], f.hi, f.lo, kG, f.d, f.h, f.w, f.c, e->pyr[i].k, P(e, e->pyr[i].p_b),
+                        nullptr, 0, 1.f, e->lat[i].f, nullptr, nullptr, 0, s, nullptr, nullptr, 0,
+                        sparse ? e->tiles_in : nullptr, sparse ? e->tile_counts + 1 : nullptr));
+      e->launches += 1;
+      DRB_TRY(drb_upsample2_add(top.f, top.d, top.h, top.w, e->lat[i].f, kG, f.d, f.h, f.w, 256, nullptr,
+                                e->sum[i].hi, e->sum[i].lo, s));
+    }
     DRB_TRY(run_igemm(e, e->ups[i], e->sum[i].hi, e->sum[i].lo, kG, f.d, f.h, f.w, 256, 3,
                       P(e, e->ups[i].p_b), nullptr, 0, 1.f, e->p[i].f, nullptr, nullptr, 0, s, nullptr, nullptr, 0,
                       sparse ? e->tiles_out : nullptr, sparse ? e->tile_counts : nullptr));
@@ -583,6 +596,7 @@ extern "C" int drb_engine_create(const drb_engine_config* cfg, drb_engine** out)
   drb_engine* e = new drb_engine();
   e->cfg = *cfg;
   if (const char* env = getenv("DRB_BN_SMALL")) e->bn_small = atoi(env) != 0;
+  if (const char* env = getenv("DRB_FUSE_TOPDOWN")) e->fuse_topdown = atoi(env) != 0;
   int rc = build(e);
   if (rc) {
     set_error("drb_engine_create: %s", e->fail.c_str());

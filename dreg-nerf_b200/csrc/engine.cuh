@@ -138,6 +138,7 @@ struct drb_engine {
   drb::Act lat[5], sum[4], p[5];    // p[0] = p1 ... p[4] = p5
   // output-sparse evaluation of the two level-1 FPN convolutions
   bool sparse_fpn = true;
+  bool fuse_topdown = true;     // FPN top-down merge in the lateral convolution's epilogue (DRB_FUSE_TOPDOWN=0: separate pass)
   bool bn_small = true;         // one-launch BatchNorm for the deep stages (DRB_BN_SMALL=0: the general path)
   bool update_running = true;   // training-mode BatchNorm writes running_mean / running_var (primary engine only)
   uint8_t* need = nullptr;
@@ -220,7 +221,8 @@ int engine_run_igemm(drb_engine* e, const ConvW& w, const plane_t* x_hi, const p
                      float* out, plane_t* out_hi, plane_t* out_lo, long long ld, cudaStream_t s,
                      const plane_t* w_hi = nullptr, const plane_t* w_lo = nullptr, int cout_override = 0,
                      const int* tile_list = nullptr, const int* tile_count = nullptr,
-                     const float* scale_dev0 = nullptr, const float* scale_dev1 = nullptr);
+                     const float* scale_dev0 = nullptr, const float* scale_dev1 = nullptr,
+                     const int* res_dims = nullptr);      // {d, h, w} of a coarser residual added with nearest x2 up-sampling
 int engine_ensure_tokens(drb_engine* e, int m);
 int engine_stem_im2col(drb_engine* e, const drb_pair_io* io, cudaStream_t s);
 int engine_im2col(drb_engine* e, const ConvW& w, const Act& in, cudaStream_t s);

@@ -57,13 +57,15 @@ struct IgemmArgs {
   plane_t* out_hi;         // [M, ld] or null
   plane_t* out_lo;         // [M, ld] or null (present => fp16 pair mode)
   long long ld;            // row pitch (elements) of out / residual / out_hi / out_lo
+  int res_d, res_h, res_w; // > 0: residual is a coarser volume added with nearest x2 up-sampling
   int* err;
 };
 
 // Fused epilogue of 32 consecutive output channels of one row.
 __device__ __forceinline__ void epilogue_store32(const IgemmArgs& a, float (&f)[32], long long m, int n,
-                                                 int split, float acc_scale) {
+                                                 int split, float acc_scale, long long m_res) {
   const long long off = m * a.ld + n;
+  const long long roff = m_res * a.ld + n;     // residual row (== m unless the residual is the coarser FPN level)
   const bool full = (n + 32 <= a.Cout);
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] *= acc_scale;
@@ -101,13 +103,13 @@ __device__ __forceinline__ void epilogue_store32(const IgemmArgs& a, float (&f)[
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 r4 = *(const float4*)(a.residual + off + j);
+        const float4 r4 = *(const float4*)(a.residual + roff + j);
         f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (n + j < a.Cout) f[j] += a.residual[off + j];
+        if (n + j < a.Cout) f[j] += a.residual[roff + j];
     }
   }
   if (a.relu) {
@@ -370,6 +372,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       const int gg = g0 + rr;
       const bool row_ok = (ww < a.W) && (hh < a.H) && (dd < a.D) && (gg < a.G);
       const long long m = (((long long)gg * a.D + dd) * a.H + hh) * a.W + ww;
+      const long long m_res = a.res_d > 0
+                                  ? (((long long)gg * a.res_d + (dd >> 1)) * a.res_h + (hh >> 1)) * a.res_w + (ww >> 1)
+                                  : m;
 #pragma unroll
       for (int j = 0; j < 128; ++j) acc[j] = 0.f;
       for (int k0 = ki0; k0 < ki1; k0 += a.chunk, ++cc) {
@@ -423,7 +428,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = acc[b * 32 + j];
-          epilogue_store32(a, f, m, n, sp, acc_scale);
+          epilogue_store32(a, f, m, n, sp, acc_scale, m_res);
         }
       }
     }
@@ -671,6 +676,11 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   a.acc_scale = d->acc_scale == 0.f ? 1.f : d->acc_scale;
   a.acc_scale_dev0 = d->acc_scale_dev[0];
   a.acc_scale_dev1 = d->acc_scale_dev[1];
+  a.res_d = d->res_d; a.res_h = d->res_h; a.res_w = d->res_w;
+  DRB_REQUIRE((a.res_d == 0 && a.res_h == 0 && a.res_w == 0) ||
+                  (d->residual && a.res_d * 2 >= a.D && a.res_h * 2 >= a.H && a.res_w * 2 >= a.W),
+              "drb_conv3d_igemm: the coarse residual volume (%d, %d, %d) does not cover the output (%d, %d, %d) at x2",
+              a.res_d, a.res_h, a.res_w, a.D, a.H, a.W);
   a.bias = d->bias; a.residual = d->residual; a.out = d->out; a.out_hi = (plane_t*)d->out_hi; a.out_lo = (plane_t*)d->out_lo;
   a.ld = ld;
   // vector stores in the epilogue need 16-byte aligned rows

@@ -93,6 +93,11 @@ typedef struct drb_conv3d_desc {
    * result is run-to-run bit-stable (no atomics).  NULL / too small: the reduction is not split.            */
   void* splitk_ws;
   size_t splitk_ws_bytes;
+  /* Optional: `residual` is a COARSER volume [g][res_d][res_h][res_w][ld_out] added with nearest x2 up-sampling
+   * (row (g, d, h, w) takes residual row (g, d / 2, h / 2, w / 2)): the FPN's top-down merge
+   * F.interpolate(top, scale_factor=2)[..., :d, :h, :w] + lateral (feature_pyramid_net.py:58-61) fused into the
+   * lateral convolution's epilogue.  All zero: residual has the output's own shape.                       */
+  int res_d, res_h, res_w;
 } drb_conv3d_desc;
 /* Geometry of the 128-row output tiles drb_conv3d_igemm uses for a [g][d][h][w] volume: box extents
  * (bg, bd, bh, bw) and tile counts (tg, td, th, tw); tile index = ((ig*td + id)*th + ih)*tw + iw. */
