@@ -172,6 +172,52 @@ __global__ void im2col_kernel(drb_im2col_desc d, int od, int oh, int ow, plane_t
   }
 }
 
+// Channels-last input with a multiple of 8 channels and no padding columns (every strided convolution of the
+// backbone): one thread per (output voxel, tap, 8 channels) - 32 contiguous bytes in, 16 contiguous bytes out per
+// plane, 32-bit index arithmetic.  (The element-per-thread kernel above spends ~100 instructions and two 64-bit
+// divisions on every 2-byte store: 275 us for layer2.0.conv2 at 128^3, 0.4 TB/s.)
+__global__ void __launch_bounds__(256) im2col_cl8_kernel(drb_im2col_desc d, int od, int oh, int ow,
+                                                         plane_t* __restrict__ hi, plane_t* __restrict__ lo) {
+  const int cg = d.c >> 3;                       // 8-channel groups per tap
+  const int taps = d.k * d.k * d.k;
+  const int per_row = taps * cg;
+  const long long rows = (long long)d.g * od * oh * ow;
+  const long long total = rows * per_row;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool pair = lo != nullptr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long row = i / per_row;
+    const int rem = (int)(i - row * per_row);
+    const int tap = rem / cg, c8 = (rem - tap * cg) << 3;
+    const int kx = tap % d.k, ky = (tap / d.k) % d.k, kz = tap / (d.k * d.k);
+    int r = (int)row;                            // rows < 2^31 (checked by the host)
+    const int x = r % ow; r /= ow;
+    const int y = r % oh; r /= oh;
+    const int z = r % od; r /= od;
+    const int g = r;
+    const int iz = z * d.stride - d.pad + kz, iy = y * d.stride - d.pad + ky, ix = x * d.stride - d.pad + kx;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (iz >= 0 && iz < d.d && iy >= 0 && iy < d.h && ix >= 0 && ix < d.w) {
+      const float* src = d.x + g * d.sg + iz * d.sd + iy * d.sh + ix * d.sw + c8;
+      a = *(const float4*)src;
+      b = *(const float4*)(src + 4);
+    }
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      plane_t h0, l0, h1, l1;
+      split16(v[2 * u], pair, h0, l0);
+      split16(v[2 * u + 1], pair, h1, l1);
+      hw[u] = pack16x2(h0, h1);
+      lw[u] = pack16x2(l0, l1);
+    }
+    const long long o = row * d.kpad + (long long)tap * d.c + c8;
+    *(uint4*)(hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (pair) *(uint4*)(lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
 extern "C" int drb_im2col(const drb_im2col_desc* d, void* hi, void* lo, cudaStream_t stream) {
   DRB_REQUIRE(d && d->x && hi, "drb_im2col: null argument");
   DRB_REQUIRE(d->k >= 1 && d->stride >= 1 && d->kpad >= d->k * d->k * d->k * d->c &&
@@ -181,6 +227,15 @@ extern "C" int drb_im2col(const drb_im2col_desc* d, void* hi, void* lo, cudaStre
   const int oh = (d->h + 2 * d->pad - d->k) / d->stride + 1;
   const int ow = (d->w + 2 * d->pad - d->k) / d->stride + 1;
   const long long total = (long long)d->g * od * oh * ow * d->kpad;
+  const long long rows = (long long)d->g * od * oh * ow;
+  const bool aligned = ((uintptr_t)d->x & 15) == 0 && ((uintptr_t)hi & 15) == 0 && (!lo || ((uintptr_t)lo & 15) == 0) &&
+                       d->sw % 4 == 0 && d->sh % 4 == 0 && d->sd % 4 == 0 && d->sg % 4 == 0;
+  if (d->sc == 1 && d->c % 8 == 0 && d->kpad == d->k * d->k * d->k * d->c && rows < (1LL << 31) && aligned) {
+    const long long groups = total / 8;
+    im2col_cl8_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, stream>>>(*d, od, oh, ow, (plane_t*)hi, (plane_t*)lo);
+    DRB_LAUNCH_OK();
+    return 0;
+  }
   im2col_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(*d, od, oh, ow, (plane_t*)hi,
                                                                     (plane_t*)lo);
   DRB_LAUNCH_OK();
@@ -553,7 +608,22 @@ __global__ void __launch_bounds__(256) bn_small_kernel(const float* __restrict__
     if (training) {
       double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
       if (ch_ok) {
-        for (int r = rl; r < m; r += 32) {
+        // four rows in flight per thread: a block is alone on its SM with 8 warps, one load at a time per
+        // thread made every pass a chain of L2 round trips (25 us per launch, ncu)
+        int r = rl;
+        for (; r + 96 < m; r += 128) {
+          float4 vv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) vv[k] = *(const float4*)(xg + (long long)(r + 32 * k) * c + ch4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            s[0] += (double)vv[k].x; ss[0] += (double)vv[k].x * (double)vv[k].x;
+            s[1] += (double)vv[k].y; ss[1] += (double)vv[k].y * (double)vv[k].y;
+            s[2] += (double)vv[k].z; ss[2] += (double)vv[k].z * (double)vv[k].z;
+            s[3] += (double)vv[k].w; ss[3] += (double)vv[k].w * (double)vv[k].w;
+          }
+        }
+        for (; r < m; r += 32) {
           const float4 v = *(const float4*)(xg + (long long)r * c + ch4);
           s[0] += (double)v.x; ss[0] += (double)v.x * (double)v.x;
           s[1] += (double)v.y; ss[1] += (double)v.y * (double)v.y;
@@ -599,6 +669,7 @@ __global__ void __launch_bounds__(256) bn_small_kernel(const float* __restrict__
     if (ch_ok) {
       const float4 sc = *(const float4*)&s_scale[4 * q], sf = *(const float4*)&s_shift[4 * q];
       const bool pair = out_lo != nullptr;
+#pragma unroll 4
       for (int r = rl; r < m; r += 32) {
         const long long i = ((long long)gi * m + r) * c + ch4;
         float4 v = *(const float4*)(x + i);

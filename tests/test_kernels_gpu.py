@@ -129,16 +129,19 @@ def test_igemm_epilogue(cuda):
     assert _rel(ohi.float() + olo.float(), ref) < 4e-6
 
 
-@pytest.mark.parametrize("cin,cout,k,stride,size", [(4, 64, 5, 2, 16), (128, 128, 3, 2, 8), (256, 512, 1, 2, 8)])
-def test_im2col_conv(cuda, cin, cout, k, stride, size):
-    """conv1 (5^3 s2, Cin 4) and the stride-2 convs via im2col + 1x1x1 igemm; strided input view."""
+@pytest.mark.parametrize("cin,cout,k,stride,size,extra", [(4, 64, 5, 2, 16, 3), (128, 128, 3, 2, 8, 3), (256, 512, 1, 2, 8, 3),
+                                                            (128, 128, 3, 2, 9, 0), (256, 512, 1, 2, 8, 0), (64, 64, 3, 2, 12, 0)])
+def test_im2col_conv(cuda, cin, cout, k, stride, size, extra):
+    """conv1 (5^3 s2, Cin 4) and the stride-2 convs via im2col + 1x1x1 igemm; strided input view (extra = 3: the
+    element-per-thread kernel) and plain channels-last storage (extra = 0: the 8-channels-per-thread fast path the
+    engine's strided convolutions take)."""
     ops = _ops()
     gen = torch.Generator().manual_seed(cin + k)
-    base = torch.randn(2, size, size, size, cin + 3, generator=gen)       # [g, X, Y, Z, C] storage
-    x = base.permute(0, 4, 3, 1, 2)[:, 3:]                                 # [g, C, Z, X, Y] strided view
+    base = torch.randn(2, size, size, size, cin + extra, generator=gen)   # [g, X, Y, Z, C] storage
+    x = base.permute(0, 4, 3, 1, 2)[:, extra:]                             # [g, C, Z, X, Y] strided view
     wt = torch.randn(cout, cin, k, k, k, generator=gen) / math.sqrt(cin * k ** 3)
     kpad = (cin * k ** 3 + 63) // 64 * 64
-    xd = base.to(cuda).permute(0, 4, 3, 1, 2)[:, 3:]
+    xd = base.to(cuda).permute(0, 4, 3, 1, 2)[:, extra:]
     cols = ops.im2col(xd, k, stride, k // 2, kpad)
     wp = ops.pack_conv_weight_im2col(wt.to(cuda), kpad)
     out, _ = ops.conv3d_igemm(cols, wp, 1)
