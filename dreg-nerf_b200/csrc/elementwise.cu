@@ -752,12 +752,65 @@ __global__ void maxpool_kernel(const float* __restrict__ x, int g, int d, int h,
   }
 }
 
+// four channels per thread: 16-byte loads, a quarter of the index arithmetic (fmaxf is exact: same result)
+__global__ void __launch_bounds__(256) maxpool4_kernel(const float* __restrict__ x, int g, int d, int h, int w, int c,
+                                                       int od, int oh, int ow, float* __restrict__ out,
+                                                       plane_t* __restrict__ out_hi, plane_t* __restrict__ out_lo) {
+  const int c4n = c >> 2;
+  const long long total = (long long)g * od * oh * ow * c4n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool pair = out_lo != nullptr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int ch = (int)(i % c4n) * 4;
+    int r = (int)(i / c4n);                      // output voxels < 2^31 (checked by the host)
+    const int ox = r % ow; r /= ow;
+    const int oy = r % oh; r /= oh;
+    const int oz = r % od; r /= od;
+    const int gi = r;
+    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int kz = 0; kz < 3; ++kz) {
+      const int iz = oz * 2 - 1 + kz;
+      if (iz < 0 || iz >= d) continue;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * 2 - 1 + ky;
+        if (iy < 0 || iy >= h) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ox * 2 - 1 + kx;
+          if (ix < 0 || ix >= w) continue;
+          const float4 v = *(const float4*)(x + ((((long long)gi * d + iz) * h + iy) * w + ix) * c + ch);
+          best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y);
+          best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
+        }
+      }
+    }
+    if (out) *(float4*)(out + i * 4) = best;
+    if (out_hi) {
+      plane_t h0, l0, h1, l1, h2, l2, h3, l3;
+      split16(best.x, pair, h0, l0); split16(best.y, pair, h1, l1);
+      split16(best.z, pair, h2, l2); split16(best.w, pair, h3, l3);
+      *(uint2*)(out_hi + i * 4) = make_uint2(pack16x2(h0, h1), pack16x2(h2, h3));
+      if (pair) *(uint2*)(out_lo + i * 4) = make_uint2(pack16x2(l0, l1), pack16x2(l2, l3));
+    }
+  }
+}
+
 extern "C" int drb_maxpool3d(const float* x, int g, int d, int h, int w, int c, float* out,
                              void* out_hi, void* out_lo, cudaStream_t stream) {
   DRB_REQUIRE(x && (out || out_hi) && g > 0 && d > 0 && h > 0 && w > 0 && c > 0,
               "drb_maxpool3d: bad arguments");
   const int od = (d - 1) / 2 + 1, oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
   const long long total = (long long)g * od * oh * ow * c;
+  const bool al = ((uintptr_t)x & 15) == 0 && (!out || ((uintptr_t)out & 15) == 0) && (!out_hi || ((uintptr_t)out_hi & 7) == 0) &&
+                  (!out_lo || ((uintptr_t)out_lo & 7) == 0);
+  if (c % 4 == 0 && al && (long long)g * od * oh * ow < (1LL << 31)) {
+    maxpool4_kernel<<<grid_for(total / 4, 256, 148 * 32), 256, 0, stream>>>(
+        x, g, d, h, w, c, od, oh, ow, out, (plane_t*)out_hi, (plane_t*)out_lo);
+    DRB_LAUNCH_OK();
+    return 0;
+  }
   maxpool_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(
       x, g, d, h, w, c, od, oh, ow, out, (plane_t*)out_hi, (plane_t*)out_lo);
   DRB_LAUNCH_OK();
