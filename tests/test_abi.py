@@ -38,3 +38,31 @@ def test_argument_validation_without_gpu(pkg):
     assert b"null" in lib.drb_last_error()
     assert lib.drb_split_planes(None, None, None, 5, None) == -1
     assert lib.drb_engine_num_params(None) == 0
+
+
+def test_integration_stub_matches_the_binding(pkg):
+    """INTEGRATION.md section 3 shows a maintainer the ctypes mirror of drb_conv3d_desc: it must list the fields of
+    the struct the library reads (a short struct would be read past its end - VERDICT r1 found it stale)."""
+    from importlib import import_module
+    lib_mod = import_module("dreg-nerf_b200._lib")
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as fh:
+        text = fh.read()
+    block = text[text.index("class Conv3dDesc"):text.index("assert lib.drb_abi_version")]
+    stub = re.findall(r'\("(\w+)", C\.', block)
+    assert stub == [f[0] for f in lib_mod.Conv3dDesc._fields_]
+    assert "drb_abi_version() == %d" % pkg.load_library().drb_abi_version() in text
+    # and the header's struct has the same member names in the same order
+    with open(os.path.join(ROOT, "include", "dregb200.h")) as fh:
+        header = re.sub(r"/\*.*?\*/", "", fh.read(), flags=re.S)
+    body = header[header.index("typedef struct drb_conv3d_desc {"):header.index("} drb_conv3d_desc;")]
+    members = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(None, 1)[1] if " " in decl else decl
+        for part in names.split(","):
+            m = re.search(r"(\w+)\s*(\[\d+\])?$", part.strip())
+            if m:
+                members.append(m.group(1))
+    assert members == stub, (members, stub)
