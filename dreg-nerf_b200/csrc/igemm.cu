@@ -443,6 +443,171 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// bf16, TWO 128-row M tiles per work item against one 256-wide weight tile (igemm2_kernel).
+// A 128 x 256 x 64 bf16 k-iteration moves 48 KB from L2 for 4 MMAs of 128 clk: 96 B/clk per SM, and 200 KB of
+// shared memory buffer only ~2100 clk of tensor work - about one TMA round trip - so the one-tile kernel reaches
+// 42-54 % of the MMA rate on the large convolutions (profiles/r02_igemm_per_shape.txt).  Sharing the weight tile
+// between two M tiles cuts the traffic to 64 B/clk per SM and makes the same shared memory buffer 3200 clk of work.
+// bf16 operands need no chunked fp32 accumulation (their own rounding is 2^-9), so the two accumulators fill TMEM
+// (2 x 256 columns) and the epilogue reads them once per item; the price is that an item's epilogue does not
+// overlap the next item's MMAs (a few % at K >= 1728).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t a_bytes = kBM * kBK * 2;              // 16 KB per M tile
+  constexpr uint32_t b_bytes = 256 * kBK * 2;              // 32 KB
+  constexpr uint32_t stage_bytes = 2 * a_bytes + b_bytes;  // 64 KB
+  uint64_t* bars = (uint64_t*)(smem + (size_t)a.stages * stage_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * kMaxStages), tempty_bar = bar0 + 8u * (2 * kMaxStages + 1);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kMaxStages + 4);
+
+  const int tiles_w = (a.W + a.bw - 1) / a.bw;
+  const int tiles_h = (a.H + a.bh - 1) / a.bh;
+  const int tiles_d = (a.D + a.bd - 1) / a.bd;
+  const int tiles_g = (a.G + a.bg - 1) / a.bg;
+  const int tiles_n = (a.Cout + 255) / 256;
+  const int tiles_m = tiles_w * tiles_h * tiles_d * tiles_g;
+  const int listed = a.tile_list ? *a.tile_count : tiles_m;
+  const int pairs_m = (listed + 1) / 2;
+  const int total_items = pairs_m * tiles_n;
+  const int kchunks = a.Cin / kBK;
+  const int taps = a.kd * a.kh * a.kw;
+  const int kiters = taps * kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, kAccWarps * 32);
+    mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> N tile and the two M tiles (index `which` of the pair); a missing second tile has all rows out of bounds
+  auto decode = [&](int it, int which, int& n0, int& w0, int& h0, int& d0, int& g0) {
+    n0 = (it % tiles_n) * 256;
+    const int li = (it / tiles_n) * 2 + which;
+    int m = li < listed ? (a.tile_list ? a.tile_list[li] : li) : tiles_m;
+    if (m >= tiles_m) { w0 = 0; h0 = 0; d0 = 0; g0 = a.G; return; }
+    int tw = m % tiles_w; m /= tiles_w;
+    int th = m % tiles_h; m /= tiles_h;
+    int td = m % tiles_d; m /= tiles_d;
+    w0 = tw * a.bw; h0 = th * a.bh; d0 = td * a.bd; g0 = m * a.bg;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+        int n0, w0, h0, d0, g0, n1, w1, h1, d1, g1;
+        decode(it, 0, n0, w0, h0, d0, g0);
+        decode(it, 1, n1, w1, h1, d1, g1);
+        for (int ki = 0; ki < kiters; ++ki) {
+          const int tap = ki / kchunks, kc = ki - tap * kchunks;
+          const int tw = tap % a.kw, th = (tap / a.kw) % a.kh, td = tap / (a.kw * a.kh);
+          mbar_wait(empty_bar(s), ph ^ 1u, a.err, 1);
+          const uint32_t fb = full_bar(s);
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          tma_load_5d(sa, &tmA, fb, kc * kBK, w0 + tw - a.pw, h0 + th - a.ph, d0 + td - a.pd, g0);
+          tma_load_5d(sa + a_bytes, &tmA, fb, kc * kBK, w1 + tw - a.pw, h1 + th - a.ph, d1 + td - a.pd, g1);
+          tma_load_3d(sa + 2 * a_bytes, &tmB, fb, kc * kBK, n0, tap);
+          if (++s == a.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_16(kBM, 256, true);
+      int s = 0;
+      uint32_t ph = 0, item = 0;
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++item) {
+        mbar_wait(tempty_bar, (item & 1u) ^ 1u, a.err, 2);        // the previous item's epilogue has read TMEM
+        tc_fence_after();
+        for (int ki = 0; ki < kiters; ++ki) {
+          mbar_wait(full_bar(s), ph, a.err, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t da0 = umma_desc_sw128(sa), da1 = umma_desc_sw128(sa + a_bytes);
+          const uint64_t db = umma_desc_sw128(sa + 2 * a_bytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t koff = (uint64_t)(k * 2);
+            const uint32_t acc = (ki != 0 || k != 0) ? 1u : 0u;
+            umma_f16(tmem_base, da0 + koff, db + koff, idesc, acc);
+            umma_f16(tmem_base + 256u, da1 + koff, db + koff, idesc, acc);
+          }
+          umma_commit(empty_bar(s));
+          if (++s == a.stages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tfull_bar);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int colhalf = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    float acc_scale = a.acc_scale;
+    if (a.acc_scale_dev0) acc_scale *= *a.acc_scale_dev0;
+    if (a.acc_scale_dev1) acc_scale *= *a.acc_scale_dev1;
+    uint32_t item = 0;
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++item) {
+      mbar_wait(tfull_bar, item & 1u, a.err, 4);
+      tc_fence_after();
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {
+        int n0, w0, h0, d0, g0;
+        decode(it, which, n0, w0, h0, d0, g0);
+        int rr = row;
+        const int ww = w0 + rr % a.bw; rr /= a.bw;
+        const int hh = h0 + rr % a.bh; rr /= a.bh;
+        const int dd = d0 + rr % a.bd; rr /= a.bd;
+        const int gg = g0 + rr;
+        const bool row_ok = (ww < a.W) && (hh < a.H) && (dd < a.D) && (gg < a.G);
+        const long long m = (((long long)gg * a.D + dd) * a.H + hh) * a.W + ww;
+        const long long m_res = a.res_d > 0
+                                    ? (((long long)gg * a.res_d + (dd >> 1)) * a.res_h + (hh >> 1)) * a.res_w + (ww >> 1)
+                                    : m;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)which * 256u + (uint32_t)(colhalf * 128);
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(b * 32), v);       // warp-collective: every lane takes part
+          tmem_ld_wait();
+          const int n = n0 + colhalf * 128 + b * 32;
+          if (row_ok && n < a.Cout) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            epilogue_store32(a, f, m, n, 0, acc_scale, m_res);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // out[m][n] = bias[n] + sum over the K slices, slices added in index order (deterministic).
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long m_total, int cout, long long ld,
                                      const float* __restrict__ bias, float* __restrict__ out) {
@@ -728,6 +893,37 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
     attr_set = true;
   }
   const int tiles_m = cdiv(a.W, a.bw) * cdiv(a.H, a.bh) * cdiv(a.D, a.bd) * cdiv(a.G, a.bg);
+  {
+    // bf16, wide weight tile, enough M tiles to keep every SM busy with pairs: the two-tile kernel
+    static int two = -1;           // DRB_IGEMM_TWO_TILES=0: always the one-tile kernel
+    if (two < 0) { const char* env = getenv("DRB_IGEMM_TWO_TILES"); two = env ? atoi(env) : 1; }
+    // chosen when the reduction is long enough for the MMAs to dominate an item (the two-tile kernel does not
+    // overlap an item's epilogue with the next item's MMAs) and when its waves of (tile pair, N tile) items finish
+    // earlier than the one-tile kernel's waves at the measured rates (86 % vs ~50 % of the MMA peak per busy SM)
+    const long long nsm2 = igemm_num_sms();
+    const long long items1 = (long long)tiles_m * cdiv(a.Cout, 256), items2 = (long long)cdiv(tiles_m, 2) * cdiv(a.Cout, 256);
+    const double time1 = (double)((items1 + nsm2 - 1) / nsm2) * 1.0 / 0.5;
+    const double time2 = (double)((items2 + nsm2 - 1) / nsm2) * 2.0 / 0.86;
+    if (two && a.planes == 1 && a.BN == 256 && a.cs == 1 && a.splits == 1 && !a.bn_accum && a.Cout % 8 == 0 &&
+        kiters_h >= 16 && items2 >= nsm2 && time2 < time1) {
+      static bool attr2[kMaxDevices] = {};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev >= 0 && dev < kMaxDevices && !attr2[dev]) {
+        DRB_CUDA_OK(cudaFuncSetAttribute(igemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr2[dev] = true;
+      }
+      IgemmArgs a2 = a;
+      a2.stages = 3;
+      const size_t smem2 = 1024 + 3 * (size_t)(2 * kBM * kBK * 2 + 256 * kBK * 2) + (2 * kMaxStages + 4) * 8 + 16;
+      // the weight map's box must be the full 256 rows (cs == 1: it is); A map: the forward's 128-row box
+      const long long items = (long long)cdiv(tiles_m, 2) * cdiv(a.Cout, 256);
+      const int grid2 = (int)(items < igemm_num_sms() ? items : igemm_num_sms());
+      igemm2_kernel<<<grid2, kThreads, smem2, stream>>>(mA[0], mB[0], a2);
+      DRB_LAUNCH_OK();
+      return 0;
+    }
+  }
   const int tiles = cdiv(tiles_m, a.cs) * cdiv(a.Cout, a.BN) * a.splits;     // work items (one per cluster)
   const int max_clusters = igemm_num_sms() / a.cs;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;

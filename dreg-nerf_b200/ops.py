@@ -68,7 +68,8 @@ def pack_conv_weight_im2col(w, kpad, pair=True):
 
 
 def conv3d_igemm(x_planes, w_planes, k, planes=2, bias=None, residual=None, relu=False, out_scale=1.0,
-                 want_f32=True, want_planes=False, cout=None, ld_out=0, bn_accum=None):
+                 want_f32=True, want_planes=False, cout=None, ld_out=0, bn_accum=None, tile_list=None,
+                 tile_count=None, res_dims=None, out=None):
     """x_planes: (hi, lo) of [g, d, h, w, cin]; w_planes: (hi, lo, scale) of [taps, cout, cin]."""
     x_hi, x_lo = x_planes
     w_hi, w_lo, w_scale = w_planes
@@ -78,7 +79,8 @@ def conv3d_igemm(x_planes, w_planes, k, planes=2, bias=None, residual=None, relu
     ld = ld_out or cout
     m = g * d * h * w
     dev = x_hi.device
-    out = torch.empty((m, ld), dtype=torch.float32, device=dev) if want_f32 else None
+    if out is None:
+        out = torch.empty((m, ld), dtype=torch.float32, device=dev) if want_f32 else None
     o_hi = torch.empty((m, ld), dtype=_plane_dtype(pair), device=dev) if want_planes else None
     o_lo = torch.empty((m, ld), dtype=torch.float16, device=dev) if (want_planes and pair) else None
     desc = _lib.Conv3dDesc(g=g, d=d, h=h, w=w, cin=cin, cout=cout, kd=k, kh=k, kw=k, planes=planes,
@@ -90,7 +92,11 @@ def conv3d_igemm(x_planes, w_planes, k, planes=2, bias=None, residual=None, relu
                            out=out.data_ptr() if out is not None else None,
                            out_hi=o_hi.data_ptr() if o_hi is not None else None,
                            out_lo=o_lo.data_ptr() if o_lo is not None else None, ld_out=ld,
-                           bn_accum=bn_accum.data_ptr() if bn_accum is not None else None)
+                           bn_accum=bn_accum.data_ptr() if bn_accum is not None else None,
+                           tile_list=tile_list.data_ptr() if tile_list is not None else None,
+                           tile_count=tile_count.data_ptr() if tile_count is not None else None)
+    if res_dims is not None:
+        desc.res_d, desc.res_h, desc.res_w = [int(v) for v in res_dims]
     ws = torch.empty(24 << 20, dtype=torch.uint8, device=dev)      # split-K slices (deterministic reduction)
     desc.splitk_ws, desc.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     with _dev(x_hi):

@@ -71,6 +71,48 @@ def test_igemm_conv3d(cuda, shape, cin, cout, k):
     assert _rel(out, ref) < 2e-6
 
 
+def test_igemm_two_tile_bf16(cuda):
+    """The bf16 kernel with two M tiles per work item (igemm2_kernel: large volumes, 256-wide weight tile): plain
+    epilogue, bias + ReLU + planes, the FPN's coarse residual, and an odd-length tile list - against torch on the
+    same bf16-rounded operands."""
+    ops = _ops()
+    g, d, h, w, cin, cout, k = 2, 34, 35, 33, 64, 256, 3
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(g, cin, d, h, w, generator=gen)
+    wt = torch.randn(cout, cin, k, k, k, generator=gen) / math.sqrt(cin * k ** 3)
+    bias = torch.randn(cout, generator=gen)
+    top = torch.randn(g, cout, (d + 1) // 2, (h + 1) // 2, (w + 1) // 2, generator=gen)
+    r16 = lambda t: t.to(torch.bfloat16).float()
+    ref = F.conv3d(r16(x), r16(wt), bias, padding=1)                       # fp32 accumulate of exact bf16 products
+    up = F.interpolate(top, scale_factor=2)[:, :, :d, :h, :w]
+    cl = lambda t: t.permute(0, 2, 3, 4, 1).reshape(-1, cout)
+    xp = ops.split_planes(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda), want_lo=False)
+    wp = ops.pack_conv_weight(wt.to(cuda), pair=False)
+    box, tiles = ops.conv3d_tile_shape(g, d, h, w)
+    n_tiles = tiles[0] * tiles[1] * tiles[2] * tiles[3]
+    assert n_tiles >= 4 * 148, "the shape must be large enough to select the two-tile kernel"
+    out, _ = ops.conv3d_igemm(xp, wp, k, planes=1, bias=bias.to(cuda))
+    assert _rel(out, cl(ref)) < 2e-5
+    out, (hi, _) = ops.conv3d_igemm(xp, wp, k, planes=1, bias=bias.to(cuda), relu=True, want_planes=True)
+    assert _rel(out, cl(torch.relu(ref))) < 2e-5 and _rel(hi.float(), cl(torch.relu(ref))) < 5e-3
+    res_cl = top.permute(0, 2, 3, 4, 1).contiguous().to(cuda)
+    out, _ = ops.conv3d_igemm(xp, wp, k, planes=1, bias=bias.to(cuda), residual=res_cl, res_dims=top.shape[2:])
+    assert _rel(out, cl(ref + up)) < 2e-5
+    # output-sparse: an odd number of listed tiles, the others keep what they held
+    pick = torch.randperm(n_tiles, generator=gen)[: n_tiles // 2 * 2 - 1].sort().values.int()
+    keep = torch.full((g * d * h * w, cout), 7.0, device=cuda)
+    out, _ = ops.conv3d_igemm(xp, wp, k, planes=1, bias=bias.to(cuda), tile_list=pick.to(cuda),
+                              tile_count=torch.tensor([pick.numel()], dtype=torch.int32, device=cuda), out=keep)
+    tile_of = torch.zeros(g, d, h, w, dtype=torch.long)
+    ig, iz, iy, ix = torch.meshgrid(torch.arange(g), torch.arange(d), torch.arange(h), torch.arange(w), indexing="ij")
+    tile_of = ((ig // box[0] * tiles[1] + iz // box[1]) * tiles[2] + iy // box[2]) * tiles[3] + ix // box[3]
+    listed = torch.isin(tile_of.reshape(-1), pick.long())
+    torch.cuda.synchronize()
+    assert ops.igemm_error_flag() == 0
+    assert _rel(out.cpu()[listed], cl(ref)[listed]) < 2e-5
+    assert bool((out.cpu()[~listed] == 7.0).all())
+
+
 @pytest.mark.parametrize("shape,cin,cout,k", [((2, 4, 4, 4), 512, 512, 3), ((2, 8, 8, 8), 256, 256, 3),
                                               ((1, 1, 1, 90), 2048, 256, 1)])
 def test_igemm_split_k(cuda, shape, cin, cout, k):
