@@ -24,6 +24,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 RES = 128
+HOST_WAIT = "default (spin)"     # how host threads wait for the GPU (set by _blocking_sync)
 DEFAULT_FULL_STREAMS = 4        # pairs in flight of the full stage (1 = one pair at a time, as round 1 ran it)
 N_RESIDENT_PAIRS = 3        # distinct synthetic pairs cycled through the timed steps
 FPN_FLOPS_PER_GRID_128 = 1384.0e9   # BASELINE.md section 2 (measured, 2*MAC)
@@ -235,6 +236,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU: there is no CPU fallback for our arm"
+    global HOST_WAIT
+    HOST_WAIT = _blocking_sync(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -552,7 +555,7 @@ def run_ours(args):
                                     "render_step_size": meta_host["render_step_size"],
                                     "stage_ms": {k: (v / max(stage_ms["n"], 1)) for k, v in stage_ms.items() if k != "n"}}
                                    if full else None),
-                       "resolution": RES, "pairs_per_step_per_gpu": 1, "masked_voxels": masked,
+                       "resolution": RES, "pairs_per_step_per_gpu": 1, "masked_voxels": masked, "host_wait": HOST_WAIT,
                        "tokens": [ns, nt], "bn_mode": "batch statistics",
                        "l2": "working set per step (2 x 58.7 MB grids, 0.6 GB weight planes, >3 GB activations) exceeds the 126 MB L2",
                        "parallelism": ("%d pairs per step over %d GPU(s), %d resident per rank: " % (world, world, N_RESIDENT_PAIRS)
@@ -623,6 +626,26 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def _blocking_sync(dev_index):
+    """Host threads that wait for the GPU (stream synchronisations of the down-sampler, of the mask read-back, of the
+    worker threads of a stream pipeline) can sleep instead of spinning (DRB_BLOCKING_SYNC=1 ->
+    cudaDeviceScheduleBlockingSync on the rank's device, set before torch creates the context): with 4 worker threads
+    per rank a spinning wait keeps 4-5 cores per GPU busy, which matters on a box with few cores per GPU.  Measured
+    on a 16-core box with one GPU: sleeping costs 3 % of the pipelined throughput (51.8 -> 50.1 pairs/s) and 11 % of
+    the one-pair-at-a-time latency (wake-ups on the down-sampler's synchronisations), so the default stays the
+    driver's (spin).  Returns what is in effect for the JSON line."""
+    if os.environ.get("DRB_BLOCKING_SYNC", "0") != "1":
+        return "default (spin)"
+    import ctypes
+    try:
+        rt = ctypes.CDLL("libcudart.so.12")
+        if rt.cudaSetDevice(int(dev_index)) == 0 and rt.cudaSetDeviceFlags(4) == 0:      # cudaDeviceScheduleBlockingSync
+            return "cudaDeviceScheduleBlockingSync"
+    except OSError:
+        pass
+    return "default (spin; cudaSetDeviceFlags unavailable)"
+
+
 def _setup_dist():
     import torch
     import torch.distributed as dist
@@ -630,6 +653,8 @@ def _setup_dist():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU: there is no CPU fallback for our arm"
+    global HOST_WAIT
+    HOST_WAIT = _blocking_sync(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
