@@ -768,10 +768,24 @@ extern "C" int drb_conv3d_igemm(const drb_conv3d_desc* d, cudaStream_t stream) {
   const long long tiles_m_h = (long long)cdiv(a.W, a.bw) * cdiv(a.H, a.bh) * cdiv(a.D, a.bd) * cdiv(a.G, a.bg);
   // N tile: the widest of 256 / 128 / 64 that still yields at least one tile per SM (small problems are
   // latency bound: more, narrower tiles beat fewer wide ones); never wider than Cout rounded to 64.
+  // A narrow tile re-reads the activation box once per N tile (128 B/clk per SM at BN = 64 against an L2 -> SM
+  // budget of ~43): when the reduction is long and the epilogue plain, a WIDE tile with the reduction split over the
+  // idle SMs (deterministic slices, see below) beats more, narrower tiles (measured: 8192 x 256 x 6912 157 -> ~40 us).
+  const int kiters_pre = d->kd * d->kh * d->kw * (d->cin / kBK);
+  const bool plain_pre = d->out && !d->out_hi && !d->residual && !d->relu && (d->out_scale == 0.f || d->out_scale == 1.f) &&
+                         !d->tile_list && !d->bn_accum;
+  static int wide_split = -1;      // DRB_IGEMM_WIDE_SPLIT=0: the round-1 rule (narrow tiles first)
+  if (wide_split < 0) { const char* env = getenv("DRB_IGEMM_WIDE_SPLIT"); wide_split = env ? atoi(env) : 1; }
   a.BN = 64;
   for (int bn = 256; bn >= 64; bn >>= 1) {
     if (bn > ((d->cout + 63) / 64) * 64 && bn != 64) continue;
-    if (tiles_m_h * cdiv(d->cout, bn) >= nsm || bn == 64) { a.BN = bn; break; }
+    const long long t = tiles_m_h * cdiv(d->cout, bn);
+    if (t >= nsm || bn == 64) { a.BN = bn; break; }
+    if (wide_split && plain_pre && d->splitk_ws && bn > 64 && t * 2 <= nsm && kiters_pre >= 8 * a.chunk &&
+        2 * (size_t)a.G * a.D * a.H * a.W * (size_t)ld * sizeof(float) <= d->splitk_ws_bytes) {
+      a.BN = bn;                   // few wide tiles: the split-K rule below fills the machine
+      break;
+    }
   }
   if (a.BN > ((d->cout + 63) / 64) * 64) a.BN = ((d->cout + 63) / 64) * 64;
   // split-K: few tiles but a long reduction (deep backbone layers: 1-8 tiles, K up to 13824).  Only for
