@@ -31,7 +31,8 @@ class WgradDesc(C.Structure):
                 ("kd", c_int), ("kh", c_int), ("kw", c_int), ("planes", c_int),
                 ("dy_hi", c_void_p), ("dy_lo", c_void_p), ("x_hi", c_void_p), ("x_lo", c_void_p),
                 ("scale", c_float), ("scale_dev", c_void_p), ("dw", c_void_p),
-                ("c_real", c_int), ("taps_real", c_int), ("tile_list", c_void_p), ("tile_count", c_void_p)]
+                ("c_real", c_int), ("taps_real", c_int), ("tile_list", c_void_p), ("tile_count", c_void_p),
+                ("stage", c_void_p), ("stage_elems", c_ll)]
 
 
 class PairGrad(C.Structure):
@@ -237,7 +238,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.drb_abi_version() != 3:
+    if lib.drb_abi_version() != 4:
         raise DrbError("libdregb200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -176,6 +176,7 @@ struct drb_engine {
   drb::plane_t *gp_hi = nullptr, *gp_lo = nullptr;
   float* dF[5] = {};                // gradients of the backbone features c1..c5 from the lateral convolutions
   float* dcol = nullptr; long long dcol_elems = 0;
+  float* wg_stage = nullptr; long long wg_stage_elems = 0;   // weight-gradient tile staging ([Cout][taps * Cin])
   double* bn_sums = nullptr;
   // backward scratch (token part)
   float *t_dx = nullptr, *t_dy = nullptr, *t_dh = nullptr, *t_dqkv = nullptr, *t_datt = nullptr, *t_dxn = nullptr;

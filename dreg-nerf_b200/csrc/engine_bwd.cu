@@ -54,6 +54,13 @@ int engine_ensure_grad_buffers(drb_engine* e) {
   const Act* feats[5] = {&e->c1, &e->c[0], &e->c[1], &e->c[2], &e->c[3]};
   for (int i = 0; i < 5; ++i) e->dF[i] = e->alloc<float>(feats[i]->numel());
   e->bn_sums = e->alloc<double>((long long)kG * 2048 * 2);
+  // staging buffer of the weight-gradient kernel: the largest [Cout][taps * Cin] (or [Cout][kpad]) result
+  long long stage = 1;
+  for (const ConvW* w : e->all_convs)
+    if (w->im2col || w->k > 1)
+      stage = std::max(stage, (long long)w->cout * (w->im2col ? w->kpad : w->k * w->k * w->k * w->cin));
+  e->wg_stage_elems = stage;
+  e->wg_stage = e->alloc<float>(stage);
   e->ds_tape_cap = (long long)e->cfg.num_downsample * (4LL * e->cfg.max_mask + 2);
   e->ds_tape_buf = e->alloc<int>(e->ds_tape_cap);
   if (!e->fail.empty()) {
@@ -111,7 +118,8 @@ static int wgrad(drb_engine* e, const ConvW& w, const GradPlanes& dy, const plan
   wd_.dw = dw_base;
   wd_.c_real = c_real; wd_.taps_real = taps_real;
   wd_.tile_list = tile_list; wd_.tile_count = tile_count;
-  e->launches += 1;
+  wd_.stage = e->wg_stage; wd_.stage_elems = e->wg_stage_elems;
+  e->launches += (k > 1 || c_real != cin) && e->wg_stage ? 2 : 1;      // + the transposition kernel when staged
   if (!e->profile) return drb_conv3d_wgrad(&wd_, s);
   drb_engine::ProfRec r;
   cudaEventCreate(&r.a);

@@ -14,8 +14,17 @@
 //   warps 2-9: drain each finished chunk from TMEM into fp32 registers (the tensor core accumulates with
 //              truncation, see igemm.cu), then red.add the tile into the fp32 gradient in torch's
 //              [co][ci][tap] layout
-// Work item = (tap, 128-wide co tile, BN-wide ci tile, K split).  With a tile list (output-sparse level-1
-// FPN convolutions) only the listed 128-voxel tiles are reduced over.
+// Work item = (128-wide co tile, BN-wide tile of the flattened (tap, ci) axis, K split): the dY box of a K step
+// is shared by every tap, so a narrow layer (Cin = 64 / 128) puts 4 / 2 taps side by side in one 256-wide N tile
+// (one dY box + four tap-shifted X boxes per step instead of four steps with a dY box each).  With a tile list
+// (output-sparse level-1 FPN convolutions) only the listed 128-voxel tiles are reduced over.
+//
+// Output: the accumulator row of a thread is 32 consecutive columns of the GEMM's [co][tap * Cin + ci] result;
+// torch's layout is [co][ci][tap], i.e. every element of a 3^3 convolution would be a lone 4-byte atomic in its
+// own sector (measured: ~65 G atomics/s, 100 us for the 7 M elements of a 512 x 512 x 27 weight whatever the
+// voxel count).  With a staging buffer (drb_wgrad_desc.stage) the tile is added with 16-byte vector reductions
+// into the GEMM layout and `wgrad_unstage_kernel` transposes it into torch's layout through shared memory;
+// 1 x 1 x 1 layers are already in that layout and take the vector path directly.
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -43,8 +52,14 @@ struct WgradArgs {
   const float* scale_dev;
   float* out;
   int c_real, taps_real;
+  int kflat;                // taps * Cin: extent of the flattened (tap, ci) axis
+  int vec;                  // out is [Cout][kflat] (staging buffer or a 1x1x1 layer): 16-byte vector reductions
   int* err;
 };
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 // MN-major, SWIZZLE_128B shared-memory matrix descriptor: rows (K) of 128 B = 64 MN elements, 8-row groups
 // `sbo` bytes apart, the next 64 MN elements `lbo` bytes away.
@@ -88,9 +103,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   const int nboxes = 2 * ntiles;
   const int per = (nboxes + a.splits - 1) / a.splits;
   const int tiles_mo = (a.Cout + kWM - 1) / kWM;
-  const int tiles_n = (a.Cin + a.BN - 1) / a.BN;
-  const int taps = a.kd * a.kh * a.kw;
-  const int total_items = taps * tiles_mo * tiles_n * a.splits;
+  const int tiles_n = (a.kflat + a.BN - 1) / a.BN;
+  const int total_items = tiles_mo * tiles_n * a.splits;
   const uint32_t tmem_cols = (2 * a.BN <= 128) ? 128 : (2 * a.BN <= 256) ? 256 : 512;
 
   if (threadIdx.x == 0) {
@@ -118,12 +132,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto decode_item = [&](int it, int& tap, int& mt, int& nt, int& j0, int& j1) {
+  auto decode_item = [&](int it, int& mt, int& nt, int& j0, int& j1) {
     const int sp = it % a.splits;
-    int r = it / a.splits;
-    nt = r % tiles_n; r /= tiles_n;
-    mt = r % tiles_mo;
-    tap = r / tiles_mo;
+    const int r = it / a.splits;
+    nt = r % tiles_n;
+    mt = r / tiles_n;
     j0 = sp * per;
     j1 = min(nboxes, j0 + per);
   };
@@ -148,9 +161,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       int s = 0;
       uint32_t ph = 0;
       for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-        int tap, mt, nt, j0, j1;
-        decode_item(it, tap, mt, nt, j0, j1);
-        const int tw = tap % a.kw, th = (tap / a.kw) % a.kh, td = tap / (a.kw * a.kh);
+        int mt, nt, j0, j1;
+        decode_item(it, mt, nt, j0, j1);
+        // the 64-wide sub-boxes of this N tile: (first channel, tap offset); columns past the end of the
+        // flattened axis re-load the last valid sub-box (the epilogue drops them)
+        int vc[4], vw[4], vh[4], vd[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          int kl = nt * a.BN + 64 * v;
+          if (kl >= a.kflat) kl = a.kflat - 64;
+          const int tap = kl / a.Cin;
+          vc[v] = kl - tap * a.Cin;
+          vw[v] = tap % a.kw - a.pw;
+          vh[v] = (tap / a.kw) % a.kh - a.ph;
+          vd[v] = tap / (a.kw * a.kh) - a.pd;
+        }
         for (int j = j0; j < j1; ++j) {
           int w0, h0, d0, g0;
           decode_box(j, w0, h0, d0, g0);
@@ -165,9 +190,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 #pragma unroll
             for (int u = 0; u < 2; ++u)
               tma_load_5d(sa + p * a_bytes + u * sub_bytes, mA, fb, mt * kWM + 64 * u, w0, h0, d0, g0);
-            for (int v = 0; v < a.BN / 64; ++v)
-              tma_load_5d(sb + p * b_bytes + v * sub_bytes, mB, fb, nt * a.BN + 64 * v, w0 + tw - a.pw,
-                          h0 + th - a.ph, d0 + td - a.pd, g0);
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              if (v * 64 < a.BN)
+                tma_load_5d(sb + p * b_bytes + v * sub_bytes, mB, fb, vc[v], w0 + vw[v], h0 + vh[v], d0 + vd[v], g0);
           }
           if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
@@ -183,8 +209,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       uint32_t ph = 0;
       uint32_t cc = 0;
       for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-        int tap, mt, nt, j0, j1;
-        decode_item(it, tap, mt, nt, j0, j1);
+        int mt, nt, j0, j1;
+        decode_item(it, mt, nt, j0, j1);
         for (int k0 = j0; k0 < j1; k0 += a.chunk, ++cc) {
           const uint32_t r = cc & 1u, rph = (cc >> 1) & 1u;
           mbar_wait(tempty_bar(r), rph ^ 1u, a.err, 12);
@@ -227,8 +253,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     float acc[128];
     uint32_t cc = 0;
     for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-      int tap, mt, nt, j0, j1;
-      decode_item(it, tap, mt, nt, j0, j1);
+      int mt, nt, j0, j1;
+      decode_item(it, mt, nt, j0, j1);
       if (j0 >= j1) continue;
 #pragma unroll
       for (int j = 0; j < 128; ++j) acc[j] = 0.f;
@@ -252,18 +278,34 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       }
       const int co = mt * kWM + row;
       if (co < a.Cout) {
+        const int kl0 = nt * a.BN + colhalf * half;
+        if (a.vec) {
+          float* dst = a.out + (long long)co * a.kflat;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          if (b * 32 < half) {
+          for (int b = 0; b < 4; ++b) {
+            if (b * 32 < half) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int ci = nt * a.BN + colhalf * half + b * 32 + j;
-              if (ci < a.Cin) {
-                const long long klin = (long long)tap * a.Cin + ci;
-                const int tp = (int)(klin / a.c_real);
-                const int c = (int)(klin - (long long)tp * a.c_real);
-                if (tp < a.taps_real)
-                  atomicAdd(a.out + ((long long)co * a.c_real + c) * a.taps_real + tp, acc[b * 32 + j] * sc);
+              for (int j = 0; j < 32; j += 4) {
+                const int kl = kl0 + b * 32 + j;
+                if (kl < a.kflat)
+                  red_add_v4(dst + kl, acc[b * 32 + j] * sc, acc[b * 32 + j + 1] * sc, acc[b * 32 + j + 2] * sc,
+                             acc[b * 32 + j + 3] * sc);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            if (b * 32 < half) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int klin = kl0 + b * 32 + j;
+                if (klin < a.kflat) {
+                  const int tp = klin / a.c_real;
+                  const int c = klin - tp * a.c_real;
+                  if (tp < a.taps_real)
+                    atomicAdd(a.out + ((long long)co * a.c_real + c) * a.taps_real + tp, acc[b * 32 + j] * sc);
+                }
               }
             }
           }
@@ -277,6 +319,28 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// stage [Cout][kflat] (GEMM layout, k = tap * c_real + c) -> out [Cout][c_real][taps_real] += ; one block per
+// (32 channels, co): coalesced 128-byte reads per tap, one contiguous run of 32 * taps_real floats written.
+__global__ void __launch_bounds__(256)
+wgrad_unstage_kernel(const float* __restrict__ stage, int kflat, int c_real, int taps_real, float* __restrict__ out) {
+  extern __shared__ float tile[];                 // [taps_real][33]
+  const int co = blockIdx.y;
+  const int c0 = blockIdx.x * 32;
+  const int cw = min(32, c_real - c0);
+  const float* srow = stage + (long long)co * kflat + c0;
+  for (int i = threadIdx.x; i < taps_real * 32; i += blockDim.x) {
+    const int tp = i >> 5, c = i & 31;
+    if (c < cw) tile[tp * 33 + c] = srow[(long long)tp * c_real + c];
+  }
+  __syncthreads();
+  float* orow = out + ((long long)co * c_real + c0) * taps_real;
+  for (int i = threadIdx.x; i < cw * taps_real; i += blockDim.x) {
+    const int c = i / taps_real;
+    const int tp = i - c * taps_real;
+    orow[i] += tile[tp * 33 + c];
   }
 }
 
@@ -313,6 +377,24 @@ extern "C" int drb_conv3d_wgrad(const drb_wgrad_desc* d, cudaStream_t stream) {
   a.scale = d->scale == 0.f ? 1.f : d->scale;
   a.scale_dev = d->scale_dev;
   a.out = d->dw;
+  DRB_REQUIRE((long long)taps * d->cin < (1LL << 31), "drb_conv3d_wgrad: taps * Cin too large");
+  a.kflat = taps * d->cin;
+  // Output path: the GEMM layout [Cout][kflat] IS torch's layout for a plain 1x1x1 layer; otherwise go through the
+  // caller's staging buffer when it is large enough (else: scattered scalar atomics, correct but slow).
+  const bool same_layout = a.taps_real == 1 && a.c_real == d->cin && taps == 1;
+  const long long stage_need = (long long)d->cout * a.kflat;
+  const size_t unstage_smem = (size_t)a.taps_real * 33 * sizeof(float);
+  static int use_stage = -1;
+  if (use_stage < 0) { const char* env = getenv("DRB_WGRAD_STAGE"); use_stage = env ? atoi(env) : 1; }
+  const bool staged = !same_layout && use_stage && d->stage != nullptr && d->stage_elems >= stage_need &&
+                      unstage_smem <= 48 * 1024 && ((uintptr_t)d->stage & 15) == 0;
+  if (staged) {
+    a.out = d->stage;
+    a.vec = 1;
+    DRB_CUDA_OK(cudaMemsetAsync(d->stage, 0, (size_t)stage_need * sizeof(float), stream));
+  } else if (same_layout && ((uintptr_t)d->dw & 15) == 0) {
+    a.vec = 1;
+  }
   a.tile_list = d->tile_list;
   a.tile_count = d->tile_count;
   {
@@ -323,16 +405,19 @@ extern "C" int drb_conv3d_wgrad(const drb_wgrad_desc* d, cudaStream_t stream) {
   const int nsm = igemm_num_sms();
   const long long ftiles = (long long)cdiv(a.W, a.fbw) * cdiv(a.H, a.fbh) * cdiv(a.D, a.fbd) * cdiv(a.G, a.fbg);
   const long long nboxes = 2 * ftiles;
-  // Work decomposition: (tap, 128 co, BN ci) tiles x K splits.  Small problems (a few hundred tokens, deep
+  // Work decomposition: (128 co, BN columns of the flattened (tap, ci) axis) tiles x K splits.  Small problems (a few hundred tokens, deep
   // backbone levels) are latency bound: prefer narrower ci tiles and finer K splits until every SM has an item;
   // large ones (level-1 FPN: thousands of boxes) take the widest tile and ~2 items per SM.
   long long max_splits = nboxes / a.chunk;
   if (max_splits < 1) max_splits = 1;
   long long base_items = 0;
+  static int flat_n = -1;       // DRB_WGRAD_FLAT_N=0: N tiles never span taps (the round-2 first version)
+  if (flat_n < 0) { const char* env = getenv("DRB_WGRAD_FLAT_N"); flat_n = env ? atoi(env) : 1; }
+  const int n_extent = (flat_n || d->cin % 256 == 0) ? a.kflat : d->cin;
   for (int bn = 256; bn >= 64; bn >>= 1) {
-    if (bn > d->cin && bn != 64) continue;
+    if ((bn > n_extent || (!flat_n && d->cin % bn != 0)) && bn != 64) continue;
     a.BN = bn;
-    base_items = (long long)taps * cdiv(a.Cout, kWM) * cdiv(a.Cin, bn);
+    base_items = (long long)cdiv(a.Cout, kWM) * cdiv(a.kflat, bn);
     if (base_items * max_splits >= nsm) break;
   }
   long long splits = (2LL * nsm + base_items - 1) / base_items;
@@ -375,6 +460,11 @@ extern "C" int drb_conv3d_wgrad(const drb_wgrad_desc* d, cudaStream_t stream) {
   const int grid = (int)(items < nsm ? items : nsm);
   wgrad_kernel<<<grid, kWThreads, smem, stream>>>(mA[0], mA[1], mB[0], mB[1], a);
   DRB_LAUNCH_OK();
+  if (staged) {
+    const dim3 ug((unsigned)cdiv(a.c_real, 32), (unsigned)d->cout);
+    wgrad_unstage_kernel<<<ug, 256, unstage_smem, stream>>>(d->stage, a.kflat, a.c_real, a.taps_real, d->dw);
+    DRB_LAUNCH_OK();
+  }
   return 0;
 }
 

@@ -332,21 +332,25 @@ def grad_split(x, pair=True, ld_out=None):
 
 
 def conv3d_wgrad(dy_planes, x_planes, k, cout, cin, planes=2, c_real=0, taps_real=0, tile_list=None,
-                 tile_count=None, scale=1.0):
+                 tile_count=None, scale=1.0, stage=True):
     """dy_planes: (hi, lo, inv_scale) of [g, d, h, w, cout]; x_planes: (hi, lo) of [g, d, h, w, cin]
-    -> dw fp32 [cout, c_real or cin, taps_real or k^3]."""
+    -> dw fp32 [cout, c_real or cin, taps_real or k^3].  stage: hand the kernel a [cout][k^3 cin] workspace
+    (vector reductions + one transposition) instead of scattered atomics into dw."""
     dy_hi, dy_lo, inv = dy_planes
     x_hi, x_lo = x_planes
     g, d, h, w, _ = x_hi.shape
     cr, tr = (c_real or cin), (taps_real or k ** 3)
     dw = torch.zeros((cout, cr, tr), dtype=torch.float32, device=x_hi.device)
+    ws = torch.empty(cout * k ** 3 * cin, dtype=torch.float32, device=x_hi.device) if stage else None
     desc = _lib.WgradDesc(g=g, d=d, h=h, w=w, cout=cout, cin=cin, kd=k, kh=k, kw=k, planes=planes,
                           dy_hi=dy_hi.data_ptr(), dy_lo=dy_lo.data_ptr() if dy_lo is not None else None,
                           x_hi=x_hi.data_ptr(), x_lo=x_lo.data_ptr() if x_lo is not None else None,
                           scale=scale, scale_dev=inv.data_ptr() if inv is not None else None,
                           dw=dw.data_ptr(), c_real=c_real, taps_real=taps_real,
                           tile_list=tile_list.data_ptr() if tile_list is not None else None,
-                          tile_count=tile_count.data_ptr() if tile_count is not None else None)
+                          tile_count=tile_count.data_ptr() if tile_count is not None else None,
+                          stage=ws.data_ptr() if ws is not None else None,
+                          stage_elems=ws.numel() if ws is not None else 0)
     with _dev(x_hi):
         check(_lib.load().drb_conv3d_wgrad(C.byref(desc), stream_ptr()), "drb_conv3d_wgrad")
     return dw

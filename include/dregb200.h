@@ -34,7 +34,7 @@ extern "C" {
 #define DRB_ENOMEM (-3)
 #define DRB_ESTATE (-4)
 
-#define DRB_ABI_VERSION 3
+#define DRB_ABI_VERSION 4
 
 typedef struct CUstream_st* drb_stream_t; /* == cudaStream_t */
 
@@ -370,6 +370,9 @@ typedef struct drb_wgrad_desc {
   int c_real, taps_real;                   /* 0 -> cin, kd*kh*kw                               */
   const int* tile_list;
   const int* tile_count;
+  float* stage;                            /* optional workspace, >= cout * kd*kh*kw * cin floats: the    */
+  long long stage_elems;                   /* tile is reduced in GEMM layout and transposed into dw;      */
+                                           /* NULL: scattered atomics straight into dw (slow for k > 1)   */
 } drb_wgrad_desc;
 int drb_conv3d_wgrad(const drb_wgrad_desc* desc, drb_stream_t stream);
 

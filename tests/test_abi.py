@@ -26,7 +26,7 @@ def test_header_symbols_exported_and_bound(pkg):
 
 def test_library_loads_and_reports_version(pkg):
     lib = pkg.load_library()
-    assert lib.drb_abi_version() == 3
+    assert lib.drb_abi_version() == 4
     assert lib.drb_ngp_table_entries() == 6299960
     assert lib.drb_downsample_workspace_bytes(1000, 260) > 1000 * 260 * 4
 

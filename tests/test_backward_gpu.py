@@ -45,9 +45,12 @@ def _wgrad_ref(dy, x, k):
     dict(g=2, d=1, h=1, w=1, cin=512, cout=512, k=3),          # deepest level at 32^3: one voxel per grid
     dict(g=2, d=4, h=4, w=4, cin=64, cout=64, k=1),            # Cout below the 128-lane tile
     dict(g=1, d=1, h=1, w=300, cin=1024, cout=256, k=1),       # linear2
+    dict(g=2, d=16, h=16, w=16, cin=64, cout=64, k=3),         # four taps side by side in one 256-wide N tile
+    dict(g=1, d=8, h=16, w=32, cin=128, cout=256, k=3),        # two taps per tile; 27 * 128 = 13.5 tiles (clamped tail)
 ])
 @pytest.mark.parametrize("planes", [2, 1])
-def test_wgrad_tcgen05(pkg, cuda, case, planes):
+@pytest.mark.parametrize("stage", [True, False])
+def test_wgrad_tcgen05(pkg, cuda, case, planes, stage):
     ops = _ops()
     torch.manual_seed(3)
     g, d, h, w, cin, cout, k = [case[n] for n in ("g", "d", "h", "w", "cin", "cout", "k")]
@@ -59,11 +62,11 @@ def test_wgrad_tcgen05(pkg, cuda, case, planes):
     dyp = ops.grad_split(dy.to(cuda).reshape(-1, cout), pair=pair)
     xh = xh.view(g, d, h, w, cin)
     xl = xl.view(g, d, h, w, cin) if xl is not None else None
-    dw = ops.conv3d_wgrad(dyp, (xh, xl), k, cout, cin, planes=planes)
+    dw = ops.conv3d_wgrad(dyp, (xh, xl), k, cout, cin, planes=planes, stage=stage)
     torch.cuda.synchronize()
     assert ops.igemm_error_flag() == 0
     err = _rel(dw, ref)
-    print("wgrad", case, "planes", planes, "rel err %.2e" % err)
+    print("wgrad", case, "planes", planes, "stage", stage, "rel err %.2e" % err)
     assert err < (2e-5 if pair else 2e-2)
 
 
@@ -79,11 +82,12 @@ def test_wgrad_im2col_unpack_and_tile_list(pkg, cuda):
     ref = (dy.double().t() @ col.double())[:, :c * taps].reshape(cout, taps, c).permute(0, 2, 1)
     xh, xl = ops.split_planes(col.to(cuda))
     dyp = ops.grad_split(dy.to(cuda))
-    dw = ops.conv3d_wgrad(dyp, (xh.view(1, 1, 1, rows, kpad), xl.view(1, 1, 1, rows, kpad)), 1, cout, kpad,
-                          c_real=c, taps_real=taps)
-    err = _rel(dw, ref)
-    print("wgrad im2col rel err %.2e" % err)
-    assert err < 2e-5
+    for stage in (True, False):
+        dw = ops.conv3d_wgrad(dyp, (xh.view(1, 1, 1, rows, kpad), xl.view(1, 1, 1, rows, kpad)), 1, cout, kpad,
+                              c_real=c, taps_real=taps, stage=stage)
+        err = _rel(dw, ref)
+        print("wgrad im2col (stage %s) rel err %.2e" % (stage, err))
+        assert err < 2e-5
     # (b) tile list: only voxels of the listed 128-voxel tiles contribute
     g, d, h, w, cin, cout, k = 2, 16, 16, 16, 64, 64, 3
     box, tiles = ops.conv3d_tile_shape(g, d, h, w)
