@@ -41,6 +41,15 @@ xh, _ = ops.split_planes(x, want_lo=False)
 dyp = ops.grad_split(dy, pair=False)
 ops.conv3d_wgrad(dyp, (xh.view(1, 1, 1, n, 256), None), 1, 1024, 256, planes=1)
 
+# 2b. layer1.conv2 wgrad: 64 -> 64, 3^3 at 2 x 32^3 (four taps side by side in one 256-wide N tile)
+g, d, h, w, c = 2, 32, 32, 32, 64
+x = torch.randn(g * d * h * w, c, device=dev)
+dy = torch.randn(g * d * h * w, c, device=dev) * 1e-3
+xh, _ = ops.split_planes(x, want_lo=False)
+dyp = ops.grad_split(dy, pair=False)
+ops.conv3d_wgrad(dyp, (xh.view(g, d, h, w, c), None), 3, c, c, planes=1)
+del x, dy, xh, dyp
+
 # 3. attention, 8k x 8k
 n = 8192
 qkv = torch.randn(2 * n, 768, device=dev)

@@ -25,5 +25,21 @@ if which in ("elem", "all"):
     ops.sgemm_strided(A, (333 * 257, 257, 1), B, (257 * 32, 32, 1), Cm, (333 * 32, 32), 333, 32, 257, batch=8)
     At = torch.randn(8, 257, 333, device=dev)
     ops.sgemm_strided(At, (333 * 257, 1, 333), B, (257 * 32, 32, 1), Cm, (333 * 32, 32), 333, 32, 257, batch=8)
+if which in ("wgrad", "all"):
+    # staged vector reductions + transposition, taps side by side in the N tile (clamped tail), im2col unpacking
+    for planes in (1, 2):
+        for (g, d, h, w, cin, cout, k) in ((1, 8, 16, 32, 128, 136, 3), (2, 16, 16, 16, 64, 64, 3), (1, 1, 1, 300, 256, 72, 1)):
+            x = torch.randn(g * d * h * w, cin, device=dev)
+            dy = torch.randn(g * d * h * w, cout, device=dev)
+            xh, xl = ops.split_planes(x, want_lo=planes == 2)
+            dyp = ops.grad_split(dy, pair=planes == 2)
+            xh = xh.view(g, d, h, w, cin)
+            xl = xl.view(g, d, h, w, cin) if xl is not None else None
+            for stage in (True, False):
+                ops.conv3d_wgrad(dyp, (xh, xl), k, cout, cin, planes=planes, stage=stage)
+    col = torch.randn(512, 512, device=dev)
+    xh, xl = ops.split_planes(col)
+    dyp = ops.grad_split(torch.randn(512, 64, device=dev))
+    ops.conv3d_wgrad(dyp, (xh.view(1, 1, 1, 512, 512), xl.view(1, 1, 1, 512, 512)), 1, 64, 512, c_real=4, taps_real=125)
 torch.cuda.synchronize()
 print("flag", ops.igemm_error_flag(), "done", which)
