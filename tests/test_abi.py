@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -66,3 +68,30 @@ def test_integration_stub_matches_the_binding(pkg):
             if m:
                 members.append(m.group(1))
     assert members == stub, (members, stub)
+
+
+def _header_members(struct):
+    with open(os.path.join(ROOT, "include", "dregb200.h")) as fh:
+        header = re.sub(r"/\*.*?\*/", "", fh.read(), flags=re.S)
+    body = header[header.index("typedef struct %s {" % struct):header.index("} %s;" % struct)]
+    members = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(None, 1)[1] if " " in decl else decl
+        for part in names.split(","):
+            m = re.search(r"(\w+)\s*(\[\d+\])?$", part.strip())
+            if m:
+                members.append(m.group(1))
+    return members
+
+
+@pytest.mark.parametrize("struct,cls", [("drb_wgrad_desc", "WgradDesc"), ("drb_conv3d_desc", "Conv3dDesc"),
+                                        ("drb_extract_desc", "ExtractDesc"), ("drb_engine_config", "EngineConfig")])
+def test_ctypes_structs_mirror_the_header(pkg, struct, cls):
+    """Every descriptor the binding fills has the header's members, in the header's order (ABI 4 appended
+    `stage` / `stage_elems` to drb_wgrad_desc: a binding built for ABI 3 would pass a short struct)."""
+    from importlib import import_module
+    lib_mod = import_module("dreg-nerf_b200._lib")
+    assert [f[0] for f in getattr(lib_mod, cls)._fields_] == _header_members(struct)
