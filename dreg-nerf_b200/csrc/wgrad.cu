@@ -420,9 +420,26 @@ extern "C" int drb_conv3d_wgrad(const drb_wgrad_desc* d, cudaStream_t stream) {
     base_items = (long long)cdiv(a.Cout, kWM) * cdiv(a.kflat, bn);
     if (base_items * max_splits >= nsm) break;
   }
+  // K splits from a wave model: the persistent CTAs stride over the items, so a launch lasts
+  // ceil(items / SMs) x (boxes per item + the item's fixed cost: pipeline fill, TMEM drain, reductions ~ 6 boxes).
+  // "About two items per SM" (the first rule) often meant 2.01-2.2 waves, i.e. three items on a few SMs while the
+  // rest idle: 324 items of 171 boxes for 256 x 256 x 27 at 2 x 32^3 where 432 items of 128 boxes finish 24 % sooner.
+  static int split_model = -1;   // DRB_WGRAD_SPLIT_MODEL=0: the first rule
+  if (split_model < 0) { const char* env = getenv("DRB_WGRAD_SPLIT_MODEL"); split_model = env ? atoi(env) : 1; }
   long long splits = (2LL * nsm + base_items - 1) / base_items;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
+  if (split_model) {
+    const double item_cost = 6.0;
+    double best = 1e300;
+    const long long s_hi = max_splits < 4096 ? max_splits : 4096;
+    for (long long s = 1; s <= s_hi; ++s) {
+      const long long waves = (base_items * s + nsm - 1) / nsm;
+      const long long per_s = (nboxes + s - 1) / s;
+      const double cost = (double)waves * ((double)per_s + item_cost);
+      if (cost < best * 0.995) { best = cost; splits = s; }     // ties: the fewer splits (less reduction traffic)
+    }
+  }
   a.splits = (int)splits;
 
   const size_t stage_bytes = (size_t)a.planes * ((size_t)kWM * kWK * 2 + (size_t)a.BN * kWK * 2);
